@@ -1,0 +1,269 @@
+/* racu.h - C ABI of the B200 execution back end for ra-ra's traversal hot path.
+ *
+ * The reference (lloda/ra-ra, header-only C++23) has no FFI. Its de-facto operator interface for
+ * this path is the single traversal entry `ra::ply(Iterator&&)` (ra/ply.hh:157-166) that every
+ * assignment (ra/expr.hh:50-60), reduction (ra/ra.hh:279-401) and gemm/gemv (ra/ra.hh:403-456)
+ * funnels into, plus the ten-method Iterator concept (ra/base.hh:298-311) that expression nodes
+ * implement. This header is the seam introduced AT `ply`: a flattened expression tree
+ * (racu_desc) crosses it and is executed by hand-written sm_100a kernels.
+ *
+ * Plain C: pointers, sizes, POD structs, int status returns. No torch / C++ types.
+ *
+ *   reference interface replaced                          entry point here
+ *   ----------------------------------------------------  ---------------------------------
+ *   ply(map(op, dst, src...)) / dst OP= expr               racu_map
+ *     ra/ply.hh:21-86,157-168; ra/expr.hh:50-60
+ *   Match::check / agree (prefix shape agreement)          racu_agree
+ *     ra/expr.hh:529-608,639
+ *   sum prod amin amax dot reduce_sqrm                     racu_reduce / racu_reduce_dev
+ *     ra/ra.hh:306-322,348-401
+ *   Anext(I,J,K) = -6*A(I,J,K) + A(I+1,J,K)... ; swap      racu_stencil (also reached from racu_map
+ *     bench/bench-stencil3.cc:55-64, bench-stencil2.cc:49-58,    by pattern recognition)
+ *     examples/laplace2d.cc:36
+ *   gemm / gemv / gevm                                     racu_gemm / racu_gemv
+ *     ra/ra.hh:403-456
+ *   Array(shape, none|value) storage, default_init         racu_alloc / racu_free / racu_memcpy_* / racu_fill
+ *     ra/arrays.hh:224-327
+ *   (none: the reference is single process)                racu_comm_* (NCCL over NVLink)
+ */
+#ifndef RACU_H
+#define RACU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RACU_VERSION 1
+#define RACU_MAX_RANK 8    /* the reference's own examples reach expression rank 6 (examples/maxwell.cc:34) */
+#define RACU_MAX_OPND 12
+#define RACU_MAX_INS 48
+
+/* ra/base.hh:232-234. UNB marks a dead / unbounded axis (insert<n>, tindex, unbounded iota). */
+#define RACU_ANY ((int64_t)-1944444444)
+#define RACU_UNB ((int64_t)-1988888888)
+#define RACU_MIS ((int64_t)-1922222222)
+
+typedef enum {
+    RACU_OK = 0,
+    RACU_ERR_BAD_DESC = 1,     /* malformed descriptor / program */
+    RACU_ERR_SHAPE = 2,        /* operands do not agree: RA_CK "Bad shapes" ra/expr.hh:562; or unbounded */
+    RACU_ERR_UNSUPPORTED = 3,  /* well formed, outside what the kernels implement */
+    RACU_ERR_CUDA = 4,
+    RACU_ERR_NCCL = 5,
+    RACU_ERR_ALLOC = 6,
+    RACU_ERR_BOUNDS = 7
+} racu_status;
+
+typedef enum {
+    RACU_BOOL = 0, /* 1 byte, 0/1 (C++ bool) */
+    RACU_I32 = 1,
+    RACU_I64 = 2,
+    RACU_F32 = 3,
+    RACU_F64 = 4,
+    RACU_NDTYPE = 5
+} racu_dtype;
+
+typedef enum {
+    RACU_MEM = 0,    /* Cell over memory: base.ptr + sum idx[k]*stride[k] (elements). ra/expr.hh:266-312 */
+    RACU_SEQ = 1,    /* Cell over Seq (iota, tindex): value = base + T(sum idx[k]*stride[k]). ra/expr.hh:79-100 */
+    RACU_SCALAR = 2  /* Scalar<C>: rank 0, step 0. ra/expr.hh:104-120 */
+} racu_kind;
+
+typedef union {
+    void * ptr;
+    int64_t i;
+    double f;
+} racu_base;
+
+/* One leaf of the expression tree. Axes k >= rank have step 0 (Cell::step, ra/expr.hh:294-295) so a
+ * lower rank operand repeats along TRAILING axes (prefix matching, docs/ra-ra.texi:633-681).
+ * len[k] may be RACU_UNB (dead axis: insert<n> ra/ply.hh:423-427, Reframe ra/expr.hh:425-436). */
+typedef struct {
+    int32_t kind;   /* racu_kind */
+    int32_t dtype;  /* racu_dtype of the element */
+    int32_t rank;
+    int32_t reserved;
+    racu_base base; /* MEM: device pointer to element [0,..,0]. SEQ: origin (i for integer dtypes, f for float). SCALAR: value */
+    int64_t len[RACU_MAX_RANK];
+    int64_t stride[RACU_MAX_RANK]; /* in elements; 0 = broadcast, <0 = reversed */
+} racu_operand;
+
+/* Postfix op program. Every arithmetic instruction works in ONE type: the flattener inserts explicit
+ * CASTs where C++'s usual arithmetic conversions would apply (float+double -> double, int*float ->
+ * float, ...), so `type` is both the operand and the result type, except comparisons and NOT, whose
+ * result is RACU_BOOL. */
+typedef enum {
+    RACU_OP_PUSH = 0,  /* arg = operand index; type = its dtype */
+    RACU_OP_CAST = 1,  /* aux = source type; type = destination type. ra::cast ra/expr.hh:680 */
+    /* unary T -> T */
+    RACU_OP_NEG = 2,
+    RACU_OP_ABS = 3,
+    RACU_OP_SQRT = 4,
+    RACU_OP_SQR = 5,   /* sqr / sqrm(x) ra/ra.hh:65,71 */
+    RACU_OP_EXP = 6,
+    RACU_OP_LOG = 7,
+    RACU_OP_SIN = 8,
+    RACU_OP_COS = 9,
+    RACU_OP_NOT = 10,  /* T -> BOOL */
+    /* binary T,T -> T */
+    RACU_OP_ADD = 16,
+    RACU_OP_SUB = 17,
+    RACU_OP_MUL = 18,
+    RACU_OP_DIV = 19,
+    RACU_OP_MOD = 20,  /* integer % ; fmod for floats */
+    RACU_OP_MIN = 21,  /* std::min(a,b) = b<a ? b : a   (ra/ra.hh:216) */
+    RACU_OP_MAX = 22,  /* std::max(a,b) = a<b ? b : a */
+    RACU_OP_POW = 23,
+    RACU_OP_ATAN2 = 24,
+    RACU_OP_BAND = 25,
+    RACU_OP_BOR = 26,
+    RACU_OP_BXOR = 27,
+    /* binary T,T -> BOOL */
+    RACU_OP_EQ = 32,
+    RACU_OP_NE = 33,
+    RACU_OP_LT = 34,
+    RACU_OP_LE = 35,
+    RACU_OP_GT = 36,
+    RACU_OP_GE = 37,
+    /* other */
+    RACU_OP_FMA = 40,  /* a b c -> fma(a,b,c) */
+    RACU_OP_PICK = 41  /* sel x0 .. x(n-1) -> x[sel]; arg = n, aux = selector type, type = T of branches.
+                          ra::pick ra/expr.hh:686-728; where(w,t,f) = pick(bool(w), f, t) ra/ra.hh:255-256.
+                          Only the chosen branch is observable: the opcode set is side-effect free. */
+} racu_opcode;
+
+typedef struct {
+    uint8_t op;   /* racu_opcode */
+    uint8_t type; /* racu_dtype */
+    uint8_t arg;
+    uint8_t aux;
+} racu_ins;
+
+/* `dst OP= program(srcs)`. ra/expr.hh:50-53: every assignment is for_each([](y, x){ y OP= x; }, dst, rhs)
+ * and the destination takes part in shape agreement like any operand. When dst has step 0 along an
+ * expression axis longer than 1, the sequential reference turns the assignment into a fold
+ * (c(m) += a(m,n) sums over n: docs/ra-ra.texi:684-690, test/reduction.cc:155-158); the device does it
+ * with a deterministic tree. AMIN/AMAX are the combiners of ra::amin/amax (ra/ra.hh:306-322). */
+typedef enum {
+    RACU_ASSIGN_SET = 0,
+    RACU_ASSIGN_ADD = 1,
+    RACU_ASSIGN_SUB = 2,
+    RACU_ASSIGN_MUL = 3,
+    RACU_ASSIGN_DIV = 4,
+    RACU_ASSIGN_AMIN = 5, /* if (x<y) y=x */
+    RACU_ASSIGN_AMAX = 6  /* if (y<x) y=x */
+} racu_assign;
+
+typedef struct {
+    int32_t nopnd;
+    int32_t nins;
+    int32_t dst;    /* index of the destination operand (kind MEM), or -1 for racu_reduce */
+    int32_t assign; /* racu_assign */
+    racu_operand opnd[RACU_MAX_OPND];
+    racu_ins ins[RACU_MAX_INS];
+} racu_desc;
+
+/* ---- library ---- */
+int racu_version(void);
+/* Thread-local text for the last non-OK status returned on this thread. */
+const char * racu_last_error_string(void);
+int racu_device_count(void);
+int racu_set_device(int dev);
+
+/* ---- storage ---- */
+int racu_alloc(void ** ptr, size_t bytes);
+int racu_free(void * ptr);
+int racu_memcpy_h2d(void * dst_dev, const void * src_host, size_t bytes, void * stream);
+int racu_memcpy_d2h(void * dst_host, const void * src_dev, size_t bytes, void * stream);
+int racu_memcpy_d2d(void * dst_dev, const void * src_dev, size_t bytes, void * stream);
+int racu_fill(void * dst_dev, int dtype, racu_base value, size_t count, void * stream);
+int racu_stream_sync(void * stream);
+/* Pinned host staging used by the host header for std::vector operands. */
+int racu_host_alloc(void ** ptr, size_t bytes);
+int racu_host_free(void * ptr);
+
+/* ---- traversal ---- */
+/* Shape agreement only (Match::len / check). rank_out and len_out (RACU_MAX_RANK entries) may be NULL. */
+int racu_agree(const racu_desc * d, int32_t * rank_out, int64_t * len_out);
+/* dst OP= program. Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+int racu_map(const racu_desc * d, void * stream);
+
+/* ---- whole-array reductions of a fused map (d->dst must be -1) ---- */
+typedef enum {
+    RACU_RED_SUM = 1,  /* sum, dot, reduce_sqrm: start T(0), c += x */
+    RACU_RED_PROD = 3, /* start T(1), c *= x */
+    RACU_RED_AMIN = 5, /* start +inf / max, if (x<c) c=x : NaN never enters */
+    RACU_RED_AMAX = 6
+} racu_redop;
+/* Result has the program's result type. out_host receives it after a stream synchronise. */
+int racu_reduce(const racu_desc * d, int redop, void * out_host, void * stream);
+/* Same, result left in device memory (asynchronous). */
+int racu_reduce_dev(const racu_desc * d, int redop, void * out_dev, void * stream);
+/* Kernel configuration introspection for tests/bench: how many of this library's kernels were
+ * launched by this thread since the last reset. */
+int64_t racu_launch_count(void);
+void racu_launch_count_reset(void);
+/* Name of the kernel family the last racu_map / racu_reduce on this thread dispatched to. */
+const char * racu_last_kernel(void);
+
+/* ---- stencils ---- */
+typedef enum {
+    RACU_STENCIL_3D7 = 1, /* bench/bench-stencil3.cc:59-61  -6*c + (i+1) + (j+1) + (k+1) + (i-1) + (j-1) + (k-1) */
+    RACU_STENCIL_2D5 = 2, /* bench/bench-stencil2.cc:53-55  -4*c + (i+1) + (j+1) + (i-1) + (j-1) */
+    RACU_STENCIL_1D3 = 3, /* bench/bench-stencil1.cc:45     -2*c + (i+1) + (i-1) */
+    RACU_STENCIL_2D5_STIFF = 4 /* examples/laplace2d.cc:36  4*c - (i-1) - (j-1) - (i+1) - (j+1) */
+} racu_stencil_kind;
+
+/* One sweep over the interior [1, len-1) of every axis; boundary cells of dst are NOT written
+ * (bench/bench-stencil3.cc:125-126). lo0/hi0 restrict the sweep on axis 0 to planes [lo0, hi0)
+ * (clipped to the interior) so a slab-sharded caller can do boundary planes first. */
+typedef struct {
+    int32_t kind;  /* racu_stencil_kind */
+    int32_t dtype; /* RACU_F32 or RACU_F64 */
+    int32_t rank;
+    int32_t reserved;
+    const void * src;
+    void * dst;
+    int64_t len[3];
+    int64_t src_stride[3]; /* elements; innermost must be 1 */
+    int64_t dst_stride[3];
+    int64_t lo0, hi0;      /* 0,0 = whole interior */
+} racu_stencil_desc;
+int racu_stencil(const racu_stencil_desc * s, void * stream);
+
+/* ---- dense contraction ---- */
+/* c(M,N) += a(M,K) * b(K,N), row-major with leading dimensions in elements. ra/ra.hh:403-412.
+ * F64 uses FP64 tensor-core MMA; F32 uses the 3xTF32 split (error bound in DESIGN.md). */
+typedef struct {
+    int32_t dtype;
+    int32_t reserved;
+    int64_t M, N, K;
+    const void * a; int64_t lda;
+    const void * b; int64_t ldb;
+    void * c; int64_t ldc;
+} racu_gemm_desc;
+int racu_gemm(const racu_gemm_desc * g, void * stream);
+/* c(M) += a(M,N) * b(N)   (ra/ra.hh:414-425), trans=0;  c(N) += a(M) * b(M,N) (gevm ra/ra.hh:427-438), trans=1. */
+int racu_gemv(int dtype, int trans, int64_t M, int64_t N, const void * a, int64_t lda,
+              const void * x, int64_t incx, void * y, int64_t incy, void * stream);
+
+/* ---- multi GPU (one process per GPU; NCCL over NVLink/NVSwitch) ---- */
+#define RACU_UNIQUE_ID_BYTES 128
+typedef struct racu_comm racu_comm;
+int racu_comm_unique_id(void * id_out /* RACU_UNIQUE_ID_BYTES */);
+int racu_comm_init_rank(racu_comm ** comm, const void * id, int nranks, int rank);
+int racu_comm_destroy(racu_comm * comm);
+/* In-place allreduce of count elements of dtype with redop SUM/PROD/AMIN/AMAX. */
+int racu_allreduce(racu_comm * comm, void * buf_dev, size_t count, int dtype, int redop, void * stream);
+/* Slab halo exchange along axis 0: send `count` elements at send_lo to rank-1 and send_hi to rank+1, receive
+ * into recv_lo (from rank-1) and recv_hi (from rank+1). Ends are non periodic: missing neighbours are skipped. */
+int racu_halo_exchange(racu_comm * comm, const void * send_lo, void * recv_lo, const void * send_hi, void * recv_hi,
+                       size_t count, int dtype, void * stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RACU_H */

@@ -1,0 +1,683 @@
+"""Host-side mirror of ra-ra's array surface for the traversal hot path, in Python.
+
+The reference is a C++ header library; the product host side is the C++ header include/ra/cuda.hh. This module
+is the same surface for Python callers (tests, bench.py): views with prefix-matching rank extension, beaten
+slicing (iota / all / dots / insert / len), transpose / reverse, operator expression trees, reductions and
+gemm/gemv. It does no arithmetic on array contents: every operation is flattened into a racu_desc
+(include/racu.h) and handed to an executor, which for the product is the CUDA library (ra_ra_b200.cuda).
+
+Reference lines mirrored are cited per function (relative to the reference root).
+"""
+import builtins as _builtins
+
+import numpy as np
+
+from . import abi
+from .abi import ANY, BOOL, F32, F64, I32, I64, MEM, SCALAR, SEQ, UNB  # noqa: F401
+
+builtins_len = _builtins.len
+
+NP2RACU = {np.dtype(np.bool_): BOOL, np.dtype(np.int32): I32, np.dtype(np.int64): I64,
+           np.dtype(np.float32): F32, np.dtype(np.float64): F64}
+RACU2NP = {v: k for k, v in NP2RACU.items()}
+
+
+class RaError(RuntimeError):
+    """RA_CK failure (ra/expr.hh:17-43): raised before any kernel is launched."""
+
+    def __init__(self, status, msg):
+        super().__init__(f"{abi.STATUS_NAMES[status] if 0 <= status < builtins_len(abi.STATUS_NAMES) else status}: {msg}")
+        self.status = status
+
+
+def _ck(cond, msg, status=abi.ERR_BOUNDS):
+    if not cond:
+        raise RaError(status, msg)
+
+
+# ---------------- C++ usual arithmetic conversions over the five element types ----------------
+
+def promote(t):
+    """Integer promotion: bool -> int."""
+    return I32 if t == BOOL else t
+
+
+def common_type(a, b):
+    a, b = promote(a), promote(b)
+    if F64 in (a, b):
+        return F64
+    if F32 in (a, b):
+        return F32
+    if I64 in (a, b):
+        return I64
+    return I32
+
+
+def is_float(t):
+    return t in (F32, F64)
+
+
+# ---------------- subscripts: ra/ply.hh:314-330 ----------------
+
+class LenExpr:
+    """ra::len inside subscripts (ra/base.hh:278-291), resolved by wlen (ra/ply.hh:243-295) against the axis length."""
+
+    def __init__(self, f=lambda n: n):
+        self.f = f
+
+    def resolve(self, n):
+        return int(self.f(n))
+
+    def _bin(self, other, op):
+        g = other.f if isinstance(other, LenExpr) else (lambda n, o=other: o)
+        return LenExpr(lambda n, f=self.f, g=g: op(f(n), g(n)))
+
+    def _rbin(self, other, op):
+        return LenExpr(lambda n, f=self.f, o=other: op(o, f(n)))
+
+    @staticmethod
+    def _cdiv(a, b):  # C++ integer division truncates toward zero
+        q = _builtins.abs(a) // _builtins.abs(b)
+        return q if (a >= 0) == (b >= 0) else -q
+
+    def __add__(self, o): return self._bin(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._rbin(o, lambda a, b: a + b)
+    def __sub__(self, o): return self._bin(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._rbin(o, lambda a, b: a - b)
+    def __mul__(self, o): return self._bin(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._rbin(o, lambda a, b: a * b)
+    def __floordiv__(self, o): return self._bin(o, LenExpr._cdiv)
+    def __truediv__(self, o): return self._bin(o, LenExpr._cdiv)
+    def __neg__(self): return LenExpr(lambda n, f=self.f: -f(n))
+
+
+len = LenExpr()  # noqa: A001  (ra::len)
+
+
+def _wlen(x, n):
+    return x.resolve(n) if isinstance(x, LenExpr) else x
+
+
+class Dots:
+    def __init__(self, n):
+        self.n = n
+
+
+class Insert:
+    def __init__(self, n):
+        self.n = n
+
+
+def dots(n=UNB):
+    return Dots(n)
+
+
+def insert(n=1):
+    return Insert(n)
+
+
+all = Dots(1)  # noqa: A001  (ra::all = dots<1>, ra/ply.hh:318)
+
+
+class Iota:
+    """ra::iota(n, o, s): rank-1 view over Seq{o} with {len n, step s} (ra/ply.hh:320-321). Usable as a subscript
+    (beaten, ra/ply.hh:399-415) and as an expression operand (kind SEQ)."""
+
+    __array_ufunc__ = None
+
+    def __init__(self, n=UNB, o=None, s=1, dtype=None):
+        self.n, self.s = n, s
+        if dtype is None:
+            dtype = I64 if o is None else (F64 if isinstance(o, float) else I32)
+        self.o = 0 if o is None else o
+        self.dtype = dtype
+
+    # iota arithmetic stays iota: ra/ra.hh:129-143 (opt). Needed so A(I+1, J, K) is a view (bench/bench-stencil3.cc:59-61).
+    def _isint(self, k):
+        return isinstance(k, (int, np.integer)) and not isinstance(k, bool)
+
+    def __add__(self, k):
+        if isinstance(k, Iota):
+            return Iota(_colen_py(self.n, k.n), self.o + k.o, self.s + k.s, common_type(self.dtype, k.dtype))
+        if self._isint(k) or isinstance(k, LenExpr):
+            return Iota(self.n, self.o + k, self.s, self.dtype)
+        return as_expr(self) + k
+
+    __radd__ = __add__
+
+    def __sub__(self, k):
+        if isinstance(k, Iota):
+            return Iota(_colen_py(self.n, k.n), self.o - k.o, self.s - k.s, common_type(self.dtype, k.dtype))
+        if self._isint(k) or isinstance(k, LenExpr):
+            return Iota(self.n, self.o - k, self.s, self.dtype)
+        return as_expr(self) - k
+
+    def __rsub__(self, k):
+        if self._isint(k) or isinstance(k, LenExpr):
+            return Iota(self.n, k - self.o, -self.s, self.dtype)
+        return k - as_expr(self)
+
+    def __mul__(self, k):
+        if self._isint(k):
+            return Iota(self.n, self.o * k, self.s * k, self.dtype)
+        return as_expr(self) * k
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return Iota(self.n, -self.o, -self.s, self.dtype)
+
+
+def _colen_py(a, b):
+    if a == UNB:
+        return b
+    if b == UNB:
+        return a
+    _ck(a == b, f"Bad shapes {a} {b}.", abi.ERR_SHAPE)
+    return a
+
+
+def iota(n=UNB, o=None, s=1, dtype=None):
+    return Iota(n, o, s, dtype)
+
+
+# ---------------- expression tree ----------------
+
+class Expr:
+    """A node of the expression template tree (Map / Pick / Cell / Scalar, ra/expr.hh:104-120,266-312,652-722)."""
+    dtype = None
+    __array_ufunc__ = None  # numpy operands defer to our reflected operators
+
+    def _b(self, other, op, rev=False):
+        o = as_expr(other)
+        a, b = (o, self) if rev else (self, o)
+        return binop(op, a, b)
+
+    def __add__(self, o): return self._b(o, abi.OP_ADD)
+    def __radd__(self, o): return self._b(o, abi.OP_ADD, True)
+    def __sub__(self, o): return self._b(o, abi.OP_SUB)
+    def __rsub__(self, o): return self._b(o, abi.OP_SUB, True)
+    def __mul__(self, o): return self._b(o, abi.OP_MUL)
+    def __rmul__(self, o): return self._b(o, abi.OP_MUL, True)
+    def __truediv__(self, o): return self._b(o, abi.OP_DIV)
+    def __rtruediv__(self, o): return self._b(o, abi.OP_DIV, True)
+    def __mod__(self, o): return self._b(o, abi.OP_MOD)
+    def __rmod__(self, o): return self._b(o, abi.OP_MOD, True)
+    def __and__(self, o): return self._b(o, abi.OP_BAND)
+    def __or__(self, o): return self._b(o, abi.OP_BOR)
+    def __xor__(self, o): return self._b(o, abi.OP_BXOR)
+    def __lt__(self, o): return self._b(o, abi.OP_LT)
+    def __le__(self, o): return self._b(o, abi.OP_LE)
+    def __gt__(self, o): return self._b(o, abi.OP_GT)
+    def __ge__(self, o): return self._b(o, abi.OP_GE)
+    def eq(self, o): return self._b(o, abi.OP_EQ)
+    def ne(self, o): return self._b(o, abi.OP_NE)
+
+    def __neg__(self):
+        t = promote(self.dtype)
+        return Op(abi.OP_NEG, [cast(t, self)], t, t)
+
+    def __pos__(self):
+        return cast(promote(self.dtype), self)
+
+    def __invert__(self):
+        """operator! of the reference (Python has no overloadable `not`)."""
+        return Op(abi.OP_NOT, [self], self.dtype, BOOL)
+
+
+class Leaf(Expr):
+    def __init__(self, view):
+        self.view = view
+        self.dtype = view.dtype
+
+
+class SeqLeaf(Expr):
+    """Cell over Seq: iota operands and tindex (ra/arrays.hh:361-364)."""
+
+    def __init__(self, dtype, org, lens, steps):
+        self.dtype, self.org, self.lens, self.steps = dtype, org, list(lens), list(steps)
+
+
+class ScalarLeaf(Expr):
+    def __init__(self, value, dtype):
+        self.value, self.dtype = value, dtype
+
+
+class HostVec(Expr):
+    """A foreign rank-1 range (std::vector, ra/expr.hh:385): uploaded when the expression executes."""
+
+    def __init__(self, arr):
+        self.arr = np.ascontiguousarray(arr)
+        _ck(self.arr.ndim == 1, "foreign vectors are rank 1")
+        _ck(self.arr.dtype in NP2RACU, f"unsupported dtype {self.arr.dtype}", abi.ERR_UNSUPPORTED)
+        self.dtype = NP2RACU[self.arr.dtype]
+
+
+class Op(Expr):
+    def __init__(self, op, args, optype, rtype, arg=0, aux=0):
+        self.op, self.args, self.optype, self.dtype, self.arg, self.aux = op, args, optype, rtype, arg, aux
+
+
+def tindex(w, dtype=I64):
+    """ra::_0 .. : index along axis w, dead on the axes before it (Reframe, ra/expr.hh:402-455)."""
+    return SeqLeaf(dtype, 0, [UNB] * (w + 1), [0] * w + [1])
+
+
+_0, _1, _2, _3, _4 = (tindex(w) for w in range(5))
+
+
+def as_expr(x):
+    if isinstance(x, Expr):
+        return x
+    if isinstance(x, View):
+        return Leaf(x)
+    if isinstance(x, Iota):
+        n = x.n
+        _ck(not isinstance(n, LenExpr) and not isinstance(x.o, LenExpr), "Stray ra::len.")  # ra/expr.hh:513
+        return SeqLeaf(x.dtype, x.o, [n], [x.s])
+    if isinstance(x, (bool, np.bool_)):
+        return ScalarLeaf(bool(x), BOOL)
+    if isinstance(x, (np.float32,)):
+        return ScalarLeaf(float(x), F32)
+    if isinstance(x, (np.int64,)):
+        return ScalarLeaf(int(x), I64)
+    if isinstance(x, (int, np.integer)):
+        return ScalarLeaf(int(x), I32)  # C++ int literal
+    if isinstance(x, (float, np.floating)):
+        return ScalarLeaf(float(x), F64)  # C++ double literal
+    if isinstance(x, np.ndarray):
+        return HostVec(x)
+    if isinstance(x, (list, tuple)):
+        return HostVec(np.asarray(x))
+    raise TypeError(f"cannot use {type(x)} in an array expression")
+
+
+def cast(t, e):
+    """ra::cast<T> (ra/expr.hh:680-681)."""
+    e = as_expr(e)
+    if e.dtype == t:
+        return e
+    return Op(abi.OP_CAST, [e], t, t, aux=e.dtype)
+
+
+_CMP = (abi.OP_EQ, abi.OP_NE, abi.OP_LT, abi.OP_LE, abi.OP_GT, abi.OP_GE)
+_BIT = (abi.OP_BAND, abi.OP_BOR, abi.OP_BXOR)
+
+
+def binop(op, a, b):
+    """RA_BINOP (ra/ra.hh:181-190): the node's type is the C++ type of `a OP b`."""
+    a, b = as_expr(a), as_expr(b)
+    if op in _BIT and a.dtype == BOOL and b.dtype == BOOL:
+        t = BOOL
+    else:
+        t = common_type(a.dtype, b.dtype)
+        _ck(not (op in _BIT and is_float(t)), "bit op on floating point", abi.ERR_BAD_DESC)
+    return Op(op, [cast(t, a), cast(t, b)], t, BOOL if op in _CMP else t)
+
+
+def _unary_float(op, a):
+    a = as_expr(a)
+    t = a.dtype if is_float(a.dtype) else F64  # std::sqrt(int) -> double
+    return Op(op, [cast(t, a)], t, t)
+
+
+def sqrt(a): return _unary_float(abi.OP_SQRT, a)
+def exp(a): return _unary_float(abi.OP_EXP, a)
+def log(a): return _unary_float(abi.OP_LOG, a)
+def sin(a): return _unary_float(abi.OP_SIN, a)
+def cos(a): return _unary_float(abi.OP_COS, a)
+
+
+def abs(a):  # noqa: A001
+    a = as_expr(a)
+    t = promote(a.dtype)
+    return Op(abi.OP_ABS, [cast(t, a)], t, t)
+
+
+def sqr(a):
+    """ra/ra.hh:65."""
+    a = as_expr(a)
+    t = promote(a.dtype)
+    return Op(abi.OP_SQR, [cast(t, a)], t, t)
+
+
+def sqrm(a, b=None):
+    """ra/ra.hh:71-72: sqrm(x) = x*x, sqrm(x, y) = sqr(x-y)."""
+    return sqr(a) if b is None else sqr(as_expr(a) - b)
+
+
+def max(a, b): return binop(abi.OP_MAX, a, b)  # noqa: A001
+def min(a, b): return binop(abi.OP_MIN, a, b)  # noqa: A001
+
+
+def pow(a, b):  # noqa: A001
+    a, b = as_expr(a), as_expr(b)
+    t = F32 if (a.dtype == F32 and b.dtype == F32) else F64
+    return Op(abi.OP_POW, [cast(t, a), cast(t, b)], t, t)
+
+
+def atan2(a, b):
+    a, b = as_expr(a), as_expr(b)
+    t = F32 if (a.dtype == F32 and b.dtype == F32) else F64
+    return Op(abi.OP_ATAN2, [cast(t, a), cast(t, b)], t, t)
+
+
+def fma(a, b, c):
+    a, b, c = as_expr(a), as_expr(b), as_expr(c)
+    t = common_type(common_type(a.dtype, b.dtype), c.dtype)
+    t = t if is_float(t) else F64
+    return Op(abi.OP_FMA, [cast(t, a), cast(t, b), cast(t, c)], t, t)
+
+
+def pick(sel, *branches):
+    """ra::pick(sel, a0, a1, ...) (ra/expr.hh:686-728)."""
+    sel = as_expr(sel)
+    _ck(not is_float(sel.dtype) and builtins_len(branches) >= 1, "bad pick", abi.ERR_BAD_DESC)
+    bs = [as_expr(b) for b in branches]
+    t = bs[0].dtype
+    for b in bs[1:]:
+        t = b.dtype if b.dtype == t else common_type(t, b.dtype)
+    return Op(abi.OP_PICK, [sel] + [cast(t, b) for b in bs], t, t, arg=builtins_len(bs), aux=sel.dtype)
+
+
+def where(w, t, f):
+    """ra/ra.hh:255-256: pick(cast<bool>(w), f, t)."""
+    return pick(cast(BOOL, w), f, t)
+
+
+def logical_and(a, b):
+    """operator&& ra/ra.hh:262-263: where(a, cast<bool>(b), false)."""
+    return where(a, cast(BOOL, b), False)
+
+
+def logical_or(a, b):
+    """operator|| ra/ra.hh:265-266: where(a, true, cast<bool>(b))."""
+    return where(a, True, cast(BOOL, b))
+
+
+
+
+# ---------------- views: ra/arrays.hh:84-149 ----------------
+
+class View:
+    """Non-owning pointer + dims (ViewBig, ra/expr.hh:233). `owner` keeps the memory alive; `ptr` is the byte address
+    of element [0,...,0]; dims is a list of [len, step] in elements. `ex` is the executor that runs traversals."""
+
+    __array_ufunc__ = None
+
+    def __init__(self, ex, owner, ptr, dtype, dims):
+        self.ex, self.owner, self.ptr, self.dtype = ex, owner, int(ptr), dtype
+        self.dims = [[int(l), int(s)] for l, s in dims]
+
+    # -- queries
+    @property
+    def rank(self):
+        return builtins_len(self.dims)
+
+    def len(self, k):
+        return self.dims[k][0]
+
+    def step(self, k):
+        return self.dims[k][1] if k < self.rank else 0  # ra/expr.hh:294-295
+
+    @property
+    def shape(self):
+        return tuple(d[0] for d in self.dims)
+
+    @property
+    def size(self):
+        s = 1
+        for l, _ in self.dims:
+            if l < 0:
+                return l
+            s *= l
+        return s
+
+    def _at(self, off, dims):
+        return View(self.ex, self.owner, self.ptr + off * abi.DTYPE_SIZE[self.dtype], self.dtype, dims)
+
+    # -- beaten slicing: from() / fromb(), ra/ply.hh:367-435,503-551
+    def __call__(self, *subs):
+        a, ak, pl, bv = self.dims, 0, 0, []
+        subs = list(subs)
+
+        def fsrc(i):  # ra/ply.hh:344-348
+            return i.n if isinstance(i, Dots) else 0 if isinstance(i, Insert) else 1
+
+        for q, i0 in enumerate(subs):
+            if isinstance(i0, Dots):
+                n = i0.n
+                if n == UNB:  # :417
+                    n = self.rank - ak - _builtins.sum(fsrc(i) for i in subs[q + 1:] if not (isinstance(i, Dots) and i.n == UNB))
+                _ck(n >= 0 and ak + n <= self.rank, "Too many subscripts.")
+                bv += [list(d) for d in a[ak:ak + n]]
+                ak += n
+            elif isinstance(i0, Insert):  # :423-427
+                bv += [[UNB, 0] for _ in range(i0.n)]
+            elif isinstance(i0, Iota):  # :399-415
+                _ck(ak < self.rank, "Too many subscripts.")
+                la, st = a[ak]
+                n, o, s = _wlen(i0.n, la), _wlen(i0.o, la), _wlen(i0.s, la)
+                _ck(n != UNB, "unbounded iota subscripts are not beatable (ra/ply.hh:341)", abi.ERR_UNSUPPORTED)
+                _ck(n == 0 or (0 <= o < la and 0 <= o + (n - 1) * s < la),
+                    f"Bad iota len {n} step {s} in len[{ak}]={la}.")  # :407
+                bv.append([n, s * st])
+                pl += o * st
+                ak += 1
+            elif isinstance(i0, (int, np.integer, LenExpr)):  # :390-398
+                _ck(ak < self.rank, "Too many subscripts.")
+                la, st = a[ak]
+                i = _wlen(i0, la)
+                _ck(0 <= i < la or (la == UNB and st == 0), f"Bad index {i} in len[{ak}]={la}.")  # :395
+                pl += i * st
+                ak += 1
+            else:
+                raise RaError(abi.ERR_UNSUPPORTED, "unbeaten (gather) subscripts are not on the device path yet")
+        bv += [list(d) for d in a[ak:]]  # trailing axes implied, :374-381
+        _ck(builtins_len(bv) <= abi.MAX_RANK, "Rank too large.")
+        return self._at(pl, bv)
+
+    def __getitem__(self, subs):
+        if subs is Ellipsis:
+            return self
+        return self(*subs) if isinstance(subs, tuple) else self(subs)
+
+    def __setitem__(self, subs, rhs):
+        dst = self[subs]
+        if isinstance(rhs, View) and rhs.ptr == dst.ptr and rhs.dims == dst.dims and rhs.owner is dst.owner:
+            return  # result of `A[I] += x`
+        dst.assign(rhs)
+
+    # -- assignment ops: ra/expr.hh:50-60, ra/arrays.hh:131-135
+    def assign(self, rhs): return self._assign(abi.ASSIGN_SET, rhs)
+    def __iadd__(self, rhs): return self._assign(abi.ASSIGN_ADD, rhs)
+    def __isub__(self, rhs): return self._assign(abi.ASSIGN_SUB, rhs)
+    def __imul__(self, rhs): return self._assign(abi.ASSIGN_MUL, rhs)
+    def __itruediv__(self, rhs): return self._assign(abi.ASSIGN_DIV, rhs)
+
+    def _assign(self, op, rhs):
+        d, keep = flatten(as_expr(rhs), dst=self, assign=op, ex=self.ex)
+        self.ex.map(d)
+        del keep
+        return self
+
+    # -- operators build expressions
+    def _e(self):
+        return Leaf(self)
+
+    def __add__(self, o): return self._e() + o
+    def __radd__(self, o): return o + self._e()
+    def __sub__(self, o): return self._e() - o
+    def __rsub__(self, o): return o - self._e()
+    def __mul__(self, o): return self._e() * o
+    def __rmul__(self, o): return o * self._e()
+    def __truediv__(self, o): return self._e() / o
+    def __rtruediv__(self, o): return o / self._e()
+    def __mod__(self, o): return self._e() % o
+    def __and__(self, o): return self._e() & o
+    def __or__(self, o): return self._e() | o
+    def __xor__(self, o): return self._e() ^ o
+    def __lt__(self, o): return self._e() < o
+    def __le__(self, o): return self._e() <= o
+    def __gt__(self, o): return self._e() > o
+    def __ge__(self, o): return self._e() >= o
+    def eq(self, o): return self._e().eq(o)
+    def ne(self, o): return self._e().ne(o)
+    def __neg__(self): return -self._e()
+    def __invert__(self): return ~self._e()
+
+    def numpy(self):
+        """Copy the viewed elements to a host numpy array of the view's shape (dead axes not allowed)."""
+        return self.ex.to_numpy(self)
+
+
+def reverse(a, k=0):
+    """ra/arrays.hh:408-428."""
+    _ck(0 <= k < a.rank, f"Bad axis {k} for rank {a.rank}.")
+    _ck(a.len(k) != UNB, f"Cannot reverse unbounded axis {k}.")
+    dv = [list(d) for d in a.dims]
+    off = 0 if dv[k][0] == 0 else dv[k][1] * (dv[k][0] - 1)
+    dv[k][1] *= -1
+    return a._at(off, dv)
+
+
+def transpose(a, s=(1, 0)):
+    """ra/arrays.hh:431-461: axis k of a goes to axis s[k] of the result; repeated targets give diagonals."""
+    s = list(s)
+    _ck(builtins_len(s) == a.rank, f"Bad rank {a.rank} for {builtins_len(s)} transposed axes.")
+    r = 0 if not s else 1 + _builtins.max(s)
+    dst = [[UNB, 0] for _ in range(r)]
+    for k, sk in enumerate(s):
+        dst[sk][1] += a.dims[k][1]
+        dst[sk][0] = _builtins.min(dst[sk][0], a.dims[k][0]) if dst[sk][0] >= 0 else a.dims[k][0]
+    return a._at(0, dst)
+
+
+def diag(a):
+    return transpose(a, (0, 0))
+
+
+# ---------------- flattening: expression tree -> racu_desc ----------------
+
+def flatten(e, dst=None, assign=abi.ASSIGN_SET, ex=None):
+    """What ra::cuda::ply does in the C++ header: leaves -> operands, nodes -> postfix program.
+    Returns (desc, keepalive)."""
+    d = abi.Desc()
+    keep = []
+    nopnd = [0]
+    nins = [0]
+
+    def add_operand(kind, dtype, rank, base, lens, steps):
+        _ck(nopnd[0] < abi.MAX_OPND, "too many operands", abi.ERR_UNSUPPORTED)
+        _ck(rank <= abi.MAX_RANK, "Rank too large.")
+        p = d.opnd[nopnd[0]]
+        p.kind, p.dtype, p.rank = kind, dtype, rank
+        if kind == MEM:
+            p.base.ptr = base
+        elif is_float(dtype):
+            p.base.f = float(base)
+        else:
+            p.base.i = int(base)
+        for k in range(rank):
+            p.len[k], p.stride[k] = lens[k], steps[k]
+        nopnd[0] += 1
+        return nopnd[0] - 1
+
+    def emit(op, t, arg=0, aux=0):
+        _ck(nins[0] < abi.MAX_INS, "program too long", abi.ERR_UNSUPPORTED)
+        i = d.ins[nins[0]]
+        i.op, i.type, i.arg, i.aux = op, t, arg, aux
+        nins[0] += 1
+
+    def view_operand(v):
+        keep.append(v.owner)
+        return add_operand(MEM, v.dtype, v.rank, v.ptr, [x[0] for x in v.dims], [x[1] for x in v.dims])
+
+    def walk(n):
+        if isinstance(n, Leaf):
+            emit(abi.OP_PUSH, n.dtype, view_operand(n.view))
+        elif isinstance(n, HostVec):
+            v = ex.from_numpy(n.arr)
+            emit(abi.OP_PUSH, n.dtype, view_operand(v))
+        elif isinstance(n, SeqLeaf):
+            emit(abi.OP_PUSH, n.dtype, add_operand(SEQ, n.dtype, builtins_len(n.lens), n.org, n.lens, n.steps))
+        elif isinstance(n, ScalarLeaf):
+            emit(abi.OP_PUSH, n.dtype, add_operand(SCALAR, n.dtype, 0, n.value, [], []))
+        else:
+            for a in n.args:
+                walk(a)
+            emit(n.op, n.optype, n.arg, n.aux)
+
+    if dst is not None:
+        d.dst = view_operand(dst)
+    else:
+        d.dst = -1
+    d.assign = assign
+    walk(e)
+    d.nopnd, d.nins = nopnd[0], nins[0]
+    return d, keep
+
+
+# ---------------- whole-array reductions: ra/ra.hh:306-322,348-401 ----------------
+
+def _reduce(e, redop):
+    e = as_expr(e)
+    ex = _find_ex(e)
+    d, keep = flatten(e, ex=ex)
+    out = ex.reduce(d, redop, e.dtype)
+    del keep
+    return out
+
+
+def _find_ex(e):
+    if isinstance(e, Leaf):
+        return e.view.ex
+    if isinstance(e, Op):
+        for a in e.args:
+            x = _find_ex(a)
+            if x is not None:
+                return x
+    return None
+
+
+def sum(a): return _reduce(a, abi.RED_SUM)  # noqa: A001
+def prod(a): return _reduce(a, abi.RED_PROD)
+def amin(a): return _reduce(a, abi.RED_AMIN)
+def amax(a): return _reduce(a, abi.RED_AMAX)
+
+
+def dot(a, b):
+    """ra/ra.hh:379-385 with RA_FMA=0: c += a*b."""
+    return _reduce(as_expr(a) * b, abi.RED_SUM)
+
+
+def reduce_sqrm(a):
+    """ra/ra.hh:395-401."""
+    return _reduce(sqrm(a), abi.RED_SUM)
+
+
+def norm2(a):
+    """ra/ra.hh:376."""
+    return float(np.sqrt(reduce_sqrm(a)))
+
+
+# ---------------- BLAS-like: ra/ra.hh:403-456 ----------------
+
+def gemm(a, b, c):
+    """c(all, insert<1>) += a * b(insert<1>)   (ra/ra.hh:407)."""
+    cc = c(all, insert(1))
+    cc += a * b(insert(1))
+    return c
+
+
+def gemv(a, b, c):
+    """c += a * b(insert<1>)   (ra/ra.hh:418)."""
+    c += a * b(insert(1))
+    return c
+
+
+def gevm(a, b, c):
+    """c(insert<1>) += a * b   (ra/ra.hh:431)."""
+    cc = c(insert(1))
+    cc += a * b
+    return c

@@ -1,0 +1,526 @@
+"""Known-answer tests ported from the reference's own test suite (values and shapes only; no code).
+
+Each case is a function of an executor `ex` and is run twice, like the reference's TEST(plier) macro runs ply_ravel
+and ply_fixed side by side (test/ply.cc:35-44): once on the CPU oracle (tests/test_oracle_golden.py, pins the
+oracle) and once on the CUDA library (tests/test_gpu_kat.py, -m gpu). Citations are file:line in the reference.
+"""
+import numpy as np
+
+from ra_ra_b200 import abi, ra
+
+CASES = []
+
+
+def case(f):
+    CASES.append(f)
+    return f
+
+
+def arr(ex, values, dtype):
+    return ex.from_numpy(np.array(values, dtype=dtype))
+
+
+def zeros(ex, shape, dtype):
+    return ex.from_numpy(np.zeros(shape, dtype=dtype))
+
+
+def full(ex, shape, value, dtype):
+    return ex.from_numpy(np.full(shape, value, dtype=dtype))
+
+
+def eq(view_or_value, expected):
+    got = view_or_value.numpy() if isinstance(view_or_value, ra.View) else np.asarray(view_or_value)
+    expected = np.asarray(expected)
+    assert got.shape == expected.shape, (got.shape, expected.shape)
+    assert np.array_equal(got, expected), (got, expected)
+
+
+def concrete(ex, e, shape, dtype):
+    out = zeros(ex, shape, dtype)
+    out.assign(e)
+    return out
+
+
+# ---------------- traversal / maps ----------------
+
+@case
+def ply_c_eq_a_minus_scalar(ex):
+    """test/ply.cc:31-44: c = a - 3.0 on 3x2 -> {-3..2}."""
+    a = arr(ex, np.arange(6).reshape(3, 2), np.float64)
+    c = zeros(ex, (3, 2), np.float64)
+    c.assign(a - 3.0)
+    eq(c, np.arange(6).reshape(3, 2) - 3.0)
+
+
+@case
+def ply_int_neg_mul(ex):
+    """test/ply.cc:51-61: c = -a -> {-1,-2,-3}; c = a*b -> {1,-4,9}."""
+    A = arr(ex, [1, 2, 3], np.int32)
+    B = arr(ex, [1, -2, 3], np.int32)
+    C = zeros(ex, (3,), np.int32)
+    C.assign(-A)
+    eq(C, [-1, -2, -3])
+    C.assign(A * B)
+    eq(C, [1, -4, 9])
+
+
+@case
+def ply_rank3_vs_rank2_prefix(ex):
+    """test/ply.cc:262-288: a(3,2,4) - b(3,2), 24-value check at :265-266."""
+    a = arr(ex, np.arange(1, 25).reshape(3, 2, 4), np.float64)
+    b = arr(ex, np.arange(1, 7).reshape(3, 2), np.float64)
+    c = zeros(ex, (3, 2, 4), np.float64)
+    check = [0, 1, 2, 3, 3, 4, 5, 6, 6, 7, 8, 9, 9, 10, 11, 12, 12, 13, 14, 15, 15, 16, 17, 18]
+    c.assign(a - b)
+    eq(c, np.array(check, dtype=np.float64).reshape(3, 2, 4))
+    c.assign(0.)
+    c.assign(-(b - a))
+    eq(c, np.array(check, dtype=np.float64).reshape(3, 2, 4))
+
+
+@case
+def ply_empty_and_rank0(ex):
+    """test/ply.cc:107-151,318-333: a zero-length axis means the op never runs; rank 0 runs once."""
+    a = zeros(ex, (0, 11, 2), np.float64)
+    c = full(ex, (1,), 99., np.float64)
+    c0 = c(0)  # rank 0 view
+    assert c0.rank == 0
+    c0.assign(77.)
+    eq(c, [77.])
+    c0 += 1.
+    eq(c, [78.])
+    e = zeros(ex, (0, 11, 2), np.float64)
+    e.assign(a + 1.)  # nothing to do, nothing to fail
+    assert ra.sum(a) == 0. and ra.prod(a) == 1.  # test/reduction.cc:199-201
+
+
+@case
+def ply_tindex_and_scalar(ex):
+    """test/ply.cc:245-259, test/frame-old.cc:28-58: _0/_1 index operands."""
+    c = zeros(ex, (3, 2), np.int32)
+    c.assign(ra._0 + ra._1)
+    eq(c, [[0, 1], [1, 2], [2, 3]])
+    c.assign(ra._0 * 2)
+    eq(c, [[0, 0], [2, 2], [4, 4]])
+
+
+@case
+def mismatched_steps_transpose(ex):
+    """test/ra-1.cc:183-203: c = a - transpose(b) with a(2,3), b(3,2) -> {0,-1,-2,2,1,0}; also through a transposed LHS."""
+    a = arr(ex, np.arange(1, 7).reshape(2, 3), np.int32)
+    b = arr(ex, np.arange(1, 7).reshape(3, 2), np.int32)
+    c = zeros(ex, (2, 3), np.int32)
+    c.assign(a - ra.transpose(b, (1, 0)))
+    eq(c, [[0, -1, -2], [2, 1, 0]])
+    c.assign(0)
+    ra.transpose(c, (1, 0)).assign(ra.transpose(a, (1, 0)) - b)
+    eq(c, [[0, -1, -2], [2, 1, 0]])
+
+
+@case
+def operators_sum_and_mask(ex):
+    """test/operators.cc:122-137: a(3,2)+b(3) -> {11,12,23,40,35,36}; a==b mask; !(a!=b)."""
+    a = arr(ex, [[1, 2], [3, 20], [5, 6]], np.int32)
+    b = arr(ex, [10, 20, 30], np.int32)
+    eq(concrete(ex, a + b, (3, 2), np.int32), [[11, 12], [23, 40], [35, 36]])
+    mask = [[False, False], [False, True], [False, False]]
+    eq(concrete(ex, a.eq(b), (3, 2), np.bool_), mask)
+    eq(concrete(ex, ~(a.ne(b)), (3, 2), np.bool_), mask)
+
+
+@case
+def readme_first_example(ex):
+    """examples/read-me.cc:26-37: B += A + C + std::vector{100., 200.}; B(all, iota(len/2, len/2)) *= -1."""
+    v = [[1, 2, 3, 4], [5, 6, 7, 8]]
+    A, B, Cc = arr(ex, v, np.float32), arr(ex, v, np.float32), arr(ex, v, np.float32)
+    B += A + Cc + np.array([100., 200.])
+    B(ra.all, ra.iota(ra.len / 2, ra.len / 2)).__imul__(-1)
+    eq(B, np.array([[103, 106, -109, -112], [215, 218, -221, -224]], dtype=np.float32))
+
+
+@case
+def readme_vector_float(ex):
+    """examples/read-me.cc:162-165: B += std::vector<float>{10, 20} -> {{11,12},{23,24}}."""
+    B = arr(ex, [[1, 2], [3, 4]], np.float32)
+    B += np.array([10, 20], dtype=np.float32)
+    eq(B, np.array([[11, 12], [23, 24]], dtype=np.float32))
+
+
+@case
+def ra12_map_broadcast_reduce(ex):
+    """test/ra-12.cc:30-43, examples/read-me.cc:82-91: C = A*B; D += A*B -> {-6, 6}."""
+    A = arr(ex, [[1, 2, 3], [1, 2, 3]], np.float32)
+    B = arr(ex, [-1, 1], np.float32)
+    Cc = full(ex, (2, 3), 99., np.float32)
+    Cc.assign(A * B)
+    eq(Cc, np.array([[-1, -2, -3], [1, 2, 3]], dtype=np.float32))
+    D = zeros(ex, (2,), np.float32)
+    D += A * B
+    eq(D, np.array([-6, 6], dtype=np.float32))
+
+
+@case
+def compat_vector_plus_big(ex):
+    """test/compatibility.cc:22-40,61-66: foreign vector matched on axis 0, also through a transposed LHS."""
+    a = zeros(ex, (2, 3), np.int32)
+    a.assign(np.array([10, 20], dtype=np.int32) + ra._1)
+    eq(a, [[10, 11, 12], [20, 21, 22]])
+    b = zeros(ex, (3, 2), np.int32)
+    ra.transpose(b).assign(np.array([10, 20], dtype=np.int32) + ra._1)
+    eq(b, [[10, 20], [11, 21], [12, 22]])
+
+
+@case
+def frame_periodic_axes(ex):
+    """test/frame-new.cc:146-172: b = a(all, insert<1>, iota(4, 0, 0)) gives a rank 4 match 2x3x4x4."""
+    a = zeros(ex, (2, 3, 4), np.int32)
+    a.assign((ra._0 + 1) * 100 + (ra._1 + 1) * 10 + (ra._2 + 1))
+    b = a(ra.all, ra.insert(1), ra.iota(4, 0, 0))
+    assert [d[0] for d in b.dims] == [2, abi.UNB, 4, 4]
+    out = zeros(ex, (2, 3, 4, 4), np.int32)
+    out.assign(a + b)
+    an = a.numpy()
+    expect = an[:, :, :, None] + an[:, None, 0, :][:, :, None, :].repeat(4, axis=2)
+    # c(all, j) = a(all, iota(4,0,0)) for every j: c[i,j,k,l] = a[i,0,l]; a is matched on its prefix: a[i,j,k]
+    expect = an[:, :, :, None] + an[:, 0, :][:, None, None, :]
+    eq(out, expect)
+    out.assign(b + a)  # order doesn't affect prefix matching
+    eq(out, expect)
+
+
+@case
+def frame_outer_product(ex):
+    """test/frame-new.cc:175-190: a(dots<2>, insert<1>) - b(insert<2>, dots<1>) is 4x3x5."""
+    a = zeros(ex, (4, 3), np.int32)
+    a.assign(10 * ra._1 + 100 * ra._0)
+    b = zeros(ex, (5,), np.int32)
+    b.assign(ra._0)
+    out = zeros(ex, (4, 3, 5), np.int32)
+    out.assign(a(ra.dots(2), ra.insert(1)) - b(ra.insert(2), ra.dots(1)))
+    eq(out, a.numpy()[:, :, None] - b.numpy()[None, None, :])
+
+
+@case
+def operators_pluseq_chain(ex):
+    """test/operators.cc:195-218: array+scalar and += chains."""
+    a = arr(ex, [1, 2, 3], np.float64)
+    a += 1
+    a += a
+    eq(a, [4., 6., 8.])
+    a -= arr(ex, [1, 1, 1], np.int32)
+    a /= 2.
+    a *= a
+    eq(a, [2.25, 6.25, 12.25])
+
+
+# ---------------- views ----------------
+
+@case
+def viewops_reverse(ex):
+    """test/view-ops.cc:19-52: reverse on each axis of 3x2x4; equivalence with iota(len, len-1, -1)."""
+    a = arr(ex, np.arange(1, 25).reshape(3, 2, 4), np.float64)
+    an = a.numpy()
+    check0 = [17, 18, 19, 20, 21, 22, 23, 24, 9, 10, 11, 12, 13, 14, 15, 16, 1, 2, 3, 4, 5, 6, 7, 8]
+    check1 = [5, 6, 7, 8, 1, 2, 3, 4, 13, 14, 15, 16, 9, 10, 11, 12, 21, 22, 23, 24, 17, 18, 19, 20]
+    check2 = [4, 3, 2, 1, 8, 7, 6, 5, 12, 11, 10, 9, 16, 15, 14, 13, 20, 19, 18, 17, 24, 23, 22, 21]
+    rev = ra.iota(ra.len, ra.len - 1, -1)
+    for k, check, sub in ((0, check0, (rev,)), (1, check1, (ra.dots(1), rev)), (2, check2, (ra.dots(2), rev))):
+        b = ra.reverse(a, k)
+        eq(b, np.array(check, dtype=np.float64).reshape(3, 2, 4))
+        c = a(*sub)
+        assert c.ptr == b.ptr and c.dims == b.dims
+        eq(b, np.flip(an, axis=k))
+
+
+@case
+def viewops_transpose(ex):
+    """test/view-ops.cc:54-75: transpose of 3x2 iota(1..6) reads {1,3,5,2,4,6}; :121-138 diag."""
+    a = arr(ex, np.arange(1, 7).reshape(3, 2), np.float64)
+    eq(ra.transpose(a, (1, 0)), np.array([[1, 3, 5], [2, 4, 6]], dtype=np.float64))
+    eq(ra.transpose(a), np.array([[1, 3, 5], [2, 4, 6]], dtype=np.float64))
+    s = arr(ex, np.arange(9).reshape(3, 3), np.float64)
+    eq(ra.diag(s), [0., 4., 8.])
+
+
+@case
+def fromb_offsets(ex):
+    """test/fromb.cc:46-81: base pointer offsets 30, 0, 40, 34, 2, 12, 92 and values of beaten subscripts on a 10x10."""
+    a = zeros(ex, (10, 10), np.int32)
+    a.assign(ra._1 + 10 * ra._0)
+    an = a.numpy()
+
+    def off(b):
+        return (b.ptr - a.ptr) // 4
+
+    b = a(3, ra.all)
+    assert off(b) == 30
+    eq(b, an[3])
+    b = a(ra.iota(4))
+    assert off(b) == 0
+    eq(b, an[:4])
+    b = a(ra.iota(4, 4))
+    assert off(b) == 40
+    eq(b, an[4:8])
+    b = a(3, ra.iota(5, 4))
+    assert off(b) == 34
+    eq(b, an[3, 4:9])
+    b = a(ra.all, ra.iota(4, 2, 2))
+    assert off(b) == 2
+    eq(b, an[:, 2:10:2])
+    b = a(ra.iota(3, 1, 2), ra.iota(2, 2, 3))
+    assert off(b) == 12
+    eq(b, an[1:7:2, 2:8:3])
+    b = a(ra.iota(3, 9, -2), ra.iota(2, 2, 3))
+    assert off(b) == 92
+    eq(b, an[9:3:-2, 2:8:3])
+
+
+@case
+def fromb_len_and_insert(ex):
+    """test/fromb.cc:131-162 (ra::len in subscripts), :195-211 (insert), :253-274 (a(iota(2,0,2), iota(2,0,2)))."""
+    a = zeros(ex, (10, 10), np.int32)
+    a.assign(ra._1 + 10 * ra._0)
+    an = a.numpy()
+    eq(a(ra.len - 1, ra.all), an[9])
+    eq(a(ra.all, ra.len - 1), an[:, 9])
+    eq(a(ra.iota(ra.len - 6, 3)), an[3:7])
+    eq(a(ra.iota(2, 0, 2), ra.iota(2, 0, 2)), an[0:4:2, 0:4:2])
+    b = a(ra.insert(1), ra.all)
+    assert [d[0] for d in b.dims] == [abi.UNB, 10, 10] and b.dims[0][1] == 0
+
+
+@case
+def fromb_bounds_errors(ex):
+    """ra/ply.hh:395,407 RA_CK; test/checks.cc:215-233 dynamic mismatch raises at ply."""
+    a = zeros(ex, (10, 10), np.int32)
+    for bad in ((10,), (-1,), (ra.iota(4, 8),), (ra.iota(3, 9, -5),)):
+        try:
+            a(*bad)
+        except ra.RaError as e:
+            assert e.status == abi.ERR_BOUNDS
+        else:
+            raise AssertionError("bounds not checked")
+    b = zeros(ex, (3,), np.int32)
+    try:
+        a += b
+    except ra.RaError as e:
+        assert e.status == abi.ERR_SHAPE
+    else:
+        raise AssertionError("agreement not checked")
+    c = zeros(ex, (3,), np.float64)
+    try:
+        c.assign(ra._1)  # test/checks.cc:159-193: unbounded
+    except ra.RaError as e:
+        assert e.status == abi.ERR_SHAPE
+    else:
+        raise AssertionError("unbounded expression not rejected")
+
+
+@case
+def iota_values(ex):
+    """test/iota.cc:21-34 values; :36-49 transpose(b,{0,2,1}) = iota(3,1) ; :51-67 unbounded + bounded."""
+    a = zeros(ex, (4,), np.int32)
+    a.assign(ra.iota(4, 3))
+    eq(a, [3, 4, 5, 6])
+    a.assign(ra.iota(4, 3, 2))
+    eq(a, [3, 5, 7, 9])
+    a.assign(ra.iota(4) + ra.iota(4, 10))
+    eq(a, [10, 12, 14, 16])
+    b = zeros(ex, (3, 2, 4), np.int32)
+    ra.transpose(b, (0, 2, 1)).assign(ra.iota(3, 1))
+    eq(b, np.broadcast_to(np.array([1, 2, 3], dtype=np.int32)[:, None, None], (3, 2, 4)))
+    c = zeros(ex, (3,), np.int32)
+    c.assign(ra.iota() + ra.iota(3, 10))
+    eq(c, [10, 12, 14])
+
+
+# ---------------- where / pick ----------------
+
+@case
+def where_pick(ex):
+    """test/where.cc:22-38: pick(p, a0, a1) -> {1,20,3}; where(p, a0, a1) -> {10,2,30}."""
+    a0, a1 = arr(ex, [1, 2, 3], np.float64), arr(ex, [10, 20, 30], np.float64)
+    p = arr(ex, [0, 1, 0], np.int32)
+    a = zeros(ex, (3,), np.float64)
+    a.assign(ra.pick(p, a0, a1))
+    eq(a, [1., 20., 3.])
+    a.assign(ra.where(p, a0, a1))
+    eq(a, [10., 2., 30.])
+
+
+@case
+def where_rvalue(ex):
+    """test/where.cc:98-109."""
+    w = arr(ex, [True, False, False, True], np.bool_)
+    eq(concrete(ex, ra.where(w, 1, 2), (4,), np.int32), [1, 2, 2, 1])
+    v = arr(ex, [1, 2, 3, 4], np.int32)
+    eq(concrete(ex, ra.where(ra.logical_and(ra._0 > 0, ra._0 < 3), v, 17), (4,), np.int32), [17, 2, 3, 17])
+    eq(concrete(ex, ra.where(w, 2 * ra._0 + 1, 2 * ra._0), (4,), np.int32), [1, 2, 4, 7])
+    a = zeros(ex, (4, 3), np.int32)
+    a.assign(ra._0 - ra._1)
+    eq(concrete(ex, ra.where(w, 99, a), (4, 3), np.int32), [[99, 99, 99], [1, 0, -1], [2, 1, 0], [99, 99, 99]])
+
+
+@case
+def where_nested(ex):
+    """test/where.cc:110-122."""
+    a = arr(ex, [-1, 0, 1], np.int32)
+    eq(concrete(ex, ra.where(a >= 0, ra.where(a < 1, 77, 99), 44), (3,), np.int32), [44, 77, 99])
+
+
+# ---------------- reductions ----------------
+
+@case
+def reductions_dot_sqrm(ex):
+    """test/reduction.cc:85-109: dot({1,2},{3,4}) = 11, reduce_sqrm(a-b) = 8, norm2 = sqrt(8)."""
+    a, b = arr(ex, [1, 2], np.float64), arr(ex, [3, 4], np.float64)
+    assert ra.dot(a, b) == 11.
+    assert ra.reduce_sqrm(a - b) == 8.
+    assert ra.norm2(a - b) == np.sqrt(8.)
+
+
+@case
+def reductions_sum_prod_amax_amin(ex):
+    """test/reduction.cc:123-138: sum/prod/amax/amin; NaN never enters amax/amin; empty defaults."""
+    a = arr(ex, [4, 6, -3, 2], np.float64)
+    assert ra.sum(a) == 9. and ra.prod(a) == -144. and ra.amax(a) == 6. and ra.amin(a) == -3.
+    assert ra.amax(ra.abs(a)) == 6. and ra.amin(ra.abs(a)) == 2.
+    q = full(ex, (3,), np.nan, np.float64)
+    assert ra.amax(q) == -np.inf and ra.amin(q) == np.inf
+    i = arr(ex, [4, 6, -3, 2], np.int32)
+    assert ra.sum(i) == 9 and ra.amax(i) == 6 and ra.amin(i) == -3 and ra.prod(i) == -144
+    e = zeros(ex, (0,), np.int32)
+    assert ra.amax(e) == np.iinfo(np.int32).min and ra.amin(e) == np.iinfo(np.int32).max  # :224-239
+
+
+@case
+def reductions_sum_cols(ex):
+    """test/reduction.cc:141-165: A(100,111) = _0-_1; C(100) += A and C = C + A."""
+    A = zeros(ex, (100, 111), np.float64)
+    A.assign(ra._0 - ra._1)
+    B = A.numpy().sum(axis=1)
+    Cc = zeros(ex, (100,), np.float64)
+    Cc += A
+    eq(Cc, B)
+    Cc.assign(0.)
+    Cc.assign(Cc + A)  # sequentially every step reads the C just written: a running sum (:160-164)
+    eq(Cc, B)
+    Cc.assign(A)  # without the self reference the last one wins per row (docs/ra-ra.texi:1986-2007)
+    eq(Cc, A.numpy()[:, 110])
+
+
+@case
+def reductions_sum_rows(ex):
+    """test/reduction.cc:182-222: sum rows of A(100,111) via transposed += and via leading insert."""
+    A = zeros(ex, (100, 111), np.float64)
+    A.assign(ra._0 - ra._1)
+    B = A.numpy().sum(axis=0)
+    Cc = zeros(ex, (111,), np.float64)
+    Cc += ra.transpose(A)
+    eq(Cc, B)
+    Cc.assign(0.)
+    cc = Cc(ra.insert(1))
+    cc += A
+    eq(Cc, B)
+
+
+@case
+def reductions_max_rows_cols(ex):
+    """test/reduction.cc:224-239: m = max(m, c) with a broadcast destination is a running max: {1,3,2},{7,1,3} -> cols {7,3,3}, rows {3,7}."""
+    c = arr(ex, [[1, 3, 2], [7, 1, 3]], np.int32)
+    m = zeros(ex, (3,), np.int32)
+    mm = m(ra.insert(1))
+    mm.assign(ra.max(mm, c))
+    eq(m, [7, 3, 3])
+    r = zeros(ex, (2,), np.int32)
+    r.assign(ra.max(r, c))
+    eq(r, [3, 7])
+    r.assign(100)
+    r.assign(ra.min(r, c))
+    eq(r, [1, 1])
+
+
+@case
+def gemv_gevm(ex):
+    """test/reduction.cc:241-279: gemv/gevm -> {-20,-10,0}."""
+    a = zeros(ex, (3, 4), np.float64)
+    a.assign(ra._0 - ra._1)
+    an = a.numpy()
+    b = arr(ex, [1, 2, 3, 4], np.float64)
+    c = zeros(ex, (3,), np.float64)
+    ra.gemv(a, b, c)
+    eq(c, an @ b.numpy())
+    eq(c, [-20., -10., 0.])
+    at = zeros(ex, (4, 3), np.float64)
+    at.assign(ra._1 - ra._0)
+    c.assign(0.)
+    ra.gevm(b, at, c)
+    eq(c, [-20., -10., 0.])
+
+
+@case
+def gemm_small(ex):
+    """test/reduction.cc:280-333: 3x2 of 2s times 2x4 of 3s -> 12; c += form -> 13; 0x0 corner."""
+    a, b = full(ex, (3, 2), 2., np.float64), full(ex, (2, 4), 3., np.float64)
+    c = zeros(ex, (3, 4), np.float64)
+    ra.gemm(a, b, c)
+    eq(c, np.full((3, 4), 12.))
+    c.assign(1.)
+    ra.gemm(a, b, c)
+    eq(c, np.full((3, 4), 13.))
+    a0, b0, c0 = zeros(ex, (0, 2), np.float64), zeros(ex, (2, 0), np.float64), zeros(ex, (0, 0), np.float64)
+    ra.gemm(a0, b0, c0)
+
+
+@case
+def gemm_integer_valued(ex):
+    """bench/bench-gemm.cc:229-237: a = _0-_1, b = _1-2*_0, exact in any summation order."""
+    m, k, n = 13, 17, 11
+    a, b = zeros(ex, (m, k), np.float64), zeros(ex, (k, n), np.float64)
+    a.assign(ra._0 - ra._1)
+    b.assign(ra._1 - 2 * ra._0)
+    c = zeros(ex, (m, n), np.float64)
+    ra.gemm(a, b, c)
+    eq(c, a.numpy() @ b.numpy())
+
+
+# ---------------- stencils ----------------
+
+@case
+def stencil3_slices_vs_raw(ex):
+    """bench/bench-stencil3.cc:55-64,130: f_slices equals f_raw; boundary never written; pointer swap semantics."""
+    rng = np.random.default_rng(41)
+    n = (9, 8, 11)
+    A0 = rng.uniform(-1, 1, n).astype(np.float32)
+    A, An = ex.from_numpy(A0), zeros(ex, n, np.float32)
+    I, J, K = ra.iota(n[0] - 2, 1), ra.iota(n[1] - 2, 1), ra.iota(n[2] - 2, 1)
+    ref, refn = A0.copy(), np.zeros(n, np.float32)
+    for _ in range(4):  # "must be even bc of swap" test/wrank.cc:234
+        An(I, J, K).assign(-6 * A(I, J, K) + A(I + 1, J, K) + A(I, J + 1, K) + A(I, J, K + 1)
+                           + A(I - 1, J, K) + A(I, J - 1, K) + A(I, J, K - 1))
+        A, An = An, A
+        c = ref[1:-1, 1:-1, 1:-1]
+        refn[1:-1, 1:-1, 1:-1] = ((((((np.float32(-6) * c + ref[2:, 1:-1, 1:-1]) + ref[1:-1, 2:, 1:-1]) + ref[1:-1, 1:-1, 2:])
+                                    + ref[:-2, 1:-1, 1:-1]) + ref[1:-1, :-2, 1:-1]) + ref[1:-1, 1:-1, :-2])
+        ref, refn = refn, ref
+    eq(A, ref)
+    eq(An, refn)
+
+
+@case
+def laplace2d_stiff_and_mass(ex):
+    """examples/laplace2d.cc:36,48: 5-point stiffness and 7-point mass stencils on (N+1)^2 doubles."""
+    rng = np.random.default_rng(7)
+    N = 12
+    v0 = rng.uniform(-1, 1, (N + 1, N + 1))
+    v, w = ex.from_numpy(v0), zeros(ex, (N + 1, N + 1), np.float64)
+    i, j = ra.iota(N - 1, 1), ra.iota(N - 1, 1)
+    w(i, j).assign(4 * v(i, j) - v(i - 1, j) - v(i, j - 1) - v(i + 1, j) - v(i, j + 1))
+    c = v0[1:-1, 1:-1]
+    ref = np.zeros_like(v0)
+    ref[1:-1, 1:-1] = (((4 * c - v0[:-2, 1:-1]) - v0[1:-1, :-2]) - v0[2:, 1:-1]) - v0[1:-1, 2:]
+    eq(w, ref)
+    h = 1. / N
+    w(i, j).assign(ra.sqrm(h) * (v(i, j) / 2. + (v(i - 1, j) + v(i, j - 1) + v(i + 1, j) + v(i, j + 1) + v(i + 1, j + 1) + v(i - 1, j - 1)) / 12.))
+    ref[1:-1, 1:-1] = (h * h) * (c / 2. + (((((v0[:-2, 1:-1] + v0[1:-1, :-2]) + v0[2:, 1:-1]) + v0[1:-1, 2:]) + v0[2:, 2:]) + v0[:-2, :-2]) / 12.)
+    eq(w, ref)
