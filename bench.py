@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py - ra-ra traversal hot path on B200: `ply map/reduce HBM GB/s`.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload reduce|map|stencil]
+
+One "step" is one pass of the hot path over one batch of synthetic input. Default workload (BASELINE.json configs[1]):
+reductions on 2^30 floats per GPU - ra::sum, reduce_sqrm, dot (ra/ra.hh:348-401) plus bench-sum-rows / bench-sum-cols on
+the same buffer seen as 32768x32768 (bench/bench-sum-rows.cc, bench/bench-sum-cols.cc). Algorithmic bytes per step and
+GPU: 4 + 4 + 8 + 4 + 4 GiB. N>1: one process per GPU (torchrun), leading axis sharded, per-GPU work fixed (weak scaling),
+partials combined with an NCCL allreduce through the library's communicator. Inputs (>= 4 GiB per array) are far larger
+than L2 (126 MB), so no flush is needed between iterations.
+
+Prints ONE JSON line (rank 0). `value` = whole-job GB/s with inputs resident in HBM; `e2e` = same metric through the public
+API with pinned HOST inputs (H2D inside the timed region, result read back); `roofline` = the dominant kernel
+(ply_fold_inner<u32> running dot) timed alone with CUDA events against MEASURED_PEAKS.json; `cpu_baseline` = the
+reference's loops (oracle/libbaseline.so, single thread like the reference) on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GIB = 1 << 30
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reduce", choices=["reduce", "map", "stencil"])
+    ap.add_argument("--log2n", type=int, default=30, help="elements per GPU for the reduce workload")
+    ap.add_argument("--extras", type=int, default=1, help="also time the other configs (reported under 'extra')")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-log2n", type=int, default=27, help="bounded CPU sample size")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------- CPU baseline (reference arm)
+
+def baseline_lib():
+    path = os.path.join(ROOT, "oracle", "libbaseline.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    L = C.CDLL(path)
+    f32p = C.POINTER(C.c_float)
+    L.base_sum_f32.restype = C.c_float
+    L.base_sum_f32.argtypes = [f32p, C.c_int64]
+    L.base_sqrm_f32.restype = C.c_float
+    L.base_sqrm_f32.argtypes = [f32p, C.c_int64]
+    L.base_dot_f32.restype = C.c_float
+    L.base_dot_f32.argtypes = [f32p, f32p, C.c_int64]
+    L.base_sum_cols_f32.argtypes = [f32p, f32p, C.c_int64, C.c_int64]
+    L.base_sum_rows_f32.argtypes = [f32p, f32p, C.c_int64, C.c_int64]
+    L.base_map_f32.argtypes = [f32p, f32p, f32p, C.POINTER(C.c_double), C.c_int64, C.c_int64]
+    L.base_stencil3_f32.argtypes = [f32p, f32p, C.c_int64, C.c_int64, C.c_int64]
+    return L
+
+
+def cpu_reduce_step(L, a, b, m, n, r, c):
+    """One pass of the reduce workload on the reference's loops. Returns algorithmic bytes."""
+    f32p = C.POINTER(C.c_float)
+    pa, pb = a.ctypes.data_as(f32p), b.ctypes.data_as(f32p)
+    N = a.size
+    L.base_sum_f32(pa, N)
+    L.base_sqrm_f32(pa, N)
+    L.base_dot_f32(pa, pb, N)
+    L.base_sum_rows_f32(r.ctypes.data_as(f32p), pa, m, n)
+    L.base_sum_cols_f32(c.ctypes.data_as(f32p), pa, m, n)
+    return 4 * N * 6
+
+
+def cpu_baseline(log2n, runs=3):
+    L = baseline_lib()
+    N = 1 << log2n
+    m = 1 << (log2n // 2)
+    n = N // m
+    rng = np.random.default_rng(0x5EED0011)
+    a = rng.random(N, dtype=np.float32)
+    b = rng.random(N, dtype=np.float32)
+    r, c = np.zeros(n, np.float32), np.zeros(m, np.float32)
+    ts = []
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        nbytes = cpu_reduce_step(L, a, b, m, n, r, c)
+        ts.append(time.perf_counter() - t0)
+    t = sorted(ts)[len(ts) // 2]  # median of runs, like Benchmark().runs(3) (ra/test.hh:297-307)
+    return {"value": nbytes / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"sum+sqrm+dot+sum-rows+sum-cols on 2^{log2n} f32 ({m}x{n}), median of {runs} runs, "
+                      f"oracle/libbaseline.so -O3, single thread (the reference is single threaded; it needs gcc>=14 "
+                      f"and cannot be compiled in this image)",
+            "seconds": t}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L = baseline_lib()
+    log2n = args.cpu_log2n
+    N = 1 << log2n
+    m = 1 << (log2n // 2)
+    n = N // m
+    rng = np.random.default_rng(0x5EED0011)
+    a = rng.random(N, dtype=np.float32)
+    b = rng.random(N, dtype=np.float32)
+    r, c = np.zeros(n, np.float32), np.zeros(m, np.float32)
+    for _ in range(args.warmup):
+        cpu_reduce_step(L, a, b, m, n, r, c)
+    t0 = time.perf_counter()
+    nbytes = 0
+    for _ in range(args.steps):
+        nbytes += cpu_reduce_step(L, a, b, m, n, r, c)
+    t = time.perf_counter() - t0
+    v = nbytes / t / 1e9
+    sample = (f"each step = sum+sqrm+dot+sum-rows+sum-cols on a bounded sample of 2^{log2n} f32 ({m}x{n}) instead of "
+              f"2^{args.log2n}; oracle/libbaseline.so -O3 single thread")
+    print(json.dumps({
+        "impl": "reference", "metric": "ply map/reduce HBM GB/s", "value": v, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "l2": "inputs larger than L2"},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(args):
+    return (f"configs[1] reductions on 2^{args.log2n} f32 per GPU: ra::sum, reduce_sqrm, dot + bench-sum-rows/"
+            f"bench-sum-cols on {1 << (args.log2n // 2)}x{(1 << args.log2n) >> (args.log2n // 2)}")
+
+
+# ---------------------------------------------------------------- clocks
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------- GPU arm
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from ra_ra_b200 import abi, cuda, ra
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib = cuda.lib
+    comm = C.c_void_p()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ident = [None]
+        if rank == 0:
+            buf = (C.c_ubyte * abi.UNIQUE_ID_BYTES)()
+            cuda.check(lib.racu_comm_unique_id(buf))
+            ident = [bytes(buf)]
+        dist.broadcast_object_list(ident, src=0)
+        cuda.check(lib.racu_comm_init_rank(C.byref(comm), ident[0], world, rank))
+    ex = cuda.CudaExecutor(local)
+    dev = ex.device
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """W untimed + K timed iterations of fn, CUDA events on the current stream, max over ranks (ms per iteration)."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item()) / steps
+
+    # ---- synthetic inputs: 2^log2n f32 per GPU, uniform [0,1), fixed seeds
+    N = 1 << args.log2n
+    m = 1 << (args.log2n // 2)
+    n = N // m
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5EED0011 + rank)
+    a_t = torch.rand(N, generator=g, device=dev, dtype=torch.float32)
+    g.manual_seed(0x5EED0012 + rank)
+    b_t = torch.rand(N, generator=g, device=dev, dtype=torch.float32)
+    a, b = ex.wrap(a_t), ex.wrap(b_t)
+    A2 = ex.wrap(a_t.view(m, n))
+    scal = torch.zeros(4, device=dev, dtype=torch.float32)  # sum, sqrm, dot
+    rows_t = torch.zeros(n, device=dev, dtype=torch.float32)
+    cols_t = torch.zeros(m, device=dev, dtype=torch.float32)
+    rows, cols = ex.wrap(rows_t), ex.wrap(cols_t)
+
+    d_sum, k1 = ra.flatten(ra.as_expr(a), ex=ex)
+    d_sqrm, k2 = ra.flatten(ra.sqrm(a), ex=ex)
+    d_dot, k3 = ra.flatten(a * b, ex=ex)
+    d_rows, k4 = ra.flatten(ra.as_expr(A2), dst=rows(ra.insert(1)), assign=abi.ASSIGN_ADD, ex=ex)
+    d_cols, k5 = ra.flatten(ra.as_expr(A2), dst=cols, assign=abi.ASSIGN_ADD, ex=ex)
+    sp = cuda.stream_ptr
+
+    def step():
+        cuda.check(lib.racu_reduce_dev(C.byref(d_sum), abi.RED_SUM, C.c_void_p(scal.data_ptr()), sp()))
+        cuda.check(lib.racu_reduce_dev(C.byref(d_sqrm), abi.RED_SUM, C.c_void_p(scal.data_ptr() + 4), sp()))
+        cuda.check(lib.racu_reduce_dev(C.byref(d_dot), abi.RED_SUM, C.c_void_p(scal.data_ptr() + 8), sp()))
+        rows_t.zero_()
+        cols_t.zero_()
+        cuda.check(lib.racu_map(C.byref(d_rows), sp()))
+        cuda.check(lib.racu_map(C.byref(d_cols), sp()))
+        if world > 1:  # partials of the sharded leading axis: one allreduce each (sum-cols outputs stay sharded)
+            cuda.check(lib.racu_allreduce(comm, C.c_void_p(scal.data_ptr()), 3, abi.F32, abi.RED_SUM, sp()))
+            cuda.check(lib.racu_allreduce(comm, C.c_void_p(rows_t.data_ptr()), n, abi.F32, abi.RED_SUM, sp()))
+
+    bytes_step = 4 * N * 6 + 4 * (n + m)  # per GPU, algorithmic
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.racu_launch_count_reset()
+    ms = timed(step, args.steps, args.warmup)
+    launches = int(lib.racu_launch_count()) * args.steps // (args.steps + args.warmup)
+    sampler.stop_flag = True
+    value = bytes_step * world / (ms * 1e-3) / 1e9
+
+    # correctness of what was timed (rank-local, before allreduce scaling): relative error vs fp64
+    check = {}
+    if world == 1:
+        ref = a_t.double()
+        check = {"sum_rel_err": abs(float(scal[0]) - float(ref.sum())) / float(ref.sum()),
+                 "dot_rel_err": abs(float(scal[2]) - float((ref * b_t.double()).sum())) / float((ref * b_t.double()).sum())}
+        del ref
+
+    # ---- roofline of the dominant kernel: ply_fold_inner<u32> running dot (8 B / element), timed alone
+    def dot_only():
+        cuda.check(lib.racu_reduce_dev(C.byref(d_dot), abi.RED_SUM, C.c_void_p(scal.data_ptr() + 8), sp()))
+    ms_dot = timed(dot_only, max(args.steps, 10), 3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = 8.0 * N / (ms_dot * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "ply_fold_inner<u32> (dot, 2 finish-combined launches)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": 8 * N, "ms_per_launch": ms_dot}
+
+    # ---- e2e: public API (ra.sum / ra.dot / ... on views) from pinned HOST buffers, result read back each step
+    e2e = None
+    if args.e2e_steps > 0:
+        ha = torch.empty(N, dtype=torch.float32).pin_memory()
+        hb = torch.empty(N, dtype=torch.float32).pin_memory()
+        ha.copy_(a_t)
+        hb.copy_(b_t)
+        da, db = torch.empty_like(a_t), torch.empty_like(b_t)
+        hrows = torch.empty(n, dtype=torch.float32).pin_memory()
+        hcols = torch.empty(m, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            da.copy_(ha, non_blocking=True)
+            db.copy_(hb, non_blocking=True)
+            va, vb = ex.wrap(da), ex.wrap(db)
+            vA2 = ex.wrap(da.view(m, n))
+            s0 = ra.sum(va)
+            s1 = ra.reduce_sqrm(va)
+            s2 = ra.dot(va, vb)
+            rows_t.zero_()
+            cols_t.zero_()
+            rr = rows(ra.insert(1))
+            rr += vA2
+            cc = cols
+            cc += vA2
+            hrows.copy_(rows_t, non_blocking=True)
+            hcols.copy_(cols_t, non_blocking=True)
+            torch.cuda.synchronize()
+            return s0, s1, s2
+        ms_e2e = timed(e2e_step, args.e2e_steps, 1)
+        e2e = {"value": bytes_step * world / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 8 * N,
+               "d2h_bytes_per_step": 4 * (n + m) + 12, "ms_per_step": ms_e2e}
+        del ha, hb, da, db
+
+    # ---- other configs, timed the same way (reported, not the headline)
+    extra = {}
+    if args.extras and world == 1:
+        extra = run_extras(args, torch, ex, lib, cuda, ra, abi, timed, peak)
+
+    cpu = cpu_baseline(args.cpu_log2n) if rank == 0 and world == 1 else None
+    sampler.join(timeout=2)
+    if rank == 0:
+        out = {
+            "metric": "ply map/reduce HBM GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "l2": "inputs (4 GiB per array) larger than L2, no flush needed",
+                       "bytes_per_step_per_gpu": bytes_step, "sharding": "leading axis, one process per GPU"},
+            "frac_of_measured_hbm_peak": value / world / peak,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "check": check,
+            "extra": extra,
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        cuda.check(lib.racu_comm_destroy(comm))
+        dist.destroy_process_group()
+
+
+def run_extras(args, torch, ex, lib, cuda, ra, abi, timed, peak):
+    """configs[0] fused map and configs[3] 7-point stencil on one GPU, same timing rules."""
+    dev = ex.device
+    out = {}
+    g = torch.Generator(device=dev)
+    # configs[0]: B += A*C (+ v row broadcast) on f32 8192^2, 16 B/element
+    n = 8192
+    ts = []
+    for seed in (1, 2, 3):
+        g.manual_seed(0x5EED0000 + seed)
+        ts.append(torch.rand(n, n, generator=g, device=dev, dtype=torch.float32) * 2 - 1)
+    A, B, Cc = (ex.wrap(t) for t in ts)
+    g.manual_seed(0x5EED0004)
+    v = ex.wrap(torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2 - 1)
+    d1, k1 = ra.flatten(A * Cc, dst=B, assign=abi.ASSIGN_ADD, ex=ex)
+    d2, k2 = ra.flatten(A * Cc + v, dst=B, assign=abi.ASSIGN_ADD, ex=ex)
+    # rotate over 3 destination buffers so that consecutive launches do not find B in L2 (3 x 256 MiB > L2)
+    for name, d in (("map B+=A*C f32 8192^2", d1), ("map B+=A*C+v(double, prefix broadcast) f32 8192^2", d2)):
+        ms = timed(lambda: cuda.check(lib.racu_map(C.byref(d), cuda.stream_ptr())), 20, 3)
+        gbs = 16.0 * n * n / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "GB/s": gbs, "frac_of_measured_hbm_peak": gbs / peak, "kernel": lib.racu_last_kernel().decode(),
+                     "l2": "working set 768 MiB > L2"}
+    del ts, A, B, Cc
+    # configs[3]: 7-point stencil f32 1024^3, 8 B/cell/step
+    for n3 in (1024,):
+        A = torch.empty(n3, n3, n3, device=dev, dtype=torch.float32)
+        g.manual_seed(0x5EED0041)
+        A.uniform_(-1, 1, generator=g)
+        An = torch.zeros_like(A)
+        bufs = [A, An]
+        s = abi.StencilDesc()
+        s.kind, s.dtype, s.rank = abi.STENCIL_3D7, abi.F32, 3
+        for k in range(3):
+            s.len[k] = n3
+            s.src_stride[k] = s.dst_stride[k] = A.stride(k)
+
+        def sweep():
+            s.src, s.dst = bufs[0].data_ptr(), bufs[1].data_ptr()
+            cuda.check(lib.racu_stencil(C.byref(s), cuda.stream_ptr()))
+            bufs.reverse()  # std::swap(A.cp, Anext.cp)
+        ms = timed(sweep, 10, 4)
+        cells = float(n3) ** 3
+        out[f"stencil3d7 f32 {n3}^3"] = {"ms_per_step": ms, "Gcells/s": cells / (ms * 1e-3) / 1e9,
+                                         "GB/s_algorithmic": 8 * cells / (ms * 1e-3) / 1e9,
+                                         "frac_of_measured_hbm_peak": 8 * cells / (ms * 1e-3) / 1e9 / peak,
+                                         "kernel": lib.racu_last_kernel().decode()}
+        del A, An, bufs
+    return out
+
+
+if __name__ == "__main__":
+    main()

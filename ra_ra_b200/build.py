@@ -1,0 +1,59 @@
+"""Builds ra_ra_b200/libracu.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc. No JIT, no torch extension."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libracu.so")
+SOURCES = ["ply_kernels.cu", "special_kernels.cu", "plan.cc", "api.cc", "special.cc", "comm.cc"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O3", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
+
+
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+    hs.append(os.path.join(HERE, "..", "include", "racu.h"))
+    return hs
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_lib(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    bdir = os.path.join(CSRC, "build")
+    os.makedirs(bdir, exist_ok=True)
+    hdrs = _headers()
+    jobs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(bdir, s + ".o")
+        if force or _stale(obj, [src] + hdrs):
+            if s.endswith(".cc"):  # host-only translation units
+                cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++20", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
+                       "-I", os.path.join(os.path.dirname(os.path.dirname(nvcc)), "include"), "-c", src, "-o", obj]
+            else:
+                cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            jobs.append(cmd)
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if verbose and (r.stdout or r.stderr):
+            sys.stderr.write(r.stdout + r.stderr)
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
+    objs = [os.path.join(bdir, s + ".o") for s in SOURCES]
+    if force or jobs or _stale(OUT, objs):
+        run([nvcc, "-shared", "-o", OUT] + objs + ["-lnccl", "-Xlinker", "-rpath", "-Xlinker", "/usr/lib/x86_64-linux-gnu"])
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose=True))

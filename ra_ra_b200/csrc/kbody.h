@@ -1,0 +1,107 @@
+// kbody.h - the per-vector bodies of the ply kernels: operand staging, destination store, fold finish.
+// Shared by ply_kernels.cu (device; BE = cp.async) and sim/plan_sim.cc (host, tests only; BE = memcpy).
+#pragma once
+#include "kcore.h"
+
+namespace racu {
+
+// Stage every used operand of one vector (V elements starting at group-A position `a`, group-B position `b`)
+// into this thread's slots. Slot s lives at stage + s*sstride.
+template <class W, class BE> RACU_HD void
+stage_vector(KParams const & p, KIdx const & a, KIdx const & b, unsigned char * stage, int sstride, BE be)
+{
+    constexpr int V = Lanes<W>::V;
+    int64_t const rem = p.len0-a.e0;
+    int const nvalid = rem<V ? int(rem) : V;
+    for (int o=0; o<p.nopnd; ++o) {
+        KOpnd const & k = p.opnd[o];
+        if (S_NONE==k.stage || 255==k.slot) continue;
+        int64_t off = offsetA(p, k, a);
+        if (p.rankB>0) off += offsetB(p, k, b);
+        unsigned char * sl = stage + int(k.slot)*sstride;
+        int const es = k.esize;
+        if (S_VEC==k.stage && nvalid==V) {
+            unsigned char const * src = reinterpret_cast<unsigned char const *>(k.base) + off*es;
+            switch (V*es) {
+            case 16: be.copy16(sl, src); break;
+            case 8: be.copy8(sl, src); break;
+            case 4: if (4==es) be.copy4(sl, src); else *reinterpret_cast<uint32_t *>(sl) = *reinterpret_cast<uint32_t const *>(src); break;
+            default: *reinterpret_cast<uint16_t *>(sl) = *reinterpret_cast<uint16_t const *>(src); break;
+            }
+        } else if (S_VEC==k.stage || S_GATHER==k.stage) {
+            int64_t const s0 = k.sA[0];
+#pragma unroll
+            for (int j=0; j<V; ++j) {
+                if (j<nvalid) {
+                    unsigned char const * src = reinterpret_cast<unsigned char const *>(k.base) + (off+j*s0)*es;
+                    if (4==es) be.copy4(sl+4*j, src); else if (8==es) be.copy8(sl+8*j, src); else sl[j] = *src;
+                } else {
+                    if (4==es) *reinterpret_cast<uint32_t *>(sl+4*j) = 0; else if (8==es) *reinterpret_cast<uint64_t *>(sl+8*j) = 0; else sl[j] = 0;
+                }
+            }
+        } else if (S_BCAST==k.stage) {
+            W v = load_elem<W>(reinterpret_cast<unsigned char const *>(k.base) + off*es, k.dtype);
+#pragma unroll
+            for (int j=0; j<V; ++j) store_elem<W>(sl+j*es, k.dtype, v);
+        } else { // S_SEQ
+            int64_t const s0 = k.sA[0];
+#pragma unroll
+            for (int j=0; j<V; ++j) store_elem<W>(sl+j*es, k.dtype, seq_value<W>(k, off+j*s0));
+        }
+    }
+}
+
+// Store the V result lanes of a map to the destination.
+template <class W> RACU_HD void
+store_vector(KParams const & p, KIdx const & a, W const * t)
+{
+    constexpr int V = Lanes<W>::V;
+    KOpnd const & k = p.opnd[p.dst];
+    int64_t const rem = p.len0-a.e0;
+    int const nvalid = rem<V ? int(rem) : V;
+    int const es = k.esize;
+    int64_t const off = offsetA(p, k, a);
+    unsigned char * dst = reinterpret_cast<unsigned char *>(k.base) + off*es;
+    if (S_VEC==k.stage && nvalid==V) {
+        if constexpr (sizeof(W)==4) {
+            if (4==es) { uint4 q; q.x = t[0]; q.y = t[1]; q.z = t[2]; q.w = t[3]; *reinterpret_cast<uint4 *>(dst) = q; }
+            else { *reinterpret_cast<uint32_t *>(dst) = (t[0]&1u) | ((t[1]&1u)<<8) | ((t[2]&1u)<<16) | ((t[3]&1u)<<24); }
+        } else {
+            if (8==es) { ulonglong2 q; q.x = t[0]; q.y = t[1]; *reinterpret_cast<ulonglong2 *>(dst) = q; }
+            else if (4==es) { uint2 q; q.x = uint32_t(t[0]); q.y = uint32_t(t[1]); *reinterpret_cast<uint2 *>(dst) = q; }
+            else { *reinterpret_cast<uint16_t *>(dst) = uint16_t((uint32_t(t[0])&1u) | ((uint32_t(t[1])&1u)<<8)); }
+        }
+    } else {
+        int64_t const s0 = k.sA[0];
+#pragma unroll
+        for (int j=0; j<V; ++j) { if (j<nvalid) store_elem<W>(dst+j*s0*es, k.dtype, t[j]); }
+    }
+}
+
+// dst[kept n] = overwrite ? total : dst[kept n] OP total, with the accumulator <-> destination conversions.
+template <class W> RACU_HD void
+finish_apply(FinishParams const & f, int64_t n, W total)
+{
+    int64_t off = 0;
+    if (1==f.rank) {
+        off = n*f.stride[0];
+    } else if (f.rank>1) {
+        uint32_t m = uint32_t(n), q;
+#pragma unroll
+        for (int j=0; j<KMAXR; ++j) {
+            if (j<f.rank) {
+                if (j+1<f.rank) { q = fastdiv(m, f.d[j]); off += int64_t(m-q*f.d[j].len)*f.stride[j]; m = q; }
+                else { off += int64_t(m)*f.stride[j]; }
+            }
+        }
+    }
+    unsigned char * dst = static_cast<unsigned char *>(f.dst) + off*int64_t(f.dst_dtype==RACU_BOOL ? 1 : (f.dst_dtype==RACU_I32 || f.dst_dtype==RACU_F32) ? 4 : 8);
+    W val = total;
+    if (!f.overwrite) {
+        W old = cast_any<W>(f.dst_dtype, f.acc_type, load_elem<W>(dst, f.dst_dtype));
+        val = finish_op<W>(f.fold_op, f.acc_type, old, total);
+    }
+    store_elem<W>(dst, f.dst_dtype, cast_any<W>(f.acc_type, f.dst_dtype, val));
+}
+
+} // namespace racu

@@ -1,0 +1,514 @@
+// kcore.h - kernel-side data layout and the per-element machinery of the fused ply kernels:
+// fast index decomposition, operand offsets, the typed op table and the postfix interpreter.
+//
+// Everything here is RACU_HD so that (a) the sm_100a kernels (ply_kernels.cu) and (b) the planner's CPU
+// simulator (sim/plan_sim.cc, built only for tests, never linked into libracu.so) run the SAME code.
+//
+// Execution model. A thread owns "vectors": V consecutive elements along the innermost canonical dimension
+// (V = 4 with 32-bit value slots when every type in the program is <= 4 bytes, V = 2 with 64-bit slots otherwise),
+// so a full vector of a 4- or 8-byte operand is one 16-byte access. Operand elements are first STAGED into a
+// per-thread 16-byte slot (shared memory on the device; cp.async, so all operand loads of a thread are in flight
+// at once), then the postfix program runs over the V lanes with the top of stack in registers and the rest of the
+// value stack in per-thread shared memory rows (level `lvl`, fixed per instruction by the planner).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <type_traits>
+#include "../../include/racu.h"
+
+#if defined(__CUDACC__)
+#define RACU_HD __host__ __device__ __forceinline__
+#define RACU_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define RACU_HD inline
+#define RACU_HD_NOINLINE inline
+#endif
+
+#if !defined(__CUDACC__) && !defined(__VECTOR_TYPES_H__)
+// host stand-ins for the CUDA vector types used by the shared kernel bodies (CPU plan simulator only)
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+struct ulonglong2 { unsigned long long x, y; };
+#endif
+
+namespace racu {
+
+constexpr int KBLOCK = 256;      // threads per CTA of the ply kernels
+constexpr int KMAXR = RACU_MAX_RANK;
+constexpr int KSLOT = 16;        // bytes of one staged vector / one stack row per thread
+
+enum KMode { K_MAP = 0, K_FOLD_INNER = 1, K_FOLD_OUTER = 2 };
+enum KStage { S_NONE = 0 /* scalar immediate */, S_VEC = 1, S_GATHER = 2, S_BCAST = 3, S_SEQ = 4 };
+
+struct KDim { uint32_t len, mul, shift, pad; }; // n / len == (umulhi(n, mul) + n) >> shift for n < 2^31
+
+struct KOpnd
+{
+    uint64_t base;            // MEM: address of element [0..0] after canonicalisation. SEQ/SCALAR: value bits (i64 or f64)
+    int64_t sA[KMAXR];        // element strides over group A dims (sA[0]: innermost, the vectorised one)
+    int64_t sB[KMAXR];        // element strides over group B dims
+    uint8_t kind, dtype, stage, esize;
+    uint8_t slot;             // staging slot index (S_NONE: unused)
+    uint8_t pad[3];
+};
+
+struct KIns { uint8_t op, type, arg, aux, lvl, pad[3]; };
+
+struct KParams
+{
+    int32_t mode;             // KMode
+    int32_t wide;             // 0: 32-bit slots, V=4.  1: 64-bit slots, V=2
+    int32_t rankA, rankB;
+    int32_t nopnd, nins, nstage, depth;
+    int32_t U;                // vectors staged per thread per iteration
+    int32_t dst;              // MAP: operand index of the destination. folds: operand index of dst, or -1
+    int32_t fold_op;          // racu_assign of a fold
+    int32_t acc_type;         // racu_dtype of the accumulator
+    int32_t overwrite;        // folds: result replaces dst instead of combining with its old value (racu_reduce)
+    int32_t nchunks;
+    uint64_t identity;        // accumulator start value, slot bits
+    int64_t len0;             // length of A dim 0 in elements
+    int64_t vpr;              // vectors per row = ceil(len0 / V)
+    int64_t nvecA;            // vpr * prod(lenA[1..])
+    int64_t nB;               // prod(lenB)
+    int64_t chunk_len;        // FOLD_INNER: A-vectors per chunk. FOLD_OUTER: B indices per chunk
+    int64_t nk;               // folds: number of kept elements
+    void * partial;           // folds: [nchunks][nk] accumulator slots
+    KDim vprdiv;
+    KDim dA[KMAXR];           // dA[0] unused (see vpr)
+    KDim dB[KMAXR];
+    KOpnd opnd[RACU_MAX_OPND];
+    KIns ins[RACU_MAX_INS];
+};
+
+struct FinishParams
+{
+    int32_t wide, fold_op, acc_type, dst_dtype, overwrite, rank, nchunks, per_warp;
+    uint64_t identity;
+    int64_t nk;
+    void * partial;
+    void * dst;
+    KDim d[KMAXR];
+    int64_t len0;         // length of kept dim 0 (not limited to 2^31 when rank==1)
+    int64_t stride[KMAXR];
+};
+
+// ---------------- index math ----------------
+
+RACU_HD uint32_t umulhi32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return uint32_t((uint64_t(a)*uint64_t(b))>>32);
+#endif
+}
+RACU_HD uint32_t fastdiv(uint32_t n, KDim const & d) { return (umulhi32(n, d.mul)+n)>>d.shift; }
+
+struct KIdx { int64_t e0; uint32_t i[KMAXR]; }; // group A: e0 = element index along dim 0, i[1..] the others. group B: i[0..]
+
+// vector id g (< nvecA) -> position in group A
+RACU_HD void decompA(KParams const & p, int64_t g, KIdx & x)
+{
+    if (1==p.rankA) { x.e0 = g*(p.wide ? 2 : 4); return; }
+    uint32_t n = uint32_t(g);
+    uint32_t q = fastdiv(n, p.vprdiv);
+    x.e0 = int64_t(n-q*uint32_t(p.vpr))*(p.wide ? 2 : 4);
+    n = q;
+#pragma unroll
+    for (int j=1; j<KMAXR; ++j) {
+        if (j<p.rankA) {
+            if (j+1<p.rankA) { q = fastdiv(n, p.dA[j]); x.i[j] = n-q*p.dA[j].len; n = q; }
+            else { x.i[j] = n; }
+        }
+    }
+}
+
+// linear index b (< nB) -> position in group B
+RACU_HD void decompB(KParams const & p, int64_t b, KIdx & x)
+{
+    uint32_t n = uint32_t(b), q;
+#pragma unroll
+    for (int j=0; j<KMAXR; ++j) {
+        if (j<p.rankB) {
+            if (j+1<p.rankB) { q = fastdiv(n, p.dB[j]); x.i[j] = n-q*p.dB[j].len; n = q; }
+            else { x.i[j] = n; }
+        }
+    }
+}
+
+RACU_HD int64_t offsetA(KParams const & p, KOpnd const & o, KIdx const & a)
+{
+    int64_t off = a.e0*o.sA[0];
+#pragma unroll
+    for (int j=1; j<KMAXR; ++j) { if (j<p.rankA) off += int64_t(a.i[j])*o.sA[j]; }
+    return off;
+}
+RACU_HD int64_t offsetB(KParams const & p, KOpnd const & o, KIdx const & b)
+{
+    int64_t off = 0;
+#pragma unroll
+    for (int j=0; j<KMAXR; ++j) { if (j<p.rankB) off += int64_t(b.i[j])*o.sB[j]; }
+    return off;
+}
+
+// ---------------- value slots ----------------
+// A slot holds one value as raw bits: BOOL 0/1, I32 / F32 in the low 32 bits, I64 / F64 in 64 bits.
+
+template <class W> struct Lanes { static constexpr int V = sizeof(W)==4 ? 4 : 2; };
+
+RACU_HD float bits_f32(uint32_t a)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(a);
+#else
+    union { uint32_t u; float f; } c; c.u = a; return c.f;
+#endif
+}
+RACU_HD uint32_t f32_bits(float a)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(a);
+#else
+    union { uint32_t u; float f; } c; c.f = a; return c.u;
+#endif
+}
+RACU_HD double bits_f64(uint64_t a)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)a);
+#else
+    union { uint64_t u; double f; } c; c.u = a; return c.f;
+#endif
+}
+RACU_HD uint64_t f64_bits(double a)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(a);
+#else
+    union { uint64_t u; double f; } c; c.f = a; return c.u;
+#endif
+}
+
+template <class T> struct Ty;
+template <> struct Ty<bool> { template <class W> static RACU_HD bool get(W a) { return (uint32_t(a)&0xffu)!=0; } template <class W> static RACU_HD W put(bool x) { return W(x ? 1 : 0); } };
+template <> struct Ty<int32_t> { template <class W> static RACU_HD int32_t get(W a) { return int32_t(uint32_t(a)); } template <class W> static RACU_HD W put(int32_t x) { return W(uint32_t(x)); } };
+template <> struct Ty<float> { template <class W> static RACU_HD float get(W a) { return bits_f32(uint32_t(a)); } template <class W> static RACU_HD W put(float x) { return W(f32_bits(x)); } };
+template <> struct Ty<int64_t> { template <class W> static RACU_HD int64_t get(W a) { return int64_t(uint64_t(a)); } template <class W> static RACU_HD W put(int64_t x) { return W(uint64_t(x)); } };
+template <> struct Ty<double> { template <class W> static RACU_HD double get(W a) { return bits_f64(uint64_t(a)); } template <class W> static RACU_HD W put(double x) { return W(f64_bits(x)); } };
+
+// Transcendentals and other long sequences are kept out of line: they would otherwise be unrolled V times per case.
+RACU_HD_NOINLINE float slow_un_f32(int op, float a)
+{
+    switch (op) { case RACU_OP_EXP: return expf(a); case RACU_OP_LOG: return logf(a); case RACU_OP_SIN: return sinf(a); default: return cosf(a); }
+}
+RACU_HD_NOINLINE double slow_un_f64(int op, double a)
+{
+    switch (op) { case RACU_OP_EXP: return exp(a); case RACU_OP_LOG: return log(a); case RACU_OP_SIN: return sin(a); default: return cos(a); }
+}
+RACU_HD_NOINLINE float slow_bin_f32(int op, float a, float b)
+{
+    switch (op) { case RACU_OP_POW: return powf(a, b); case RACU_OP_ATAN2: return atan2f(a, b); default: return fmodf(a, b); }
+}
+RACU_HD_NOINLINE double slow_bin_f64(int op, double a, double b)
+{
+    switch (op) { case RACU_OP_POW: return pow(a, b); case RACU_OP_ATAN2: return atan2(a, b); case RACU_OP_MOD: return fmod(a, b); default: return a/b; }
+}
+RACU_HD_NOINLINE int64_t slow_div_i64(int op, int64_t a, int64_t b) { return 0==b ? 0 : (op==RACU_OP_DIV ? a/b : a%b); }
+
+template <class T> RACU_HD T t_abs(T a) { return a<T(0) ? T(-a) : a; }
+template <> RACU_HD float t_abs<float>(float a) { return fabsf(a); }
+template <> RACU_HD double t_abs<double>(double a) { return fabs(a); }
+
+// unary, one lane. T is the operand type.
+template <class W, class T> RACU_HD W un1(int op, W a)
+{
+    T x = Ty<T>::template get<W>(a);
+    if (op==RACU_OP_NOT) return Ty<bool>::template put<W>(!x);
+    if constexpr (!std::is_same_v<T, bool>) {
+        switch (op) {
+        case RACU_OP_NEG: return Ty<T>::template put<W>(T(-x));
+        case RACU_OP_ABS: return Ty<T>::template put<W>(t_abs<T>(x));
+        case RACU_OP_SQR: return Ty<T>::template put<W>(T(x*x));
+        }
+        if constexpr (std::is_same_v<T, float>) {
+            if (op==RACU_OP_SQRT) return Ty<T>::template put<W>(sqrtf(x));
+            return Ty<T>::template put<W>(slow_un_f32(op, x));
+        } else if constexpr (std::is_same_v<T, double>) {
+            if (op==RACU_OP_SQRT) return Ty<T>::template put<W>(sqrt(x));
+            return Ty<T>::template put<W>(slow_un_f64(op, x));
+        }
+    }
+    return a;
+}
+
+// binary, one lane.
+template <class W, class T> RACU_HD W bin1(int op, W a, W b)
+{
+    T x = Ty<T>::template get<W>(a), y = Ty<T>::template get<W>(b);
+    switch (op) {
+    case RACU_OP_EQ: return Ty<bool>::template put<W>(x==y);
+    case RACU_OP_NE: return Ty<bool>::template put<W>(x!=y);
+    case RACU_OP_LT: return Ty<bool>::template put<W>(x<y);
+    case RACU_OP_LE: return Ty<bool>::template put<W>(x<=y);
+    case RACU_OP_GT: return Ty<bool>::template put<W>(x>y);
+    case RACU_OP_GE: return Ty<bool>::template put<W>(x>=y);
+    }
+    if constexpr (std::is_same_v<T, bool>) {
+        switch (op) {
+        case RACU_OP_BAND: return Ty<bool>::template put<W>(x & y);
+        case RACU_OP_BOR: return Ty<bool>::template put<W>(x | y);
+        case RACU_OP_BXOR: return Ty<bool>::template put<W>(x ^ y);
+        }
+    } else {
+        switch (op) {
+        case RACU_OP_ADD: return Ty<T>::template put<W>(T(x+y));
+        case RACU_OP_SUB: return Ty<T>::template put<W>(T(x-y));
+        case RACU_OP_MUL: return Ty<T>::template put<W>(T(x*y));
+        case RACU_OP_MIN: return Ty<T>::template put<W>(y<x ? y : x);
+        case RACU_OP_MAX: return Ty<T>::template put<W>(x<y ? y : x);
+        }
+        if constexpr (std::is_same_v<T, int32_t>) {
+            switch (op) {
+            case RACU_OP_DIV: return Ty<T>::template put<W>(0==y ? 0 : (y==-1 ? T(-x) : x/y));
+            case RACU_OP_MOD: return Ty<T>::template put<W>((0==y || y==-1) ? 0 : x%y);
+            case RACU_OP_BAND: return Ty<T>::template put<W>(x & y);
+            case RACU_OP_BOR: return Ty<T>::template put<W>(x | y);
+            case RACU_OP_BXOR: return Ty<T>::template put<W>(x ^ y);
+            }
+        } else if constexpr (std::is_same_v<T, int64_t>) {
+            switch (op) {
+            case RACU_OP_DIV: case RACU_OP_MOD: return Ty<T>::template put<W>(slow_div_i64(op, x, y));
+            case RACU_OP_BAND: return Ty<T>::template put<W>(x & y);
+            case RACU_OP_BOR: return Ty<T>::template put<W>(x | y);
+            case RACU_OP_BXOR: return Ty<T>::template put<W>(x ^ y);
+            }
+        } else if constexpr (std::is_same_v<T, float>) {
+            if (op==RACU_OP_DIV) return Ty<T>::template put<W>(x/y);
+            return Ty<T>::template put<W>(slow_bin_f32(op, x, y));
+        } else {
+            return Ty<T>::template put<W>(slow_bin_f64(op, x, y));
+        }
+    }
+    return a;
+}
+
+template <class W, class S, class D> RACU_HD W cast1(W a)
+{
+    S x = Ty<S>::template get<W>(a);
+    if constexpr (std::is_same_v<D, bool>) return Ty<bool>::template put<W>(x!=S(0));
+    else return Ty<D>::template put<W>(static_cast<D>(x));
+}
+
+template <class W, class S> RACU_HD W cast_from(int dt, W a)
+{
+    switch (dt) {
+    case RACU_BOOL: return cast1<W, S, bool>(a);
+    case RACU_I32: return cast1<W, S, int32_t>(a);
+    case RACU_F32: return cast1<W, S, float>(a);
+    default:
+        if constexpr (sizeof(W)==8) { return dt==RACU_I64 ? cast1<W, S, int64_t>(a) : cast1<W, S, double>(a); }
+        return a;
+    }
+}
+
+template <class W> RACU_HD W cast_any(int st, int dt, W a)
+{
+    switch (st) {
+    case RACU_BOOL: return cast_from<W, bool>(dt, a);
+    case RACU_I32: return cast_from<W, int32_t>(dt, a);
+    case RACU_F32: return cast_from<W, float>(dt, a);
+    default:
+        if constexpr (sizeof(W)==8) { return st==RACU_I64 ? cast_from<W, int64_t>(dt, a) : cast_from<W, double>(dt, a); }
+        return a;
+    }
+}
+
+template <class W> RACU_HD W un_any(int op, int type, W a)
+{
+    switch (type) {
+    case RACU_BOOL: return un1<W, bool>(op, a);
+    case RACU_I32: return un1<W, int32_t>(op, a);
+    case RACU_F32: return un1<W, float>(op, a);
+    default:
+        if constexpr (sizeof(W)==8) { return type==RACU_I64 ? un1<W, int64_t>(op, a) : un1<W, double>(op, a); }
+        return a;
+    }
+}
+
+template <class W> RACU_HD W bin_any(int op, int type, W a, W b)
+{
+    switch (type) {
+    case RACU_BOOL: return bin1<W, bool>(op, a, b);
+    case RACU_I32: return bin1<W, int32_t>(op, a, b);
+    case RACU_F32: return bin1<W, float>(op, a, b);
+    default:
+        if constexpr (sizeof(W)==8) { return type==RACU_I64 ? bin1<W, int64_t>(op, a, b) : bin1<W, double>(op, a, b); }
+        return a;
+    }
+}
+
+template <class W> RACU_HD W fma_any(int type, W a, W b, W c)
+{
+    if (type==RACU_F32) return Ty<float>::template put<W>(fmaf(Ty<float>::template get<W>(a), Ty<float>::template get<W>(b), Ty<float>::template get<W>(c)));
+    if constexpr (sizeof(W)==8) { if (type==RACU_F64) return Ty<double>::template put<W>(fma(Ty<double>::template get<W>(a), Ty<double>::template get<W>(b), Ty<double>::template get<W>(c))); }
+    return c;
+}
+
+// Fold combiners over accumulator type `type`. SUB and DIV accumulate the sum / product; the finish applies dst - s, dst / s.
+template <class W> RACU_HD W combine(int fold_op, int type, W acc, W x)
+{
+    switch (fold_op) {
+    case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: return bin_any<W>(RACU_OP_ADD, type, acc, x);
+    case RACU_ASSIGN_MUL: case RACU_ASSIGN_DIV: return bin_any<W>(RACU_OP_MUL, type, acc, x);
+    case RACU_ASSIGN_AMIN: return Ty<bool>::template get<W>(bin_any<W>(RACU_OP_LT, type, x, acc)) ? x : acc; // if (x<c) c=x
+    default: return Ty<bool>::template get<W>(bin_any<W>(RACU_OP_LT, type, acc, x)) ? x : acc;              // if (c<x) c=x
+    }
+}
+// dst_old OP total
+template <class W> RACU_HD W finish_op(int fold_op, int type, W old, W total)
+{
+    switch (fold_op) {
+    case RACU_ASSIGN_SUB: return bin_any<W>(RACU_OP_SUB, type, old, total);
+    case RACU_ASSIGN_DIV: return bin_any<W>(RACU_OP_DIV, type, old, total);
+    default: return combine<W>(fold_op, type, old, total);
+    }
+}
+
+// ---------------- element <-> slot ----------------
+
+template <class W> RACU_HD W load_elem(void const * ptr, int dtype)
+{
+    switch (dtype) {
+    case RACU_BOOL: return W(*static_cast<uint8_t const *>(ptr) ? 1 : 0);
+    case RACU_I32: case RACU_F32: return W(*static_cast<uint32_t const *>(ptr));
+    default:
+        if constexpr (sizeof(W)==8) return W(*static_cast<uint64_t const *>(ptr));
+        return W(0);
+    }
+}
+template <class W> RACU_HD void store_elem(void * ptr, int dtype, W v)
+{
+    switch (dtype) {
+    case RACU_BOOL: *static_cast<uint8_t *>(ptr) = uint8_t(uint32_t(v)&1u); break;
+    case RACU_I32: case RACU_F32: *static_cast<uint32_t *>(ptr) = uint32_t(v); break;
+    default:
+        if constexpr (sizeof(W)==8) *static_cast<uint64_t *>(ptr) = uint64_t(v);
+    }
+}
+
+// SEQ value at element offset `off`: Seq: *p = i, p + d = i + I(d)  (ra/expr.hh:86-91).
+template <class W> RACU_HD W seq_value(KOpnd const & o, int64_t off)
+{
+    switch (o.dtype) {
+    case RACU_I32: return Ty<int32_t>::template put<W>(int32_t(int32_t(int64_t(o.base))+int32_t(off)));
+    case RACU_F32: return Ty<float>::template put<W>(float(bits_f64(o.base))+float(off));
+    case RACU_BOOL: return Ty<bool>::template put<W>((int64_t(o.base)+off)!=0);
+    default:
+        if constexpr (sizeof(W)==8) {
+            if (o.dtype==RACU_I64) return Ty<int64_t>::template put<W>(int64_t(o.base)+off);
+            return Ty<double>::template put<W>(bits_f64(o.base)+double(off));
+        }
+        return W(0);
+    }
+}
+template <class W> RACU_HD W scalar_value(KOpnd const & o)
+{
+    switch (o.dtype) {
+    case RACU_I32: return Ty<int32_t>::template put<W>(int32_t(int64_t(o.base)));
+    case RACU_F32: return Ty<float>::template put<W>(float(bits_f64(o.base)));
+    case RACU_BOOL: return Ty<bool>::template put<W>(int64_t(o.base)!=0);
+    default:
+        if constexpr (sizeof(W)==8) {
+            if (o.dtype==RACU_I64) return Ty<int64_t>::template put<W>(int64_t(o.base));
+            return Ty<double>::template put<W>(bits_f64(o.base));
+        }
+        return W(0);
+    }
+}
+
+// ---------------- the postfix interpreter over V lanes ----------------
+// stage: this thread's staged operand slots for the vector being evaluated; slot k at stage + k*stage_stride bytes,
+//        holding V raw elements of the operand's dtype.
+// stack: this thread's value stack rows; level l at stack + l*stack_stride bytes, V slots of W.
+// Result (V lanes) in t[].
+template <class W> RACU_HD void
+interp(KParams const & p, unsigned char const * stage, int stage_stride, unsigned char * stack, int stack_stride, W * t)
+{
+    constexpr int V = Lanes<W>::V;
+    for (int pc=0; pc<p.nins; ++pc) {
+        KIns const in = p.ins[pc];
+        W * lv = reinterpret_cast<W *>(stack + int(in.lvl)*stack_stride);
+        switch (in.op) {
+        case RACU_OP_PUSH: {
+            if (in.lvl!=255) {
+#pragma unroll
+                for (int j=0; j<V; ++j) lv[j] = t[j];
+            }
+            KOpnd const & o = p.opnd[in.arg];
+            if (S_NONE==o.stage) {
+                W s = scalar_value<W>(o);
+#pragma unroll
+                for (int j=0; j<V; ++j) t[j] = s;
+            } else {
+                unsigned char const * sl = stage + int(o.slot)*stage_stride;
+                if (4==o.esize) {
+#pragma unroll
+                    for (int j=0; j<V; ++j) t[j] = W(reinterpret_cast<uint32_t const *>(sl)[j]);
+                } else if (1==o.esize) {
+#pragma unroll
+                    for (int j=0; j<V; ++j) t[j] = W(sl[j] ? 1 : 0);
+                } else {
+                    if constexpr (sizeof(W)==8) {
+#pragma unroll
+                        for (int j=0; j<V; ++j) t[j] = reinterpret_cast<uint64_t const *>(sl)[j];
+                    }
+                }
+            }
+            break;
+        }
+        case RACU_OP_CAST:
+#pragma unroll
+            for (int j=0; j<V; ++j) t[j] = cast_any<W>(in.aux, in.type, t[j]);
+            break;
+        case RACU_OP_NEG: case RACU_OP_ABS: case RACU_OP_SQRT: case RACU_OP_SQR: case RACU_OP_EXP:
+        case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS: case RACU_OP_NOT:
+#pragma unroll
+            for (int j=0; j<V; ++j) t[j] = un_any<W>(in.op, in.type, t[j]);
+            break;
+        case RACU_OP_FMA: {
+            W const * lb = reinterpret_cast<W const *>(stack + (int(in.lvl)+1)*stack_stride);
+#pragma unroll
+            for (int j=0; j<V; ++j) t[j] = fma_any<W>(in.type, lv[j], lb[j], t[j]);
+            break;
+        }
+        case RACU_OP_PICK: {
+            int n = in.arg;
+            W sel[V];
+#pragma unroll
+            for (int j=0; j<V; ++j) {
+                sel[j] = lv[j];
+                if (in.aux==RACU_BOOL) sel[j] = W(uint32_t(sel[j])&0xffu);
+                else if (in.aux==RACU_I32) sel[j] = W(uint32_t(sel[j]));
+            }
+            for (int b=0; b+1<n; ++b) {
+                W const * lb = reinterpret_cast<W const *>(stack + (int(in.lvl)+1+b)*stack_stride);
+#pragma unroll
+                for (int j=0; j<V; ++j) { if (sel[j]==W(b)) t[j] = lb[j]; }
+            }
+            if (n>1) { // out of contract selectors take branch 0, like the oracle
+                W const * l0 = reinterpret_cast<W const *>(stack + (int(in.lvl)+1)*stack_stride);
+#pragma unroll
+                for (int j=0; j<V; ++j) { if (!(sel[j]<W(n))) t[j] = l0[j]; }
+            }
+            break;
+        }
+        default:
+#pragma unroll
+            for (int j=0; j<V; ++j) t[j] = bin_any<W>(in.op, in.type, lv[j], t[j]);
+            break;
+        }
+    }
+}
+
+} // namespace racu

@@ -1,0 +1,623 @@
+// plan.cc - the flattener's second half: racu_desc -> canonical kernel parameters.
+//
+// The host header (include/ra/cuda.hh) turns an expression tree into a racu_desc: leaves + postfix program, in the
+// reference's own terms (per-operand rank/len/step, prefix matching). This file does what ra::ply_ravel does before its
+// hot loop (ra/ply.hh:21-57) - validate, agree shapes, find what can be raveled - but for a machine where the order is
+// free (docs/ra-ra.texi:2142: "shouldn't be relied upon") and the inner loop is 148 SMs wide:
+//   * Match::len / check (ra/expr.hh:555-608) -> agree()
+//   * the collapse rule `ss*step(z)==step(j)` (ra/ply.hh:42-46, Cell::keep ra/expr.hh:296-297) applied to ANY adjacent
+//     pair after sorting the axes by destination stride (maps) or source stride (folds)
+//   * negative destination steps are flipped so the innermost destination step is +1 where possible
+//   * `dst OP= rhs` is folded into the program (maps), or becomes a tree fold when dst has step 0 on an axis (ra/expr.hh:50-53)
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace racu {
+
+size_t dtype_size(int t) { return t==RACU_BOOL ? 1 : (t==RACU_I32 || t==RACU_F32) ? 4 : 8; }
+
+static bool is_float(int t) { return t==RACU_F32 || t==RACU_F64; }
+static int promote(int t) { return t==RACU_BOOL ? RACU_I32 : t; }
+// C++ usual arithmetic conversions over the five element types.
+static int common_type(int a, int b)
+{
+    a = promote(a); b = promote(b);
+    if (a==RACU_F64 || b==RACU_F64) return RACU_F64;
+    if (a==RACU_F32 || b==RACU_F32) return RACU_F32;
+    if (a==RACU_I64 || b==RACU_I64) return RACU_I64;
+    return RACU_I32;
+}
+
+// Type-checks the postfix program by simulating its type stack. Returns the result dtype, or -1.
+static int
+check_ins(racu_ins const * ins, int nins, racu_operand const * opnd, int nopnd, std::string & err)
+{
+    int st[RACU_MAX_INS+1], sp = 0;
+    auto bad = [&](int pc, char const * what) { err = "bad program at instruction " + std::to_string(pc) + ": " + what; return -1; };
+    if (nins<=0 || nins>RACU_MAX_INS) { err = "bad program length"; return -1; }
+    for (int pc=0; pc<nins; ++pc) {
+        racu_ins const & in = ins[pc];
+        if (in.type>=RACU_NDTYPE) return bad(pc, "type");
+        bool isf = is_float(in.type), isb = in.type==RACU_BOOL;
+        auto need = [&](int n) { if (sp<n) return false; for (int j=0; j<n; ++j) { if (st[sp-1-j]!=in.type) return false; } return true; };
+        switch (in.op) {
+        case RACU_OP_PUSH:
+            if (in.arg>=nopnd || opnd[in.arg].dtype!=in.type) return bad(pc, "push");
+            st[sp++] = in.type; break;
+        case RACU_OP_CAST:
+            if (sp<1 || st[sp-1]!=in.aux || in.aux>=RACU_NDTYPE) return bad(pc, "cast");
+            st[sp-1] = in.type; break;
+        case RACU_OP_NEG: case RACU_OP_ABS: case RACU_OP_SQR:
+            if (!need(1) || isb) return bad(pc, "unary"); break;
+        case RACU_OP_SQRT: case RACU_OP_EXP: case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS:
+            if (!need(1) || !isf) return bad(pc, "float unary"); break;
+        case RACU_OP_NOT:
+            if (!need(1)) return bad(pc, "not");
+            st[sp-1] = RACU_BOOL; break;
+        case RACU_OP_ADD: case RACU_OP_SUB: case RACU_OP_MUL: case RACU_OP_DIV: case RACU_OP_MOD: case RACU_OP_MIN: case RACU_OP_MAX:
+            if (!need(2) || isb) return bad(pc, "binary");
+            --sp; break;
+        case RACU_OP_POW: case RACU_OP_ATAN2:
+            if (!need(2) || !isf) return bad(pc, "float binary");
+            --sp; break;
+        case RACU_OP_BAND: case RACU_OP_BOR: case RACU_OP_BXOR:
+            if (!need(2) || isf) return bad(pc, "bit op");
+            --sp; break;
+        case RACU_OP_EQ: case RACU_OP_NE: case RACU_OP_LT: case RACU_OP_LE: case RACU_OP_GT: case RACU_OP_GE:
+            if (!need(2)) return bad(pc, "comparison");
+            --sp; st[sp-1] = RACU_BOOL; break;
+        case RACU_OP_FMA:
+            if (!need(3) || !isf) return bad(pc, "fma");
+            sp -= 2; break;
+        case RACU_OP_PICK: {
+            int n = in.arg;
+            if (n<1 || sp<n+1 || !need(n)) return bad(pc, "pick");
+            int sel = st[sp-1-n];
+            if (sel!=in.aux || is_float(sel)) return bad(pc, "pick selector");
+            sp -= n; st[sp-1] = in.type; break;
+        }
+        default: return bad(pc, "opcode");
+        }
+    }
+    if (1!=sp) { err = "bad program: stack not reduced to one value"; return -1; }
+    return st[0];
+}
+
+int
+check_program(racu_desc const * d, std::string & err)
+{
+    if (d->nopnd<=0 || d->nopnd>RACU_MAX_OPND) { err = "bad operand count"; return -1; }
+    for (int o=0; o<d->nopnd; ++o) {
+        racu_operand const & p = d->opnd[o];
+        if (p.dtype<0 || p.dtype>=RACU_NDTYPE || p.kind<RACU_MEM || p.kind>RACU_SCALAR) { err = "bad operand kind/dtype"; return -1; }
+        if (p.kind==RACU_MEM && !p.base.ptr) { err = "null operand pointer"; return -1; }
+    }
+    return check_ins(d->ins, d->nins, d->opnd, d->nopnd, err);
+}
+
+// Match::rank / len / check: ra/expr.hh:529-608.
+static int64_t colen(int64_t a, int64_t b) { return a>=0 ? (a==b ? a : b>=0 ? RACU_MIS : a) : RACU_UNB==a ? b : RACU_UNB==b ? a : b; }
+
+int
+agree(racu_desc const * d, Shape & s, std::string & err)
+{
+    if (d->nopnd<=0 || d->nopnd>RACU_MAX_OPND) { err = "bad operand count"; return RACU_ERR_BAD_DESC; }
+    s.rank = 0;
+    for (int o=0; o<d->nopnd; ++o) {
+        racu_operand const & p = d->opnd[o];
+        if (p.rank<0 || p.rank>RACU_MAX_RANK || (p.kind==RACU_SCALAR && p.rank!=0)) { err = "bad operand rank"; return RACU_ERR_BAD_DESC; }
+        s.rank = std::max(s.rank, int(p.rank));
+    }
+    for (int k=0; k<s.rank; ++k) {
+        int64_t l = RACU_UNB;
+        for (int o=0; o<d->nopnd && l!=RACU_MIS; ++o) {
+            racu_operand const & p = d->opnd[o];
+            if (k<p.rank) {
+                if (p.len[k]<0 && p.len[k]!=RACU_UNB) { err = "bad operand len"; return RACU_ERR_BAD_DESC; }
+                l = colen(p.len[k], l);
+            }
+        }
+        if (l<0) {
+            err = "Bad shapes: axis " + std::to_string(k) + (l==RACU_MIS ? " is mismatched." : " is unbounded.");
+            return RACU_ERR_SHAPE;
+        }
+        s.len[k] = l;
+    }
+    return RACU_OK;
+}
+
+static KDim
+make_div(int64_t len)
+{
+    KDim d {};
+    d.len = uint32_t(len);
+    uint32_t sh = 0;
+    while (sh<32 && (uint64_t(1)<<sh)<uint64_t(len)) ++sh;
+    d.shift = sh;
+    d.mul = uint32_t(((uint64_t(1)<<32)*((uint64_t(1)<<sh)-uint64_t(len)))/uint64_t(len)+1);
+    return d;
+}
+
+static uint64_t
+identity_bits(int fold_op, int t)
+{
+    auto pack = [&](double f, int64_t i) -> uint64_t {
+        switch (t) {
+        case RACU_F32: return f32_bits(float(f));
+        case RACU_F64: return f64_bits(f);
+        case RACU_I32: return uint32_t(int32_t(i));
+        case RACU_BOOL: return i ? 1 : 0;
+        default: return uint64_t(i);
+        }
+    };
+    switch (fold_op) {
+    case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: return pack(0, 0);
+    case RACU_ASSIGN_MUL: case RACU_ASSIGN_DIV: return pack(1, 1);
+    case RACU_ASSIGN_AMIN: // ra/ra.hh:310
+        return pack(std::numeric_limits<double>::infinity(), t==RACU_I32 ? std::numeric_limits<int32_t>::max() : t==RACU_BOOL ? 1 : std::numeric_limits<int64_t>::max());
+    default: // AMAX ra/ra.hh:319
+        return pack(-std::numeric_limits<double>::infinity(), t==RACU_I32 ? std::numeric_limits<int32_t>::lowest() : t==RACU_BOOL ? 0 : std::numeric_limits<int64_t>::lowest());
+    }
+}
+
+namespace {
+
+struct WOp // working operand
+{
+    int kind, dtype;
+    uint64_t base;   // MEM: byte address; else value bits
+    int64_t st[KMAXR];
+};
+
+struct Work
+{
+    int rank = 0;
+    int64_t len[KMAXR];
+    std::vector<WOp> op;
+    std::vector<racu_ins> ins;
+    void drop(int k)
+    {
+        for (int j=k; j+1<rank; ++j) { len[j] = len[j+1]; for (auto & o: op) o.st[j] = o.st[j+1]; }
+        --rank;
+    }
+    void flip(int k) // traverse axis k backwards
+    {
+        for (auto & o: op) {
+            if (o.kind==RACU_MEM) o.base += uint64_t((len[k]-1)*o.st[k]*int64_t(dtype_size(o.dtype)));
+            else if (o.kind==RACU_SEQ) { // value offset
+                int64_t d = (len[k]-1)*o.st[k];
+                if (is_float(o.dtype)) o.base = f64_bits(bits_f64(o.base)+double(d)); else o.base = uint64_t(int64_t(o.base)+d);
+            }
+            o.st[k] = -o.st[k];
+        }
+    }
+    void swap(int a, int b)
+    {
+        std::swap(len[a], len[b]);
+        for (auto & o: op) std::swap(o.st[a], o.st[b]);
+    }
+    // merge axis `outer` into axis `inner` when every operand has st[outer] == len[inner]*st[inner] (Cell::keep generalised)
+    bool can_merge(int inner, int outer) const
+    {
+        for (auto const & o: op) { if (o.st[outer]!=len[inner]*o.st[inner]) return false; }
+        return true;
+    }
+};
+
+// byte range touched by a MEM operand
+void
+extent(Work const & w, WOp const & o, uint64_t & lo, uint64_t & hi)
+{
+    int64_t mn = 0, mx = 0;
+    for (int k=0; k<w.rank; ++k) { int64_t d = (w.len[k]-1)*o.st[k]; if (d<0) mn += d; else mx += d; }
+    int64_t es = int64_t(dtype_size(o.dtype));
+    lo = o.base + uint64_t(mn*es);
+    hi = o.base + uint64_t(mx*es) + uint64_t(es);
+}
+
+bool
+same_view(Work const & w, WOp const & a, WOp const & b)
+{
+    if (a.base!=b.base || a.dtype!=b.dtype) return false;
+    for (int k=0; k<w.rank; ++k) { if (a.st[k]!=b.st[k]) return false; }
+    return true;
+}
+
+void
+emit(std::vector<racu_ins> & v, int op, int type, int arg=0, int aux=0)
+{
+    racu_ins i; i.op = uint8_t(op); i.type = uint8_t(type); i.arg = uint8_t(arg); i.aux = uint8_t(aux);
+    v.push_back(i);
+}
+void emit_cast(std::vector<racu_ins> & v, int from, int to) { if (from!=to) emit(v, RACU_OP_CAST, to, 0, from); }
+
+// orders axes [lo, hi) of w by key ascending (stable), key(k) computed once
+template <class Key> void
+sort_axes(Work & w, int lo, int hi, Key && key)
+{
+    for (int i=lo+1; i<hi; ++i) {
+        for (int j=i; j>lo && key(j)<key(j-1); --j) w.swap(j, j-1);
+    }
+}
+
+// merges adjacent axes within [lo, hi); returns new hi
+int
+merge_axes(Work & w, int lo, int hi)
+{
+    for (int k=lo; k+1<hi;) {
+        if (w.can_merge(k, k+1)) { w.len[k] *= w.len[k+1]; w.drop(k+1); --hi; } else { ++k; }
+    }
+    return hi;
+}
+
+} // namespace
+
+int
+make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::string & err)
+{
+    if (!d) { err = "null descriptor"; return RACU_ERR_BAD_DESC; }
+    int rt = check_program(d, err);
+    if (rt<0) return RACU_ERR_BAD_DESC;
+    Shape sh;
+    if (int e = agree(d, sh, err)) return e;
+
+    bool const reducing = reduce_out!=nullptr;
+    int assign = d->assign;
+    if (reducing) {
+        if (d->dst!=-1) { err = "reduce needs dst = -1"; return RACU_ERR_BAD_DESC; }
+        switch (redop) {
+        case RACU_RED_SUM: assign = RACU_ASSIGN_ADD; break;
+        case RACU_RED_PROD: assign = RACU_ASSIGN_MUL; break;
+        case RACU_RED_AMIN: assign = RACU_ASSIGN_AMIN; break;
+        case RACU_RED_AMAX: assign = RACU_ASSIGN_AMAX; break;
+        default: err = "bad redop"; return RACU_ERR_BAD_DESC;
+        }
+        if (rt==RACU_BOOL && (assign==RACU_ASSIGN_ADD || assign==RACU_ASSIGN_MUL)) { err = "arithmetic reduction of bool"; return RACU_ERR_BAD_DESC; }
+    } else {
+        if (d->dst<0 || d->dst>=d->nopnd || d->opnd[d->dst].kind!=RACU_MEM) { err = "bad destination"; return RACU_ERR_BAD_DESC; }
+        if (assign<RACU_ASSIGN_SET || assign>RACU_ASSIGN_AMAX) { err = "bad assign op"; return RACU_ERR_BAD_DESC; }
+        int dt = d->opnd[d->dst].dtype;
+        if (assign>=RACU_ASSIGN_ADD && assign<=RACU_ASSIGN_DIV && (dt==RACU_BOOL || rt==RACU_BOOL)) { err = "arithmetic assign on bool"; return RACU_ERR_BAD_DESC; }
+        if ((assign==RACU_ASSIGN_AMIN || assign==RACU_ASSIGN_AMAX) && dt!=rt) { err = "amin/amax need matching types"; return RACU_ERR_BAD_DESC; }
+    }
+
+    // ---- working copy: expression axes, outermost first as in the reference
+    Work w;
+    w.rank = sh.rank;
+    for (int k=0; k<sh.rank; ++k) w.len[k] = sh.len[k];
+    for (int o=0; o<d->nopnd; ++o) {
+        racu_operand const & p = d->opnd[o];
+        WOp x {};
+        x.kind = p.kind; x.dtype = p.dtype;
+        if (p.kind==RACU_MEM) x.base = uint64_t(uintptr_t(p.base.ptr));
+        else if (is_float(p.dtype)) x.base = f64_bits(p.base.f);
+        else x.base = uint64_t(p.base.i);
+        for (int k=0; k<KMAXR; ++k) x.st[k] = (k<p.rank && p.kind!=RACU_SCALAR) ? p.stride[k] : 0; // Cell::step ra/expr.hh:294-295
+        w.op.push_back(x);
+    }
+    w.ins.assign(d->ins, d->ins+d->nins);
+    int dst = d->dst;
+    if (reducing) { // synthetic rank-0 destination holding the result
+        if (int(w.op.size())>=RACU_MAX_OPND) { err = "too many operands"; return RACU_ERR_UNSUPPORTED; }
+        WOp x {};
+        x.kind = RACU_MEM; x.dtype = rt; x.base = uint64_t(uintptr_t(reduce_out));
+        w.op.push_back(x);
+        dst = int(w.op.size())-1;
+    }
+    int const D = w.op[dst].dtype;
+
+    // ---- empty: the op never runs (ra/ply.hh:47-56)
+    for (int k=0; k<w.rank; ++k) {
+        if (0==w.len[k]) {
+            plan.empty = true;
+            plan.fill_identity = reducing;
+            plan.kp.identity = identity_bits(assign, rt);
+            plan.kp.acc_type = rt;
+            return RACU_OK;
+        }
+    }
+    // ---- drop axes of length 1
+    for (int k=0; k<w.rank;) { if (1==w.len[k]) w.drop(k); else ++k; }
+
+    // ---- destination with step 0 on a live axis => fold over those axes
+    bool red[KMAXR];
+    int nred = 0;
+    for (int k=0; k<w.rank; ++k) { red[k] = 0==w.op[dst].st[k]; nred += red[k]; }
+    bool fold = nred>0 || reducing;
+
+    // aliasing between dst and sources
+    bool alias_same = false, alias_other = false;
+    {
+        uint64_t dlo, dhi; extent(w, w.op[dst], dlo, dhi);
+        for (int o=0; o<int(w.op.size()); ++o) {
+            if (o==dst || w.op[o].kind!=RACU_MEM) continue;
+            uint64_t lo, hi; extent(w, w.op[o], lo, hi);
+            if (lo<dhi && dlo<hi) { if (same_view(w, w.op[o], w.op[dst])) alias_same = true; else alias_other = true; }
+        }
+    }
+    if (alias_other) { err = "destination overlaps a source that is not the same view: traversal order would be observable"; return RACU_ERR_UNSUPPORTED; }
+
+    if (fold && assign==RACU_ASSIGN_SET) {
+        if (!alias_same) {
+            // "last one wins" in row-major order (docs/ra-ra.texi:1986-2007): evaluate at the last index of the folded axes
+            for (int k=0; k<w.rank;) {
+                if (red[k]) {
+                    for (auto & o: w.op) {
+                        if (o.kind==RACU_MEM) o.base += uint64_t((w.len[k]-1)*o.st[k]*int64_t(dtype_size(o.dtype)));
+                        else if (o.kind==RACU_SEQ) { int64_t dd = (w.len[k]-1)*o.st[k]; if (is_float(o.dtype)) o.base = f64_bits(bits_f64(o.base)+double(dd)); else o.base = uint64_t(int64_t(o.base)+dd); }
+                    }
+                    for (int j=k; j+1<w.rank; ++j) red[j] = red[j+1];
+                    w.drop(k);
+                } else ++k;
+            }
+            fold = false;
+        } else {
+            // dst = dst OP rest  (test/reduction.cc:160-164,230-234): running sum / product / max / min
+            // program must be: PUSH dst' [CAST] <rest> OP [CAST]   with dst' the same view as dst and no other use of it
+            std::vector<racu_ins> & in = w.ins;
+            int n = int(in.size());
+            int last = n-1;
+            if (last>=0 && in[last].op==RACU_OP_CAST) --last;
+            int newop = -1;
+            if (last>=1) {
+                switch (in[last].op) {
+                case RACU_OP_ADD: newop = RACU_ASSIGN_ADD; break;
+                case RACU_OP_MUL: newop = RACU_ASSIGN_MUL; break;
+                case RACU_OP_MAX: newop = RACU_ASSIGN_AMAX; break;
+                case RACU_OP_MIN: newop = RACU_ASSIGN_AMIN; break;
+                }
+            }
+            int first = 0;
+            bool ok = newop>=0 && in[0].op==RACU_OP_PUSH && same_view(w, w.op[in[0].arg], w.op[dst]);
+            if (ok) {
+                first = 1;
+                if (in[1].op==RACU_OP_CAST) first = 2;
+                for (int pc=first; pc<last; ++pc) { if (in[pc].op==RACU_OP_PUSH && w.op[in[pc].arg].kind==RACU_MEM && same_view(w, w.op[in[pc].arg], w.op[dst])) ok = false; }
+                // <rest> must be a complete subexpression: its stack effect is exactly +1
+                std::string e2;
+                std::vector<racu_operand> tmp(w.op.size());
+                for (size_t o=0; o<w.op.size(); ++o) tmp[o].dtype = w.op[o].dtype;
+                if (ok && check_ins(in.data()+first, last-first, tmp.data(), int(tmp.size()), e2)<0) ok = false;
+            }
+            if (!ok) { err = "assignment to a broadcast destination that reads itself is only supported as dst = dst OP expr with OP in + * max min"; return RACU_ERR_UNSUPPORTED; }
+            if ((newop==RACU_ASSIGN_AMIN || newop==RACU_ASSIGN_AMAX) && in[last].type!=D) { err = "running max/min needs matching types"; return RACU_ERR_UNSUPPORTED; }
+            std::vector<racu_ins> rest(in.begin()+first, in.begin()+last);
+            w.ins = rest;
+            assign = newop;
+            std::string e2;
+            std::vector<racu_operand> tmp(w.op.size());
+            for (size_t o=0; o<w.op.size(); ++o) tmp[o].dtype = w.op[o].dtype;
+            rt = check_ins(w.ins.data(), int(w.ins.size()), tmp.data(), int(tmp.size()), e2);
+        }
+    }
+    if (fold && alias_same && assign!=RACU_ASSIGN_SET && d->assign!=RACU_ASSIGN_SET) {
+        // c += f(c, a) with broadcast c: sequential dependence through c
+        for (auto const & i: w.ins) {
+            if (i.op==RACU_OP_PUSH && w.op[i.arg].kind==RACU_MEM && int(i.arg)!=dst && same_view(w, w.op[i.arg], w.op[dst])) {
+                err = "fold whose right hand side reads the destination"; return RACU_ERR_UNSUPPORTED;
+            }
+        }
+    }
+
+    KParams & kp = plan.kp;
+    std::memset(&kp, 0, sizeof(kp));
+
+    // ---- program: fold `dst OP= rhs` into it (maps) or end in the accumulator type (folds)
+    std::vector<racu_ins> prog;
+    int A = rt; // accumulator type
+    if (!fold) {
+        if (assign==RACU_ASSIGN_SET) {
+            prog = w.ins;
+            emit_cast(prog, rt, D);
+        } else {
+            int C = (assign==RACU_ASSIGN_AMIN || assign==RACU_ASSIGN_AMAX) ? D : common_type(D, rt);
+            emit(prog, RACU_OP_PUSH, D, dst);
+            emit_cast(prog, D, C);
+            prog.insert(prog.end(), w.ins.begin(), w.ins.end());
+            emit_cast(prog, rt, C);
+            int op = assign==RACU_ASSIGN_ADD ? RACU_OP_ADD : assign==RACU_ASSIGN_SUB ? RACU_OP_SUB : assign==RACU_ASSIGN_MUL ? RACU_OP_MUL
+                : assign==RACU_ASSIGN_DIV ? RACU_OP_DIV : assign==RACU_ASSIGN_AMIN ? RACU_OP_MIN : RACU_OP_MAX;
+            emit(prog, op, C);
+            emit_cast(prog, C, D);
+        }
+    } else {
+        A = (assign==RACU_ASSIGN_AMIN || assign==RACU_ASSIGN_AMAX) ? rt : common_type(D, rt);
+        if ((assign==RACU_ASSIGN_AMIN || assign==RACU_ASSIGN_AMAX) && rt!=D) { err = "amin/amax need matching types"; return RACU_ERR_BAD_DESC; }
+        prog = w.ins;
+        emit_cast(prog, rt, A);
+    }
+    if (int(prog.size())>RACU_MAX_INS) { err = "program too long"; return RACU_ERR_UNSUPPORTED; }
+
+    // ---- axis order. Work axes are outermost-first; build fastest-first.
+    // reverse to fastest-first
+    for (int a=0, b=w.rank-1; a<b; ++a, --b) { w.swap(a, b); std::swap(red[a], red[b]); }
+    int nA = 0, nB = 0; // group sizes after ordering: axes [0,nA) = group A, [nA, nA+nB) = group B
+    int mode = K_MAP;
+    if (!fold) {
+        for (int k=0; k<w.rank; ++k) { if (w.op[dst].st[k]<0) w.flip(k); }
+        sort_axes(w, 0, w.rank, [&](int k) { return w.op[dst].st[k]; });
+        nA = merge_axes(w, 0, w.rank);
+        nB = 0;
+        if (0==nA) { w.len[0] = 1; for (auto & o: w.op) o.st[0] = 0; w.rank = 1; nA = 1; } // rank 0: one element
+    } else {
+        // dominant source: the MEM operand (not dst) moving along most axes
+        int dom = -1, best = -1;
+        for (int o=0; o<int(w.op.size()); ++o) {
+            if (o==dst || w.op[o].kind!=RACU_MEM) continue;
+            int c = 0; for (int k=0; k<w.rank; ++k) c += w.op[o].st[k]!=0;
+            if (c>best) { best = c; dom = o; }
+        }
+        auto skey = [&](int k) -> int64_t {
+            int64_t s = dom>=0 ? w.op[dom].st[k] : 0;
+            if (0==s) s = w.op[dst].st[k];
+            if (0==s) return std::numeric_limits<int64_t>::max();
+            return s<0 ? -s : s;
+        };
+        for (int k=0; k<w.rank; ++k) { int64_t s = dom>=0 && w.op[dom].st[k]!=0 ? w.op[dom].st[k] : w.op[dst].st[k]; if (s<0) w.flip(k); }
+        // kept axes first, then folded ones; each sorted fastest-first
+        int nk = 0;
+        for (int k=0; k<w.rank; ++k) {
+            if (!red[k]) { for (int j=k; j>nk; --j) { w.swap(j, j-1); std::swap(red[j], red[j-1]); } ++nk; }
+        }
+        sort_axes(w, 0, nk, skey);
+        sort_axes(w, nk, w.rank, skey);
+        int nr = w.rank-nk;
+        int nk2 = merge_axes(w, 0, nk);
+        int nr2 = merge_axes(w, nk2, nk2+nr) - nk2;
+        nk = nk2; nr = nr2;
+        int64_t NK = 1, NR = 1;
+        for (int k=0; k<nk; ++k) NK *= w.len[k];
+        for (int k=nk; k<nk+nr; ++k) NR *= w.len[k];
+        bool wide_guess = false;
+        for (auto const & o: w.op) wide_guess |= dtype_size(o.dtype)==8;
+        int V = wide_guess ? 2 : 4;
+        int64_t nkvec = nk>0 ? ((w.len[0]+V-1)/V)*(NK/w.len[0]) : 1;
+        bool red_fastest = nr>0 && (0==nk || skey(nk)<=skey(0));
+        bool inner = 0==nk || nkvec<64 || (red_fastest && NR>=256);
+        if (0==nr) { // reducing over nothing (rank 0 expression, or every folded axis had length 1): one element per kept
+            w.len[w.rank] = 1; for (auto & o: w.op) o.st[w.rank] = 0; ++w.rank; nr = 1; inner = false; if (0==nk) inner = true;
+        }
+        if (inner) {
+            // group A = folded axes, group B = kept axes: rotate folded axes to the front
+            Work r = w;
+            for (int k=0; k<nr; ++k) { r.len[k] = w.len[nk+k]; for (size_t o=0; o<w.op.size(); ++o) r.op[o].st[k] = w.op[o].st[nk+k]; }
+            for (int k=0; k<nk; ++k) { r.len[nr+k] = w.len[k]; for (size_t o=0; o<w.op.size(); ++o) r.op[o].st[nr+k] = w.op[o].st[k]; }
+            w = r;
+            nA = nr; nB = nk; mode = K_FOLD_INNER;
+        } else {
+            nA = nk; nB = nr; mode = K_FOLD_OUTER;
+        }
+        kp.nk = NK;
+    }
+
+    // ---- slot width
+    bool wide = dtype_size(A)==8;
+    for (auto const & o: w.op) wide |= dtype_size(o.dtype)==8;
+    for (auto const & i: prog) wide |= dtype_size(i.type)==8 || (i.op==RACU_OP_CAST && dtype_size(i.aux)==8) || (i.op==RACU_OP_PICK && dtype_size(i.aux)==8);
+    int const V = wide ? 2 : 4;
+
+    // ---- limits of the 32-bit index decomposition
+    for (int k=(1==nA ? 1 : 0); k<nA+nB; ++k) { if (w.len[k]>=(int64_t(1)<<31)) { err = "axis longer than 2^31 after collapsing"; return RACU_ERR_UNSUPPORTED; } }
+    kp.mode = mode; kp.wide = wide; kp.rankA = nA; kp.rankB = nB;
+    kp.len0 = w.len[0];
+    kp.vpr = (w.len[0]+V-1)/V;
+    kp.nvecA = kp.vpr;
+    for (int k=1; k<nA; ++k) kp.nvecA *= w.len[k];
+    kp.nB = 1;
+    for (int k=nA; k<nA+nB; ++k) kp.nB *= w.len[k];
+    if ((nA>1 && kp.nvecA>=(int64_t(1)<<31)) || kp.nB>=(int64_t(1)<<31)) { err = "more than 2^31 rows in one traversal"; return RACU_ERR_UNSUPPORTED; }
+    if (nA>1) kp.vprdiv = make_div(kp.vpr);
+    for (int k=1; k<nA; ++k) kp.dA[k] = make_div(w.len[k]);
+    for (int k=0; k<nB; ++k) kp.dB[k] = make_div(w.len[nA+k]);
+
+    // ---- operands: staging mode and slot
+    kp.nopnd = int(w.op.size());
+    kp.dst = dst;
+    int nstage = 0, nasync = 0;
+    bool used[RACU_MAX_OPND] = {};
+    for (auto const & i: prog) { if (i.op==RACU_OP_PUSH) used[i.arg] = true; }
+    for (int o=0; o<kp.nopnd; ++o) {
+        WOp const & x = w.op[o];
+        KOpnd & k = kp.opnd[o];
+        k.base = x.base; k.kind = uint8_t(x.kind); k.dtype = uint8_t(x.dtype); k.esize = uint8_t(dtype_size(x.dtype));
+        k.slot = 255;
+        for (int j=0; j<nA; ++j) k.sA[j] = x.st[j];
+        for (int j=0; j<nB; ++j) k.sB[j] = x.st[nA+j];
+        if (x.kind==RACU_SCALAR) { k.stage = S_NONE; continue; }
+        if (x.kind==RACU_SEQ) { k.stage = S_SEQ; continue; }
+        if (0==x.st[0]) { k.stage = S_BCAST; continue; }
+        bool vec = 1==x.st[0] && 0==(x.base % uint64_t(V*k.esize));
+        for (int j=1; j<nA+nB && vec; ++j) vec = 0==(x.st[j] % V);
+        k.stage = vec ? S_VEC : S_GATHER;
+    }
+    for (int pass=0; pass<2; ++pass) { // cp.async operands first so their loads are in flight before the synchronous ones
+        for (int o=0; o<kp.nopnd; ++o) {
+            KOpnd & k = kp.opnd[o];
+            if (!used[o] || S_NONE==k.stage) continue;
+            bool async = (k.stage==S_VEC || k.stage==S_GATHER) && k.esize>=4;
+            if (async==(0==pass)) { k.slot = uint8_t(nstage++); nasync += async; }
+        }
+    }
+    kp.nstage = nstage;
+
+    // ---- stack levels
+    kp.nins = int(prog.size());
+    int depth = 0, sd = 0;
+    for (int pc=0; pc<kp.nins; ++pc) {
+        KIns & k = kp.ins[pc];
+        racu_ins const & i = prog[pc];
+        k.op = i.op; k.type = i.type; k.arg = i.arg; k.aux = i.aux; k.lvl = 255;
+        switch (i.op) {
+        case RACU_OP_PUSH: if (sd>=1) { k.lvl = uint8_t(sd-1); depth = std::max(depth, sd); } ++sd; break;
+        case RACU_OP_CAST: case RACU_OP_NEG: case RACU_OP_ABS: case RACU_OP_SQRT: case RACU_OP_SQR: case RACU_OP_EXP:
+        case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS: case RACU_OP_NOT: break;
+        case RACU_OP_FMA: k.lvl = uint8_t(sd-3); sd -= 2; break;
+        case RACU_OP_PICK: k.lvl = uint8_t(sd-1-i.arg); sd -= i.arg; break;
+        default: k.lvl = uint8_t(sd-2); --sd; break;
+        }
+    }
+    kp.depth = depth;
+
+    // ---- launch geometry
+    int U = nasync>0 ? std::max(1, std::min(4, 8/nasync)) : 1;
+    auto smem_for = [&](int u) { return size_t(u*nstage+depth)*KBLOCK*KSLOT; };
+    while (U>1 && smem_for(U)>size_t(160*1024)) U /= 2;
+    if (smem_for(U)>size_t(220*1024)) { err = "expression needs too much staging memory"; return RACU_ERR_UNSUPPORTED; }
+    kp.U = U;
+    plan.smem = smem_for(U);
+    kp.fold_op = assign; kp.acc_type = A; kp.overwrite = reducing;
+    kp.identity = identity_bits(assign, A);
+    int const target = 148*8;
+    if (mode==K_MAP) {
+        int64_t nb = (kp.nvecA+int64_t(KBLOCK)*U-1)/(int64_t(KBLOCK)*U);
+        plan.grid_x = unsigned(std::min<int64_t>(nb, int64_t(target)*4));
+        kp.nchunks = 1;
+        plan.kernel = wide ? "ply_map<u64>" : "ply_map<u32>";
+    } else if (mode==K_FOLD_INNER) {
+        int64_t per = int64_t(KBLOCK)*U;
+        int64_t maxchunks = std::max<int64_t>(1, kp.nvecA/(per*2));
+        int64_t want = std::max<int64_t>(1, (int64_t(target)*2)/std::max<int64_t>(1, kp.nk));
+        int64_t nch = std::min(maxchunks, want);
+        kp.chunk_len = (kp.nvecA+nch-1)/nch;
+        kp.chunk_len = ((kp.chunk_len+per-1)/per)*per;
+        nch = (kp.nvecA+kp.chunk_len-1)/kp.chunk_len;
+        kp.nchunks = int(nch);
+        if (kp.nk*nch>=(int64_t(1)<<31)) { err = "too many fold groups"; return RACU_ERR_UNSUPPORTED; }
+        plan.grid_x = unsigned(kp.nk*nch);
+        plan.kernel = wide ? "ply_fold_inner<u64>" : "ply_fold_inner<u32>";
+    } else {
+        int64_t nbx = (kp.nvecA+KBLOCK-1)/KBLOCK;
+        int64_t want = std::max<int64_t>(1, (int64_t(target)*2)/nbx);
+        int64_t maxchunks = std::max<int64_t>(1, kp.nB/(int64_t(U)*8));
+        int64_t nch = std::min<int64_t>(std::min(maxchunks, want), 65535);
+        kp.chunk_len = (kp.nB+nch-1)/nch;
+        kp.chunk_len = ((kp.chunk_len+U-1)/U)*U;
+        nch = (kp.nB+kp.chunk_len-1)/kp.chunk_len;
+        kp.nchunks = int(nch);
+        if (nbx>=(int64_t(1)<<31)) { err = "too many fold groups"; return RACU_ERR_UNSUPPORTED; }
+        plan.grid_x = unsigned(nbx); plan.grid_y = unsigned(nch);
+        plan.kernel = wide ? "ply_fold_outer<u64>" : "ply_fold_outer<u32>";
+    }
+    if (mode!=K_MAP) {
+        plan.need_finish = kp.nchunks>1;
+        plan.partial_bytes = plan.need_finish ? size_t(kp.nchunks)*size_t(kp.nk)*(wide ? 8 : 4) : 0;
+        FinishParams & f = plan.fp;
+        std::memset(&f, 0, sizeof(f));
+        f.wide = wide; f.fold_op = assign; f.acc_type = A; f.dst_dtype = D; f.overwrite = reducing; f.nchunks = kp.nchunks;
+        f.nk = kp.nk; f.dst = reinterpret_cast<void *>(uintptr_t(w.op[dst].base));
+        f.per_warp = mode==K_FOLD_INNER;
+        // kept axes, fastest first, with the destination's strides
+        int k0 = mode==K_FOLD_INNER ? nA : 0, kn = mode==K_FOLD_INNER ? nB : nA;
+        f.rank = kn;
+        for (int k=0; k<kn; ++k) { f.stride[k] = w.op[dst].st[k0+k]; if (k>0 || kn>1) f.d[k] = make_div(w.len[k0+k]); }
+        f.len0 = kn>0 ? w.len[k0] : 1;
+        if (kn>1 && f.len0>=(int64_t(1)<<31)) { err = "axis longer than 2^31 after collapsing"; return RACU_ERR_UNSUPPORTED; }
+    }
+    return RACU_OK;
+}
+
+} // namespace racu

@@ -1,0 +1,32 @@
+// plan.h - host-side planner: racu_desc -> canonical kernel parameters (see plan.cc).
+#pragma once
+#include <string>
+#include "kcore.h"
+
+namespace racu {
+
+
+struct Plan
+{
+    bool empty = false;          // nothing to traverse
+    bool fill_identity = false;  // empty reduction in overwrite mode: store the identity
+    KParams kp;
+    unsigned grid_x = 0, grid_y = 1;
+    size_t smem = 0;
+    bool need_finish = false;
+    FinishParams fp;
+    size_t partial_bytes = 0;
+    const char * kernel = "";
+};
+
+// What the expression computes, before any layout decision.
+struct Shape { int rank; int64_t len[KMAXR]; };
+
+int check_program(racu_desc const * d, std::string & err);                 // result dtype or -1
+int agree(racu_desc const * d, Shape & s, std::string & err);             // racu_status
+// reduce_out != nullptr: whole-expression reduction into *reduce_out (device, dtype = program result type).
+int make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::string & err);
+
+size_t dtype_size(int t);
+
+} // namespace racu

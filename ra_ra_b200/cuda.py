@@ -1,0 +1,76 @@
+"""Executor over the CUDA library (ra_ra_b200/libracu.so): the product path.
+
+Importing this module loads the library and fails loudly if it has not been built (python -m ra_ra_b200.build, or
+__graft_entry__.build()). There is no CPU fallback: every map / reduction here is a kernel launch through the C ABI.
+PyTorch is used only for device memory and streams.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import abi, ra
+
+_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libracu.so")
+if not os.path.exists(_PATH):
+    raise ImportError(f"{_PATH} is missing: build the CUDA library first (python -m ra_ra_b200.build). "
+                      "There is no CPU fallback for the ply path.")
+lib = abi.bind(C.CDLL(_PATH))
+
+_TORCH = {abi.BOOL: torch.bool, abi.I32: torch.int32, abi.I64: torch.int64, abi.F32: torch.float32, abi.F64: torch.float64}
+_RACU = {v: k for k, v in _TORCH.items()}
+
+
+def check(st):
+    if st != abi.OK:
+        raise ra.RaError(st, lib.racu_last_error_string().decode())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CudaExecutor:
+    name = "cuda"
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ra_ra_b200.cuda needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+
+    def wrap(self, t):
+        """View over a torch CUDA tensor (any strides)."""
+        assert t.is_cuda
+        return ra.View(self, t, t.data_ptr(), _RACU[t.dtype], list(zip(t.shape, t.stride())))
+
+    def empty(self, shape, dtype):
+        return self.wrap(torch.empty(tuple(shape), dtype=_TORCH[dtype], device=self.device))
+
+    def from_numpy(self, arr):
+        return self.wrap(torch.from_numpy(np.ascontiguousarray(arr)).to(self.device))
+
+    def to_numpy(self, v):
+        out = self.empty(v.shape, v.dtype)
+        out.assign(v)
+        return out.owner.cpu().numpy()
+
+    def map(self, d):
+        check(lib.racu_map(C.byref(d), stream_ptr()))
+
+    def agree(self, d):
+        rank = C.c_int32()
+        lens = (C.c_int64 * abi.MAX_RANK)()
+        check(lib.racu_agree(C.byref(d), C.byref(rank), lens))
+        return [lens[k] for k in range(rank.value)]
+
+    def reduce(self, d, redop, rtype):
+        out = np.zeros(2, dtype=ra.RACU2NP[rtype])
+        check(lib.racu_reduce(C.byref(d), redop, out.ctypes.data, stream_ptr()))
+        return out[0]
+
+    def reduce_dev(self, d, redop, out_tensor):
+        check(lib.racu_reduce_dev(C.byref(d), redop, C.c_void_p(out_tensor.data_ptr()), stream_ptr()))
+
+    def last_kernel(self):
+        return lib.racu_last_kernel().decode()

@@ -589,20 +589,31 @@ def flatten(e, dst=None, assign=abi.ASSIGN_SET, ex=None):
         i.op, i.type, i.arg, i.aux = op, t, arg, aux
         nins[0] += 1
 
+    seen = {}
+
+    def once(key, make):
+        """The same leaf used twice in the tree is one operand (one load)."""
+        if key not in seen:
+            seen[key] = make()
+        return seen[key]
+
     def view_operand(v):
         keep.append(v.owner)
         return add_operand(MEM, v.dtype, v.rank, v.ptr, [x[0] for x in v.dims], [x[1] for x in v.dims])
 
+    def view_key(v):
+        return ("mem", v.ptr, v.dtype, tuple(map(tuple, v.dims)))
+
     def walk(n):
         if isinstance(n, Leaf):
-            emit(abi.OP_PUSH, n.dtype, view_operand(n.view))
+            emit(abi.OP_PUSH, n.dtype, once(view_key(n.view), lambda: view_operand(n.view)))
         elif isinstance(n, HostVec):
-            v = ex.from_numpy(n.arr)
-            emit(abi.OP_PUSH, n.dtype, view_operand(v))
+            emit(abi.OP_PUSH, n.dtype, once(("vec", id(n)), lambda: view_operand(ex.from_numpy(n.arr))))
         elif isinstance(n, SeqLeaf):
-            emit(abi.OP_PUSH, n.dtype, add_operand(SEQ, n.dtype, builtins_len(n.lens), n.org, n.lens, n.steps))
+            emit(abi.OP_PUSH, n.dtype, once(("seq", n.dtype, n.org, tuple(n.lens), tuple(n.steps)),
+                                            lambda: add_operand(SEQ, n.dtype, builtins_len(n.lens), n.org, n.lens, n.steps)))
         elif isinstance(n, ScalarLeaf):
-            emit(abi.OP_PUSH, n.dtype, add_operand(SCALAR, n.dtype, 0, n.value, [], []))
+            emit(abi.OP_PUSH, n.dtype, once(("scalar", n.dtype, repr(n.value)), lambda: add_operand(SCALAR, n.dtype, 0, n.value, [], [])))
         else:
             for a in n.args:
                 walk(a)

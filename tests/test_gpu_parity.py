@@ -1,0 +1,157 @@
+"""CUDA path vs the CPU oracle on the same seeded inputs: bit-exact for maps, strided copies, integer folds and stencils;
+stated tolerance vs an fp64 reference for float reductions."""
+import numpy as np
+import pytest
+
+from oracle_exec import OracleExecutor
+from randexpr import DT, SHAPES, random_expr, random_view
+from ra_ra_b200 import abi, ra
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def exc():
+    from ra_ra_b200 import cuda
+    return cuda.CudaExecutor()
+
+
+def snapshot(ex, dst):
+    if ex.name == "cuda":
+        return dst.owner.cpu().numpy().copy()
+    return np.array(dst.owner, copy=True)
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_maps_cuda_vs_oracle(seed, exc):
+    rng = np.random.default_rng(1000 + seed)
+    shape = SHAPES[seed % len(SHAPES)]
+    for assign in ("assign", "__iadd__", "__isub__", "__imul__"):
+        state = rng.bit_generator.state
+        outs = []
+        for ex in (OracleExecutor(), exc):
+            rng.bit_generator.state = state
+            dst, _ = random_view(rng, ex, shape, DT[rng.integers(0, 4)])
+            e = random_expr(rng, ex, shape, 2)
+            try:
+                getattr(dst, assign)(e)
+            except ra.RaError as err:
+                assert err.status == abi.ERR_UNSUPPORTED and ("too long" in str(err) or "too many" in str(err)), err
+                outs = None
+                break
+            outs.append(snapshot(ex, dst))
+        if outs is None:
+            continue
+        assert np.array_equal(outs[0], outs[1], equal_nan=True), (seed, assign)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_folds_cuda_vs_oracle(seed, exc):
+    rng = np.random.default_rng(5000 + seed)
+    shape = [s for s in SHAPES if len(s) >= 2][seed % 8]
+    for variant in range(3):
+        state = rng.bit_generator.state
+        outs = []
+        for ex in (OracleExecutor(), exc):
+            rng.bit_generator.state = state
+            rank = len(shape)
+            if variant == 0:
+                r = int(rng.integers(0, rank))
+                dst, _ = random_view(rng, ex, shape[:r], DT[rng.integers(0, 4)], True)
+            elif variant == 1:
+                r = int(rng.integers(1, rank))
+                dst, _ = random_view(rng, ex, shape[r:], DT[rng.integers(0, 4)], True)
+                dst = dst(ra.insert(r))
+            else:
+                k = int(rng.integers(0, rank))
+                dst, _ = random_view(rng, ex, shape[:k] + shape[k + 1:], DT[rng.integers(0, 4)], True)
+                dst = dst(ra.dots(k), ra.insert(1))
+            a, _ = random_view(rng, ex, shape, DT[rng.integers(0, 4)], True)
+            b, _ = random_view(rng, ex, shape[:int(rng.integers(0, rank + 1))], DT[rng.integers(0, 4)], True)
+            op = ["__iadd__", "__isub__", "assign"][int(rng.integers(0, 3))]
+            getattr(dst, op)(a * b + 1)
+            outs.append(snapshot(ex, dst))
+        assert np.array_equal(outs[0], outs[1]), (seed, variant)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 255, 256, 257, 1023, 4096, 65537, 1 << 20, (1 << 22) + 3])
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+def test_contiguous_map_sizes(n, dt, exc):
+    """B += A*C and B += A*C + scalar over every tail / alignment case of the vectorised fast path."""
+    rng = np.random.default_rng(n)
+    a, b, c = (rng.integers(-50, 50, n).astype(dt) for _ in range(3))
+    outs = []
+    for ex in (OracleExecutor(), exc):
+        A, B, Cc = ex.from_numpy(a), ex.from_numpy(b), ex.from_numpy(c)
+        B += A * Cc
+        B += A * Cc + 3
+        Bs = B(ra.iota(max(n - 1, 0), min(1, n - 1) if n > 1 else 0)) if n > 1 else B  # misaligned start
+        Bs -= 1
+        outs.append(snapshot(ex, B))
+    assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("shape", [(1000,), (1 << 20,), (333, 777), (17, 19, 23), (4099, 513)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_float_reductions_tolerance(shape, dt, exc):
+    """sum / reduce_sqrm / dot in unspecified order (docs/ra-ra.texi:3102): relative error vs an fp64 reference.
+    Tolerance: 8 eps(dt) relative to sum|x| (pairwise-tree bound, far below the sequential CPU fold's n*eps)."""
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-1, 1, shape).astype(dt)
+    y = rng.uniform(-1, 1, shape).astype(dt)
+    X, Y = exc.from_numpy(x), exc.from_numpy(y)
+    eps = np.finfo(dt).eps
+    x64, y64 = x.astype(np.float64), y.astype(np.float64)
+    for got, ref, scale in ((ra.sum(X), x64.sum(), np.abs(x64).sum()),
+                            (ra.reduce_sqrm(X), (x64 * x64).sum(), (x64 * x64).sum()),
+                            (ra.dot(X, Y), (x64 * y64).sum(), np.abs(x64 * y64).sum()),
+                            (ra.reduce_sqrm(X - Y), ((x64 - y64) ** 2).sum(), ((x64 - y64) ** 2).sum())):
+        assert abs(float(got) - ref) <= 8 * eps * scale, (got, ref, scale)
+    assert ra.amax(X) == x.max() and ra.amin(X) == x.min()
+    # deterministic: identical bits run to run
+    assert ra.sum(X) == ra.sum(X) and ra.dot(X, Y) == ra.dot(X, Y)
+
+
+@pytest.mark.parametrize("shape", [(300, 1024), (1024, 300), (64, 64), (5, 100000), (100000, 5), (2000, 33)])
+def test_row_col_sums(shape, exc):
+    """bench/bench-sum-rows.cc:26-34, bench/bench-sum-cols.cc:23-31: a = _0 - _1 is integer valued, so exact."""
+    m, n = shape
+    a = exc.empty(shape, abi.F32)
+    a.assign(ra._0 - ra._1)
+    an = (np.arange(m)[:, None] - np.arange(n)[None, :]).astype(np.float64)
+    cols = exc.from_numpy(np.zeros(m, dtype=np.float64))
+    cols += a
+    assert np.array_equal(cols.numpy(), an.sum(axis=1))
+    rows = exc.from_numpy(np.zeros(n, dtype=np.float64))
+    rr = rows(ra.insert(1))
+    rr += a
+    assert np.array_equal(rows.numpy(), an.sum(axis=0))
+    rows.assign(0.)
+    rows += ra.transpose(a)
+    assert np.array_equal(rows.numpy(), an.sum(axis=0))
+
+
+@pytest.mark.parametrize("n", [(40, 36, 50), (64, 64, 64), (9, 130, 7)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_stencil3d_bitexact(n, dt, exc):
+    """bench/bench-stencil3.cc:55-64 through racu_map, against the oracle's f_raw loops: bit-exact, boundaries untouched."""
+    import ctypes as C
+    from oracle_exec import lib as olib
+    rng = np.random.default_rng(41)
+    A0 = rng.uniform(-1, 1, n).astype(dt)
+    A, An = exc.from_numpy(A0), exc.from_numpy(np.zeros(n, dtype=dt))
+    I, J, K = ra.iota(n[0] - 2, 1), ra.iota(n[1] - 2, 1), ra.iota(n[2] - 2, 1)
+    ref, refn = A0.copy(), np.zeros(n, dtype=dt)
+    for _ in range(4):
+        An(I, J, K).assign(-6 * A(I, J, K) + A(I + 1, J, K) + A(I, J + 1, K) + A(I, J, K + 1)
+                           + A(I - 1, J, K) + A(I, J - 1, K) + A(I, J, K - 1))
+        A, An = An, A
+        s = abi.StencilDesc()
+        s.kind, s.dtype, s.rank = abi.STENCIL_3D7, ra.NP2RACU[np.dtype(dt)], 3
+        s.src, s.dst = ref.ctypes.data, refn.ctypes.data
+        for k in range(3):
+            s.len[k] = n[k]
+            s.src_stride[k] = s.dst_stride[k] = ref.strides[k] // ref.itemsize
+        assert olib().oracle_stencil_raw(C.byref(s)) == 0
+        ref, refn = refn, ref
+    assert np.array_equal(A.numpy(), ref) and np.array_equal(An.numpy(), refn)

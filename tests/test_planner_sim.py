@@ -1,0 +1,121 @@
+"""The planner (ra_ra_b200/csrc/plan.cc) and the kernels' per-vector bodies, run on the CPU simulator and compared
+with the oracle: known-answer tests first, then random expression trees over random strided views."""
+import numpy as np
+import pytest
+
+import kat
+from oracle_exec import OracleExecutor
+from sim_exec import SimExecutor, plan_info
+from ra_ra_b200 import abi, ra
+
+
+@pytest.mark.parametrize("case", kat.CASES, ids=lambda f: f.__name__)
+def test_kat_on_planner_sim(case):
+    case(SimExecutor())
+
+
+from randexpr import DT, SHAPES, random_expr, random_view
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_maps_sim_vs_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    shape = SHAPES[seed % len(SHAPES)]
+    exo, exs = OracleExecutor(), SimExecutor()
+    for assign in ("assign", "__iadd__", "__isub__", "__imul__"):
+        state = rng.bit_generator.state
+        outs = []
+        for ex in (exo, exs):
+            rng.bit_generator.state = state
+            dst, _ = random_view(rng, ex, shape, DT[rng.integers(0, 4)])
+            e = random_expr(rng, ex, shape, 2)
+            try:
+                getattr(dst, assign)(e)
+            except ra.RaError as err:  # descriptor capacity (MAX_INS / MAX_OPND): same on both sides
+                assert err.status == abi.ERR_UNSUPPORTED and ("too long" in str(err) or "too many" in str(err)), err
+                outs = None
+                break
+            outs.append(np.array(dst.owner, copy=True))
+        if outs is None:
+            continue
+        assert outs[0].dtype == outs[1].dtype
+        assert np.array_equal(outs[0], outs[1], equal_nan=True), (seed, assign)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_folds_sim_vs_oracle(seed):
+    """dst with a lower rank (prefix) or inserted axes: += folds, integer-valued so any order is exact."""
+    rng = np.random.default_rng(5000 + seed)
+    shape = [s for s in SHAPES if len(s) >= 2][seed % 8]
+    exo, exs = OracleExecutor(), SimExecutor()
+    for variant in range(3):
+        state = rng.bit_generator.state
+        outs = []
+        for ex in (exo, exs):
+            rng.bit_generator.state = state
+            rank = len(shape)
+            if variant == 0:  # trailing axes folded: dst is a prefix
+                r = int(rng.integers(0, rank))
+                dst, _ = random_view(rng, ex, shape[:r], DT[rng.integers(0, 4)], True)
+            elif variant == 1:  # leading axes folded: insert<n> in front
+                r = int(rng.integers(1, rank))
+                dst, _ = random_view(rng, ex, shape[r:], DT[rng.integers(0, 4)], True)
+                dst = dst(ra.insert(r))
+            else:  # middle axis folded (the gemm pattern)
+                k = int(rng.integers(0, rank))
+                dst, _ = random_view(rng, ex, shape[:k] + shape[k + 1:], DT[rng.integers(0, 4)], True)
+                dst = dst(ra.dots(k), ra.insert(1))
+            a, _ = random_view(rng, ex, shape, DT[rng.integers(0, 4)], True)  # integer valued: exact in any order, and under narrowing
+            b, _ = random_view(rng, ex, shape[:int(rng.integers(0, rank + 1))], DT[rng.integers(0, 4)], True)
+            op = ["__iadd__", "__isub__", "assign"][int(rng.integers(0, 3))]
+            getattr(dst, op)(a * b + 1)
+            outs.append(np.array(dst.owner, copy=True))
+        assert np.array_equal(outs[0], outs[1]), (seed, variant)
+
+
+def test_reductions_sim_vs_oracle():
+    rng = np.random.default_rng(9)
+    exo, exs = OracleExecutor(), SimExecutor()
+    for shape in [(1,), (5,), (1000,), (40, 50), (3, 4, 300), (2049,), (70000,)]:
+        for dt in DT:
+            x = rng.integers(-4, 5, shape).astype(dt)
+            y = rng.integers(-4, 5, shape).astype(dt)
+            for f in (ra.sum, ra.amax, ra.amin, ra.reduce_sqrm):
+                assert f(exo.wrap(x)) == f(exs.wrap(x)), (shape, dt, f.__name__)
+            assert ra.dot(exo.wrap(x), exo.wrap(y)) == ra.dot(exs.wrap(x), exs.wrap(y))
+            s = (x % 2 + 1).astype(dt)
+            if np.prod(shape) <= 50:
+                assert ra.prod(exo.wrap(s)) == ra.prod(exs.wrap(s))
+
+
+def test_planner_decisions():
+    """The contiguous fast path is found: B += A*C collapses to one axis with 16-byte staging (ra/ply.hh:42-46 analogue)."""
+    ex = SimExecutor()
+    A, B, Cc = (ex.from_numpy(np.ones((64, 48), dtype=np.float32)) for _ in range(3))
+    B += A * Cc
+    pi = plan_info()
+    assert pi["mode"] == 0 and pi["rankA"] == 1 and pi["len0"] == 64 * 48 and pi["wide"] == 0 and pi["nvec"] == 3
+    v = np.arange(64, dtype=np.float32)
+    B += A * Cc + v  # prefix broadcast: v has step 0 on the inner axis, so rows do not collapse
+    pi = plan_info()
+    assert pi["rankA"] == 2 and pi["len0"] == 48 and pi["nvec"] == 3
+    # transposed destination: axes are sorted by destination step, so dst stays the coalesced one
+    T = ex.from_numpy(np.zeros((48, 64), dtype=np.float32))
+    ra.transpose(T).assign(A)
+    pi = plan_info()
+    assert pi["rankA"] == 2 and pi["len0"] == 64
+    # full reduction -> fold-inner over one collapsed axis; row sums -> fold-inner per kept row when rows are long
+    ra.sum(A)
+    pi = plan_info()
+    assert pi["mode"] == 1 and pi["rankA"] == 1 and pi["rankB"] == 0 and pi["nk"] == 1
+    big = ex.from_numpy(np.ones((300, 1024), dtype=np.float32))
+    c = ex.from_numpy(np.zeros(300, dtype=np.float32))
+    c += big
+    pi = plan_info()
+    assert pi["mode"] == 1 and pi["nk"] == 300 and pi["len0"] == 1024
+    c2 = ex.from_numpy(np.zeros(1024, dtype=np.float32))
+    cc = c2(ra.insert(1))
+    cc += big
+    pi = plan_info()
+    assert pi["mode"] == 2 and pi["nk"] == 1024 and pi["nB"] == 300
+    assert np.array_equal(c2.numpy(), np.full(1024, 300, dtype=np.float32))
