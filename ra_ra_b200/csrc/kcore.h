@@ -427,88 +427,194 @@ template <class W> RACU_HD W scalar_value(KOpnd const & o)
     }
 }
 
-// ---------------- the postfix interpreter over V lanes ----------------
-// stage: this thread's staged operand slots for the vector being evaluated; slot k at stage + k*stage_stride bytes,
-//        holding V raw elements of the operand's dtype.
-// stack: this thread's value stack rows; level l at stack + l*stack_stride bytes, V slots of W.
-// Result (V lanes) in t[].
-template <class W> RACU_HD void
-interp(KParams const & p, unsigned char const * stage, int stage_stride, unsigned char * stack, int stack_stride, W * t)
+// ---------------- the postfix interpreter over U x V lanes ----------------
+// One decode per instruction serves the U vectors a thread has staged (U*V lanes): the dispatch is a two level switch
+// (type, then opcode) OUTSIDE the lane loops, so its cost is amortised over every lane.
+//
+// stage: this thread's staged operand slots; slot s of vector u at stage + (u*nstage + s)*sstride, holding V raw
+//        elements of the operand's dtype.
+// stack: this thread's value stack rows; level l of vector u at stack + (l*U + u)*sstride, V slots of W.
+// Result in t[u][j].
+
+#define RACU_LANES for (int u=0; u<U; ++u) _Pragma("unroll") for (int j=0; j<V; ++j)
+
+template <class W, int U, class T> RACU_HD void
+group_unary(int op, W (*t)[Lanes<W>::V])
 {
     constexpr int V = Lanes<W>::V;
+    switch (op) {
+    case RACU_OP_NOT:
+#pragma unroll
+        RACU_LANES { t[u][j] = Ty<bool>::template put<W>(!Ty<T>::template get<W>(t[u][j])); } break;
+    case RACU_OP_NEG:
+        if constexpr (!std::is_same_v<T, bool>) {
+#pragma unroll
+            RACU_LANES { t[u][j] = Ty<T>::template put<W>(T(-Ty<T>::template get<W>(t[u][j]))); }
+        } break;
+    case RACU_OP_ABS:
+        if constexpr (!std::is_same_v<T, bool>) {
+#pragma unroll
+            RACU_LANES { t[u][j] = Ty<T>::template put<W>(t_abs<T>(Ty<T>::template get<W>(t[u][j]))); }
+        } break;
+    case RACU_OP_SQR:
+        if constexpr (!std::is_same_v<T, bool>) {
+#pragma unroll
+            RACU_LANES { T x = Ty<T>::template get<W>(t[u][j]); t[u][j] = Ty<T>::template put<W>(T(x*x)); }
+        } break;
+    default:
+#pragma unroll
+        RACU_LANES { t[u][j] = un1<W, T>(op, t[u][j]); } break; // sqrt and the out-of-line transcendentals
+    }
+}
+
+template <class W, int U, class T> RACU_HD void
+group_binary(int op, unsigned char const * lv, int sstride, W (*t)[Lanes<W>::V])
+{
+    constexpr int V = Lanes<W>::V;
+#define RACU_A(u, j) Ty<T>::template get<W>(reinterpret_cast<W const *>(lv + (u)*sstride)[j])
+#define RACU_B(u, j) Ty<T>::template get<W>(t[u][j])
+#define RACU_BINCASE(OPC, R, EXPR) case OPC: _Pragma("unroll") RACU_LANES { T x = RACU_A(u, j), y = RACU_B(u, j); t[u][j] = Ty<R>::template put<W>(EXPR); } break;
+    switch (op) {
+    RACU_BINCASE(RACU_OP_EQ, bool, x==y) RACU_BINCASE(RACU_OP_NE, bool, x!=y) RACU_BINCASE(RACU_OP_LT, bool, x<y)
+    RACU_BINCASE(RACU_OP_LE, bool, x<=y) RACU_BINCASE(RACU_OP_GT, bool, x>y) RACU_BINCASE(RACU_OP_GE, bool, x>=y)
+    default:
+        if constexpr (std::is_same_v<T, bool>) {
+#pragma unroll
+            RACU_LANES { t[u][j] = bin1<W, T>(op, reinterpret_cast<W const *>(lv + u*sstride)[j], t[u][j]); }
+        } else {
+            switch (op) {
+            RACU_BINCASE(RACU_OP_ADD, T, T(x+y)) RACU_BINCASE(RACU_OP_SUB, T, T(x-y)) RACU_BINCASE(RACU_OP_MUL, T, T(x*y))
+            RACU_BINCASE(RACU_OP_MIN, T, (y<x ? y : x)) RACU_BINCASE(RACU_OP_MAX, T, (x<y ? y : x))
+            default:
+#pragma unroll
+                RACU_LANES { t[u][j] = bin1<W, T>(op, reinterpret_cast<W const *>(lv + u*sstride)[j], t[u][j]); } break; // div, mod, bit ops, pow, atan2
+            }
+        }
+        break;
+    }
+#undef RACU_BINCASE
+#undef RACU_A
+#undef RACU_B
+}
+
+template <class W, int U, class S> RACU_HD void
+group_cast_from(int dt, W (*t)[Lanes<W>::V])
+{
+    constexpr int V = Lanes<W>::V;
+#define RACU_CASTCASE(D) _Pragma("unroll") RACU_LANES { t[u][j] = cast1<W, S, D>(t[u][j]); } break;
+    switch (dt) {
+    case RACU_BOOL: RACU_CASTCASE(bool)
+    case RACU_I32: RACU_CASTCASE(int32_t)
+    case RACU_F32: RACU_CASTCASE(float)
+    default:
+        if constexpr (sizeof(W)==8) { if (dt==RACU_I64) { RACU_CASTCASE(int64_t) } else { RACU_CASTCASE(double) } }
+        break;
+    }
+#undef RACU_CASTCASE
+}
+
+#define RACU_TYPE_SWITCH(TYPE, CALL)                                            \
+    switch (TYPE) {                                                             \
+    case RACU_BOOL: { using T = bool; CALL; } break;                            \
+    case RACU_I32: { using T = int32_t; CALL; } break;                          \
+    case RACU_F32: { using T = float; CALL; } break;                            \
+    default:                                                                    \
+        if constexpr (sizeof(W)==8) {                                           \
+            if ((TYPE)==RACU_I64) { using T = int64_t; CALL; } else { using T = double; CALL; } \
+        }                                                                       \
+        break;                                                                  \
+    }
+
+template <class W, int U> RACU_HD void
+interp(KParams const & p, unsigned char const * stage, unsigned char * stack, int sstride, W (*t)[Lanes<W>::V])
+{
+    constexpr int V = Lanes<W>::V;
+    int const nstage = p.nstage;
     for (int pc=0; pc<p.nins; ++pc) {
         KIns const in = p.ins[pc];
-        W * lv = reinterpret_cast<W *>(stack + int(in.lvl)*stack_stride);
+        unsigned char * lv = stack + int(in.lvl)*U*sstride;
         switch (in.op) {
         case RACU_OP_PUSH: {
             if (in.lvl!=255) {
 #pragma unroll
-                for (int j=0; j<V; ++j) lv[j] = t[j];
+                RACU_LANES { reinterpret_cast<W *>(lv + u*sstride)[j] = t[u][j]; }
             }
             KOpnd const & o = p.opnd[in.arg];
             if (S_NONE==o.stage) {
                 W s = scalar_value<W>(o);
 #pragma unroll
-                for (int j=0; j<V; ++j) t[j] = s;
+                RACU_LANES { t[u][j] = s; }
             } else {
-                unsigned char const * sl = stage + int(o.slot)*stage_stride;
+                unsigned char const * sl = stage + int(o.slot)*sstride;
+                int const us = nstage*sstride;
                 if (4==o.esize) {
 #pragma unroll
-                    for (int j=0; j<V; ++j) t[j] = W(reinterpret_cast<uint32_t const *>(sl)[j]);
+                    RACU_LANES { t[u][j] = W(reinterpret_cast<uint32_t const *>(sl + u*us)[j]); }
                 } else if (1==o.esize) {
 #pragma unroll
-                    for (int j=0; j<V; ++j) t[j] = W(sl[j] ? 1 : 0);
+                    RACU_LANES { t[u][j] = W((sl + u*us)[j] ? 1 : 0); }
                 } else {
                     if constexpr (sizeof(W)==8) {
 #pragma unroll
-                        for (int j=0; j<V; ++j) t[j] = reinterpret_cast<uint64_t const *>(sl)[j];
+                        RACU_LANES { t[u][j] = reinterpret_cast<uint64_t const *>(sl + u*us)[j]; }
                     }
                 }
             }
             break;
         }
         case RACU_OP_CAST:
-#pragma unroll
-            for (int j=0; j<V; ++j) t[j] = cast_any<W>(in.aux, in.type, t[j]);
+            RACU_TYPE_SWITCH(in.aux, (group_cast_from<W, U, T>(in.type, t)))
             break;
         case RACU_OP_NEG: case RACU_OP_ABS: case RACU_OP_SQRT: case RACU_OP_SQR: case RACU_OP_EXP:
         case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS: case RACU_OP_NOT:
-#pragma unroll
-            for (int j=0; j<V; ++j) t[j] = un_any<W>(in.op, in.type, t[j]);
+            RACU_TYPE_SWITCH(in.type, (group_unary<W, U, T>(in.op, t)))
             break;
         case RACU_OP_FMA: {
-            W const * lb = reinterpret_cast<W const *>(stack + (int(in.lvl)+1)*stack_stride);
-#pragma unroll
-            for (int j=0; j<V; ++j) t[j] = fma_any<W>(in.type, lv[j], lb[j], t[j]);
+            RACU_LANES {
+                W const * la = reinterpret_cast<W const *>(lv + u*sstride);
+                W const * lb = reinterpret_cast<W const *>(lv + (U+u)*sstride);
+                t[u][j] = fma_any<W>(in.type, la[j], lb[j], t[u][j]);
+            }
             break;
         }
         case RACU_OP_PICK: {
             int n = in.arg;
-            W sel[V];
-#pragma unroll
-            for (int j=0; j<V; ++j) {
-                sel[j] = lv[j];
-                if (in.aux==RACU_BOOL) sel[j] = W(uint32_t(sel[j])&0xffu);
-                else if (in.aux==RACU_I32) sel[j] = W(uint32_t(sel[j]));
-            }
-            for (int b=0; b+1<n; ++b) {
-                W const * lb = reinterpret_cast<W const *>(stack + (int(in.lvl)+1+b)*stack_stride);
-#pragma unroll
-                for (int j=0; j<V; ++j) { if (sel[j]==W(b)) t[j] = lb[j]; }
-            }
-            if (n>1) { // out of contract selectors take branch 0, like the oracle
-                W const * l0 = reinterpret_cast<W const *>(stack + (int(in.lvl)+1)*stack_stride);
-#pragma unroll
-                for (int j=0; j<V; ++j) { if (!(sel[j]<W(n))) t[j] = l0[j]; }
+            RACU_LANES {
+                W sel = reinterpret_cast<W const *>(lv + u*sstride)[j];
+                if (in.aux==RACU_BOOL) sel = W(uint32_t(sel)&0xffu);
+                else if (in.aux==RACU_I32) sel = W(uint32_t(sel));
+                if (!(sel<W(n))) sel = 0; // out of contract selectors take branch 0, like the oracle
+                if (sel+1<W(n)) t[u][j] = reinterpret_cast<W const *>(lv + ((1+int(sel))*U+u)*sstride)[j];
             }
             break;
         }
         default:
-#pragma unroll
-            for (int j=0; j<V; ++j) t[j] = bin_any<W>(in.op, in.type, lv[j], t[j]);
+            RACU_TYPE_SWITCH(in.type, (group_binary<W, U, T>(in.op, lv, sstride, t)))
             break;
         }
     }
+}
+
+// acc[j] = combine(acc[j], t[u][j]) over the lanes selected by `valid(u, j)`; dispatch hoisted out of the lane loops.
+template <class W, int U, class T, class Valid> RACU_HD void
+group_combine_t(int fold_op, W * acc, W (*t)[Lanes<W>::V], Valid valid)
+{
+    constexpr int V = Lanes<W>::V;
+#define RACU_ACC(EXPR) _Pragma("unroll") RACU_LANES { if (valid(u, j)) { T c = Ty<T>::template get<W>(acc[j]), x = Ty<T>::template get<W>(t[u][j]); acc[j] = Ty<T>::template put<W>(EXPR); } } break;
+    switch (fold_op) {
+    case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB:
+        if constexpr (!std::is_same_v<T, bool>) { RACU_ACC(T(c+x)) } break;
+    case RACU_ASSIGN_MUL: case RACU_ASSIGN_DIV:
+        if constexpr (!std::is_same_v<T, bool>) { RACU_ACC(T(c*x)) } break;
+    case RACU_ASSIGN_AMIN: RACU_ACC((x<c ? x : c))
+    default: RACU_ACC((c<x ? x : c))
+    }
+#undef RACU_ACC
+}
+template <class W, int U, class Valid> RACU_HD void
+group_combine(int fold_op, int type, W * acc, W (*t)[Lanes<W>::V], Valid valid)
+{
+    RACU_TYPE_SWITCH(type, (group_combine_t<W, U, T>(fold_op, acc, t, valid)))
 }
 
 } // namespace racu

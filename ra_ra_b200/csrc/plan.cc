@@ -94,7 +94,6 @@ check_program(racu_desc const * d, std::string & err)
     for (int o=0; o<d->nopnd; ++o) {
         racu_operand const & p = d->opnd[o];
         if (p.dtype<0 || p.dtype>=RACU_NDTYPE || p.kind<RACU_MEM || p.kind>RACU_SCALAR) { err = "bad operand kind/dtype"; return -1; }
-        if (p.kind==RACU_MEM && !p.base.ptr) { err = "null operand pointer"; return -1; }
     }
     return check_ins(d->ins, d->nins, d->opnd, d->nopnd, err);
 }
@@ -320,6 +319,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
             return RACU_OK;
         }
     }
+    for (auto const & o: w.op) { if (o.kind==RACU_MEM && 0==o.base) { err = "null operand pointer"; return RACU_ERR_BAD_DESC; } }
     // ---- drop axes of length 1
     for (int k=0; k<w.rank;) { if (1==w.len[k]) w.drop(k); else ++k; }
 
@@ -565,7 +565,8 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     // ---- launch geometry
     int U = nasync>0 ? std::max(1, std::min(4, 8/nasync)) : 1;
     auto smem_for = [&](int u) { return size_t(u*nstage+depth)*KBLOCK*KSLOT; };
-    while (U>1 && smem_for(U)>size_t(160*1024)) U /= 2;
+    if (3==U) U = 2;
+    while (U>1 && smem_for(U)>size_t(100*1024)) U /= 2;
     if (smem_for(U)>size_t(220*1024)) { err = "expression needs too much staging memory"; return RACU_ERR_UNSUPPORTED; }
     kp.U = U;
     plan.smem = smem_for(U);

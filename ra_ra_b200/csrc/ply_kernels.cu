@@ -26,31 +26,30 @@ template <> __device__ __forceinline__ uint32_t shfl_xor<uint32_t>(uint32_t v, i
 template <> __device__ __forceinline__ uint64_t shfl_xor<uint64_t>(uint64_t v, int o) { return __shfl_xor_sync(0xffffffffu, (unsigned long long)v, o); }
 
 // ---- map: dst[...] = program(operands)
-template <class W> __global__ void __launch_bounds__(KBLOCK)
+template <class W, int U> __global__ void __launch_bounds__(KBLOCK)
 ply_map_kernel(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int V = Lanes<W>::V;
     int const tid = threadIdx.x;
-    int const sstride = KBLOCK*KSLOT;
+    constexpr int sstride = KBLOCK*KSLOT;
     unsigned char * const stage = smem + tid*KSLOT;
-    unsigned char * const stack = smem + size_t(p.U)*p.nstage*sstride + tid*KSLOT;
-    int64_t const per = int64_t(KBLOCK)*p.U;
+    unsigned char * const stack = smem + size_t(U)*p.nstage*sstride + tid*KSLOT;
+    constexpr int64_t per = int64_t(KBLOCK)*U;
     KIdx b;
     for (int64_t g0 = int64_t(blockIdx.x)*per; g0<p.nvecA; g0 += int64_t(gridDim.x)*per) {
-        for (int u=0; u<p.U; ++u) {
+#pragma unroll
+        for (int u=0; u<U; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK + tid;
             if (g<p.nvecA) { KIdx a; decompA(p, g, a); stage_vector<W>(p, a, b, stage + size_t(u)*p.nstage*sstride, sstride, CpAsync {}); }
         }
         cp_async_wait_all();
-        for (int u=0; u<p.U; ++u) {
+        W t[U][V];
+        interp<W, U>(p, stage, stack, sstride, t);
+#pragma unroll
+        for (int u=0; u<U; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK + tid;
-            if (g<p.nvecA) {
-                KIdx a; decompA(p, g, a);
-                W t[V];
-                interp<W>(p, stage + size_t(u)*p.nstage*sstride, sstride, stack, sstride, t);
-                store_vector<W>(p, a, t);
-            }
+            if (g<p.nvecA) { KIdx a; decompA(p, g, a); store_vector<W>(p, a, t[u]); }
         }
     }
 }
@@ -70,42 +69,42 @@ block_combine(KParams const & p, W r, W * red)
 }
 
 // ---- fold-inner: CTA = (kept element kb, chunk c of the folded vectors); threads stride over the chunk
-template <class W> __global__ void __launch_bounds__(KBLOCK)
+template <class W, int U> __global__ void __launch_bounds__(KBLOCK)
 ply_fold_inner_kernel(const __grid_constant__ KParams p, const __grid_constant__ FinishParams f)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ W red[KBLOCK/32];
     constexpr int V = Lanes<W>::V;
     int const tid = threadIdx.x;
-    int const sstride = KBLOCK*KSLOT;
+    constexpr int sstride = KBLOCK*KSLOT;
     unsigned char * const stage = smem + tid*KSLOT;
-    unsigned char * const stack = smem + size_t(p.U)*p.nstage*sstride + tid*KSLOT;
+    unsigned char * const stack = smem + size_t(U)*p.nstage*sstride + tid*KSLOT;
     uint32_t const kb = blockIdx.x/uint32_t(p.nchunks), c = blockIdx.x-kb*uint32_t(p.nchunks);
     KIdx b;
     if (p.rankB>0) decompB(p, kb, b);
     int64_t const start = int64_t(c)*p.chunk_len;
     int64_t const end = start+p.chunk_len<p.nvecA ? start+p.chunk_len : p.nvecA;
-    int64_t const per = int64_t(KBLOCK)*p.U;
+    constexpr int64_t per = int64_t(KBLOCK)*U;
     W acc[V];
 #pragma unroll
     for (int j=0; j<V; ++j) acc[j] = W(p.identity);
     for (int64_t g0 = start; g0<end; g0 += per) {
-        for (int u=0; u<p.U; ++u) {
+        int nvalid[U];
+#pragma unroll
+        for (int u=0; u<U; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK + tid;
-            if (g<end) { KIdx a; decompA(p, g, a); stage_vector<W>(p, a, b, stage + size_t(u)*p.nstage*sstride, sstride, CpAsync {}); }
-        }
-        cp_async_wait_all();
-        for (int u=0; u<p.U; ++u) {
-            int64_t g = g0 + int64_t(u)*KBLOCK + tid;
+            nvalid[u] = 0;
             if (g<end) {
                 KIdx a; decompA(p, g, a);
-                W t[V];
-                interp<W>(p, stage + size_t(u)*p.nstage*sstride, sstride, stack, sstride, t);
                 int64_t const rem = p.len0-a.e0;
-#pragma unroll
-                for (int j=0; j<V; ++j) { if (j<rem) acc[j] = combine<W>(p.fold_op, p.acc_type, acc[j], t[j]); }
+                nvalid[u] = rem<V ? int(rem) : V;
+                stage_vector<W>(p, a, b, stage + size_t(u)*p.nstage*sstride, sstride, CpAsync {});
             }
         }
+        cp_async_wait_all();
+        W t[U][V];
+        interp<W, U>(p, stage, stack, sstride, t);
+        group_combine<W, U>(p.fold_op, p.acc_type, acc, t, [&](int u, int j) { return j<nvalid[u]; });
     }
     W r = acc[0];
 #pragma unroll
@@ -118,15 +117,15 @@ ply_fold_inner_kernel(const __grid_constant__ KParams p, const __grid_constant__
 }
 
 // ---- fold-outer: thread = kept vector (lanes are distinct kept elements); blockIdx.y = chunk of the folded index space
-template <class W> __global__ void __launch_bounds__(KBLOCK)
+template <class W, int U> __global__ void __launch_bounds__(KBLOCK)
 ply_fold_outer_kernel(const __grid_constant__ KParams p, const __grid_constant__ FinishParams f)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int V = Lanes<W>::V;
     int const tid = threadIdx.x;
-    int const sstride = KBLOCK*KSLOT;
+    constexpr int sstride = KBLOCK*KSLOT;
     unsigned char * const stage = smem + tid*KSLOT;
-    unsigned char * const stack = smem + size_t(p.U)*p.nstage*sstride + tid*KSLOT;
+    unsigned char * const stack = smem + size_t(U)*p.nstage*sstride + tid*KSLOT;
     int64_t const g = int64_t(blockIdx.x)*KBLOCK + tid;
     bool const valid = g<p.nvecA;
     KIdx a; a.e0 = 0;
@@ -138,19 +137,16 @@ ply_fold_outer_kernel(const __grid_constant__ KParams p, const __grid_constant__
 #pragma unroll
     for (int j=0; j<V; ++j) acc[j] = W(p.identity);
     if (valid) {
-        for (int64_t r = r0; r<r1; r += p.U) {
-            for (int u=0; u<p.U; ++u) {
+        for (int64_t r = r0; r<r1; r += U) {
+#pragma unroll
+            for (int u=0; u<U; ++u) {
                 if (r+u<r1) { KIdx b; decompB(p, r+u, b); stage_vector<W>(p, a, b, stage + size_t(u)*p.nstage*sstride, sstride, CpAsync {}); }
             }
             cp_async_wait_all();
-            for (int u=0; u<p.U; ++u) {
-                if (r+u<r1) {
-                    W t[V];
-                    interp<W>(p, stage + size_t(u)*p.nstage*sstride, sstride, stack, sstride, t);
-#pragma unroll
-                    for (int j=0; j<V; ++j) acc[j] = combine<W>(p.fold_op, p.acc_type, acc[j], t[j]);
-                }
-            }
+            W t[U][V];
+            interp<W, U>(p, stage, stack, sstride, t);
+            int const nu = int(r1-r<U ? r1-r : U);
+            group_combine<W, U>(p.fold_op, p.acc_type, acc, t, [&](int u, int) { return u<nu; });
         }
         int64_t const rem = p.len0-a.e0;
         int64_t row = 0;
@@ -213,16 +209,20 @@ launch_plan(Plan const & plan, cudaStream_t stream)
     KParams const & p = plan.kp;
     cudaError_t e = cudaSuccess;
     dim3 grid(plan.grid_x, plan.grid_y), block(KBLOCK);
+#define RACU_LAUNCH_U(KERNEL, WT, UU, ...) \
+    do { if ((e = set_smem(KERNEL<WT, UU>, plan.smem))) return e; KERNEL<WT, UU><<<grid, block, plan.smem, stream>>>(__VA_ARGS__); } while (0)
+#define RACU_LAUNCH_W(KERNEL, WT, ...) \
+    do { switch (p.U) { case 1: RACU_LAUNCH_U(KERNEL, WT, 1, __VA_ARGS__); break; case 2: RACU_LAUNCH_U(KERNEL, WT, 2, __VA_ARGS__); break; \
+         default: RACU_LAUNCH_U(KERNEL, WT, 4, __VA_ARGS__); break; } } while (0)
 #define RACU_LAUNCH(KERNEL, ...) \
-    do { \
-        if (p.wide) { if ((e = set_smem(KERNEL<uint64_t>, plan.smem))) return e; KERNEL<uint64_t><<<grid, block, plan.smem, stream>>>(__VA_ARGS__); } \
-        else { if ((e = set_smem(KERNEL<uint32_t>, plan.smem))) return e; KERNEL<uint32_t><<<grid, block, plan.smem, stream>>>(__VA_ARGS__); } \
-    } while (0)
+    do { if (p.wide) RACU_LAUNCH_W(KERNEL, uint64_t, __VA_ARGS__); else RACU_LAUNCH_W(KERNEL, uint32_t, __VA_ARGS__); } while (0)
     switch (p.mode) {
     case K_MAP: RACU_LAUNCH(ply_map_kernel, p); break;
     case K_FOLD_INNER: RACU_LAUNCH(ply_fold_inner_kernel, p, plan.fp); break;
     default: RACU_LAUNCH(ply_fold_outer_kernel, p, plan.fp); break;
     }
+#undef RACU_LAUNCH_U
+#undef RACU_LAUNCH_W
 #undef RACU_LAUNCH
     ++g_launches;
     if ((e = cudaGetLastError())) return e;

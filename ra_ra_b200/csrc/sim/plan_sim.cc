@@ -37,9 +37,9 @@ sim_run(Plan & plan)
         for (int64_t g=0; g<p.nvecA; ++g) {
             decompA(p, g, a);
             stage_vector<W>(p, a, b, stage, ss, HostCopy {});
-            W t[V];
-            interp<W>(p, stage, ss, stack, ss, t);
-            store_vector<W>(p, a, t);
+            W t[1][V];
+            interp<W, 1>(p, stage, stack, ss, t);
+            store_vector<W>(p, a, t[0]);
         }
     } else if (p.mode==K_FOLD_INNER) {
         for (int64_t kb=0; kb<p.nk; ++kb) {
@@ -50,9 +50,9 @@ sim_run(Plan & plan)
                 for (int64_t g=start; g<end; ++g) {
                     decompA(p, g, a);
                     stage_vector<W>(p, a, b, stage, ss, HostCopy {});
-                    W t[V];
-                    interp<W>(p, stage, ss, stack, ss, t);
-                    for (int j=0; j<V; ++j) { if (j<p.len0-a.e0) r = combine<W>(p.fold_op, p.acc_type, r, t[j]); }
+                    W t[1][V];
+                    interp<W, 1>(p, stage, stack, ss, t);
+                    for (int j=0; j<V; ++j) { if (j<p.len0-a.e0) r = combine<W>(p.fold_op, p.acc_type, r, t[0][j]); }
                 }
                 if (p.nchunks>1) partial[int64_t(c)*p.nk+kb] = r; else finish_apply<W>(f, kb, r);
             }
@@ -69,9 +69,9 @@ sim_run(Plan & plan)
                 for (int64_t r=r0; r<r1; ++r) {
                     decompB(p, r, b);
                     stage_vector<W>(p, a, b, stage, ss, HostCopy {});
-                    W t[V];
-                    interp<W>(p, stage, ss, stack, ss, t);
-                    for (int j=0; j<V; ++j) acc[j] = combine<W>(p.fold_op, p.acc_type, acc[j], t[j]);
+                    W t[1][V];
+                    interp<W, 1>(p, stage, stack, ss, t);
+                    group_combine<W, 1>(p.fold_op, p.acc_type, acc, t, [](int, int) { return true; });
                 }
                 for (int j=0; j<V; ++j) {
                     if (j<p.len0-a.e0) { if (p.nchunks>1) partial[int64_t(c)*p.nk+n0+j] = acc[j]; else finish_apply<W>(f, n0+j, acc[j]); }

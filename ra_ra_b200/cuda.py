@@ -48,7 +48,7 @@ class CudaExecutor:
         return self.wrap(torch.empty(tuple(shape), dtype=_TORCH[dtype], device=self.device))
 
     def from_numpy(self, arr):
-        return self.wrap(torch.from_numpy(np.ascontiguousarray(arr)).to(self.device))
+        return self.wrap(torch.from_numpy(np.array(arr, order="C", copy=True)).to(self.device))  # (ascontiguousarray would promote 0-d to 1-d)
 
     def to_numpy(self, v):
         out = self.empty(v.shape, v.dtype)

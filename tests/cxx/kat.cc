@@ -1,0 +1,268 @@
+// kat.cc - the reference's known-answer tests for the traversal path, written against ra/cuda.hh so that they read like
+// the reference's own test files. Linked twice by tests/test_cxx_header.py: against oracle/libracu_oracle.so (the racu_* ABI
+// over host memory, run by the CPU oracle: checks this header without a GPU) and against ra_ra_b200/libracu.so (-m gpu).
+// Values and shapes are the reference's (file:line cited per section); no reference code is used.
+#include <numeric>
+
+#include "harness.hh"
+
+namespace rc = ra::cuda;
+using real = double;
+template <class T> using vec = std::vector<T>;
+
+template <class T, rc::rank_t R> rc::Big<T, R> iota_filled(std::initializer_list<rc::dim_t> s, T first)
+{
+    rc::Big<T, R> a(s, rc::none);
+    vec<T> h(a.size());
+    std::iota(h.begin(), h.end(), first);
+    a.from_host(h.data(), rc::dim_t(h.size()));
+    return a;
+}
+
+int main()
+{
+    TestRecorder tr;
+    tr.section("traversal - Map with scalar: test/ply.cc:31-44");
+    {
+        auto a = iota_filled<real, 2>({3, 2}, 0);
+        rc::Big<real, 2> c({3, 2}, 0.);
+        c = a - 3.0;
+        tr.test_eq(vec<real> {-3, -2, -1, 0, 1, 2}, c);
+    }
+    tr.section("traversal - int neg / mul: test/ply.cc:51-61");
+    {
+        rc::Big<int, 1> A {1, 2, 3}, B {+1, -2, +3}, C({3}, 0);
+        C = -A;
+        tr.test_eq(vec<int> {-1, -2, -3}, C);
+        C = A*B;
+        tr.test_eq(vec<int> {1, -4, 9}, C);
+    }
+    tr.section("rank matching - rank 3 vs rank 2 prefix: test/ply.cc:262-288");
+    {
+        auto a = iota_filled<real, 3>({3, 2, 4}, 1);
+        auto b = iota_filled<real, 2>({3, 2}, 1);
+        vec<real> check { 0, 1, 2, 3, 3, 4, 5, 6, 6, 7, 8, 9, 9, 10, 11, 12, 12, 13, 14, 15, 15, 16, 17, 18 };
+        rc::Big<real, 3> c0(a-b);
+        tr.test_eq(check, c0);
+        rc::Big<real, 3> c({3, 2, 4}, 0.);
+        c = -(b-a);
+        tr.test_eq(check, c);
+        tr.test(rc::shape(a-b)==vec<rc::dim_t> {3, 2, 4}, "shape of expression");
+    }
+    tr.section("mismatched steps with transpose: test/ra-1.cc:183-203");
+    {
+        auto a = iota_filled<int, 2>({2, 3}, 1);
+        auto b = iota_filled<int, 2>({3, 2}, 1);
+        rc::Big<int, 2> c({2, 3}, 0);
+        c = a - rc::transpose<1, 0>(b);
+        tr.test_eq(vec<int> {0, -1, -2, 2, 1, 0}, c);
+        c = 0;
+        rc::transpose<1, 0>(c) = rc::transpose<1, 0>(a) - b;
+        tr.test_eq(vec<int> {0, -1, -2, 2, 1, 0}, c);
+    }
+    tr.section("operators: test/operators.cc:122-137");
+    {
+        rc::Big<int, 2> a({3, 2}, { 1, 2, 3, 20, 5, 6 });
+        rc::Big<int, 1> b { 10, 20, 30 };
+        tr.test_eq(vec<int> {11, 12, 23, 40, 35, 36}, a+b);
+        tr.test_eq(vec<bool> {false, false, false, true, false, false}, a==b);
+        tr.test_eq(vec<bool> {false, false, false, true, false, false}, !(a!=b));
+    }
+    tr.section("README first example: examples/read-me.cc:26-37");
+    {
+        rc::Big<float> A({2, 4}, {1, 2, 3, 4, 5, 6, 7, 8});
+        rc::Big<float, 2> B({2, 4}, {1, 2, 3, 4, 5, 6, 7, 8});
+        rc::Big<float, 2> C({2, 4}, {1, 2, 3, 4, 5, 6, 7, 8});
+        B += A + C + std::vector {100., 200.};
+        B(rc::all, rc::iota(rc::len/2, rc::len/2)) *= -1;
+        tr.test_eq(vec<float> {103, 106, -109, -112, 215, 218, -221, -224}, B);
+    }
+    tr.section("rank extension with std::vector<float>: examples/read-me.cc:162-165");
+    {
+        rc::Big<float, 2> B({2, 2}, {1, 2, 3, 4});
+        B += std::vector<float> {10, 20};
+        tr.test_eq(vec<float> {11, 12, 23, 24}, B);
+    }
+    tr.section("C = A*B, D += A*B: test/ra-12.cc:30-55, examples/read-me.cc:82-91");
+    {
+        rc::Big<float, 2> A({2, 3}, {1, 2, 3, 1, 2, 3});
+        rc::Big<float, 1> B {-1, +1};
+        rc::Big<float, 2> C({2, 3}, 99.f);
+        C = A * B;
+        tr.test_eq(vec<float> {-1, -2, -3, 1, 2, 3}, C);
+        rc::Big<float, 1> D({2}, 0.f);
+        D += A * B;
+        tr.test_eq(vec<float> {-6, 6}, D);
+        rc::Big<float> Ad({2, 3}, {1, 2, 3, 1, 2, 3}), Bd({2}, {-1, 1}), Dd({2}, 0.f); // run time rank (case III)
+        Dd += Ad * Bd;
+        tr.test_eq(vec<float> {-6, 6}, Dd);
+    }
+    tr.section("index operands: test/frame-old.cc:28-58");
+    {
+        rc::Big<int, 2> c({3, 2}, 0);
+        c = rc::_0 + rc::_1;
+        tr.test_eq(vec<int> {0, 1, 1, 2, 2, 3}, c);
+        c = rc::_0 * 2;
+        tr.test_eq(vec<int> {0, 0, 2, 2, 4, 4}, c);
+    }
+    tr.section("periodic axes and outer product with insert: test/frame-new.cc:146-190");
+    {
+        rc::Big<int, 3> a({2, 3, 4}, (rc::_0+1)*100 + (rc::_1+1)*10 + (rc::_2+1));
+        auto b = a(rc::all, rc::insert<1>, rc::iota(4, 0, 0));
+        tr.test(4==b.rank() && 2==b.len(0) && rc::UNB==b.len(1) && 4==b.len(2) && 4==b.len(3), "shape of a(all, insert<1>, iota(4, 0, 0))");
+        tr.test(rc::shape(a+b)==vec<rc::dim_t> {2, 3, 4, 4}, "rank 4 match");
+        rc::Big<int, 4> c({2, 3, 4, 4}, 0);
+        for (int j=0; j<3; ++j) c(rc::all, j) = a(rc::all, rc::iota(4, 0, 0));
+        rc::Big<int, 4> e(a+c), f(a+b), g(b+a);
+        tr.test_eq(e.to_host(), f);
+        tr.test_eq(e.to_host(), g);
+        rc::Big<int, 2> p({4, 3}, 10*rc::_1+100*rc::_0);
+        rc::Big<int, 1> q({5}, rc::_0);
+        rc::Big<int, 3> o(p(rc::dots<2>, rc::insert<1>) - q(rc::insert<2>, rc::dots<1>));
+        vec<int> check;
+        for (int i=0; i<4; ++i) for (int j=0; j<3; ++j) for (int k=0; k<5; ++k) check.push_back(10*j+100*i-k);
+        tr.test_eq(check, o);
+    }
+    tr.section("reverse: test/view-ops.cc:19-52");
+    {
+        auto a = iota_filled<real, 3>({3, 2, 4}, 1);
+        vec<real> check0 { 17, 18, 19, 20, 21, 22, 23, 24, 9, 10, 11, 12, 13, 14, 15, 16, 1, 2, 3, 4, 5, 6, 7, 8 };
+        vec<real> check1 { 5, 6, 7, 8, 1, 2, 3, 4, 13, 14, 15, 16, 9, 10, 11, 12, 21, 22, 23, 24, 17, 18, 19, 20 };
+        vec<real> check2 { 4, 3, 2, 1, 8, 7, 6, 5, 12, 11, 10, 9, 16, 15, 14, 13, 20, 19, 18, 17, 24, 23, 22, 21 };
+        tr.test_eq(check0, rc::reverse(a.view(), 0));
+        tr.test_eq(check0, a(rc::iota(rc::len, rc::len-1, -1)));
+        tr.test_eq(check1, rc::reverse(a.view(), 1));
+        tr.test_eq(check1, a(rc::dots<1>, rc::iota(rc::len, rc::len-1, -1)));
+        tr.test_eq(check2, rc::reverse(a.view(), 2));
+        tr.test_eq(check2, a(rc::dots<2>, rc::iota(rc::len, rc::len-1, -1)));
+    }
+    tr.section("transpose / diag: test/view-ops.cc:54-75,121-138");
+    {
+        auto a = iota_filled<real, 2>({3, 2}, 1);
+        tr.test_eq(vec<real> {1, 3, 5, 2, 4, 6}, rc::transpose<1, 0>(a.view()));
+        tr.test_eq(vec<real> {1, 3, 5, 2, 4, 6}, rc::transpose(a.view()));
+        tr.test_eq(vec<real> {1, 3, 5, 2, 4, 6}, rc::transpose(a.view(), {1, 0}));
+        auto s = iota_filled<real, 2>({3, 3}, 0);
+        tr.test_eq(vec<real> {0, 4, 8}, rc::diag(s.view()));
+    }
+    tr.section("beaten subscripts, base pointer offsets: test/fromb.cc:46-81");
+    {
+        rc::Big<int, 2> a({10, 10}, rc::_1 + 10*rc::_0);
+        auto off = [&](auto const & b) { return b.data()-a.data(); };
+        { auto b = a(3, rc::all); tr.test(30==off(b)); tr.test_eq(vec<int> {30, 31, 32, 33, 34, 35, 36, 37, 38, 39}, b); }
+        { auto b = a(rc::iota(4)); tr.test(0==off(b) && 4==b.len(0) && 10==b.len(1)); }
+        { auto b = a(rc::iota(4, 4)); tr.test(40==off(b)); }
+        { auto b = a(3, rc::iota(5, 4)); tr.test(34==off(b)); tr.test_eq(vec<int> {34, 35, 36, 37, 38}, b); }
+        { auto b = a(rc::all, rc::iota(4, 2, 2)); tr.test(2==off(b) && 10==b.len(0) && 4==b.len(1)); }
+        { auto b = a(rc::iota(3, 1, 2), rc::iota(2, 2, 3)); tr.test(12==off(b)); tr.test_eq(vec<int> {12, 15, 32, 35, 52, 55}, b); }
+        { auto b = a(rc::iota(3, 9, -2), rc::iota(2, 2, 3)); tr.test(92==off(b)); tr.test_eq(vec<int> {92, 95, 72, 75, 52, 55}, b); }
+        tr.test_eq(vec<int> {90, 91, 92, 93, 94, 95, 96, 97, 98, 99}, a(rc::len-1, rc::all)); // test/fromb.cc:131-162
+        tr.test(int(a(2, 3))==23, "rank 0 subscript converts to a value");
+    }
+    tr.section("bounds and agreement are checked before launch: ra/ply.hh:395,407; test/checks.cc:159-233");
+    {
+        rc::Big<int, 2> a({10, 10}, 0);
+        tr.test_throws([&]{ a(10, rc::all); }, RACU_ERR_BOUNDS);
+        tr.test_throws([&]{ a(rc::iota(4, 8)); }, RACU_ERR_BOUNDS);
+        rc::Big<int, 1> b({3}, 0);
+        tr.test_throws([&]{ a += b; }, RACU_ERR_SHAPE);
+        rc::Big<real, 1> c({3}, 0.);
+        tr.test_throws([&]{ c = rc::_1; }, RACU_ERR_SHAPE, "unbounded expression");
+    }
+    tr.section("iota: test/iota.cc:21-67");
+    {
+        rc::Big<int, 1> a({4}, 0);
+        a = rc::iota(4, 3);
+        tr.test_eq(vec<int> {3, 4, 5, 6}, a);
+        a = rc::iota(4, 3, 2);
+        tr.test_eq(vec<int> {3, 5, 7, 9}, a);
+        rc::Big<int, 3> b({3, 2, 4}, 0);
+        rc::transpose<0, 2, 1>(b.view()) = rc::iota(3, 1);
+        vec<int> check;
+        for (int i=0; i<3; ++i) for (int j=0; j<8; ++j) check.push_back(i+1);
+        tr.test_eq(check, b);
+    }
+    tr.section("where / pick: test/where.cc:22-38,98-122");
+    {
+        rc::Big<real, 1> a0 { 1, 2, 3 }, a1 { 10, 20, 30 }, a({3}, 0.);
+        rc::Big<int, 1> p { 0, 1, 0 };
+        a = rc::pick(p, a0, a1);
+        tr.test_eq(vec<real> {1, 20, 3}, a);
+        a = rc::where(p, a0, a1);
+        tr.test_eq(vec<real> {10, 2, 30}, a);
+        rc::Big<bool, 1> w({4}, {true, false, false, true});
+        tr.test_eq(vec<int> {1, 2, 2, 1}, rc::where(w, 1, 2));
+        rc::Big<int, 1> v { 1, 2, 3, 4 };
+        tr.test_eq(vec<int> {17, 2, 3, 17}, rc::where(rc::_0>0 && rc::_0<3, v, 17));
+        rc::Big<int, 1> s {-1, 0, 1};
+        tr.test_eq(vec<int> {44, 77, 99}, rc::where(s>=0, rc::where(s<1, 77, 99), 44));
+    }
+    tr.section("reductions: test/reduction.cc:85-138,199-201");
+    {
+        rc::Big<real, 1> a {1, 2}, b {3, 4};
+        tr.test(11.==rc::dot(a, b));
+        tr.test(8.==rc::reduce_sqrm(a-b));
+        tr.test(std::sqrt(8.)==rc::norm2(a-b));
+        rc::Big<real, 1> c {4, 6, -3, 2};
+        tr.test(9.==rc::sum(c) && -144.==rc::prod(c) && 6.==rc::amax(c) && -3.==rc::amin(c));
+        rc::Big<real, 1> q({3}, std::numeric_limits<real>::quiet_NaN());
+        tr.test(-std::numeric_limits<real>::infinity()==rc::amax(q) && std::numeric_limits<real>::infinity()==rc::amin(q), "amax/amin ignore NaN");
+        rc::Big<real, 2> e({0, 3}, 0.);
+        tr.test(0.==rc::sum(e) && 1.==rc::prod(e), "empty");
+    }
+    tr.section("sum columns / rows by rank extension: test/reduction.cc:141-222");
+    {
+        rc::Big<real, 2> A({100, 111}, rc::_0 - rc::_1);
+        vec<real> B(100, 0.), Br(111, 0.);
+        for (int i=0; i<100; ++i) for (int j=0; j<111; ++j) { B[i] += i-j; Br[j] += i-j; }
+        rc::Big<real, 1> C({100}, 0.);
+        C += A;
+        tr.test_eq(B, C);
+        C = 0.;
+        C = C + A;
+        tr.test_eq(B, C, "C = C + A is a running sum");
+        rc::Big<real, 1> D({111}, 0.);
+        D += rc::transpose(A.view());
+        tr.test_eq(Br, D);
+        D = 0.;
+        D(rc::insert<1>) += A;
+        tr.test_eq(Br, D);
+    }
+    tr.section("gemv / gevm / gemm: test/reduction.cc:241-333, bench/bench-gemm.cc:229-237");
+    {
+        rc::Big<real, 2> a({3, 4}, rc::_0 - rc::_1);
+        rc::Big<real, 1> b {1, 2, 3, 4};
+        tr.test_eq(vec<real> {-20, -10, 0}, rc::gemv(a, b));
+        rc::Big<real, 2> at({4, 3}, rc::_1 - rc::_0);
+        tr.test_eq(vec<real> {-20, -10, 0}, rc::gevm(b, at));
+        rc::Big<real, 2> x({3, 2}, 2.), y({2, 4}, 3.);
+        tr.test_eq(vec<real>(12, 12.), rc::gemm(x, y));
+        rc::Big<real, 2> c({3, 4}, 1.);
+        rc::gemm(x, y, c);
+        tr.test_eq(vec<real>(12, 13.), c);
+        int const M = 13, K = 17, N = 11;
+        rc::Big<real, 2> g({M, K}, rc::_0 - rc::_1), h({K, N}, rc::_1 - 2*rc::_0);
+        vec<real> check(M*N, 0.);
+        for (int i=0; i<M; ++i) for (int k=0; k<K; ++k) for (int j=0; j<N; ++j) check[i*N+j] += real(i-k)*real(j-2*k);
+        tr.test_eq(check, rc::gemm(g, h));
+    }
+    tr.section("3-D 7-point stencil as slices: bench/bench-stencil3.cc:55-64");
+    {
+        int const nx = 7, ny = 6, nz = 9;
+        rc::Big<float, 3> A({nx, ny, nz}, rc::cast<float>((rc::_0*7 + rc::_1*3 + rc::_2*5) % 11) - 5.f), Anext({nx, ny, nz}, 0.f);
+        vec<float> ref = A.to_host(), refn(ref.size(), 0.f);
+        auto I = rc::iota(nx-2, 1), J = rc::iota(ny-2, 1), K = rc::iota(nz-2, 1);
+        auto at = [&](vec<float> const & v, int i, int j, int k) { return v[(i*ny+j)*nz+k]; };
+        for (int t=0; t<2; ++t) {
+            Anext(I, J, K) = -6*A(I, J, K) + A(I+1, J, K) + A(I, J+1, K) + A(I, J, K+1) + A(I-1, J, K) + A(I, J-1, K) + A(I, J, K-1);
+            std::swap(A.cp, Anext.cp);
+            for (int i=1; i+1<nx; ++i) for (int j=1; j+1<ny; ++j) for (int k=1; k+1<nz; ++k) {
+                refn[(i*ny+j)*nz+k] = -6*at(ref, i, j, k) + at(ref, i+1, j, k) + at(ref, i, j+1, k) + at(ref, i, j, k+1) + at(ref, i-1, j, k) + at(ref, i, j-1, k) + at(ref, i, j, k-1);
+            }
+            std::swap(ref, refn);
+        }
+        tr.test_eq(ref, A);
+        tr.test_eq(refn, Anext);
+    }
+    return tr.summary();
+}
