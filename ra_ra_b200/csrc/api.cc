@@ -27,7 +27,19 @@ run_plan(racu_desc const * d, int redop, void * reduce_out, cudaStream_t stream)
 {
     Plan plan;
     std::string err;
-    if (int e = make_plan(d, redop, reduce_out, plan, err)) return fail(e, err);
+    if (int e = make_plan(d, redop, reduce_out, plan, err)) {
+        if (e!=RACU_ERR_PEEL) return fail(e, err);
+        // more uncollapsible axes than one launch handles: peel the outermost expression axis here
+        if (!can_peel(d, reduce_out!=nullptr)) return fail(RACU_ERR_UNSUPPORTED, err);
+        Shape sh;
+        if (int e2 = agree(d, sh, err)) return fail(e2, err);
+        racu_desc sub;
+        for (int64_t i=0; i<sh.len[0]; ++i) {
+            peel_axis0(*d, i, sub);
+            if (int e2 = run_plan(&sub, redop, reduce_out, stream)) return e2;
+        }
+        return RACU_OK;
+    }
     if (plan.empty) {
         g_kernel = "none (empty)";
         if (plan.fill_identity) { // empty reduction: the start value (test/reduction.cc:199-201, :236-238)

@@ -5,48 +5,71 @@
 
 namespace racu {
 
-// Stage every used operand of one vector (V elements starting at group-A position `a`, group-B position `b`)
-// into this thread's slots. Slot s lives at stage + s*sstride.
-template <class W, class BE> RACU_HD void
-stage_vector(KParams const & p, KIdx const & a, KIdx const & b, unsigned char * stage, int sstride, BE be)
+// Stage every used operand of the U vectors a thread evaluates together. Vector u sits at group-A position a[u*(UA>1)]
+// and group-B position b[u*(UB>1)] (maps: UB = 0; fold-inner: one shared b; fold-outer: one shared a). nvalid[u] is the
+// number of live lanes of vector u (0: skip it). Slot s of vector u lives at stage + (u*nstage + s)*sstride.
+// Each operand is decoded once for all U vectors.
+template <class W, int U, int UA, int UB, class BE> RACU_HD void
+stage_group(KParams const & p, KIdx const * a, KIdx const * b, int const * nvalid, unsigned char * stage, int sstride, BE be)
 {
     constexpr int V = Lanes<W>::V;
-    int64_t const rem = p.len0-a.e0;
-    int const nvalid = rem<V ? int(rem) : V;
+    int const ustride = p.nstage*sstride;
     for (int o=0; o<p.nopnd; ++o) {
         KOpnd const & k = p.opnd[o];
         if (S_NONE==k.stage || 255==k.slot) continue;
-        int64_t off = offsetA(p, k, a);
-        if (p.rankB>0) off += offsetB(p, k, b);
-        unsigned char * sl = stage + int(k.slot)*sstride;
+        unsigned char * const sl0 = stage + int(k.slot)*sstride;
+        unsigned char const * const base = reinterpret_cast<unsigned char const *>(k.base);
         int const es = k.esize;
-        if (S_VEC==k.stage && nvalid==V) {
-            unsigned char const * src = reinterpret_cast<unsigned char const *>(k.base) + off*es;
-            switch (V*es) {
-            case 16: be.copy16(sl, src); break;
-            case 8: be.copy8(sl, src); break;
-            case 4: if (4==es) be.copy4(sl, src); else *reinterpret_cast<uint32_t *>(sl) = *reinterpret_cast<uint32_t const *>(src); break;
-            default: *reinterpret_cast<uint16_t *>(sl) = *reinterpret_cast<uint16_t const *>(src); break;
-            }
-        } else if (S_VEC==k.stage || S_GATHER==k.stage) {
-            int64_t const s0 = k.sA[0];
+        int64_t offb = 0;
+        if constexpr (1==UB) offb = offsetB(p, k, b[0]);
+        if (S_VEC==k.stage && 4==es) { // the common case first: 16-byte (V=4) or 8-byte (V=2) vectors of 4-byte elements
 #pragma unroll
-            for (int j=0; j<V; ++j) {
-                if (j<nvalid) {
-                    unsigned char const * src = reinterpret_cast<unsigned char const *>(k.base) + (off+j*s0)*es;
-                    if (4==es) be.copy4(sl+4*j, src); else if (8==es) be.copy8(sl+8*j, src); else sl[j] = *src;
-                } else {
-                    if (4==es) *reinterpret_cast<uint32_t *>(sl+4*j) = 0; else if (8==es) *reinterpret_cast<uint64_t *>(sl+8*j) = 0; else sl[j] = 0;
+            for (int u=0; u<U; ++u) {
+                if (nvalid[u]>0) {
+                    int64_t off = offsetA(p, k, a[UA>1 ? u : 0]) + offb;
+                    if constexpr (UB>1) off += offsetB(p, k, b[u]);
+                    unsigned char * sl = sl0 + u*ustride;
+                    unsigned char const * src = base + off*4;
+                    if (nvalid[u]==V) { if constexpr (4==V) be.copy16(sl, src); else be.copy8(sl, src); }
+                    else {
+#pragma unroll
+                        for (int j=0; j<V; ++j) { if (j<nvalid[u]) be.copy4(sl+4*j, src+4*j); else *reinterpret_cast<uint32_t *>(sl+4*j) = 0; }
+                    }
                 }
             }
-        } else if (S_BCAST==k.stage) {
-            W v = load_elem<W>(reinterpret_cast<unsigned char const *>(k.base) + off*es, k.dtype);
+            continue;
+        }
 #pragma unroll
-            for (int j=0; j<V; ++j) store_elem<W>(sl+j*es, k.dtype, v);
-        } else { // S_SEQ
-            int64_t const s0 = k.sA[0];
+        for (int u=0; u<U; ++u) {
+            if (nvalid[u]<=0) continue;
+            int64_t off = offsetA(p, k, a[UA>1 ? u : 0]) + offb;
+            if constexpr (UB>1) off += offsetB(p, k, b[u]);
+            unsigned char * sl = sl0 + u*ustride;
+            if (S_VEC==k.stage && nvalid[u]==V) {
+                unsigned char const * src = base + off*es;
+                if (8==es) be.copy16(sl, src);                                                            // V = 2
+                else if (4==V) *reinterpret_cast<uint32_t *>(sl) = *reinterpret_cast<uint32_t const *>(src); // 4 bools
+                else *reinterpret_cast<uint16_t *>(sl) = *reinterpret_cast<uint16_t const *>(src);          // 2 bools
+            } else if (S_VEC==k.stage || S_GATHER==k.stage) {
+                int64_t const s0 = k.sA[0];
 #pragma unroll
-            for (int j=0; j<V; ++j) store_elem<W>(sl+j*es, k.dtype, seq_value<W>(k, off+j*s0));
+                for (int j=0; j<V; ++j) {
+                    if (j<nvalid[u]) {
+                        unsigned char const * src = base + (off+j*s0)*es;
+                        if (4==es) be.copy4(sl+4*j, src); else if (8==es) be.copy8(sl+8*j, src); else sl[j] = *src;
+                    } else {
+                        if (4==es) *reinterpret_cast<uint32_t *>(sl+4*j) = 0; else if (8==es) *reinterpret_cast<uint64_t *>(sl+8*j) = 0; else sl[j] = 0;
+                    }
+                }
+            } else if (S_BCAST==k.stage) {
+                W v = load_elem<W>(base + off*es, k.dtype);
+#pragma unroll
+                for (int j=0; j<V; ++j) store_elem<W>(sl+j*es, k.dtype, v);
+            } else { // S_SEQ
+                int64_t const s0 = k.sA[0];
+#pragma unroll
+                for (int j=0; j<V; ++j) store_elem<W>(sl+j*es, k.dtype, seq_value<W>(k, off+j*s0));
+            }
         }
     }
 }
@@ -87,12 +110,9 @@ finish_apply(FinishParams const & f, int64_t n, W total)
         off = n*f.stride[0];
     } else if (f.rank>1) {
         uint32_t m = uint32_t(n), q;
-#pragma unroll
-        for (int j=0; j<KMAXR; ++j) {
-            if (j<f.rank) {
-                if (j+1<f.rank) { q = fastdiv(m, f.d[j]); off += int64_t(m-q*f.d[j].len)*f.stride[j]; m = q; }
-                else { off += int64_t(m)*f.stride[j]; }
-            }
+        for (int j=0; j<f.rank; ++j) {
+            if (j+1<f.rank) { q = fastdiv(m, f.d[j]); off += int64_t(m-q*f.d[j].len)*f.stride[j]; m = q; }
+            else { off += int64_t(m)*f.stride[j]; }
         }
     }
     unsigned char * dst = static_cast<unsigned char *>(f.dst) + off*int64_t(f.dst_dtype==RACU_BOOL ? 1 : (f.dst_dtype==RACU_I32 || f.dst_dtype==RACU_F32) ? 4 : 8);

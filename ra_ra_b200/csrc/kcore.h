@@ -35,6 +35,7 @@ namespace racu {
 
 constexpr int KBLOCK = 256;      // threads per CTA of the ply kernels
 constexpr int KMAXR = RACU_MAX_RANK;
+constexpr int KGR = 4;           // axes per group (A, B) after collapsing; longer traversals are peeled on the host
 constexpr int KSLOT = 16;        // bytes of one staged vector / one stack row per thread
 
 enum KMode { K_MAP = 0, K_FOLD_INNER = 1, K_FOLD_OUTER = 2 };
@@ -45,8 +46,8 @@ struct KDim { uint32_t len, mul, shift, pad; }; // n / len == (umulhi(n, mul) + 
 struct KOpnd
 {
     uint64_t base;            // MEM: address of element [0..0] after canonicalisation. SEQ/SCALAR: value bits (i64 or f64)
-    int64_t sA[KMAXR];        // element strides over group A dims (sA[0]: innermost, the vectorised one)
-    int64_t sB[KMAXR];        // element strides over group B dims
+    int64_t sA[KGR];          // element strides over group A dims (sA[0]: innermost, the vectorised one)
+    int64_t sB[KGR];          // element strides over group B dims
     uint8_t kind, dtype, stage, esize;
     uint8_t slot;             // staging slot index (S_NONE: unused)
     uint8_t pad[3];
@@ -75,8 +76,8 @@ struct KParams
     int64_t nk;               // folds: number of kept elements
     void * partial;           // folds: [nchunks][nk] accumulator slots
     KDim vprdiv;
-    KDim dA[KMAXR];           // dA[0] unused (see vpr)
-    KDim dB[KMAXR];
+    KDim dA[KGR];             // dA[0] unused (see vpr)
+    KDim dB[KGR];
     KOpnd opnd[RACU_MAX_OPND];
     KIns ins[RACU_MAX_INS];
 };
@@ -88,9 +89,9 @@ struct FinishParams
     int64_t nk;
     void * partial;
     void * dst;
-    KDim d[KMAXR];
+    KDim d[KGR];
     int64_t len0;         // length of kept dim 0 (not limited to 2^31 when rank==1)
-    int64_t stride[KMAXR];
+    int64_t stride[KGR];
 };
 
 // ---------------- index math ----------------
@@ -105,50 +106,63 @@ RACU_HD uint32_t umulhi32(uint32_t a, uint32_t b)
 }
 RACU_HD uint32_t fastdiv(uint32_t n, KDim const & d) { return (umulhi32(n, d.mul)+n)>>d.shift; }
 
-struct KIdx { int64_t e0; uint32_t i[KMAXR]; }; // group A: e0 = element index along dim 0, i[1..] the others. group B: i[0..]
+struct KIdx { int64_t e0; uint32_t i[KGR]; }; // group A: e0 = element index along dim 0, i[1..] the others. group B: i[0..]
+
+// Ranks are uniform across the grid: nested uniform branches cost one compare each, where an unrolled predicated
+// loop over the maximum rank costs the full chain for every operand of every vector.
 
 // vector id g (< nvecA) -> position in group A
 RACU_HD void decompA(KParams const & p, int64_t g, KIdx & x)
 {
-    if (1==p.rankA) { x.e0 = g*(p.wide ? 2 : 4); return; }
+    int const V = p.wide ? 2 : 4;
+    if (1==p.rankA) { x.e0 = g*V; return; }
     uint32_t n = uint32_t(g);
     uint32_t q = fastdiv(n, p.vprdiv);
-    x.e0 = int64_t(n-q*uint32_t(p.vpr))*(p.wide ? 2 : 4);
+    x.e0 = int64_t(n-q*uint32_t(p.vpr))*V;
     n = q;
-#pragma unroll
-    for (int j=1; j<KMAXR; ++j) {
-        if (j<p.rankA) {
-            if (j+1<p.rankA) { q = fastdiv(n, p.dA[j]); x.i[j] = n-q*p.dA[j].len; n = q; }
-            else { x.i[j] = n; }
-        }
-    }
+    if (2==p.rankA) { x.i[1] = n; return; }
+    q = fastdiv(n, p.dA[1]); x.i[1] = n-q*p.dA[1].len; n = q;
+    if (3==p.rankA) { x.i[2] = n; return; }
+    q = fastdiv(n, p.dA[2]); x.i[2] = n-q*p.dA[2].len; x.i[3] = q;
 }
 
 // linear index b (< nB) -> position in group B
 RACU_HD void decompB(KParams const & p, int64_t b, KIdx & x)
 {
     uint32_t n = uint32_t(b), q;
-#pragma unroll
-    for (int j=0; j<KMAXR; ++j) {
-        if (j<p.rankB) {
-            if (j+1<p.rankB) { q = fastdiv(n, p.dB[j]); x.i[j] = n-q*p.dB[j].len; n = q; }
-            else { x.i[j] = n; }
-        }
-    }
+    if (p.rankB<=1) { x.i[0] = n; return; }
+    q = fastdiv(n, p.dB[0]); x.i[0] = n-q*p.dB[0].len; n = q;
+    if (2==p.rankB) { x.i[1] = n; return; }
+    q = fastdiv(n, p.dB[1]); x.i[1] = n-q*p.dB[1].len; n = q;
+    if (3==p.rankB) { x.i[2] = n; return; }
+    q = fastdiv(n, p.dB[2]); x.i[2] = n-q*p.dB[2].len; x.i[3] = q;
 }
 
 RACU_HD int64_t offsetA(KParams const & p, KOpnd const & o, KIdx const & a)
 {
     int64_t off = a.e0*o.sA[0];
-#pragma unroll
-    for (int j=1; j<KMAXR; ++j) { if (j<p.rankA) off += int64_t(a.i[j])*o.sA[j]; }
+    if (p.rankA>1) {
+        off += int64_t(a.i[1])*o.sA[1];
+        if (p.rankA>2) {
+            off += int64_t(a.i[2])*o.sA[2];
+            if (p.rankA>3) off += int64_t(a.i[3])*o.sA[3];
+        }
+    }
     return off;
 }
 RACU_HD int64_t offsetB(KParams const & p, KOpnd const & o, KIdx const & b)
 {
     int64_t off = 0;
-#pragma unroll
-    for (int j=0; j<KMAXR; ++j) { if (j<p.rankB) off += int64_t(b.i[j])*o.sB[j]; }
+    if (p.rankB>0) {
+        off = int64_t(b.i[0])*o.sB[0];
+        if (p.rankB>1) {
+            off += int64_t(b.i[1])*o.sB[1];
+            if (p.rankB>2) {
+                off += int64_t(b.i[2])*o.sB[2];
+                if (p.rankB>3) off += int64_t(b.i[3])*o.sB[3];
+            }
+        }
+    }
     return off;
 }
 

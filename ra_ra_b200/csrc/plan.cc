@@ -255,6 +255,32 @@ merge_axes(Work & w, int lo, int hi)
 
 } // namespace
 
+bool
+can_peel(racu_desc const * d, bool reducing)
+{
+    if (reducing || d->dst<0) return false;
+    racu_operand const & y = d->opnd[d->dst];
+    if (y.rank>=1 && y.stride[0]!=0) return true;        // independent slices of the destination
+    return d->assign!=RACU_ASSIGN_SET;                    // accumulating folds compose in sequence
+}
+
+// Slice every operand at index i of expression axis 0 (prefix matching aligns operand axes from axis 0).
+void
+peel_axis0(racu_desc const & d, int64_t i, racu_desc & out)
+{
+    out = d;
+    for (int o=0; o<out.nopnd; ++o) {
+        racu_operand & p = out.opnd[o];
+        if (p.rank<1 || p.kind==RACU_SCALAR) continue;
+        int64_t off = i*p.stride[0];
+        if (p.kind==RACU_MEM) p.base.ptr = static_cast<char *>(p.base.ptr) + off*int64_t(dtype_size(p.dtype));
+        else if (is_float(p.dtype)) p.base.f += double(off);
+        else p.base.i += off;
+        for (int k=0; k+1<p.rank; ++k) { p.len[k] = p.len[k+1]; p.stride[k] = p.stride[k+1]; }
+        --p.rank;
+    }
+}
+
 int
 make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::string & err)
 {
@@ -339,6 +365,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
             if (lo<dhi && dlo<hi) { if (same_view(w, w.op[o], w.op[dst])) alias_same = true; else alias_other = true; }
         }
     }
+    for (int pc=0; pc<d->nins; ++pc) { if (d->ins[pc].op==RACU_OP_PUSH && int(d->ins[pc].arg)==dst) alias_same = true; } // the program reads the destination operand itself
     if (alias_other) { err = "destination overlaps a source that is not the same view: traversal order would be observable"; return RACU_ERR_UNSUPPORTED; }
 
     if (fold && assign==RACU_ASSIGN_SET) {
@@ -397,7 +424,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     if (fold && alias_same && assign!=RACU_ASSIGN_SET && d->assign!=RACU_ASSIGN_SET) {
         // c += f(c, a) with broadcast c: sequential dependence through c
         for (auto const & i: w.ins) {
-            if (i.op==RACU_OP_PUSH && w.op[i.arg].kind==RACU_MEM && int(i.arg)!=dst && same_view(w, w.op[i.arg], w.op[dst])) {
+            if (i.op==RACU_OP_PUSH && w.op[i.arg].kind==RACU_MEM && (int(i.arg)==dst || same_view(w, w.op[i.arg], w.op[dst]))) {
                 err = "fold whose right hand side reads the destination"; return RACU_ERR_UNSUPPORTED;
             }
         }
@@ -500,6 +527,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     for (auto const & i: prog) wide |= dtype_size(i.type)==8 || (i.op==RACU_OP_CAST && dtype_size(i.aux)==8) || (i.op==RACU_OP_PICK && dtype_size(i.aux)==8);
     int const V = wide ? 2 : 4;
 
+    if (nA>KGR || nB>KGR) { err = "more than 4 uncollapsible axes in one group"; return RACU_ERR_PEEL; }
     // ---- limits of the 32-bit index decomposition
     for (int k=(1==nA ? 1 : 0); k<nA+nB; ++k) { if (w.len[k]>=(int64_t(1)<<31)) { err = "axis longer than 2^31 after collapsing"; return RACU_ERR_UNSUPPORTED; } }
     kp.mode = mode; kp.wide = wide; kp.rankA = nA; kp.rankB = nB;
@@ -564,7 +592,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
 
     // ---- launch geometry
     int U = nasync>0 ? std::max(1, std::min(4, 8/nasync)) : 1;
-    auto smem_for = [&](int u) { return size_t(u*nstage+depth)*KBLOCK*KSLOT; };
+    auto smem_for = [&](int u) { return size_t(u)*size_t(nstage+depth)*KBLOCK*KSLOT; }; // U staged vectors + U stack rows per level
     if (3==U) U = 2;
     while (U>1 && smem_for(U)>size_t(100*1024)) U /= 2;
     if (smem_for(U)>size_t(220*1024)) { err = "expression needs too much staging memory"; return RACU_ERR_UNSUPPORTED; }

@@ -5,6 +5,8 @@
 
 namespace racu {
 
+constexpr int RACU_ERR_PEEL = 100; // internal: peel the outermost expression axis on the host and retry
+
 
 struct Plan
 {
@@ -26,6 +28,10 @@ int check_program(racu_desc const * d, std::string & err);                 // re
 int agree(racu_desc const * d, Shape & s, std::string & err);             // racu_status
 // reduce_out != nullptr: whole-expression reduction into *reduce_out (device, dtype = program result type).
 int make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::string & err);
+
+void peel_axis0(racu_desc const & d, int64_t i, racu_desc & out);
+// True when the traversal may be split along expression axis 0 into independent launches run in sequence.
+bool can_peel(racu_desc const * d, bool reducing);
 
 size_t dtype_size(int t);
 

@@ -36,21 +36,21 @@ ply_map_kernel(const __grid_constant__ KParams p)
     unsigned char * const stage = smem + tid*KSLOT;
     unsigned char * const stack = smem + size_t(U)*p.nstage*sstride + tid*KSLOT;
     constexpr int64_t per = int64_t(KBLOCK)*U;
-    KIdx b;
     for (int64_t g0 = int64_t(blockIdx.x)*per; g0<p.nvecA; g0 += int64_t(gridDim.x)*per) {
+        KIdx a[U];
+        int nvalid[U];
 #pragma unroll
         for (int u=0; u<U; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK + tid;
-            if (g<p.nvecA) { KIdx a; decompA(p, g, a); stage_vector<W>(p, a, b, stage + size_t(u)*p.nstage*sstride, sstride, CpAsync {}); }
+            nvalid[u] = 0;
+            if (g<p.nvecA) { decompA(p, g, a[u]); int64_t const rem = p.len0-a[u].e0; nvalid[u] = rem<V ? int(rem) : V; }
         }
+        stage_group<W, U, U, 0>(p, a, nullptr, nvalid, stage, sstride, CpAsync {});
         cp_async_wait_all();
         W t[U][V];
         interp<W, U>(p, stage, stack, sstride, t);
 #pragma unroll
-        for (int u=0; u<U; ++u) {
-            int64_t g = g0 + int64_t(u)*KBLOCK + tid;
-            if (g<p.nvecA) { KIdx a; decompA(p, g, a); store_vector<W>(p, a, t[u]); }
-        }
+        for (int u=0; u<U; ++u) { if (nvalid[u]>0) store_vector<W>(p, a[u], t[u]); }
     }
 }
 
@@ -80,7 +80,7 @@ ply_fold_inner_kernel(const __grid_constant__ KParams p, const __grid_constant__
     unsigned char * const stage = smem + tid*KSLOT;
     unsigned char * const stack = smem + size_t(U)*p.nstage*sstride + tid*KSLOT;
     uint32_t const kb = blockIdx.x/uint32_t(p.nchunks), c = blockIdx.x-kb*uint32_t(p.nchunks);
-    KIdx b;
+    KIdx b; b.i[0] = 0;
     if (p.rankB>0) decompB(p, kb, b);
     int64_t const start = int64_t(c)*p.chunk_len;
     int64_t const end = start+p.chunk_len<p.nvecA ? start+p.chunk_len : p.nvecA;
@@ -89,18 +89,15 @@ ply_fold_inner_kernel(const __grid_constant__ KParams p, const __grid_constant__
 #pragma unroll
     for (int j=0; j<V; ++j) acc[j] = W(p.identity);
     for (int64_t g0 = start; g0<end; g0 += per) {
+        KIdx a[U];
         int nvalid[U];
 #pragma unroll
         for (int u=0; u<U; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK + tid;
             nvalid[u] = 0;
-            if (g<end) {
-                KIdx a; decompA(p, g, a);
-                int64_t const rem = p.len0-a.e0;
-                nvalid[u] = rem<V ? int(rem) : V;
-                stage_vector<W>(p, a, b, stage + size_t(u)*p.nstage*sstride, sstride, CpAsync {});
-            }
+            if (g<end) { decompA(p, g, a[u]); int64_t const rem = p.len0-a[u].e0; nvalid[u] = rem<V ? int(rem) : V; }
         }
+        stage_group<W, U, U, 1>(p, a, &b, nvalid, stage, sstride, CpAsync {});
         cp_async_wait_all();
         W t[U][V];
         interp<W, U>(p, stage, stack, sstride, t);
@@ -137,16 +134,18 @@ ply_fold_outer_kernel(const __grid_constant__ KParams p, const __grid_constant__
 #pragma unroll
     for (int j=0; j<V; ++j) acc[j] = W(p.identity);
     if (valid) {
+        int64_t const rem0 = p.len0-a.e0;
+        int const nv = rem0<V ? int(rem0) : V;
         for (int64_t r = r0; r<r1; r += U) {
+            KIdx b[U];
+            int nvalid[U];
 #pragma unroll
-            for (int u=0; u<U; ++u) {
-                if (r+u<r1) { KIdx b; decompB(p, r+u, b); stage_vector<W>(p, a, b, stage + size_t(u)*p.nstage*sstride, sstride, CpAsync {}); }
-            }
+            for (int u=0; u<U; ++u) { nvalid[u] = 0; if (r+u<r1) { decompB(p, r+u, b[u]); nvalid[u] = nv; } }
+            stage_group<W, U, 1, U>(p, &a, b, nvalid, stage, sstride, CpAsync {});
             cp_async_wait_all();
             W t[U][V];
             interp<W, U>(p, stage, stack, sstride, t);
-            int const nu = int(r1-r<U ? r1-r : U);
-            group_combine<W, U>(p.fold_op, p.acc_type, acc, t, [&](int u, int) { return u<nu; });
+            group_combine<W, U>(p.fold_op, p.acc_type, acc, t, [&](int u, int) { return nvalid[u]>0; });
         }
         int64_t const rem = p.len0-a.e0;
         int64_t row = 0;
@@ -199,7 +198,7 @@ void launch_count_add(int64_t n) { g_launches += n; }
 template <class K> static cudaError_t
 set_smem(K kernel, size_t smem)
 {
-    if (smem>48*1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (smem>32*1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     return cudaSuccess;
 }
 

@@ -36,7 +36,7 @@ sim_run(Plan & plan)
     if (p.mode==K_MAP) {
         for (int64_t g=0; g<p.nvecA; ++g) {
             decompA(p, g, a);
-            stage_vector<W>(p, a, b, stage, ss, HostCopy {});
+            { int nv = int(std::min<int64_t>(V, p.len0-a.e0)); stage_group<W, 1, 1, 1>(p, &a, &b, &nv, stage, ss, HostCopy {}); }
             W t[1][V];
             interp<W, 1>(p, stage, stack, ss, t);
             store_vector<W>(p, a, t[0]);
@@ -49,7 +49,7 @@ sim_run(Plan & plan)
                 W r = W(p.identity);
                 for (int64_t g=start; g<end; ++g) {
                     decompA(p, g, a);
-                    stage_vector<W>(p, a, b, stage, ss, HostCopy {});
+                    { int nv = int(std::min<int64_t>(V, p.len0-a.e0)); stage_group<W, 1, 1, 1>(p, &a, &b, &nv, stage, ss, HostCopy {}); }
                     W t[1][V];
                     interp<W, 1>(p, stage, stack, ss, t);
                     for (int j=0; j<V; ++j) { if (j<p.len0-a.e0) r = combine<W>(p.fold_op, p.acc_type, r, t[0][j]); }
@@ -68,7 +68,7 @@ sim_run(Plan & plan)
                 for (int j=0; j<V; ++j) acc[j] = W(p.identity);
                 for (int64_t r=r0; r<r1; ++r) {
                     decompB(p, r, b);
-                    stage_vector<W>(p, a, b, stage, ss, HostCopy {});
+                    { int nv = int(std::min<int64_t>(V, p.len0-a.e0)); stage_group<W, 1, 1, 1>(p, &a, &b, &nv, stage, ss, HostCopy {}); }
                     W t[1][V];
                     interp<W, 1>(p, stage, stack, ss, t);
                     group_combine<W, 1>(p.fold_op, p.acc_type, acc, t, [](int, int) { return true; });
@@ -105,7 +105,18 @@ racu_sim_run(racu_desc const * d, int redop, void * reduce_out)
 {
     Plan & plan = g_sim_plan;
     plan = Plan {};
-    if (int e = make_plan(d, redop, reduce_out, plan, g_sim_err)) return e;
+    if (int e = make_plan(d, redop, reduce_out, plan, g_sim_err)) {
+        if (e!=RACU_ERR_PEEL) return e;
+        if (!can_peel(d, reduce_out!=nullptr)) return RACU_ERR_UNSUPPORTED;
+        Shape sh;
+        if (int e2 = agree(d, sh, g_sim_err)) return e2;
+        racu_desc sub;
+        for (int64_t i=0; i<sh.len[0]; ++i) {
+            peel_axis0(*d, i, sub);
+            if (int e2 = racu_sim_run(&sub, redop, reduce_out)) return e2;
+        }
+        return RACU_OK;
+    }
     if (plan.empty) {
         if (plan.fill_identity) std::memcpy(reduce_out, &plan.kp.identity, dtype_size(plan.kp.acc_type));
         return RACU_OK;

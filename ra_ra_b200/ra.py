@@ -620,7 +620,7 @@ def flatten(e, dst=None, assign=abi.ASSIGN_SET, ex=None):
             emit(n.op, n.optype, n.arg, n.aux)
 
     if dst is not None:
-        d.dst = view_operand(dst)
+        d.dst = once(view_key(dst), lambda: view_operand(dst))
     else:
         d.dst = -1
     d.assign = assign
