@@ -54,7 +54,7 @@ run_plan(racu_desc const * d, int redop, void * reduce_out, cudaStream_t stream)
     void * partial = nullptr;
     if (plan.partial_bytes) {
         if (cudaError_t e = cudaMallocAsync(&partial, plan.partial_bytes, stream)) return cuda_fail(e, "cudaMallocAsync");
-        plan.kp.partial = partial; plan.fp.partial = partial;
+        plan.kp.partial = partial; plan.fp.partial = partial; plan.sp.partial = partial;
     }
     plan.fp.identity = plan.kp.identity;
     g_kernel = plan.kernel;

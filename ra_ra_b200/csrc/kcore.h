@@ -18,7 +18,7 @@
 
 #if defined(__CUDACC__)
 #define RACU_HD __host__ __device__ __forceinline__
-#define RACU_HD_NOINLINE __host__ __device__ __noinline__
+#define RACU_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define RACU_HD inline
 #define RACU_HD_NOINLINE inline

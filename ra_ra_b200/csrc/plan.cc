@@ -12,6 +12,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -279,6 +280,79 @@ peel_axis0(racu_desc const & d, int64_t i, racu_desc & out)
         for (int k=0; k+1<p.rank; ++k) { p.len[k] = p.len[k+1]; p.stride[k] = p.stride[k+1]; }
         --p.rank;
     }
+}
+
+// Does the canonical program have a compile-time specialised kernel (static_progs.h)? Fills plan.sp if so.
+static void
+match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold)
+{
+    KParams const & kp = plan.kp;
+    plan.is_static = false;
+    if (std::getenv("RACU_NO_STATIC")) return;
+    if (kp.rankA!=1 || int(prog.size())>SP_MAXINS) return;
+    if (kp.mode==K_MAP && kp.rankB!=0) return;
+    if (kp.mode==K_FOLD_OUTER && kp.rankB!=1) return;
+    int const T = prog[0].type;
+    if (T!=RACU_F32 && T!=RACU_F64 && T!=RACU_I32) return;
+    int const V = T==RACU_F64 ? 2 : 4;
+    // roles by first appearance
+    int role_of[RACU_MAX_OPND], nrole = 0, yrole = -1;
+    for (int o=0; o<RACU_MAX_OPND; ++o) role_of[o] = -1;
+    SIns seq[SP_MAXINS];
+    for (size_t pc=0; pc<prog.size(); ++pc) {
+        racu_ins const & i = prog[pc];
+        if (i.type!=T || i.op==RACU_OP_CAST) return;
+        if (i.op==RACU_OP_PUSH) {
+            if (role_of[i.arg]<0) {
+                if (nrole>=SP_MAXIN) return;
+                KOpnd const & k = kp.opnd[i.arg];
+                if (k.dtype!=T || !(k.stage==S_VEC || k.stage==S_NONE)) return;
+                if (!fold && int(i.arg)==dst) yrole = nrole;
+                role_of[i.arg] = nrole++;
+            }
+            seq[pc] = sP(role_of[i.arg]);
+        } else {
+            seq[pc] = sO(i.op);
+        }
+    }
+    int id = -1;
+    for (int c=0; c<SP_COUNT && id<0; ++c) {
+        SProg const P = static_prog(c);
+        if (P.n!=int(prog.size()) || P.nin!=nrole || P.yrole!=yrole || P.fold!=fold) continue;
+        bool same = true;
+        for (int pc=0; pc<P.n && same; ++pc) same = P.ins[pc].op==seq[pc].op && (P.ins[pc].op!=RACU_OP_PUSH || P.ins[pc].arg==seq[pc].arg);
+        if (same) id = c;
+    }
+    if (id<0) return;
+    SParams & sp = plan.sp;
+    std::memset(&sp, 0, sizeof(sp));
+    if (fold) {
+        if (kp.acc_type!=T || plan.fp.dst_dtype!=T) return;
+        if (kp.fold_op==RACU_ASSIGN_SET) return;
+        if ((kp.nk>1 || kp.mode==K_FOLD_OUTER) && 0!=kp.len0%V) return;
+    } else {
+        KOpnd const & y = kp.opnd[dst];
+        if (y.dtype!=T || y.stage!=S_VEC) return;
+        sp.dst = reinterpret_cast<void *>(uintptr_t(y.base));
+    }
+    sp.id = id; sp.dtype = T; sp.mode = kp.mode; sp.fold_op = kp.fold_op; sp.nchunks = kp.nchunks; sp.rankB = kp.rankB;
+    sp.identity = kp.identity; sp.n = kp.len0; sp.nB = kp.nB; sp.chunk_len = kp.chunk_len; sp.nk = kp.nk;
+    for (int j=0; j<KGR; ++j) sp.dB[j] = kp.dB[j];
+    for (int o=0; o<kp.nopnd; ++o) {
+        int r = role_of[o];
+        if (r<0) continue;
+        KOpnd const & k = kp.opnd[o];
+        sp.scalar[r] = k.stage==S_NONE;
+        if (k.stage==S_NONE) { // scalar bits in T
+            if (T==RACU_F32) sp.in[r] = f32_bits(float(bits_f64(k.base))); else if (T==RACU_F64) sp.in[r] = k.base; else sp.in[r] = uint32_t(int32_t(int64_t(k.base)));
+        } else {
+            sp.in[r] = k.base;
+        }
+        for (int j=0; j<KGR; ++j) sp.sB[r][j] = k.sB[j];
+    }
+    plan.is_static = true;
+    static const char * names[3] = {"sflat_map", "sflat_fold_inner", "sflat_fold_outer"};
+    plan.kernel = names[kp.mode];
 }
 
 int
@@ -646,6 +720,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
         f.len0 = kn>0 ? w.len[k0] : 1;
         if (kn>1 && f.len0>=(int64_t(1)<<31)) { err = "axis longer than 2^31 after collapsing"; return RACU_ERR_UNSUPPORTED; }
     }
+    match_static(plan, prog, dst, fold);
     return RACU_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <string>
 #include "kcore.h"
+#include "static_progs.h"
 
 namespace racu {
 
@@ -19,6 +20,8 @@ struct Plan
     FinishParams fp;
     size_t partial_bytes = 0;
     const char * kernel = "";
+    bool is_static = false;      // a compile-time specialised kernel matched (static_kernels.cu)
+    SParams sp;
 };
 
 // What the expression computes, before any layout decision.

@@ -208,6 +208,10 @@ launch_plan(Plan const & plan, cudaStream_t stream)
     KParams const & p = plan.kp;
     cudaError_t e = cudaSuccess;
     dim3 grid(plan.grid_x, plan.grid_y), block(KBLOCK);
+    if (plan.is_static) {
+        if ((e = launch_static(plan, stream))) return e;
+        ++g_launches;
+    } else {
 #define RACU_LAUNCH_U(KERNEL, WT, UU, ...) \
     do { if ((e = set_smem(KERNEL<WT, UU>, plan.smem))) return e; KERNEL<WT, UU><<<grid, block, plan.smem, stream>>>(__VA_ARGS__); } while (0)
 #define RACU_LAUNCH_W(KERNEL, WT, ...) \
@@ -225,6 +229,7 @@ launch_plan(Plan const & plan, cudaStream_t stream)
 #undef RACU_LAUNCH
     ++g_launches;
     if ((e = cudaGetLastError())) return e;
+    }
     if (plan.need_finish) {
         FinishParams const & f = plan.fp;
         int64_t threads = f.per_warp ? f.nk*32 : f.nk;

@@ -155,3 +155,41 @@ def test_stencil3d_bitexact(n, dt, exc):
         assert olib().oracle_stencil_raw(C.byref(s)) == 0
         ref, refn = refn, ref
     assert np.array_equal(A.numpy(), ref) and np.array_equal(An.numpy(), refn)
+
+
+def test_static_specialisations_are_taken_and_bitexact(exc):
+    """Flat single-type programs run on the compile-time specialised kernels (static_kernels.cu); same bits as the oracle."""
+    rng = np.random.default_rng(77)
+    for dt in (np.float32, np.float64):
+        for n in (4096, 100003, (1 << 20) + 2):
+            a, b, c = (rng.uniform(-1, 1, n).astype(dt) for _ in range(3))
+            t = dt(0.37)
+            outs = []
+            for ex in (OracleExecutor(), exc):
+                A, B, Cc = ex.from_numpy(a), ex.from_numpy(b), ex.from_numpy(c)
+                kernels = []
+                B += A * Cc
+                kernels.append(ex.last_kernel() if ex.name == "cuda" else None)
+                B -= t * A          # cghs: g -= t*p
+                kernels.append(ex.last_kernel() if ex.name == "cuda" else None)
+                B.assign(B * t + Cc)  # cghs: r = r*gam + g
+                kernels.append(ex.last_kernel() if ex.name == "cuda" else None)
+                Cc.assign(A)
+                Cc /= B
+                outs.append((snapshot(ex, B), snapshot(ex, Cc)))
+                if ex.name == "cuda":
+                    assert all(k == "sflat_map" for k in kernels), kernels
+                    ra.sum(A)
+                    assert ex.last_kernel() == "sflat_fold_inner"
+            assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    # row / column sums of a contiguous matrix take the static fold kernels too
+    M = exc.from_numpy(rng.uniform(-1, 1, (512, 1024)).astype(np.float32))
+    c = exc.from_numpy(np.zeros(512, dtype=np.float32))
+    c += M
+    assert exc.last_kernel() == "sflat_fold_inner"
+    r = exc.from_numpy(np.zeros(1024, dtype=np.float32))
+    rr = r(ra.insert(1))
+    rr += M
+    assert exc.last_kernel() == "sflat_fold_outer"
+    Mn = M.numpy().astype(np.float64)
+    assert np.allclose(c.numpy(), Mn.sum(axis=1), rtol=1e-5, atol=1e-4) and np.allclose(r.numpy(), Mn.sum(axis=0), rtol=1e-5, atol=1e-4)
