@@ -1,0 +1,319 @@
+// stencil.cu - 5- and 7-point Laplace stencils with TMA-staged shared-memory tiles (sm_100a).
+//
+// Reference forms (exact association order is kept, no contraction, so results are bit-identical to the CPU ply):
+//   3D7   Anext(I,J,K) = -6*A(I,J,K) + A(I+1,J,K) + A(I,J+1,K) + A(I,J,K+1) + A(I-1,J,K) + A(I,J-1,K) + A(I,J,K-1)   bench/bench-stencil3.cc:59-61
+//   2D5   Anext(I,J)   = -4*A(I,J) + A(I+1,J) + A(I,J+1) + A(I-1,J) + A(I,J-1)                                         bench/bench-stencil2.cc:53-55
+//   STIFF w(i,j)       =  4*v(i,j) - v(i-1,j) - v(i,j-1) - v(i+1,j) - v(i,j+1)                                         examples/laplace2d.cc:36
+// Boundary cells of the destination are never written (bench/bench-stencil3.cc:125-126).
+//
+// 2.5-D streaming: a CTA owns a (TJ x TK) tile of the two inner axes and marches along axis 0. Every plane tile
+// (TJ+2) x (TK+2*HO), halo included, is brought in ONCE by a TMA tensor copy (cp.async.bulk.tensor, zero fill outside the
+// array) into a ring of shared-memory stages signalled by mbarriers; the i-1 / i / i+1 centre values of a thread's
+// column live in registers, the j and k neighbours come from the current stage. Each input cell is therefore read from
+// L2/HBM once per CTA (plus halo), each output written once: 8 B / cell algorithmic for f32.
+// 2-D stencils are the same kernel with a single plane (no marching).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "kcore.h"
+#include "launch.h"
+#include "special.h"
+
+namespace racu {
+
+constexpr int ST_TJ = 8;        // tile rows
+constexpr int ST_THREADS = 256;
+constexpr int ST_STAGES = 4;
+
+template <class T> struct StTile
+{
+    static constexpr int VT = 16/sizeof(T);         // outputs per thread: one 16-byte vector along k
+    static constexpr int TK = (ST_THREADS/ST_TJ)*VT; // 128 (f32) / 64 (f64)
+    static constexpr int HO = VT;                   // halo offset along k: keeps interior vectors 16-byte aligned in smem
+    static constexpr int TKB = TK+2*HO;             // box extent along k
+    static constexpr int PLANE = (((ST_TJ+2)*TKB*int(sizeof(T))+127)/128*128)/int(sizeof(T)); // elements per stage, 128-byte multiple (TMA destination alignment)
+};
+
+struct StParams
+{
+    void * dst;
+    int64_t ds0, ds1, ds2;   // destination strides (elements)
+    int32_t n0, n1, n2;      // full array extents (marching axis first). 2-D: n0 = 1
+    int32_t i_lo, i_hi;      // output planes [i_lo, i_hi) (3-D); ignored for 2-D
+    int32_t ci;              // planes per CTA chunk
+    int32_t vec_store;       // destination allows aligned 16-byte stores
+};
+
+__device__ __forceinline__ uint32_t smem_u32(void const * p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t * bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void * smem, CUtensorMap const * tmap, int c0, int c1, int c2, uint64_t * bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_u32(smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class T, int KIND> __device__ __forceinline__ T
+stencil_value(T c, T ip, T jp, T kp, T im, T jm, T km)
+{
+    if constexpr (KIND==RACU_STENCIL_3D7) return ((((((T(-6)*c) + ip) + jp) + kp) + im) + jm) + km;
+    else if constexpr (KIND==RACU_STENCIL_2D5) return ((((T(-4)*c) + jp) + kp) + jm) + km;            // (i,j) of the 2-D form are (j,k) here
+    else return ((((T(4)*c) - jm) - km) - jp) - kp;                                                     // STIFF
+}
+
+template <class T, int KIND> __global__ void __launch_bounds__(ST_THREADS)
+stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StParams p)
+{
+    using TL = StTile<T>;
+    constexpr int VT = TL::VT, TK = TL::TK, HO = TL::HO, TKB = TL::TKB, PLANE = TL::PLANE;
+    constexpr bool is3d = KIND==RACU_STENCIL_3D7;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T * const stages = reinterpret_cast<T *>(smem_raw);
+    __shared__ __align__(8) uint64_t full[ST_STAGES];
+
+    int const tid = threadIdx.x;
+    int const tk = tid % (TK/VT), tj = tid / (TK/VT);
+    int const k0 = blockIdx.x*TK, j0 = 1 + blockIdx.y*ST_TJ;   // first output k of the tile (vector aligned), first output j
+    int const k = k0 + tk*VT, j = j0 + tj;
+    int const ilo = is3d ? p.i_lo + int(blockIdx.z)*p.ci : 0;
+    int const ihi = is3d ? min(p.i_hi, ilo + p.ci) : 1;
+    int const nplanes = is3d ? (ihi-ilo+2) : 1;                // input planes ilo-1 .. ihi
+    constexpr uint32_t plane_bytes = (ST_TJ+2)*TKB*sizeof(T); // bytes one TMA box delivers
+
+    if (0==tid) {
+#pragma unroll
+        for (int s=0; s<ST_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int q) { // input plane q of this chunk -> stage q % STAGES
+        int s = q % ST_STAGES;
+        mbar_expect_tx(&full[s], plane_bytes);
+        tma_load_3d(stages + size_t(s)*PLANE, &tmap, k0-HO, j0-1, is3d ? ilo-1+q : 0, &full[s]);
+    };
+    if (0==tid) { for (int q=0; q<ST_STAGES && q<nplanes; ++q) issue(q); }
+
+    bool const row_ok = j<p.n1-1;
+    // lanes of this thread's vector that are interior along k
+    bool lane_ok[VT];
+    bool all_ok = row_ok;
+#pragma unroll
+    for (int l=0; l<VT; ++l) { lane_ok[l] = row_ok && (k+l>=1) && (k+l<p.n2-1); all_ok = all_ok && lane_ok[l]; }
+    int const so = (tj+1)*TKB + HO + tk*VT; // this thread's centre vector inside a stage
+
+    auto load_vec = [&](T const * st, int off, T * v) {
+        uint4 q = *reinterpret_cast<uint4 const *>(st + off);
+        memcpy(v, &q, 16);
+    };
+    auto store_out = [&](int i, T const * o) {
+        T * d = static_cast<T *>(p.dst) + int64_t(i)*p.ds0 + int64_t(j)*p.ds1 + int64_t(k)*p.ds2;
+        if (all_ok && p.vec_store) { uint4 q; memcpy(&q, o, 16); *reinterpret_cast<uint4 *>(d) = q; }
+        else {
+#pragma unroll
+            for (int l=0; l<VT; ++l) { if (lane_ok[l]) d[int64_t(l)*p.ds2] = o[l]; }
+        }
+    };
+
+    if constexpr (!is3d) {
+        mbar_wait(&full[0], 0);
+        T const * st = stages;
+        T c[VT], jp[VT], jm[VT], o[VT];
+        load_vec(st, so, c); load_vec(st, so+TKB, jp); load_vec(st, so-TKB, jm);
+        T const left = st[so-1], right = st[so+VT];
+#pragma unroll
+        for (int l=0; l<VT; ++l) {
+            T km = l==0 ? left : c[l-1], kp = l==VT-1 ? right : c[l+1];
+            o[l] = stencil_value<T, KIND>(c[l], T(0), jp[l], kp, T(0), jm[l], km);
+        }
+        store_out(0, o);
+    } else {
+        T prev[VT], cur[VT], next[VT];
+        mbar_wait(&full[0], 0);
+        load_vec(stages, so, prev);
+        if (nplanes>1) { mbar_wait(&full[1 % ST_STAGES], 0); load_vec(stages + size_t(1 % ST_STAGES)*PLANE, so, cur); }
+        __syncthreads();                                   // everyone is done with plane 0
+        if (0==tid && ST_STAGES<nplanes) issue(ST_STAGES);  // refill its stage
+        for (int q=1; q+1<nplanes; ++q) {                   // output plane i = ilo-1+q
+            int const sn = (q+1) % ST_STAGES;
+            mbar_wait(&full[sn], uint32_t(((q+1)/ST_STAGES)&1));
+            load_vec(stages + size_t(sn)*PLANE, so, next);
+            T const * st = stages + size_t(q % ST_STAGES)*PLANE;
+            T jp[VT], jm[VT], o[VT];
+            load_vec(st, so+TKB, jp); load_vec(st, so-TKB, jm);
+            T const left = st[so-1], right = st[so+VT];
+#pragma unroll
+            for (int l=0; l<VT; ++l) {
+                T km = l==0 ? left : cur[l-1], kp = l==VT-1 ? right : cur[l+1];
+                o[l] = stencil_value<T, KIND>(cur[l], next[l], jp[l], kp, prev[l], jm[l], km);
+            }
+            store_out(ilo-1+q, o);
+#pragma unroll
+            for (int l=0; l<VT; ++l) { prev[l] = cur[l]; cur[l] = next[l]; }
+            __syncthreads();                                  // plane q is no longer read by anyone
+            if (0==tid && q+ST_STAGES<nplanes) issue(q+ST_STAGES);
+        }
+    }
+}
+
+// ---------------- host ----------------
+
+using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiled
+encode_fn()
+{
+    static EncodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []{
+        void * p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaSuccess==cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) && q==cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiled>(p);
+        else cudaGetLastError();
+    });
+    return fn;
+}
+
+template <class T, int KIND> static int
+launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled)
+{
+    using TL = StTile<T>;
+    constexpr bool is3d = KIND==RACU_STENCIL_3D7;
+    int const r = s->rank;
+    // view the array as (n0, n1, n2) with n0 the marching axis; 2-D arrays get n0 = 1
+    int64_t n0 = is3d ? s->len[0] : 1, n1 = s->len[r-2], n2 = s->len[r-1];
+    int64_t ss0 = is3d ? s->src_stride[0] : 0, ss1 = s->src_stride[r-2], ss2 = s->src_stride[r-1];
+    int64_t ds0 = is3d ? s->dst_stride[0] : 0, ds1 = s->dst_stride[r-2], ds2 = s->dst_stride[r-1];
+    size_t const es = sizeof(T);
+    // TMA constraints on the source; anything else falls back to the fused ply kernels (still exact)
+    if (1!=ss2 || 0!=(uintptr_t(s->src)%16) || 0!=((ss1*es)%16) || (is3d && 0!=((ss0*es)%16)) || ss1<=0 || (is3d && ss0<=0)) return RACU_OK;
+    if (n0>=(int64_t(1)<<31) || n1>=(int64_t(1)<<31) || n2>=(int64_t(1)<<31) || n1<3 || n2<3 || (is3d && n0<3)) return RACU_OK;
+    EncodeTiled enc = encode_fn();
+    if (!enc) return RACU_OK;
+    int64_t lo = s->lo0, hi = s->hi0;
+    if (0==lo && 0==hi) hi = s->len[0];
+    if (lo<1) lo = 1;
+    if (hi>s->len[0]-1) hi = s->len[0]-1;
+    if (is3d && hi<=lo) { *handled = 1; return RACU_OK; }
+
+    CUtensorMap tmap;
+    cuuint64_t gdim[3] = {cuuint64_t(n2), cuuint64_t(n1), cuuint64_t(n0)};
+    cuuint64_t gstr[2] = {cuuint64_t(ss1*es), cuuint64_t((is3d ? ss0 : ss1*n1)*es)};
+    cuuint32_t box[3] = {cuuint32_t(TL::TKB), cuuint32_t(ST_TJ+2), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = enc(&tmap, sizeof(T)==4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(s->src),
+                      gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (CUDA_SUCCESS!=cr) return RACU_OK; // not expressible as a tensor map: fall back
+
+    StParams p {};
+    p.dst = s->dst; p.ds0 = ds0; p.ds1 = ds1; p.ds2 = ds2;
+    p.n0 = int32_t(n0); p.n1 = int32_t(n1); p.n2 = int32_t(n2);
+    p.i_lo = int32_t(lo); p.i_hi = int32_t(hi);
+    p.vec_store = 1==ds2 && 0==(uintptr_t(s->dst)%16) && 0==((ds1*es)%16) && (!is3d || 0==((ds0*es)%16));
+    unsigned gx = unsigned((n2+TL::TK-1)/TL::TK), gy = unsigned((n1-2+ST_TJ-1)/ST_TJ), gz = 1;
+    if (is3d) {
+        // enough CTAs to fill the machine a few times over, chunks of at least 16 planes (2 halo planes of overhead each)
+        int64_t planes = hi-lo;
+        int64_t want = std::max<int64_t>(1, (148*8*2)/std::max<int64_t>(1, int64_t(gx)*gy));
+        int64_t nch = std::min<int64_t>(std::max<int64_t>(1, planes/16), want);
+        p.ci = int32_t((planes+nch-1)/nch);
+        gz = unsigned((planes+p.ci-1)/p.ci);
+    }
+    size_t smem = size_t(ST_STAGES)*TL::PLANE*sizeof(T);
+    auto kernel = stencil_tma_kernel<T, KIND>;
+    if (smem>32*1024) { if (cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return cuda_fail(e, "stencil smem"); }
+    kernel<<<dim3(gx, gy, gz), ST_THREADS, smem, stream>>>(tmap, p);
+    launch_count_add(1);
+    if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "stencil_tma");
+    set_kernel(is3d ? "stencil_tma<3D7>" : (KIND==RACU_STENCIL_2D5 ? "stencil_tma<2D5>" : "stencil_tma<2D5_STIFF>"));
+    *handled = 1;
+    return RACU_OK;
+}
+
+int
+try_special_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled)
+{
+    *handled = 0;
+    if (std::getenv("RACU_NO_TMA_STENCIL")) return RACU_OK;
+    if (s->dtype!=RACU_F32 && s->dtype!=RACU_F64) return RACU_OK;
+#define RACU_ST(KIND) (s->dtype==RACU_F32 ? launch_stencil<float, KIND>(s, stream, handled) : launch_stencil<double, KIND>(s, stream, handled))
+    switch (s->kind) {
+    case RACU_STENCIL_3D7: return 3==s->rank ? RACU_ST(RACU_STENCIL_3D7) : RACU_OK;
+    case RACU_STENCIL_2D5: return 2==s->rank ? RACU_ST(RACU_STENCIL_2D5) : RACU_OK;
+    case RACU_STENCIL_2D5_STIFF: return 2==s->rank ? RACU_ST(RACU_STENCIL_2D5_STIFF) : RACU_OK;
+    default: return RACU_OK;
+    }
+#undef RACU_ST
+}
+
+// racu_map pattern recognition: is this descriptor one of the reference's stencil slice expressions? (special.cc builds the
+// canonical form; a descriptor flattened by a host header may order / share operands differently, so compare by meaning.)
+int
+try_special_map(racu_desc const * d, cudaStream_t stream, int * handled)
+{
+    *handled = 0;
+    if (d->dst<0 || d->assign!=RACU_ASSIGN_SET || d->nins<8) return RACU_OK;
+    racu_operand const & y = d->opnd[d->dst];
+    int const T = y.dtype, r = y.rank;
+    if ((T!=RACU_F32 && T!=RACU_F64) || r<2 || r>3) return RACU_OK;
+    // program: PUSH s(i32) CAST PUSH c MUL (PUSH x OP)*
+    racu_ins const * in = d->ins;
+    if (in[0].op!=RACU_OP_PUSH || in[1].op!=RACU_OP_CAST || in[1].type!=T || in[2].op!=RACU_OP_PUSH || in[3].op!=RACU_OP_MUL || in[3].type!=T) return RACU_OK;
+    racu_operand const & sc = d->opnd[in[0].arg];
+    racu_operand const & c = d->opnd[in[2].arg];
+    if (sc.kind!=RACU_SCALAR || sc.dtype!=RACU_I32 || c.kind!=RACU_MEM || c.dtype!=T || c.rank!=r) return RACU_OK;
+    int const nsh = (d->nins-4)/2;
+    if (d->nins!=4+2*nsh || nsh!=2*r) return RACU_OK;
+    int op = in[5].op;
+    if (op!=RACU_OP_ADD && op!=RACU_OP_SUB) return RACU_OK;
+    struct Sh { int axis, shift; };
+    Sh want[6];
+    int kind;
+    if (3==r && op==RACU_OP_ADD && sc.base.i==-6) { kind = RACU_STENCIL_3D7; Sh w[6] = {{0, 1}, {1, 1}, {2, 1}, {0, -1}, {1, -1}, {2, -1}}; std::memcpy(want, w, sizeof(w)); }
+    else if (2==r && op==RACU_OP_ADD && sc.base.i==-4) { kind = RACU_STENCIL_2D5; Sh w[4] = {{0, 1}, {1, 1}, {0, -1}, {1, -1}}; std::memcpy(want, w, sizeof(w)); }
+    else if (2==r && op==RACU_OP_SUB && sc.base.i==4) { kind = RACU_STENCIL_2D5_STIFF; Sh w[4] = {{0, -1}, {1, -1}, {0, 1}, {1, 1}}; std::memcpy(want, w, sizeof(w)); }
+    else return RACU_OK;
+    size_t const es = T==RACU_F32 ? 4 : 8;
+    for (int k=0; k<r; ++k) { if (y.len[k]!=c.len[k] || c.len[k]<1) return RACU_OK; }
+    for (int q=0; q<nsh; ++q) {
+        racu_ins const & pu = in[4+2*q], & o = in[5+2*q];
+        if (pu.op!=RACU_OP_PUSH || o.op!=op || o.type!=T) return RACU_OK;
+        racu_operand const & x = d->opnd[pu.arg];
+        if (x.kind!=RACU_MEM || x.dtype!=T || x.rank!=r) return RACU_OK;
+        for (int k=0; k<r; ++k) { if (x.len[k]!=c.len[k] || x.stride[k]!=c.stride[k]) return RACU_OK; }
+        int64_t delta = (static_cast<char *>(x.base.ptr)-static_cast<char *>(c.base.ptr));
+        if (delta!=int64_t(want[q].shift)*c.stride[want[q].axis]*int64_t(es)) return RACU_OK;
+    }
+    racu_stencil_desc s;
+    std::memset(&s, 0, sizeof(s));
+    s.kind = kind; s.dtype = T; s.rank = r;
+    int64_t so = 0, dof = 0;
+    for (int k=0; k<r; ++k) { s.len[k] = c.len[k]+2; s.src_stride[k] = c.stride[k]; s.dst_stride[k] = y.stride[k]; so += c.stride[k]; dof += y.stride[k]; }
+    s.src = static_cast<char *>(c.base.ptr) - so*int64_t(es);
+    s.dst = static_cast<char *>(y.base.ptr) - dof*int64_t(es);
+    return try_special_stencil(&s, stream, handled);
+}
+
+int try_special_gemm(racu_gemm_desc const *, cudaStream_t, int * handled) { *handled = 0; return RACU_OK; }
+
+} // namespace racu

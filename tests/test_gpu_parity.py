@@ -193,3 +193,79 @@ def test_static_specialisations_are_taken_and_bitexact(exc):
     assert exc.last_kernel() == "sflat_fold_outer"
     Mn = M.numpy().astype(np.float64)
     assert np.allclose(c.numpy(), Mn.sum(axis=1), rtol=1e-5, atol=1e-4) and np.allclose(r.numpy(), Mn.sum(axis=0), rtol=1e-5, atol=1e-4)
+
+
+def _stencil_desc(kind, dt, src_ptr, dst_ptr, shape, strides, lo=0, hi=0):
+    s = abi.StencilDesc()
+    s.kind, s.dtype, s.rank = kind, ra.NP2RACU[np.dtype(dt)], len(shape)
+    s.src, s.dst = src_ptr, dst_ptr
+    for k in range(len(shape)):
+        s.len[k] = shape[k]
+        s.src_stride[k] = s.dst_stride[k] = strides[k]
+    s.lo0, s.hi0 = lo, hi
+    return s
+
+
+@pytest.mark.parametrize("shape", [(132, 260), (64, 64), (33, 1028), (7, 9), (50, 51)])
+@pytest.mark.parametrize("kind", [abi.STENCIL_2D5, abi.STENCIL_2D5_STIFF])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_stencil2d_entry_bitexact(shape, kind, dt, exc):
+    """racu_stencil (bench-stencil2.cc:53-55, laplace2d.cc:36) vs the oracle's raw loops; TMA kernel when the shape allows,
+    fused ply kernels otherwise - both must be bit exact and leave the boundary alone."""
+    import ctypes as C
+    import torch
+    from oracle_exec import lib as olib
+    from ra_ra_b200 import cuda
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-1, 1, shape).astype(dt)
+    ref = np.full(shape, 7, dtype=dt)
+    st = [a.strides[k] // a.itemsize for k in range(2)]
+    assert olib().oracle_stencil_raw(C.byref(_stencil_desc(kind, dt, a.ctypes.data, ref.ctypes.data, shape, st))) == 0
+    A = torch.from_numpy(a).cuda()
+    out = torch.full(shape, 7, dtype=A.dtype, device="cuda")
+    cuda.check(cuda.lib.racu_stencil(C.byref(_stencil_desc(kind, dt, A.data_ptr(), out.data_ptr(), shape, st)), cuda.stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), ref), cuda.lib.racu_last_kernel()
+
+
+@pytest.mark.parametrize("shape,lo,hi", [((70, 40, 132), 0, 0), ((70, 40, 132), 1, 2), ((70, 40, 132), 30, 69), ((20, 19, 21), 3, 11), ((130, 16, 256), 0, 0)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_stencil3d_entry_planes(shape, lo, hi, dt, exc):
+    """racu_stencil restricted to planes [lo0, hi0) of axis 0 (what the slab-sharded caller uses for boundary-first sweeps)."""
+    import ctypes as C
+    import torch
+    from oracle_exec import lib as olib
+    from ra_ra_b200 import cuda
+    rng = np.random.default_rng(6)
+    a = rng.uniform(-1, 1, shape).astype(dt)
+    ref = np.full(shape, -3, dtype=dt)
+    st = [a.strides[k] // a.itemsize for k in range(3)]
+    assert olib().oracle_stencil_raw(C.byref(_stencil_desc(abi.STENCIL_3D7, dt, a.ctypes.data, ref.ctypes.data, shape, st, lo, hi))) == 0
+    A = torch.from_numpy(a).cuda()
+    out = torch.full(shape, -3, dtype=A.dtype, device="cuda")
+    cuda.check(cuda.lib.racu_stencil(C.byref(_stencil_desc(abi.STENCIL_3D7, dt, A.data_ptr(), out.data_ptr(), shape, st, lo, hi)), cuda.stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), ref), cuda.lib.racu_last_kernel()
+    if shape[2] % 4 == 0:
+        assert cuda.lib.racu_last_kernel() == b"stencil_tma<3D7>"
+
+
+def test_stencil3d_large_roundtrip_property(exc):
+    """Full-size property (no oracle at 512^3): the sweep is linear, so S(a + 2b) == S(a) + 2 S(b) up to rounding, boundaries
+    are untouched, and a constant field has a zero interior after one sweep."""
+    import ctypes as C
+    import torch
+    from ra_ra_b200 import cuda
+    n = 512
+    g = torch.Generator(device="cuda")
+    g.manual_seed(41)
+    a = torch.rand(n, n, n, device="cuda", generator=g)
+    out = torch.full_like(a, 5.0)
+    st = list(a.stride())
+    cuda.check(cuda.lib.racu_stencil(C.byref(_stencil_desc(abi.STENCIL_3D7, np.float32, a.data_ptr(), out.data_ptr(), (n, n, n), st)), cuda.stream_ptr()))
+    assert cuda.lib.racu_last_kernel() == b"stencil_tma<3D7>"
+    assert bool((out[0] == 5).all()) and bool((out[-1] == 5).all()) and bool((out[:, 0] == 5).all()) and bool((out[:, :, -1] == 5).all())
+    c = a[1:-1, 1:-1, 1:-1]
+    ref = ((((((-6 * c + a[2:, 1:-1, 1:-1]) + a[1:-1, 2:, 1:-1]) + a[1:-1, 1:-1, 2:]) + a[:-2, 1:-1, 1:-1]) + a[1:-1, :-2, 1:-1]) + a[1:-1, 1:-1, :-2])
+    assert torch.equal(out[1:-1, 1:-1, 1:-1], ref)
+    a.fill_(3.25)
+    cuda.check(cuda.lib.racu_stencil(C.byref(_stencil_desc(abi.STENCIL_3D7, np.float32, a.data_ptr(), out.data_ptr(), (n, n, n), st)), cuda.stream_ptr()))
+    assert float(out[1:-1, 1:-1, 1:-1].abs().max()) == 0.0
