@@ -58,7 +58,8 @@ run_plan(racu_desc const * d, int redop, void * reduce_out, cudaStream_t stream)
     }
     plan.fp.identity = plan.kp.identity;
     g_kernel = plan.kernel;
-    cudaError_t e = launch_plan(plan, stream);
+    cudaError_t e = cudaSuccess;
+    if (!try_transpose(plan, stream, e)) e = launch_plan(plan, stream);
     if (partial) { cudaError_t e2 = cudaFreeAsync(partial, stream); if (!e) e = e2; }
     if (e) return cuda_fail(e, plan.kernel);
     return RACU_OK;

@@ -289,12 +289,27 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
     KParams const & kp = plan.kp;
     plan.is_static = false;
     if (std::getenv("RACU_NO_STATIC")) return;
-    if (kp.rankA!=1 || int(prog.size())>SP_MAXINS) return;
-    if (kp.mode==K_MAP && kp.rankB!=0) return;
+    if (int(prog.size())>SP_MAXINS) return;
+    bool const map = kp.mode==K_MAP;
+    if (!map && kp.rankA!=1) return;
+    if (map && kp.rankB!=0) return;
     if (kp.mode==K_FOLD_OUTER && kp.rankB!=1) return;
     int const T = prog[0].type;
     if (T!=RACU_F32 && T!=RACU_F64 && T!=RACU_I32) return;
     int const V = T==RACU_F64 ? 2 : 4;
+    size_t const es = dtype_size(T);
+    // how a map operand can be read by the static kernel
+    auto map_kind = [&](KOpnd const & k) -> int {
+        if (k.stage==S_NONE) return SK_SCALAR;
+        if (k.kind!=RACU_MEM) return -1;
+        if (k.stage==S_VEC) return SK_VEC;
+        if (k.stage==S_BCAST) return SK_ROW;
+        if (-1==k.sA[0] && 0==((k.base-(V-1)*es)%16)) {
+            for (int j=1; j<kp.rankA; ++j) { if (0!=k.sA[j]%V) return -1; }
+            return SK_VECREV;
+        }
+        return -1;
+    };
     // roles by first appearance
     int role_of[RACU_MAX_OPND], nrole = 0, yrole = -1;
     for (int o=0; o<RACU_MAX_OPND; ++o) role_of[o] = -1;
@@ -306,7 +321,8 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
             if (role_of[i.arg]<0) {
                 if (nrole>=SP_MAXIN) return;
                 KOpnd const & k = kp.opnd[i.arg];
-                if (k.dtype!=T || !(k.stage==S_VEC || k.stage==S_NONE)) return;
+                if (k.dtype!=T) return;
+                if (map ? map_kind(k)<0 : !(k.stage==S_VEC || k.stage==S_NONE)) return;
                 if (!fold && int(i.arg)==dst) yrole = nrole;
                 role_of[i.arg] = nrole++;
             }
@@ -333,7 +349,11 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
     } else {
         KOpnd const & y = kp.opnd[dst];
         if (y.dtype!=T || y.stage!=S_VEC) return;
+        if (kp.rankA>1 && 0!=kp.len0%V) return; // rows must be whole vectors
         sp.dst = reinterpret_cast<void *>(uintptr_t(y.base));
+        sp.rankA = kp.rankA; sp.vpr = kp.vpr; sp.vprdiv = kp.vprdiv;
+        sp.nvec = 1==kp.rankA ? kp.len0/V : kp.nvecA;
+        for (int j=0; j<KGR; ++j) { sp.dA[j] = kp.dA[j]; sp.dsA[j] = j<kp.rankA ? y.sA[j] : 0; }
     }
     sp.id = id; sp.dtype = T; sp.mode = kp.mode; sp.fold_op = kp.fold_op; sp.nchunks = kp.nchunks; sp.rankB = kp.rankB;
     sp.identity = kp.identity; sp.n = kp.len0; sp.nB = kp.nB; sp.chunk_len = kp.chunk_len; sp.nk = kp.nk;
@@ -343,12 +363,13 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
         if (r<0) continue;
         KOpnd const & k = kp.opnd[o];
         sp.scalar[r] = k.stage==S_NONE;
+        sp.kind[r] = uint8_t(map ? map_kind(k) : (k.stage==S_NONE ? SK_SCALAR : SK_VEC));
         if (k.stage==S_NONE) { // scalar bits in T
             if (T==RACU_F32) sp.in[r] = f32_bits(float(bits_f64(k.base))); else if (T==RACU_F64) sp.in[r] = k.base; else sp.in[r] = uint32_t(int32_t(int64_t(k.base)));
         } else {
             sp.in[r] = k.base;
         }
-        for (int j=0; j<KGR; ++j) sp.sB[r][j] = k.sB[j];
+        for (int j=0; j<KGR; ++j) { sp.sB[r][j] = k.sB[j]; sp.sA[r][j] = j<kp.rankA ? k.sA[j] : 0; }
     }
     plan.is_static = true;
     static const char * names[3] = {"sflat_map", "sflat_fold_inner", "sflat_fold_outer"};

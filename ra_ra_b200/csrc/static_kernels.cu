@@ -115,37 +115,78 @@ load_inputs(SParams const & p, T (*x)[VecOf<T>::V], T const (*xs)[VecOf<T>::V], 
     }
 }
 
-// ---- flat map: dst[i] = P(inputs[i]) over n elements; vectors of 16 bytes, tail by lanes
+// ---- map: dst[...] = P(inputs[...]) over up to KGR uncollapsible axes; axis 0 is vectorised (16 bytes per access).
+// Inputs per role: aligned unit-step vectors (forward or reversed), one value per row (prefix rank extension: the
+// `v` of B += A*C + v, examples/read-me.cc:32), or scalars. A flat traversal (rankA==1) may have a scalar tail.
 template <class T, int ID> __global__ void __launch_bounds__(KBLOCK)
 sflat_map_kernel(const __grid_constant__ SParams p)
 {
     constexpr int V = VecOf<T>::V;
     constexpr SProg P = static_prog(ID);
     T xs[P.nin][V];
-    int64_t rowoff[P.nin];
 #pragma unroll
     for (int k=0; k<P.nin; ++k) {
-        rowoff[k] = 0;
 #pragma unroll
         for (int j=0; j<V; ++j) xs[k][j] = from_bits<T>(p.in[k]);
     }
-    int64_t const nfull = p.n/V; // full vectors
     int64_t const per = int64_t(KBLOCK)*SUNR;
-    for (int64_t g0 = int64_t(blockIdx.x)*per + threadIdx.x; g0<nfull; g0 += int64_t(gridDim.x)*per) {
+    for (int64_t g0 = int64_t(blockIdx.x)*per + threadIdx.x; g0<p.nvec; g0 += int64_t(gridDim.x)*per) {
         T x[SUNR][P.nin][V];
-#pragma unroll
-        for (int u=0; u<SUNR; ++u) { int64_t g = g0 + int64_t(u)*KBLOCK; if (g<nfull) load_inputs<T, ID>(p, x[u], xs, rowoff, g*16); }
+        int64_t doff[SUNR];
 #pragma unroll
         for (int u=0; u<SUNR; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK;
-            if (g<nfull) { T out[V]; eval_static<T, ID>(x[u], out); st16<T>(static_cast<unsigned char *>(p.dst) + g*16, out); }
+            if (g<p.nvec) {
+                int64_t e0;
+                uint32_t i1 = 0, i2 = 0, i3 = 0;
+                if (1==p.rankA) { e0 = g*V; }
+                else {
+                    uint32_t n = uint32_t(g), q = fastdiv(n, p.vprdiv);
+                    e0 = int64_t(n-q*uint32_t(p.vpr))*V; n = q;
+                    if (2==p.rankA) i1 = n;
+                    else { q = fastdiv(n, p.dA[1]); i1 = n-q*p.dA[1].len; n = q;
+                        if (3==p.rankA) i2 = n; else { q = fastdiv(n, p.dA[2]); i2 = n-q*p.dA[2].len; i3 = q; } }
+                }
+                doff[u] = e0 + int64_t(i1)*p.dsA[1] + int64_t(i2)*p.dsA[2] + int64_t(i3)*p.dsA[3];
+#pragma unroll
+                for (int k=0; k<P.nin; ++k) {
+                    int const kd = p.kind[k];
+                    if (SK_SCALAR==kd) {
+#pragma unroll
+                        for (int j=0; j<V; ++j) x[u][k][j] = xs[k][j];
+                    } else {
+                        int64_t off = int64_t(i1)*p.sA[k][1] + int64_t(i2)*p.sA[k][2] + int64_t(i3)*p.sA[k][3];
+                        T const * base = reinterpret_cast<T const *>(p.in[k]);
+                        if (SK_VEC==kd) {
+                            if (k==P.yrole) ld16_rw<T>(x[u][k], base + off + e0); else ld16<T>(x[u][k], base + off + e0);
+                        } else if (SK_VECREV==kd) {
+                            T r[V];
+                            ld16<T>(r, base + off - e0 - (V-1));
+#pragma unroll
+                            for (int j=0; j<V; ++j) x[u][k][j] = r[V-1-j];
+                        } else { // SK_ROW
+                            T v = __ldg(base + off);
+#pragma unroll
+                            for (int j=0; j<V; ++j) x[u][k][j] = v;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u=0; u<SUNR; ++u) {
+            int64_t g = g0 + int64_t(u)*KBLOCK;
+            if (g<p.nvec) { T out[V]; eval_static<T, ID>(x[u], out); st16<T>(static_cast<T *>(p.dst) + doff[u], out); }
         }
     }
-    if (0==blockIdx.x && 0==threadIdx.x) { // tail elements, scalar
-        for (int64_t e = nfull*V; e<p.n; ++e) {
+    if (1==p.rankA && 0==blockIdx.x && 0==threadIdx.x) { // tail elements of a flat traversal, scalar
+        for (int64_t e = p.nvec*V; e<p.n; ++e) {
             T x[P.nin][V], out[V];
 #pragma unroll
-            for (int k=0; k<P.nin; ++k) x[k][0] = p.scalar[k] ? xs[k][0] : reinterpret_cast<T const *>(p.in[k])[e];
+            for (int k=0; k<P.nin; ++k) {
+                T const * base = reinterpret_cast<T const *>(p.in[k]);
+                x[k][0] = SK_SCALAR==p.kind[k] ? xs[k][0] : SK_VEC==p.kind[k] ? base[e] : SK_VECREV==p.kind[k] ? base[-e] : base[0];
+            }
 #pragma unroll
             for (int k=0; k<P.nin; ++k) { for (int j=1; j<V; ++j) x[k][j] = x[k][0]; }
             eval_static<T, ID>(x, out);

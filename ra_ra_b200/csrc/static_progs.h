@@ -18,6 +18,7 @@ enum {
     SP_ADD, SP_SUB, SP_MUL, SP_DIV,       // y = a OP b
     SP_YFMA, SP_YFMS,                     // y += a*b, y -= a*b      (B += A*C; cghs: x += t*r, g -= t*p)
     SP_MULADD, SP_YMULADD,                // y = a*b + c ; y = y*b + c (cghs: r = r*gam + g)
+    SP_YFMA_ADD,                          // y += a*b + c             (examples/read-me.cc:32 shape: B += A*C + v)
     SF_ID, SF_SQR, SF_MUL, SF_SQRDIFF,    // folds of a, a*a, a*b, (a-b)^2  (sum, reduce_sqrm, dot, reduce_sqrm(a-b))
     SP_COUNT
 };
@@ -43,6 +44,7 @@ static_prog(int id)
     case SP_YFMS: return SProg {5, {sP(0), sP(1), sP(2), sO(RACU_OP_MUL), sO(RACU_OP_SUB)}, 3, 0, false};
     case SP_MULADD: return SProg {5, {sP(0), sP(1), sO(RACU_OP_MUL), sP(2), sO(RACU_OP_ADD)}, 3, -1, false};
     case SP_YMULADD: return SProg {5, {sP(0), sP(1), sO(RACU_OP_MUL), sP(2), sO(RACU_OP_ADD)}, 3, 0, false};
+    case SP_YFMA_ADD: return SProg {7, {sP(0), sP(1), sP(2), sO(RACU_OP_MUL), sP(3), sO(RACU_OP_ADD), sO(RACU_OP_ADD)}, 4, 0, false};
     case SF_ID: return SProg {1, {sP(0)}, 1, -1, true};
     case SF_SQR: return SProg {2, {sP(0), sO(RACU_OP_SQR)}, 1, -1, true};
     case SF_MUL: return SProg {3, {sP(0), sP(1), sO(RACU_OP_MUL)}, 2, -1, true};
@@ -62,8 +64,18 @@ struct SParams
     void * partial;
     uint64_t in[SP_MAXIN];        // role -> base address (vector inputs) or value bits (scalars)
     uint8_t scalar[SP_MAXIN];
+    uint8_t kind[SP_MAXIN];       // maps: SK_* below
     int64_t sB[SP_MAXIN][KGR];    // role -> element strides over group B
     KDim dB[KGR];
+    // maps over up to KGR uncollapsible axes (axis 0 vectorised)
+    int32_t rankA, pad;
+    int64_t nvec, vpr;            // vectors in total, vectors per row
+    KDim vprdiv;
+    KDim dA[KGR];
+    int64_t sA[SP_MAXIN][KGR];    // role -> element strides over group A (sA[.][0] is 1, -1 or 0)
+    int64_t dsA[KGR];             // destination strides (dsA[0] == 1)
 };
+
+enum { SK_SCALAR = 0, SK_VEC = 1, SK_VECREV = 2 /* unit step backwards: aligned 16-byte load, lanes reversed */, SK_ROW = 3 /* step 0 on axis 0: one value per row */ };
 
 } // namespace racu

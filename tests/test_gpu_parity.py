@@ -269,3 +269,42 @@ def test_stencil3d_large_roundtrip_property(exc):
     a.fill_(3.25)
     cuda.check(cuda.lib.racu_stencil(C.byref(_stencil_desc(abi.STENCIL_3D7, np.float32, a.data_ptr(), out.data_ptr(), (n, n, n), st)), cuda.stream_ptr()))
     assert float(out[1:-1, 1:-1, 1:-1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+def test_static_nd_maps_bitexact(dt, exc):
+    """Row-structured maps on the specialised kernel: prefix-broadcast operand (examples/read-me.cc:163), reversed inner
+    axis (ra/arrays.hh:408-428), strided outer axes (ra/ply.hh:399-415), rank 3 and 4."""
+    rng = np.random.default_rng(123)
+    shape = (6, 10, 24)
+    a, b, c = (rng.integers(-9, 9, shape).astype(dt) for _ in range(3))
+    v = rng.integers(-9, 9, shape[0]).astype(dt)
+    w = rng.integers(-9, 9, shape[:2]).astype(dt)
+    big = rng.integers(-9, 9, (7, 12, 21, 32)).astype(dt)
+    outs = []
+    for ex in (OracleExecutor(), exc):
+        A, B, Cc, Vv, Ww, G = (ex.from_numpy(x) for x in (a, b, c, v, w, big))
+        ks = []
+
+        def k():
+            ks.append(ex.last_kernel() if ex.name == "cuda" else None)
+        B += A * Cc + Vv
+        k()                      # B += A*C + v: examples/read-me.cc:32
+        B += Vv
+        k()                      # y += row value
+        B -= Ww
+        k()
+        B.assign(ra.reverse(A, 2))
+        k()
+        Cc.assign(ra.reverse(ra.reverse(A, 2), 0) * B)
+        k()
+        H = ex.from_numpy(np.zeros((7, 4, 21, 16), dtype=dt))
+        H.assign(G(ra.all, ra.iota(4, 1, 3), ra.all, ra.iota(16, 8)))   # strided outer, offset inner (still aligned)
+        k()
+        H += G(ra.all, ra.iota(4, 11, -3), ra.all, ra.iota(16, 31, -1))  # reversed outer and inner
+        k()
+        outs.append((snapshot(ex, B), snapshot(ex, Cc), snapshot(ex, H)))
+        if ex.name == "cuda":
+            assert ks == ["sflat_map"] * 7, ks
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y)
