@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--extras", type=int, default=1, help="also time the other configs (reported under 'extra')")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-log2n", type=int, default=27, help="bounded CPU sample size")
+    ap.add_argument("--n3", type=int, default=1024, help="global grid edge for --workload stencil")
+    ap.add_argument("--no-overlap", action="store_true", help="stencil: exchange then sweep, no stream overlap")
     return ap.parse_args()
 
 
@@ -198,6 +200,9 @@ def main():
         cuda.check(lib.racu_comm_init_rank(C.byref(comm), ident[0], world, rank))
     ex = cuda.CudaExecutor(local)
     dev = ex.device
+    if args.workload == "stencil":
+        run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local)
+        return
 
     def barrier():
         if world > 1:
@@ -344,6 +349,75 @@ def main():
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out))
+    if world > 1:
+        cuda.check(lib.racu_comm_destroy(comm))
+        dist.destroy_process_group()
+
+
+def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local):
+    """configs[3]: 7-point sweep (bench/bench-stencil3.cc:55-64) on a GLOBAL f32 n^3 grid, slab-sharded along axis 0 with
+    an NCCL halo exchange per step (strong scaling: the global grid is fixed as N grows). One step = one sweep + swap."""
+    from ra_ra_b200 import parallel
+    n = args.n3
+    dev = ex.device
+    sl = parallel.SlabStencil3D((n, n, n), world, rank)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5EED0041 + rank)
+    A = torch.empty(sl.local_shape, device=dev, dtype=torch.float32).uniform_(-1, 1, generator=g)
+    An = torch.zeros_like(A)
+    bufs = [A, An]
+    sweep = cuda.stencil_sweep(abi.STENCIL_3D7, abi.F32)
+    exch = parallel.RacuCommExchanger(lib, comm, abi.F32, cuda.stream_ptr, cuda.check) if world > 1 else None
+    overlap = cuda.StreamOverlap() if world > 1 and not args.no_overlap else None
+
+    def step():
+        sl.step(bufs[0].data_ptr(), bufs[1].data_ptr(), 4, sweep, exch, overlap)
+        bufs.reverse()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    lib.racu_launch_count_reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    barrier()
+    sampler.stop_flag = True
+    ms = float(ms.item()) / args.steps
+    launches = int(lib.racu_launch_count())
+    cells = float(n) ** 3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    gcells = cells / (ms * 1e-3) / 1e9
+    sampler.join(timeout=2)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "laplace3d Gcells/s", "value": gcells, "unit": "Gcells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[3] 7-point stencil f32 {n}^3 global grid, slab-sharded along axis 0, NCCL halo "
+                                   f"exchange per step, overlap={'off' if overlap is None else 'interior/edges on two streams'}",
+                       "l2": "4 GiB per buffer, larger than L2"},
+            "roofline": {"bound": "hbm", "kernel": "stencil_tma<3D7>", "achieved": 8 * cells / world / (ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": 8 * cells / world / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "note": "per GPU: 8 B/cell algorithmic x cells per GPU / step time (includes exchange when N>1)"},
+            "gpu_launches": launches, "clocks": sampler.summary()}))
     if world > 1:
         cuda.check(lib.racu_comm_destroy(comm))
         dist.destroy_process_group()

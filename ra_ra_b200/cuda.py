@@ -74,3 +74,36 @@ class CudaExecutor:
 
     def last_kernel(self):
         return lib.racu_last_kernel().decode()
+
+
+class StreamOverlap:
+    """fork()/back()/join() for parallel.SlabStencil3D.step: the halo exchange runs on a side stream while the planes that
+    read no ghost are swept on the main stream."""
+
+    def __init__(self):
+        self.main = torch.cuda.current_stream()
+        self.side = torch.cuda.Stream()
+
+    def fork(self):
+        self.main = torch.cuda.current_stream()
+        self.side.wait_stream(self.main)
+        torch.cuda.set_stream(self.side)
+
+    def back(self):
+        torch.cuda.set_stream(self.main)
+
+    def join(self):
+        self.main.wait_stream(self.side)
+
+
+def stencil_sweep(kind=abi.STENCIL_3D7, dtype=abi.F32):
+    """sweep(src_ptr, dst_ptr, shape, strides, lo0, hi0) through racu_stencil, for parallel.SlabStencil3D."""
+    def sweep(src_ptr, dst_ptr, shape, strides, lo0, hi0):
+        s = abi.StencilDesc()
+        s.kind, s.dtype, s.rank = kind, dtype, len(shape)
+        s.src, s.dst = src_ptr, dst_ptr
+        for k in range(len(shape)):
+            s.len[k], s.src_stride[k], s.dst_stride[k] = shape[k], strides[k], strides[k]
+        s.lo0, s.hi0 = lo0, hi0
+        check(lib.racu_stencil(C.byref(s), stream_ptr()))
+    return sweep

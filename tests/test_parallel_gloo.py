@@ -1,0 +1,97 @@
+"""Host logic of the multi-GPU path (ra_ra_b200/parallel.py) on CPU: world_size 2 and 3 over gloo, with the oracle as the
+local sweep. The slab-sharded stencil must reproduce the single-process result bit for bit, ghosts and boundaries included."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+from ra_ra_b200 import abi, parallel  # noqa: E402
+
+
+def _oracle_sweep(dt):
+    from oracle_exec import lib as olib
+
+    def sweep(src_ptr, dst_ptr, shape, strides, lo0, hi0):
+        s = abi.StencilDesc()
+        s.kind, s.dtype, s.rank = abi.STENCIL_3D7, abi.F32 if dt == np.float32 else abi.F64, 3
+        s.src, s.dst = src_ptr, dst_ptr
+        for k in range(3):
+            s.len[k], s.src_stride[k], s.dst_stride[k] = shape[k], strides[k], strides[k]
+        s.lo0, s.hi0 = lo0, hi0
+        assert olib().oracle_stencil_raw(C.byref(s)) == 0
+    return sweep
+
+
+class _NoOverlap:
+    def fork(self): pass
+    def back(self): pass
+    def join(self): pass
+
+
+def _reference(a0, steps, dt):
+    sweep = _oracle_sweep(dt)
+    A, An = a0.copy(), np.zeros_like(a0)
+    st = [s // A.itemsize for s in A.strides]
+    for _ in range(steps):
+        sweep(A.ctypes.data, An.ctypes.data, A.shape, st, 0, 0)
+        A, An = An, A
+    return A, An
+
+
+def _worker(rank, world, port, shape, steps, overlap, dtname, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dt = np.dtype(dtname).type
+    rng = np.random.default_rng(41)
+    a0 = rng.uniform(-1, 1, shape).astype(dt)
+    sl = parallel.SlabStencil3D(shape, world, rank)
+    A = a0[sl.global_slice()].copy()
+    An = np.zeros_like(A)
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    ct = C.c_float if dt == np.float32 else C.c_double
+
+    def view(ptr, count):
+        return torch.frombuffer((ct * count).from_address(ptr), dtype=tdt)
+    ex = parallel.TorchDistExchanger(dist, rank, world, view)
+    sweep = _oracle_sweep(dt)
+    for _ in range(steps):
+        sl.step(A.ctypes.data, An.ctypes.data, A.itemsize, sweep, ex, _NoOverlap() if overlap else None)
+        A, An = An, A
+    # also the fold path: per-rank partial + allreduce
+    part = torch.tensor([float(a0[sl.lo:sl.hi].astype(np.float64).sum())], dtype=torch.float64)
+    dist.all_reduce(part)
+    np.save(os.path.join(out_dir, f"A_{rank}.npy"), A[sl.owned_local()])
+    np.save(os.path.join(out_dir, f"An_{rank}.npy"), An[sl.owned_local()])
+    np.save(os.path.join(out_dir, f"sum_{rank}.npy"), part.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,overlap", [(2, (12, 7, 9), False), (2, (12, 7, 9), True), (3, (11, 6, 8), True), (2, (5, 6, 7), True), (3, (7, 5, 6), True)])
+def test_slab_stencil_matches_single_process(world, shape, overlap, tmp_path):
+    steps, dt = 4, np.float32
+    port = 29600 + (os.getpid() + world * 7 + shape[0]) % 300
+    mp.spawn(_worker, args=(world, port, shape, steps, overlap, np.dtype(dt).name, str(tmp_path)), nprocs=world, join=True)
+    a0 = np.random.default_rng(41).uniform(-1, 1, shape).astype(dt)
+    A, An = _reference(a0, steps, dt)
+    gotA = np.concatenate([np.load(tmp_path / f"A_{r}.npy") for r in range(world)])
+    gotAn = np.concatenate([np.load(tmp_path / f"An_{r}.npy") for r in range(world)])
+    assert np.array_equal(gotA, A) and np.array_equal(gotAn, An)
+    s = np.load(tmp_path / "sum_0.npy")[0]
+    assert abs(s - a0.astype(np.float64).sum()) < 1e-9
+
+
+def test_shard_bounds_cover_axis():
+    for n in (1, 7, 8, 1024, 1025):
+        for world in (1, 2, 3, 4, 8):
+            b = [parallel.shard_bounds(n, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
