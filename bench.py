@@ -12,7 +12,7 @@ than L2 (126 MB), so no flush is needed between iterations.
 
 Prints ONE JSON line (rank 0). `value` = whole-job GB/s with inputs resident in HBM; `e2e` = same metric through the public
 API with pinned HOST inputs (H2D inside the timed region, result read back); `roofline` = the dominant kernel
-(ply_fold_inner<u32> running dot) timed alone with CUDA events against MEASURED_PEAKS.json; `cpu_baseline` = the
+(sflat_fold_inner<f32, dot>) timed alone with CUDA events against MEASURED_PEAKS.json; `cpu_baseline` = the
 reference's loops (oracle/libbaseline.so, single thread like the reference) on a bounded sample.
 """
 import argparse
@@ -289,7 +289,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = 8.0 * N / (ms_dot * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "ply_fold_inner<u32> (dot, 2 finish-combined launches)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": lib.racu_last_kernel().decode() + "<f32, dot> + ply_finish", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": 8 * N, "ms_per_launch": ms_dot}
