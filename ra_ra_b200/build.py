@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libracu.so")
-SOURCES = ["ply_kernels.cu", "static_kernels.cu", "stencil.cu", "transpose.cu", "plan.cc", "api.cc", "special.cc", "comm.cc"]
+SOURCES = ["ply_kernels.cu", "static_kernels.cu", "stencil.cu", "transpose.cu", "gemm.cu", "plan.cc", "api.cc", "special.cc", "comm.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O3", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
 

@@ -1,0 +1,234 @@
+// gemm.cu - dense contraction c(M,N) += a(M,K) * b(K,N), the only tensor-core path of the back end.
+//
+// Reference: gemm(a, b, c) is `c(all, insert<1>) += a * b(insert<1>)` (ra/ra.hh:403-412): a rank-3 traversal (i, k, j)
+// whose destination has step 0 on k, i.e. per c[i,j] a sequential sum over ascending k of a[i,k]*b[k,j] with a plain
+// `c += a*b` (no fma macro on this path). The order of a fold is unspecified (docs/ra-ra.texi:3102), so this kernel sums
+// in tensor-core order; inputs whose products and sums are exactly representable (bench/bench-gemm.cc:229-237 uses
+// integer-valued a = _0-_1, b = _1-2*_0) give bit-identical results, anything else is compared by tolerance.
+//
+//   f64: FP64 tensor-core MMA (mma.sync.m8n8k4.f64; tcgen05 has no f64 kind, so DMMA is the only tensor path on sm_100).
+//   f32: 3xTF32 - a = hi + lo with hi = tf32(a), lo = tf32(a - hi); acc += lo_a*hi_b + hi_a*lo_b + hi_a*hi_b on
+//        mma.sync.m16n8k8.tf32 with fp32 accumulation. Dropped term lo*lo ~ 2^-22 |a||b|: error comparable to an fp32 FMA
+//        chain (bound stated in DESIGN.md; tests compare against an fp64 reference).
+//
+// Tiling: CTA 128x128, 8 warps as 2 (M) x 4 (N), warp tile 64x32, BK = 16 (f64) / 32 (f32), 3-stage cp.async pipeline,
+// shared-memory pitches padded so that fragment reads are bank-conflict free.
+#include <cuda_runtime.h>
+
+#include "launch.h"
+#include "special.h"
+
+namespace racu {
+
+constexpr int GM = 128, GN = 128, GSTAGES = 3, GTHREADS = 256;
+
+__device__ __forceinline__ void cp16(void * s, void const * g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(uint32_t(__cvta_generic_to_shared(s))), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ void
+dmma884(double & d0, double & d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void
+mma_tf32(float (&d)[4], uint32_t const (&a)[4], uint32_t const (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+
+struct GParams { void const * a; void const * b; void * c; int64_t lda, ldb, ldc; int32_t M, N, K; };
+
+// ---------------- f64 ----------------
+constexpr int DK = 16, DPA = DK+4 /* A pitch (doubles) */, DPB = GN+4 /* B pitch */;
+constexpr int DSTAGE = GM*DPA + DK*DPB; // doubles per stage
+
+__global__ void __launch_bounds__(GTHREADS)
+dgemm_kernel(const __grid_constant__ GParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double * const sm = reinterpret_cast<double *>(smem_raw);
+    int const tid = threadIdx.x, lane = tid&31, warp = tid>>5;
+    int const wm = warp>>2, wn = warp&3;   // 2 x 4 warps
+    int const g = lane>>2, t = lane&3;
+    int64_t const m0 = int64_t(blockIdx.y)*GM, n0 = int64_t(blockIdx.x)*GN;
+    double const * A = static_cast<double const *>(p.a) + m0*p.lda;
+    double const * B = static_cast<double const *>(p.b) + n0;
+    auto load_stage = [&](int s, int kt) {
+        double * As = sm + s*DSTAGE, * Bs = As + GM*DPA;
+        int64_t const k0 = int64_t(kt)*DK;
+#pragma unroll
+        for (int i=0; i<4; ++i) { // A tile 128 x 16: 8 x 16-byte copies per row
+            int c = tid + i*GTHREADS, r = c>>3, q = c&7;
+            cp16(As + r*DPA + q*2, A + r*p.lda + k0 + q*2);
+        }
+#pragma unroll
+        for (int i=0; i<4; ++i) { // B tile 16 x 128: 64 copies per row
+            int c = tid + i*GTHREADS, r = c>>6, q = c&63;
+            cp16(Bs + r*DPB + q*2, B + (k0+r)*p.ldb + q*2);
+        }
+    };
+    double acc[8][4][2];
+#pragma unroll
+    for (int i=0; i<8; ++i)
+#pragma unroll
+        for (int j=0; j<4; ++j) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+    int const nk = p.K/DK;
+#pragma unroll
+    for (int s=0; s<GSTAGES-1; ++s) { if (s<nk) load_stage(s, s); cp_commit(); }
+    for (int kt=0; kt<nk; ++kt) {
+        cp_wait<GSTAGES-2>();
+        __syncthreads();
+        if (kt+GSTAGES-1<nk) load_stage((kt+GSTAGES-1)%GSTAGES, kt+GSTAGES-1);
+        cp_commit();
+        double const * As = sm + (kt%GSTAGES)*DSTAGE + (wm*64)*DPA, * Bs = sm + (kt%GSTAGES)*DSTAGE + GM*DPA + wn*32;
+#pragma unroll
+        for (int kk=0; kk<DK; kk+=4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i=0; i<8; ++i) af[i] = As[(i*8+g)*DPA + kk + t];
+#pragma unroll
+            for (int j=0; j<4; ++j) bf[j] = Bs[(kk+t)*DPB + j*8 + g];
+#pragma unroll
+            for (int i=0; i<8; ++i)
+#pragma unroll
+                for (int j=0; j<4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_wait<0>();
+    double * Cp = static_cast<double *>(p.c) + (m0+wm*64)*p.ldc + n0 + wn*32;
+#pragma unroll
+    for (int i=0; i<8; ++i)
+#pragma unroll
+        for (int j=0; j<4; ++j) {
+            double2 * dst = reinterpret_cast<double2 *>(Cp + (i*8+g)*p.ldc + j*8 + t*2);
+            double2 c = *dst;
+            c.x += acc[i][j][0]; c.y += acc[i][j][1];
+            *dst = c;
+        }
+}
+
+// ---------------- f32 via 3xTF32 ----------------
+constexpr int SK = 32, SPA = SK+4 /* A pitch (floats) */, SPB = GN+8 /* B pitch */;
+constexpr int SSTAGE = GM*SPA + SK*SPB;
+
+__global__ void __launch_bounds__(GTHREADS)
+sgemm3x_kernel(const __grid_constant__ GParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float * const sm = reinterpret_cast<float *>(smem_raw);
+    int const tid = threadIdx.x, lane = tid&31, warp = tid>>5;
+    int const wm = warp>>2, wn = warp&3;
+    int const g = lane>>2, t = lane&3;
+    int64_t const m0 = int64_t(blockIdx.y)*GM, n0 = int64_t(blockIdx.x)*GN;
+    float const * A = static_cast<float const *>(p.a) + m0*p.lda;
+    float const * B = static_cast<float const *>(p.b) + n0;
+    auto load_stage = [&](int s, int kt) {
+        float * As = sm + s*SSTAGE, * Bs = As + GM*SPA;
+        int64_t const k0 = int64_t(kt)*SK;
+#pragma unroll
+        for (int i=0; i<4; ++i) { // A tile 128 x 32 floats: 8 copies per row
+            int c = tid + i*GTHREADS, r = c>>3, q = c&7;
+            cp16(As + r*SPA + q*4, A + r*p.lda + k0 + q*4);
+        }
+#pragma unroll
+        for (int i=0; i<4; ++i) { // B tile 32 x 128 floats: 32 copies per row
+            int c = tid + i*GTHREADS, r = c>>5, q = c&31;
+            cp16(Bs + r*SPB + q*4, B + (k0+r)*p.ldb + q*4);
+        }
+    };
+    float acc[4][4][4];
+#pragma unroll
+    for (int i=0; i<4; ++i)
+#pragma unroll
+        for (int j=0; j<4; ++j)
+#pragma unroll
+            for (int r=0; r<4; ++r) acc[i][j][r] = 0.f;
+    int const nk = p.K/SK;
+#pragma unroll
+    for (int s=0; s<GSTAGES-1; ++s) { if (s<nk) load_stage(s, s); cp_commit(); }
+    for (int kt=0; kt<nk; ++kt) {
+        cp_wait<GSTAGES-2>();
+        __syncthreads();
+        if (kt+GSTAGES-1<nk) load_stage((kt+GSTAGES-1)%GSTAGES, kt+GSTAGES-1);
+        cp_commit();
+        float const * As = sm + (kt%GSTAGES)*SSTAGE + (wm*64)*SPA, * Bs = sm + (kt%GSTAGES)*SSTAGE + GM*SPA + wn*32;
+#pragma unroll
+        for (int kk=0; kk<SK; kk+=8) {
+            uint32_t ah[4][4], al[4][4], bh[4][2], bl[4][2];
+#pragma unroll
+            for (int i=0; i<4; ++i) {
+                float v[4] = { As[(i*16+g)*SPA + kk + t], As[(i*16+g+8)*SPA + kk + t], As[(i*16+g)*SPA + kk + t + 4], As[(i*16+g+8)*SPA + kk + t + 4] };
+#pragma unroll
+                for (int r=0; r<4; ++r) { ah[i][r] = to_tf32(v[r]); al[i][r] = to_tf32(v[r]-__uint_as_float(ah[i][r])); }
+            }
+#pragma unroll
+            for (int j=0; j<4; ++j) {
+                float v[2] = { Bs[(kk+t)*SPB + j*8 + g], Bs[(kk+t+4)*SPB + j*8 + g] };
+#pragma unroll
+                for (int r=0; r<2; ++r) { bh[j][r] = to_tf32(v[r]); bl[j][r] = to_tf32(v[r]-__uint_as_float(bh[j][r])); }
+            }
+#pragma unroll
+            for (int i=0; i<4; ++i)
+#pragma unroll
+                for (int j=0; j<4; ++j) {
+                    mma_tf32(acc[i][j], al[i], bh[j]); // small terms first
+                    mma_tf32(acc[i][j], ah[i], bl[j]);
+                    mma_tf32(acc[i][j], ah[i], bh[j]);
+                }
+        }
+    }
+    cp_wait<0>();
+    float * Cp = static_cast<float *>(p.c) + (m0+wm*64)*p.ldc + n0 + wn*32;
+#pragma unroll
+    for (int i=0; i<4; ++i)
+#pragma unroll
+        for (int j=0; j<4; ++j) {
+            float2 * d0 = reinterpret_cast<float2 *>(Cp + (i*16+g)*p.ldc + j*8 + t*2);
+            float2 * d1 = reinterpret_cast<float2 *>(Cp + (i*16+g+8)*p.ldc + j*8 + t*2);
+            float2 c0 = *d0, c1 = *d1;
+            c0.x += acc[i][j][0]; c0.y += acc[i][j][1]; c1.x += acc[i][j][2]; c1.y += acc[i][j][3];
+            *d0 = c0; *d1 = c1;
+        }
+}
+
+int
+try_special_gemm(racu_gemm_desc const * gd, cudaStream_t stream, int * handled)
+{
+    *handled = 0;
+    if (std::getenv("RACU_NO_MMA_GEMM")) return RACU_OK;
+    bool const f64 = gd->dtype==RACU_F64;
+    int const bk = f64 ? DK : SK;
+    size_t const es = f64 ? 8 : 4;
+    if (gd->M<=0 || gd->N<=0 || gd->K<=0) { *handled = 1; return RACU_OK; } // nothing to add (test/reduction.cc:300-310: 0x0 corner)
+    // tile multiples and 16-byte rows only; anything else runs as a fold on the ply kernels
+    if (0!=gd->M%GM || 0!=gd->N%GN || 0!=gd->K%bk) return RACU_OK;
+    if (gd->M>=(int64_t(1)<<31) || gd->N>=(int64_t(1)<<31) || gd->K>=(int64_t(1)<<31)) return RACU_OK;
+    if (0!=(uintptr_t(gd->a)%16) || 0!=(uintptr_t(gd->b)%16) || 0!=(uintptr_t(gd->c)%16)) return RACU_OK;
+    if (0!=(gd->lda*es)%16 || 0!=(gd->ldb*es)%16 || 0!=(gd->ldc*es)%16) return RACU_OK;
+    GParams p {gd->a, gd->b, gd->c, gd->lda, gd->ldb, gd->ldc, int32_t(gd->M), int32_t(gd->N), int32_t(gd->K)};
+    dim3 grid {unsigned(gd->N/GN), unsigned(gd->M/GM), 1};
+    if (grid.y>65535) return RACU_OK;
+    size_t smem = size_t(GSTAGES)*(f64 ? DSTAGE*8 : SSTAGE*4);
+    cudaError_t e;
+    if (f64) {
+        if ((e = cudaFuncSetAttribute(dgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return cuda_fail(e, "dgemm smem");
+        dgemm_kernel<<<grid, GTHREADS, smem, stream>>>(p);
+        set_kernel("dgemm_dmma884");
+    } else {
+        if ((e = cudaFuncSetAttribute(sgemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return cuda_fail(e, "sgemm smem");
+        sgemm3x_kernel<<<grid, GTHREADS, smem, stream>>>(p);
+        set_kernel("sgemm_3xtf32");
+    }
+    launch_count_add(1);
+    if ((e = cudaGetLastError())) return cuda_fail(e, "gemm");
+    *handled = 1;
+    return RACU_OK;
+}
+
+} // namespace racu

@@ -272,7 +272,26 @@ int
 try_special_map(racu_desc const * d, cudaStream_t stream, int * handled)
 {
     *handled = 0;
-    if (d->dst<0 || d->assign!=RACU_ASSIGN_SET || d->nins<8) return RACU_OK;
+    if (d->dst<0) return RACU_OK;
+    // gemm as the reference writes it: c(all, insert<1>) += a * b(insert<1>)  (ra/ra.hh:407): axes (i, k, j)
+    if (d->assign==RACU_ASSIGN_ADD && 3==d->nins && d->ins[0].op==RACU_OP_PUSH && d->ins[1].op==RACU_OP_PUSH && d->ins[2].op==RACU_OP_MUL) {
+        racu_operand const & c = d->opnd[d->dst];
+        racu_operand const & a = d->opnd[d->ins[0].arg];
+        racu_operand const & b = d->opnd[d->ins[1].arg];
+        int const T = c.dtype;
+        if ((T==RACU_F32 || T==RACU_F64) && d->ins[2].type==T && a.dtype==T && b.dtype==T && a.kind==RACU_MEM && b.kind==RACU_MEM
+            && 3==c.rank && 2==a.rank && 3==b.rank && RACU_UNB==c.len[1] && 0==c.stride[1] && RACU_UNB==b.len[0] && 0==b.stride[0]
+            && 1==c.stride[2] && 1==a.stride[1] && 1==b.stride[2] && c.len[0]==a.len[0] && a.len[1]==b.len[1] && c.len[2]==b.len[2]
+            && c.stride[0]>0 && a.stride[0]>0 && b.stride[1]>0) {
+            racu_gemm_desc g;
+            std::memset(&g, 0, sizeof(g));
+            g.dtype = T; g.M = c.len[0]; g.N = c.len[2]; g.K = a.len[1];
+            g.a = a.base.ptr; g.lda = a.stride[0]; g.b = b.base.ptr; g.ldb = b.stride[1]; g.c = c.base.ptr; g.ldc = c.stride[0];
+            // c must not overlap a or b (the planner would reject it as well)
+            return try_special_gemm(&g, stream, handled);
+        }
+    }
+    if (d->assign!=RACU_ASSIGN_SET || d->nins<8) return RACU_OK;
     racu_operand const & y = d->opnd[d->dst];
     int const T = y.dtype, r = y.rank;
     if ((T!=RACU_F32 && T!=RACU_F64) || r<2 || r>3) return RACU_OK;
@@ -313,7 +332,5 @@ try_special_map(racu_desc const * d, cudaStream_t stream, int * handled)
     s.dst = static_cast<char *>(y.base.ptr) - dof*int64_t(es);
     return try_special_stencil(&s, stream, handled);
 }
-
-int try_special_gemm(racu_gemm_desc const *, cudaStream_t, int * handled) { *handled = 0; return RACU_OK; }
 
 } // namespace racu

@@ -308,3 +308,61 @@ def test_static_nd_maps_bitexact(dt, exc):
             assert ks == ["sflat_map"] * 7, ks
     for x, y in zip(*outs):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("mnk", [(128, 128, 32), (256, 384, 64), (128, 256, 96), (384, 128, 160)])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_gemm_tensor_core_path(mnk, dt, exc):
+    """gemm(a, b, c) (ra/ra.hh:403-412) on the MMA kernels: exact for the integer-valued inputs of bench/bench-gemm.cc:229-237
+    (any summation order), and within a stated bound of an fp64 reference for random inputs. `c +=` semantics, views with
+    leading dimensions larger than the extent."""
+    m, n, k = mnk
+    # (i) integer valued: bit exact vs the oracle's k-ascending loops
+    a = exc.empty((m, k), ra.NP2RACU[np.dtype(dt)])
+    b = exc.empty((k, n), ra.NP2RACU[np.dtype(dt)])
+    a.assign((ra._0 - ra._1) % 7)
+    b.assign((ra._1 - 2 * ra._0) % 5)
+    c = exc.from_numpy(np.ones((m, n), dtype=dt))
+    ra.gemm(a, b, c)
+    assert exc.last_kernel() in ("dgemm_dmma884", "sgemm_3xtf32"), exc.last_kernel()
+    ref = np.ones((m, n)) + a.numpy().astype(np.float64) @ b.numpy().astype(np.float64)
+    assert np.array_equal(c.numpy().astype(np.float64), ref)
+    # (ii) random, through views of larger buffers (lda/ldb/ldc > extents)
+    rng = np.random.default_rng(51)
+    A = rng.uniform(-1, 1, (m, k + 8)).astype(dt)
+    B = rng.uniform(-1, 1, (k, n + 16)).astype(dt)
+    C0 = rng.uniform(-1, 1, (m, n + 4)).astype(dt)
+    Av, Bv, Cv = exc.from_numpy(A)(ra.all, ra.iota(k)), exc.from_numpy(B)(ra.all, ra.iota(n)), exc.from_numpy(C0)
+    Cs = Cv(ra.all, ra.iota(n))
+    ra.gemm(Av, Bv, Cs)
+    assert exc.last_kernel() in ("dgemm_dmma884", "sgemm_3xtf32")
+    got = Cv.numpy().astype(np.float64)
+    A64, B64 = A[:, :k].astype(np.float64), B[:, :n].astype(np.float64)
+    ref = C0.astype(np.float64)
+    ref[:, :n] += A64 @ B64
+    scale = np.abs(A64) @ np.abs(B64)
+    err = np.abs(got[:, :n] - ref[:, :n])
+    if dt == np.float64:
+        bound = 2 * k * np.finfo(np.float64).eps * scale + 1e-300
+    else:  # 3xTF32: fp32 accumulation (k * 2^-24) plus the dropped lo*lo terms and tf32 rounding of lo (~2^-21 per product)
+        bound = (k * 2.0 ** -24 + 2.0 ** -20) * scale + 1e-30
+    assert (err <= bound).all(), (err.max(), (err / bound).max())
+    assert np.array_equal(got[:, n:], C0[:, n:].astype(np.float64))  # columns outside the view untouched
+
+
+def test_gemv_gevm_static_rows(exc):
+    """gemv: c += a * b(insert<1>) (ra/ra.hh:418) is a row-wise fold on the specialised kernel; bench/bench-gemv.cc:87-92 values are exact."""
+    m, n = 256, 512
+    a = exc.empty((m, n), abi.F64)
+    a.assign(ra._0 - ra._1)
+    b = exc.empty((n,), abi.F64)
+    b.assign(1 - 2 * ra._0)
+    c = exc.from_numpy(np.zeros(m))
+    ra.gemv(a, b, c)
+    assert exc.last_kernel() == "sflat_fold_inner", exc.last_kernel()
+    assert np.array_equal(c.numpy(), a.numpy() @ b.numpy())
+    c2 = exc.from_numpy(np.zeros(n))
+    x = exc.empty((m,), abi.F64)
+    x.assign(1 + ra._0)
+    ra.gevm(x, a, c2)
+    assert np.array_equal(c2.numpy(), x.numpy() @ a.numpy())
