@@ -62,4 +62,15 @@ for name, fn, nbytes in (("sum", red(d_sum), 4 * N), ("sqrm", red(d_sqrm), 4 * N
     ms = timed(fn)
     out[name] = {"ms": round(ms, 4), "GB/s": round(nbytes / ms / 1e6, 1), "kernel": lib.racu_last_kernel().decode()}
     print(f"{name:16s} {ms:8.4f} ms {nbytes / ms / 1e6:8.1f} GB/s  {out[name]['kernel']}")
+# f64 variants of the folds
+a64 = ex.wrap(a_t[: N // 2].double())
+b64 = ex.wrap(b_t[: N // 2].double())
+n64 = N // 2
+d_sum64, _q1 = ra.flatten(ra.as_expr(a64), ex=ex)
+d_dot64, _q2 = ra.flatten(a64 * b64, ex=ex)
+s64 = torch.zeros(2, device=dev, dtype=torch.float64)
+for name, d, nbytes in (("sum f64", d_sum64, 8 * n64), ("dot f64", d_dot64, 16 * n64)):
+    ms = timed(lambda: cuda.check(lib.racu_reduce_dev(C.byref(d), abi.RED_SUM, C.c_void_p(s64.data_ptr()), sp())))
+    out[name] = {"ms": round(ms, 4), "GB/s": round(nbytes / ms / 1e6, 1), "kernel": lib.racu_last_kernel().decode()}
+    print(f"{name:16s} {ms:8.4f} ms {nbytes / ms / 1e6:8.1f} GB/s  {out[name]['kernel']}")
 print(json.dumps(out))

@@ -286,7 +286,7 @@ peel_axis0(racu_desc const & d, int64_t i, racu_desc & out)
 static void
 match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold)
 {
-    KParams const & kp = plan.kp;
+    KParams & kp = plan.kp;
     plan.is_static = false;
     if (std::getenv("RACU_NO_STATIC")) return;
     if (int(prog.size())>SP_MAXINS) return;
@@ -322,7 +322,7 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
                 if (nrole>=SP_MAXIN) return;
                 KOpnd const & k = kp.opnd[i.arg];
                 if (k.dtype!=T) return;
-                if (map ? map_kind(k)<0 : !(k.stage==S_VEC || k.stage==S_NONE)) return;
+                if (map ? map_kind(k)<0 : !(k.stage==S_VEC || k.stage==S_NONE || (k.stage==S_BCAST && k.kind==RACU_MEM))) return;
                 if (!fold && int(i.arg)==dst) yrole = nrole;
                 role_of[i.arg] = nrole++;
             }
@@ -363,13 +363,40 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
         if (r<0) continue;
         KOpnd const & k = kp.opnd[o];
         sp.scalar[r] = k.stage==S_NONE;
-        sp.kind[r] = uint8_t(map ? map_kind(k) : (k.stage==S_NONE ? SK_SCALAR : SK_VEC));
+        sp.kind[r] = uint8_t(map ? map_kind(k) : (k.stage==S_NONE ? SK_SCALAR : k.stage==S_BCAST ? SK_ROW : SK_VEC));
         if (k.stage==S_NONE) { // scalar bits in T
             if (T==RACU_F32) sp.in[r] = f32_bits(float(bits_f64(k.base))); else if (T==RACU_F64) sp.in[r] = k.base; else sp.in[r] = uint32_t(int32_t(int64_t(k.base)));
         } else {
             sp.in[r] = k.base;
         }
         for (int j=0; j<KGR; ++j) { sp.sB[r][j] = k.sB[j]; sp.sA[r][j] = j<kp.rankA ? k.sA[j] : 0; }
+    }
+    sp.rb = 1; // (row blocking in registers measured slower than L1 reuse for gemv: kept off)
+    if (fold && kp.mode==K_FOLD_INNER && kp.rankB>=1 && kp.nk>1) {
+        for (int r=0; r<nrole; ++r) {
+            bool moves = false;
+            for (int j=0; j<kp.rankB; ++j) moves = moves || 0!=sp.sB[r][j];
+            sp.reused[r] = !sp.scalar[r] && !moves;
+        }
+        bool any = false;
+        for (int r=0; r<nrole; ++r) any = any || sp.reused[r];
+        // gemv shape: many rows, one operand re-read by every row. Cut the rows into column chunks of <= 32 KiB and run the
+        // CTAs chunk-major, so the resident CTAs of an SM share one chunk of that operand in L1.
+        int64_t const row_bytes = kp.len0*int64_t(es);
+        if (std::getenv("RACU_CHUNK_MAJOR") && any && 1==kp.nchunks && kp.nk>=1024 && row_bytes>64*1024 && 0==kp.len0%V) { // measured slower than plain L1 reuse on B200: opt-in only
+            int64_t nvec = kp.len0/V, nch = (row_bytes+32*1024-1)/(32*1024);
+            int64_t cl = (nvec+nch-1)/nch;
+            cl = ((cl+KBLOCK-1)/KBLOCK)*KBLOCK;
+            nch = (nvec+cl-1)/cl;
+            if (nch>1 && kp.nk*nch<(int64_t(1)<<31)) {
+                plan.kp.nchunks = int(nch); plan.kp.chunk_len = cl;
+                sp.nchunks = int(nch); sp.chunk_len = cl; sp.chunk_major = 1;
+                plan.fp.nchunks = int(nch);
+                plan.need_finish = true;
+                plan.partial_bytes = size_t(nch)*size_t(kp.nk)*(8==es ? 8 : 4);
+                plan.grid_x = unsigned(kp.nk*nch);
+            }
+        }
     }
     plan.is_static = true;
     static const char * names[3] = {"sflat_map", "sflat_fold_inner", "sflat_fold_outer"};

@@ -31,6 +31,14 @@ ld16(T * out, void const * p) // streaming 128-bit load: read once, do not keep 
     memcpy(out, w, 16);
 }
 template <class T> __device__ __forceinline__ void
+ld16_reused(T * out, void const * p) // operand re-read by every kept row (the vector of gemv): let L1 keep it
+{
+    uint32_t a, b, c, d;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+    uint32_t w[4] = {a, b, c, d};
+    memcpy(out, w, 16);
+}
+template <class T> __device__ __forceinline__ void
 ld16_rw(T * out, void const * p) // destination operand (read-modify-write): ordinary load
 {
     uint4 q = *reinterpret_cast<uint4 const *>(p);
@@ -107,8 +115,14 @@ load_inputs(SParams const & p, T (*x)[VecOf<T>::V], T const (*xs)[VecOf<T>::V], 
         if (p.scalar[k]) {
 #pragma unroll
             for (int j=0; j<V; ++j) x[k][j] = xs[k][j];
+        } else if (SK_ROW==p.kind[k]) { // step 0 along the vectorised axis: one value per row (gevm: c(j) += a(i)*b(i,j))
+            T v = __ldg(reinterpret_cast<T const *>(reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k]));
+#pragma unroll
+            for (int j=0; j<V; ++j) x[k][j] = v;
         } else if (k==P.yrole) {
             ld16_rw<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
+        } else if (p.reused[k]) {
+            ld16_reused<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
         } else {
             ld16<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
         }
@@ -209,20 +223,27 @@ block_comb(T r, T * red)
     return r;
 }
 
-// ---- fold-inner, flat rows: CTA = (row kb, chunk c); row length len0 (multiple of V unless there is a single row)
-template <class T, int ID, int FOLD> __global__ void __launch_bounds__(KBLOCK)
+// ---- fold-inner, flat rows: CTA = (RB consecutive rows starting at kb*RB, chunk c); row length len0 (multiple of V unless
+// there is a single row). RB > 1 (rankB == 1 only) blocks rows in registers so that operands that do not move along the
+// kept axis (the vector of gemv: c(i) += a(i,j)*b(j), ra/ra.hh:418) are loaded once per RB rows instead of once per row.
+template <class T, int ID, int FOLD, int RB> __global__ void __launch_bounds__(KBLOCK)
 sflat_fold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f)
 {
     using W = std::conditional_t<sizeof(T)==8, uint64_t, uint32_t>;
     constexpr int V = VecOf<T>::V;
     constexpr SProg P = static_prog(ID);
+    constexpr int UN = RB>1 ? 2 : SUNR; // vectors in flight per input per row
     __shared__ T red[KBLOCK/32];
-    uint32_t const kb = blockIdx.x/uint32_t(p.nchunks), c = blockIdx.x-kb*uint32_t(p.nchunks);
+    // chunk-major order (gemv): CTAs resident together work on the SAME column chunk of consecutive rows, so the operand
+    // every row re-reads stays in L1; row-major order otherwise
+    uint32_t kb, c;
+    if (p.chunk_major) { c = blockIdx.x/uint32_t(p.nk/RB); kb = blockIdx.x-c*uint32_t(p.nk/RB); }
+    else { kb = blockIdx.x/uint32_t(p.nchunks); c = blockIdx.x-kb*uint32_t(p.nchunks); }
     T xs[P.nin][V];
-    int64_t rowoff[P.nin];
+    int64_t rowoff[RB][P.nin];
     {
         // row kb -> group-B position -> per input byte offset
-        uint32_t n = kb, q, ib[KGR] = {0, 0, 0, 0};
+        uint32_t n = kb*RB, q, ib[KGR] = {0, 0, 0, 0};
         if (p.rankB<=1) ib[0] = n;
         else {
             q = fastdiv(n, p.dB[0]); ib[0] = n-q*p.dB[0].len; n = q;
@@ -235,7 +256,8 @@ sflat_fold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant
             int64_t off = 0;
 #pragma unroll
             for (int j=0; j<KGR; ++j) { if (j<p.rankB) off += int64_t(ib[j])*p.sB[k][j]; }
-            rowoff[k] = off*int64_t(sizeof(T));
+#pragma unroll
+            for (int r=0; r<RB; ++r) rowoff[r][k] = (off + int64_t(r)*p.sB[k][0])*int64_t(sizeof(T));
 #pragma unroll
             for (int j=0; j<V; ++j) xs[k][j] = from_bits<T>(p.in[k]);
         }
@@ -243,43 +265,76 @@ sflat_fold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant
     int64_t const nfull = p.n/V;
     int64_t const start = int64_t(c)*p.chunk_len;
     int64_t const end = start+p.chunk_len<nfull ? start+p.chunk_len : nfull;
-    T acc[V];
+    T acc[RB][V];
 #pragma unroll
-    for (int j=0; j<V; ++j) acc[j] = from_bits<T>(p.identity);
-    int64_t const per = int64_t(KBLOCK)*SUNR;
+    for (int r=0; r<RB; ++r)
+#pragma unroll
+        for (int j=0; j<V; ++j) acc[r][j] = from_bits<T>(p.identity);
+    int64_t const per = int64_t(KBLOCK)*UN;
     for (int64_t g0 = start + threadIdx.x; g0<end; g0 += per) {
-        T x[SUNR][P.nin][V];
+        T x[RB][UN][P.nin][V];
 #pragma unroll
-        for (int u=0; u<SUNR; ++u) { int64_t g = g0 + int64_t(u)*KBLOCK; if (g<end) load_inputs<T, ID>(p, x[u], xs, rowoff, g*16); }
-#pragma unroll
-        for (int u=0; u<SUNR; ++u) {
+        for (int u=0; u<UN; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK;
             if (g<end) {
-                T out[V];
-                eval_static<T, ID>(x[u], out);
 #pragma unroll
-                for (int j=0; j<V; ++j) acc[j] = comb<T, FOLD>(acc[j], out[j]);
+                for (int r=0; r<RB; ++r) {
+                    if (0==r) load_inputs<T, ID>(p, x[0][u], xs, rowoff[0], g*16);
+                    else {
+#pragma unroll
+                        for (int k=0; k<P.nin; ++k) {
+                            if (0==p.sB[k][0] || p.scalar[k]) { // does not move along the kept axis: reuse row 0's registers
+#pragma unroll
+                                for (int j=0; j<V; ++j) x[r][u][k][j] = x[0][u][k][j];
+                            } else if (SK_ROW==p.kind[k]) {
+                                T v = __ldg(reinterpret_cast<T const *>(reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[r][k]));
+#pragma unroll
+                                for (int j=0; j<V; ++j) x[r][u][k][j] = v;
+                            } else {
+                                ld16<T>(x[r][u][k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[r][k] + g*16);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u=0; u<UN; ++u) {
+            int64_t g = g0 + int64_t(u)*KBLOCK;
+            if (g<end) {
+#pragma unroll
+                for (int r=0; r<RB; ++r) {
+                    T out[V];
+                    eval_static<T, ID>(x[r][u], out);
+#pragma unroll
+                    for (int j=0; j<V; ++j) acc[r][j] = comb<T, FOLD>(acc[r][j], out[j]);
+                }
             }
         }
     }
-    T r = acc[0];
 #pragma unroll
-    for (int j=1; j<V; ++j) r = comb<T, FOLD>(r, acc[j]);
-    if (c+1==uint32_t(p.nchunks) && 0==threadIdx.x) { // tail elements of the row (single flat row only)
-        for (int64_t e = nfull*V; e<p.n; ++e) {
-            T x[P.nin][V], out[V];
+    for (int r=0; r<RB; ++r) {
+        T v = acc[r][0];
 #pragma unroll
-            for (int k=0; k<P.nin; ++k) x[k][0] = p.scalar[k] ? xs[k][0] : reinterpret_cast<T const *>(reinterpret_cast<unsigned char const *>(p.in[k])+rowoff[k])[e];
+        for (int j=1; j<V; ++j) v = comb<T, FOLD>(v, acc[r][j]);
+        if (1==RB && c+1==uint32_t(p.nchunks) && 0==threadIdx.x) { // tail elements of the row (single flat row only)
+            for (int64_t e = nfull*V; e<p.n; ++e) {
+                T x[P.nin][V], out[V];
 #pragma unroll
-            for (int k=0; k<P.nin; ++k) { for (int j=1; j<V; ++j) x[k][j] = x[k][0]; }
-            eval_static<T, ID>(x, out);
-            r = comb<T, FOLD>(r, out[0]);
+                for (int k=0; k<P.nin; ++k) x[k][0] = p.scalar[k] ? xs[k][0] : reinterpret_cast<T const *>(reinterpret_cast<unsigned char const *>(p.in[k])+rowoff[0][k])[SK_ROW==p.kind[k] ? 0 : e];
+#pragma unroll
+                for (int k=0; k<P.nin; ++k) { for (int j=1; j<V; ++j) x[k][j] = x[k][0]; }
+                eval_static<T, ID>(x, out);
+                v = comb<T, FOLD>(v, out[0]);
+            }
         }
-    }
-    r = block_comb<T, FOLD>(r, red);
-    if (0==threadIdx.x) {
-        if (p.nchunks>1) static_cast<W *>(p.partial)[int64_t(c)*p.nk+kb] = W(to_bits<T>(r));
-        else finish_apply<W>(f, kb, W(to_bits<T>(r)));
+        if (r>0) __syncthreads(); // red[] reuse
+        v = block_comb<T, FOLD>(v, red);
+        if (0==threadIdx.x) {
+            int64_t const row = int64_t(kb)*RB + r;
+            if (p.nchunks>1) static_cast<W *>(p.partial)[int64_t(c)*p.nk+row] = W(to_bits<T>(v));
+            else finish_apply<W>(f, row, W(to_bits<T>(v)));
+        }
     }
 }
 
@@ -342,14 +397,16 @@ launch_one(Plan const & plan, dim3 grid, cudaStream_t stream)
     if (p.mode==K_MAP) {
         if constexpr (!P.fold) sflat_map_kernel<T, ID><<<grid, KBLOCK, 0, stream>>>(p);
     } else if constexpr (P.fold) {
-#define RACU_SF(KERNEL) \
+#define RACU_SF(KERNEL, ...) \
         switch (p.fold_op) { \
-        case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: KERNEL<T, ID, RACU_ASSIGN_ADD><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        case RACU_ASSIGN_AMIN: KERNEL<T, ID, RACU_ASSIGN_AMIN><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        case RACU_ASSIGN_AMAX: KERNEL<T, ID, RACU_ASSIGN_AMAX><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        default: KERNEL<T, ID, RACU_ASSIGN_MUL><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
+        case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: KERNEL<T, ID, RACU_ASSIGN_ADD __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
+        case RACU_ASSIGN_AMIN: KERNEL<T, ID, RACU_ASSIGN_AMIN __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
+        case RACU_ASSIGN_AMAX: KERNEL<T, ID, RACU_ASSIGN_AMAX __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
+        default: KERNEL<T, ID, RACU_ASSIGN_MUL __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
         }
-        if (p.mode==K_FOLD_INNER) { RACU_SF(sflat_fold_inner_kernel) } else { RACU_SF(sflat_fold_outer_kernel) }
+        if (p.mode==K_FOLD_INNER) {
+            if (p.rb>1) { grid.x /= unsigned(p.rb); RACU_SF(sflat_fold_inner_kernel, , 4) } else { RACU_SF(sflat_fold_inner_kernel, , 1) }
+        } else { RACU_SF(sflat_fold_outer_kernel) }
 #undef RACU_SF
     }
     return cudaGetLastError();

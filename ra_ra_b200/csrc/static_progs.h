@@ -65,10 +65,12 @@ struct SParams
     uint64_t in[SP_MAXIN];        // role -> base address (vector inputs) or value bits (scalars)
     uint8_t scalar[SP_MAXIN];
     uint8_t kind[SP_MAXIN];       // maps: SK_* below
+    uint8_t reused[SP_MAXIN];     // folds: the operand does not move along the kept rows (every row re-reads it): cache in L1
     int64_t sB[SP_MAXIN][KGR];    // role -> element strides over group B
     KDim dB[KGR];
     // maps over up to KGR uncollapsible axes (axis 0 vectorised)
-    int32_t rankA, pad;
+    int32_t rankA, rb;            // rb: rows blocked per CTA in fold-inner (1 or 4)
+    int32_t chunk_major, pad2;    // fold-inner CTA order: blockIdx = chunk*nk + row instead of row*nchunks + chunk
     int64_t nvec, vpr;            // vectors in total, vectors per row
     KDim vprdiv;
     KDim dA[KGR];

@@ -365,4 +365,5 @@ def test_gemv_gevm_static_rows(exc):
     x = exc.empty((m,), abi.F64)
     x.assign(1 + ra._0)
     ra.gevm(x, a, c2)
+    assert exc.last_kernel() == "sflat_fold_outer", exc.last_kernel()
     assert np.array_equal(c2.numpy(), x.numpy() @ a.numpy())
