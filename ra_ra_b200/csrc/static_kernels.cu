@@ -105,7 +105,9 @@ template <> __device__ __forceinline__ uint64_t to_bits<double>(double v) { retu
 constexpr int SUNR = 4; // vectors in flight per thread per input
 
 // Fill x[k] for one vector at byte offset `off` from each input's base (+ rowoff[k]). Scalars are pre-broadcast in xs.
-template <class T, int ID> __device__ __forceinline__ void
+// REUSE is a compile-time switch: a run-time choice between the two load forms makes the compiler load into temporaries
+// and select right after each load, which serialises the loads on their latency (measured: 7.0 -> 3.0 TB/s on dot).
+template <class T, int ID, bool REUSE=false> __device__ __forceinline__ void
 load_inputs(SParams const & p, T (*x)[VecOf<T>::V], T const (*xs)[VecOf<T>::V], int64_t const * rowoff, int64_t off)
 {
     constexpr int V = VecOf<T>::V;
@@ -121,10 +123,13 @@ load_inputs(SParams const & p, T (*x)[VecOf<T>::V], T const (*xs)[VecOf<T>::V], 
             for (int j=0; j<V; ++j) x[k][j] = v;
         } else if (k==P.yrole) {
             ld16_rw<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
-        } else if (p.reused[k]) {
-            ld16_reused<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
         } else {
-            ld16<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
+            if constexpr (REUSE) {
+                if (p.reused[k]) ld16_reused<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
+                else ld16<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
+            } else {
+                ld16<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
+            }
         }
     }
 }
@@ -226,13 +231,14 @@ block_comb(T r, T * red)
 // ---- fold-inner, flat rows: CTA = (RB consecutive rows starting at kb*RB, chunk c); row length len0 (multiple of V unless
 // there is a single row). RB > 1 (rankB == 1 only) blocks rows in registers so that operands that do not move along the
 // kept axis (the vector of gemv: c(i) += a(i,j)*b(j), ra/ra.hh:418) are loaded once per RB rows instead of once per row.
-template <class T, int ID, int FOLD, int RB> __global__ void __launch_bounds__(KBLOCK)
+template <class T, int ID, int FOLD, bool REUSE> __global__ void __launch_bounds__(KBLOCK)
 sflat_fold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f)
 {
     using W = std::conditional_t<sizeof(T)==8, uint64_t, uint32_t>;
     constexpr int V = VecOf<T>::V;
     constexpr SProg P = static_prog(ID);
-    constexpr int UN = RB>1 ? 2 : SUNR; // vectors in flight per input per row
+    constexpr int RB = 1;               // (register row blocking measured slower than L1 reuse: kept at 1)
+    constexpr int UN = SUNR;            // vectors in flight per input per row
     __shared__ T red[KBLOCK/32];
     // chunk-major order (gemv): CTAs resident together work on the SAME column chunk of consecutive rows, so the operand
     // every row re-reads stays in L1; row-major order otherwise
@@ -279,7 +285,7 @@ sflat_fold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant
             if (g<end) {
 #pragma unroll
                 for (int r=0; r<RB; ++r) {
-                    if (0==r) load_inputs<T, ID>(p, x[0][u], xs, rowoff[0], g*16);
+                    if (0==r) load_inputs<T, ID, REUSE>(p, x[0][u], xs, rowoff[0], g*16);
                     else {
 #pragma unroll
                         for (int k=0; k<P.nin; ++k) {
@@ -405,7 +411,9 @@ launch_one(Plan const & plan, dim3 grid, cudaStream_t stream)
         default: KERNEL<T, ID, RACU_ASSIGN_MUL __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
         }
         if (p.mode==K_FOLD_INNER) {
-            if (p.rb>1) { grid.x /= unsigned(p.rb); RACU_SF(sflat_fold_inner_kernel, , 4) } else { RACU_SF(sflat_fold_inner_kernel, , 1) }
+            bool any = false;
+            for (int k=0; k<SP_MAXIN; ++k) any = any || p.reused[k];
+            if (any) { RACU_SF(sflat_fold_inner_kernel, , true) } else { RACU_SF(sflat_fold_inner_kernel, , false) }
         } else { RACU_SF(sflat_fold_outer_kernel) }
 #undef RACU_SF
     }
