@@ -137,7 +137,9 @@ load_inputs(SParams const & p, T (*x)[VecOf<T>::V], T const (*xs)[VecOf<T>::V], 
 // ---- map: dst[...] = P(inputs[...]) over up to KGR uncollapsible axes; axis 0 is vectorised (16 bytes per access).
 // Inputs per role: aligned unit-step vectors (forward or reversed), one value per row (prefix rank extension: the
 // `v` of B += A*C + v, examples/read-me.cc:32), or scalars. A flat traversal (rankA==1) may have a scalar tail.
-template <class T, int ID> __global__ void __launch_bounds__(KBLOCK)
+// GENERAL=false: every non-scalar input is a forward unit-step vector. The kind is then known at compile time, which matters:
+// a run-time choice between load forms makes the compiler select right after each load and serialises them.
+template <class T, int ID, bool GENERAL> __global__ void __launch_bounds__(KBLOCK)
 sflat_map_kernel(const __grid_constant__ SParams p)
 {
     constexpr int V = VecOf<T>::V;
@@ -169,14 +171,14 @@ sflat_map_kernel(const __grid_constant__ SParams p)
                 doff[u] = e0 + int64_t(i1)*p.dsA[1] + int64_t(i2)*p.dsA[2] + int64_t(i3)*p.dsA[3];
 #pragma unroll
                 for (int k=0; k<P.nin; ++k) {
-                    int const kd = p.kind[k];
+                    int const kd = GENERAL ? int(p.kind[k]) : (p.scalar[k] ? int(SK_SCALAR) : int(SK_VEC));
                     if (SK_SCALAR==kd) {
 #pragma unroll
                         for (int j=0; j<V; ++j) x[u][k][j] = xs[k][j];
                     } else {
                         int64_t off = int64_t(i1)*p.sA[k][1] + int64_t(i2)*p.sA[k][2] + int64_t(i3)*p.sA[k][3];
                         T const * base = reinterpret_cast<T const *>(p.in[k]);
-                        if (SK_VEC==kd) {
+                        if (!GENERAL || SK_VEC==kd) {
                             if (k==P.yrole) ld16_rw<T>(x[u][k], base + off + e0); else ld16<T>(x[u][k], base + off + e0);
                         } else if (SK_VECREV==kd) {
                             T r[V];
@@ -401,7 +403,11 @@ launch_one(Plan const & plan, dim3 grid, cudaStream_t stream)
     SParams const & p = plan.sp;
     constexpr SProg P = static_prog(ID);
     if (p.mode==K_MAP) {
-        if constexpr (!P.fold) sflat_map_kernel<T, ID><<<grid, KBLOCK, 0, stream>>>(p);
+        if constexpr (!P.fold) {
+            bool general = false;
+            for (int k=0; k<P.nin; ++k) general = general || p.kind[k]==SK_VECREV || p.kind[k]==SK_ROW;
+            if (general) sflat_map_kernel<T, ID, true><<<grid, KBLOCK, 0, stream>>>(p); else sflat_map_kernel<T, ID, false><<<grid, KBLOCK, 0, stream>>>(p);
+        }
     } else if constexpr (P.fold) {
 #define RACU_SF(KERNEL, ...) \
         switch (p.fold_op) { \
