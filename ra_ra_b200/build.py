@@ -7,7 +7,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libracu.so")
-SOURCES = ["ply_kernels.cu", "static_kernels.cu", "stencil.cu", "transpose.cu", "gemm.cu", "plan.cc", "api.cc", "special.cc", "comm.cc"]
+STATIC_PARTS = 4  # the static program table is compiled in this many parallel translation units
+SOURCES = ["ply_kernels.cu"] + [f"static_kernels.cu#{k}" for k in range(STATIC_PARTS)] + [ "stencil.cu", "transpose.cu", "gemm.cu", "plan.cc", "api.cc", "special.cc", "comm.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O3", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
 
@@ -32,14 +33,16 @@ def build_lib(force=False, verbose=False):
     hdrs = _headers()
     jobs = []
     for s in SOURCES:
-        src = os.path.join(CSRC, s)
-        obj = os.path.join(bdir, s + ".o")
+        name, _, part = s.partition("#")
+        src = os.path.join(CSRC, name)
+        obj = os.path.join(bdir, s.replace("#", "_") + ".o")
         if force or _stale(obj, [src] + hdrs):
-            if s.endswith(".cc"):  # host-only translation units
+            if name.endswith(".cc"):  # host-only translation units
                 cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++20", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
                        "-I", os.path.join(os.path.dirname(os.path.dirname(nvcc)), "include"), "-c", src, "-o", obj]
             else:
-                cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+                defs = [f"-DSP_PART={part}", f"-DSP_NPART={STATIC_PARTS}"] if part else []
+                cmd = [nvcc] + NVCC_FLAGS + defs + ["-c", src, "-o", obj]
             jobs.append(cmd)
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -49,7 +52,7 @@ def build_lib(force=False, verbose=False):
             sys.stderr.write(r.stdout + r.stderr)
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
-    objs = [os.path.join(bdir, s + ".o") for s in SOURCES]
+    objs = [os.path.join(bdir, s.replace("#", "_") + ".o") for s in SOURCES]
     if force or jobs or _stale(OUT, objs):
         run([nvcc, "-shared", "-o", OUT] + objs + ["-ldl", "-gencode", "arch=compute_100a,code=sm_100a"])
     return OUT

@@ -294,108 +294,129 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
     if (!map && kp.rankA!=1) return;
     if (map && kp.rankB!=0) return;
     if (kp.mode==K_FOLD_OUTER && kp.rankB!=1) return;
-    int const T = prog[0].type;
-    if (T!=RACU_F32 && T!=RACU_F64 && T!=RACU_I32) return;
-    int const V = T==RACU_F64 ? 2 : 4;
-    size_t const es = dtype_size(T);
-    // how a map operand can be read by the static kernel
-    auto map_kind = [&](KOpnd const & k) -> int {
-        if (k.stage==S_NONE) return SK_SCALAR;
+    // how the static kernels can read operand k (SV-element vectors, 16-byte accesses): from the raw strides
+    auto aligned_outer = [&](KOpnd const & k) {
+        int64_t const es = k.esize;
+        for (int j=1; j<kp.rankA; ++j) { if (0!=(k.sA[j]*es)%16) return false; }
+        for (int j=0; j<kp.rankB; ++j) { if (0!=(k.sB[j]*es)%16) return false; }
+        return true;
+    };
+    auto kind_of = [&](KOpnd const & k) -> int {
+        if (k.kind==RACU_SCALAR) return SK_SCALAR;
         if (k.kind!=RACU_MEM) return -1;
-        if (k.stage==S_VEC) return SK_VEC;
-        if (k.stage==S_BCAST) return SK_ROW;
-        if (-1==k.sA[0] && 0==((k.base-(V-1)*es)%16)) {
-            for (int j=1; j<kp.rankA; ++j) { if (0!=k.sA[j]%V) return -1; }
-            return SK_VECREV;
-        }
+        int64_t const es = k.esize;
+        if (1==k.sA[0]) return (0==k.base%16 && aligned_outer(k)) ? SK_VEC : -1;
+        if (0==k.sA[0]) return SK_ROW;
+        if (-1==k.sA[0] && map) return (0==(k.base-uint64_t((SV-1)*es))%16 && aligned_outer(k)) ? SK_VECREV : -1;
         return -1;
     };
     // roles by first appearance
     int role_of[RACU_MAX_OPND], nrole = 0, yrole = -1;
     for (int o=0; o<RACU_MAX_OPND; ++o) role_of[o] = -1;
     SIns seq[SP_MAXINS];
+    uint8_t rtype[SP_MAXIN] = {};
     for (size_t pc=0; pc<prog.size(); ++pc) {
         racu_ins const & i = prog[pc];
-        if (i.type!=T || i.op==RACU_OP_CAST) return;
+        if (i.op==RACU_OP_PICK) return;
         if (i.op==RACU_OP_PUSH) {
             if (role_of[i.arg]<0) {
                 if (nrole>=SP_MAXIN) return;
                 KOpnd const & k = kp.opnd[i.arg];
-                if (k.dtype!=T) return;
-                if (map ? map_kind(k)<0 : !(k.stage==S_VEC || k.stage==S_NONE || (k.stage==S_BCAST && k.kind==RACU_MEM))) return;
-                if (!fold && int(i.arg)==dst) yrole = nrole;
+                int kd = kind_of(k);
+                if (kd<0 || (!map && kd==SK_VECREV)) return;
+                if (!fold && int(i.arg)==dst) { if (kd!=SK_VEC) return; yrole = nrole; }
+                rtype[nrole] = k.dtype;
                 role_of[i.arg] = nrole++;
             }
-            seq[pc] = sP(role_of[i.arg]);
+            seq[pc] = SIns {RACU_OP_PUSH, uint8_t(role_of[i.arg]), i.type, 0};
         } else {
-            seq[pc] = sO(i.op);
+            seq[pc] = SIns {i.op, 0, i.type, uint8_t(i.op==RACU_OP_CAST ? i.aux : 0)};
         }
     }
+    int const otype = fold ? kp.acc_type : kp.opnd[dst].dtype;
     int id = -1;
     for (int c=0; c<SP_COUNT && id<0; ++c) {
         SProg const P = static_prog(c);
-        if (P.n!=int(prog.size()) || P.nin!=nrole || P.yrole!=yrole || P.fold!=fold) continue;
+        if (P.n!=int(prog.size()) || P.nin!=nrole || P.yrole!=yrole || P.fold!=fold || P.otype!=otype) continue;
         bool same = true;
-        for (int pc=0; pc<P.n && same; ++pc) same = P.ins[pc].op==seq[pc].op && (P.ins[pc].op!=RACU_OP_PUSH || P.ins[pc].arg==seq[pc].arg);
+        for (int r=0; r<nrole && same; ++r) same = P.rtype[r]==rtype[r];
+        for (int pc=0; pc<P.n && same; ++pc) same = P.ins[pc].op==seq[pc].op && P.ins[pc].type==seq[pc].type && P.ins[pc].aux==seq[pc].aux && P.ins[pc].arg==seq[pc].arg;
         if (same) id = c;
     }
     if (id<0) return;
     SParams & sp = plan.sp;
     std::memset(&sp, 0, sizeof(sp));
+    int64_t const nvec0 = kp.len0/SV;
+    int const target = 148*8;
     if (fold) {
-        if (kp.acc_type!=T || plan.fp.dst_dtype!=T) return;
         if (kp.fold_op==RACU_ASSIGN_SET) return;
-        if ((kp.nk>1 || kp.mode==K_FOLD_OUTER) && 0!=kp.len0%V) return;
+        if ((kp.nk>1 || kp.mode==K_FOLD_OUTER) && 0!=kp.len0%SV) return;
+        if (kp.mode==K_FOLD_INNER) { // chunk the row in units of SV-element vectors
+            int64_t per = int64_t(KBLOCK)*4; // upper bound of the kernel's vectors per iteration
+            int64_t maxchunks = std::max<int64_t>(1, nvec0/(per*2));
+            int64_t want = std::max<int64_t>(1, (int64_t(target)*2)/std::max<int64_t>(1, kp.nk));
+            int64_t nch = std::min(maxchunks, want);
+            int64_t cl = std::max<int64_t>(1, (nvec0+nch-1)/nch);
+            cl = ((cl+per-1)/per)*per;
+            nch = std::max<int64_t>(1, (nvec0+cl-1)/cl);
+            if (kp.nk*nch>=(int64_t(1)<<31)) return;
+            kp.nchunks = int(nch); kp.chunk_len = cl;
+            plan.grid_x = unsigned(kp.nk*nch); plan.grid_y = 1;
+        } else {
+            int64_t nbx = (nvec0+KBLOCK-1)/KBLOCK;
+            if (nbx<1 || nbx>=(int64_t(1)<<31)) return;
+            int64_t want = std::max<int64_t>(1, (int64_t(target)*2)/nbx);
+            int64_t maxchunks = std::max<int64_t>(1, kp.nB/32);
+            int64_t nch = std::min<int64_t>(std::min(maxchunks, want), 65535);
+            int64_t cl = (kp.nB+nch-1)/nch;
+            cl = ((cl+3)/4)*4;
+            nch = (kp.nB+cl-1)/cl;
+            kp.nchunks = int(nch); kp.chunk_len = cl;
+            plan.grid_x = unsigned(nbx); plan.grid_y = unsigned(nch);
+        }
+        plan.fp.nchunks = kp.nchunks;
+        plan.need_finish = kp.nchunks>1;
+        plan.partial_bytes = plan.need_finish ? size_t(kp.nchunks)*size_t(kp.nk)*(plan.fp.wide ? 8 : 4) : 0;
+        sp.wide_partials = plan.fp.wide;
     } else {
         KOpnd const & y = kp.opnd[dst];
-        if (y.dtype!=T || y.stage!=S_VEC) return;
-        if (kp.rankA>1 && 0!=kp.len0%V) return; // rows must be whole vectors
+        if (1!=y.sA[0] || 0!=y.base%16 || !aligned_outer(y)) return;
+        if (kp.rankA>1 && 0!=kp.len0%SV) return; // rows must be whole vectors
         sp.dst = reinterpret_cast<void *>(uintptr_t(y.base));
-        sp.rankA = kp.rankA; sp.vpr = kp.vpr; sp.vprdiv = kp.vprdiv;
-        sp.nvec = 1==kp.rankA ? kp.len0/V : kp.nvecA;
+        sp.vpr = nvec0;
+        sp.nvec = nvec0;
+        for (int j=1; j<kp.rankA; ++j) sp.nvec *= kp.dA[j].len;
+        if (kp.rankA>1) { if (nvec0<1 || sp.nvec>=(int64_t(1)<<31)) return; sp.vprdiv = make_div(nvec0); }
         for (int j=0; j<KGR; ++j) { sp.dA[j] = kp.dA[j]; sp.dsA[j] = j<kp.rankA ? y.sA[j] : 0; }
+        int64_t nb = (sp.nvec+int64_t(KBLOCK)*4-1)/(int64_t(KBLOCK)*4);
+        plan.grid_x = unsigned(std::max<int64_t>(1, std::min<int64_t>(nb, int64_t(target)*4))); plan.grid_y = 1;
     }
-    sp.id = id; sp.dtype = T; sp.mode = kp.mode; sp.fold_op = kp.fold_op; sp.nchunks = kp.nchunks; sp.rankB = kp.rankB;
+    sp.id = id; sp.mode = kp.mode; sp.fold_op = kp.fold_op; sp.nchunks = kp.nchunks; sp.rankB = kp.rankB; sp.rankA = kp.rankA;
     sp.identity = kp.identity; sp.n = kp.len0; sp.nB = kp.nB; sp.chunk_len = kp.chunk_len; sp.nk = kp.nk;
     for (int j=0; j<KGR; ++j) sp.dB[j] = kp.dB[j];
     for (int o=0; o<kp.nopnd; ++o) {
         int r = role_of[o];
         if (r<0) continue;
         KOpnd const & k = kp.opnd[o];
-        sp.scalar[r] = k.stage==S_NONE;
-        sp.kind[r] = uint8_t(map ? map_kind(k) : (k.stage==S_NONE ? SK_SCALAR : k.stage==S_BCAST ? SK_ROW : SK_VEC));
-        if (k.stage==S_NONE) { // scalar bits in T
-            if (T==RACU_F32) sp.in[r] = f32_bits(float(bits_f64(k.base))); else if (T==RACU_F64) sp.in[r] = k.base; else sp.in[r] = uint32_t(int32_t(int64_t(k.base)));
+        sp.kind[r] = uint8_t(kind_of(k));
+        if (sp.kind[r]==SK_VECREV || (map && sp.kind[r]==SK_ROW)) sp.general = 1;
+        if (k.kind==RACU_SCALAR) { // value bits in the role's type
+            switch (k.dtype) {
+            case RACU_F32: sp.in[r] = f32_bits(float(bits_f64(k.base))); break;
+            case RACU_I32: sp.in[r] = uint32_t(int32_t(int64_t(k.base))); break;
+            case RACU_BOOL: sp.in[r] = k.base!=0; break;
+            default: sp.in[r] = k.base; break;
+            }
         } else {
             sp.in[r] = k.base;
         }
-        for (int j=0; j<KGR; ++j) { sp.sB[r][j] = k.sB[j]; sp.sA[r][j] = j<kp.rankA ? k.sA[j] : 0; }
+        for (int j=0; j<KGR; ++j) { sp.sB[r][j] = j<kp.rankB ? k.sB[j] : 0; sp.sA[r][j] = j<kp.rankA ? k.sA[j] : 0; }
     }
-    sp.rb = 1; // (row blocking in registers measured slower than L1 reuse for gemv: kept off)
     if (fold && kp.mode==K_FOLD_INNER && kp.rankB>=1 && kp.nk>1) {
         for (int r=0; r<nrole; ++r) {
             bool moves = false;
             for (int j=0; j<kp.rankB; ++j) moves = moves || 0!=sp.sB[r][j];
-            sp.reused[r] = !sp.scalar[r] && !moves;
-        }
-        bool any = false;
-        for (int r=0; r<nrole; ++r) any = any || sp.reused[r];
-        // gemv shape: many rows, one operand re-read by every row. Cut the rows into column chunks of <= 32 KiB and run the
-        // CTAs chunk-major, so the resident CTAs of an SM share one chunk of that operand in L1.
-        int64_t const row_bytes = kp.len0*int64_t(es);
-        if (std::getenv("RACU_CHUNK_MAJOR") && any && 1==kp.nchunks && kp.nk>=1024 && row_bytes>64*1024 && 0==kp.len0%V) { // measured slower than plain L1 reuse on B200: opt-in only
-            int64_t nvec = kp.len0/V, nch = (row_bytes+32*1024-1)/(32*1024);
-            int64_t cl = (nvec+nch-1)/nch;
-            cl = ((cl+KBLOCK-1)/KBLOCK)*KBLOCK;
-            nch = (nvec+cl-1)/cl;
-            if (nch>1 && kp.nk*nch<(int64_t(1)<<31)) {
-                plan.kp.nchunks = int(nch); plan.kp.chunk_len = cl;
-                sp.nchunks = int(nch); sp.chunk_len = cl; sp.chunk_major = 1;
-                plan.fp.nchunks = int(nch);
-                plan.need_finish = true;
-                plan.partial_bytes = size_t(nch)*size_t(kp.nk)*(8==es ? 8 : 4);
-                plan.grid_x = unsigned(kp.nk*nch);
-            }
+            sp.reused[r] = sp.kind[r]==SK_VEC && !moves;
         }
     }
     plan.is_static = true;
@@ -716,6 +737,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     int U = nasync>0 ? std::max(1, std::min(4, 8/nasync)) : 1;
     auto smem_for = [&](int u) { return size_t(u)*size_t(nstage+depth)*KBLOCK*KSLOT; }; // U staged vectors + U stack rows per level
     if (3==U) U = 2;
+    if (char const * e = std::getenv("RACU_U")) { int u = std::atoi(e); if (1==u || 2==u || 4==u) U = u; } // tuning knob
     while (U>1 && smem_for(U)>size_t(100*1024)) U /= 2;
     if (smem_for(U)>size_t(220*1024)) { err = "expression needs too much staging memory"; return RACU_ERR_UNSUPPORTED; }
     kp.U = U;

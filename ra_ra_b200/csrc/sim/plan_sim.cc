@@ -4,6 +4,7 @@
 // code the device runs (kbody.h), so the planner (axis sorting, merging, flips, staging modes, stack levels, chunking)
 // can be checked against the oracle in this GPU-less container. Folds combine in a different (sequential) order than the
 // device tree, so float folds are compared by tolerance; integer-valued ones exactly.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -103,6 +104,8 @@ const char * racu_sim_last_error(void) { return g_sim_err.c_str(); }
 int
 racu_sim_run(racu_desc const * d, int redop, void * reduce_out)
 {
+    static int const once = setenv("RACU_NO_STATIC", "1", 1); // the simulator walks the generic kernels' bodies only
+    (void)once;
     Plan & plan = g_sim_plan;
     plan = Plan {};
     if (int e = make_plan(d, redop, reduce_out, plan, g_sim_err)) {

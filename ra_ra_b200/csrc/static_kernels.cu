@@ -1,15 +1,18 @@
 // static_kernels.cu - compile-time specialisations of the ply kernels for the hottest program shapes.
 //
-// The generic kernels (ply_kernels.cu) interpret the postfix program; on flat traversals (one collapsed contiguous axis,
-// ra/ply.hh:42-46 with `keep` true on every leaf) of a short single-type program the interpretive overhead, not HBM, is
-// the limit. Here the SAME postfix program is a constexpr array: the evaluator loop is fully unrolled by the compiler,
-// the value stack lives in registers, operands are read with 128-bit loads issued UNR deep before the first use.
-// Same ops, same order, same types, no contraction (-fmad=false): results are bit-identical to the interpreter's.
+// The generic kernels (ply_kernels.cu) interpret the postfix program; for short programs the interpretive overhead, not
+// HBM, is the limit. Here the SAME typed postfix program is a constexpr array (static_progs.h): the evaluator loop is fully
+// unrolled by the compiler, every switch on opcode / type folds away, the value stack lives in registers, and operands
+// are read with 128-bit loads issued several deep before the first use. Same ops, same order, same types, no contraction
+// (-fmad=false): results are bit-identical to the interpreter's and to the oracle's.
 //
-// The planner (plan.cc: match_static) picks a specialisation when
-//   * every instruction has one type T in {f32, f64, i32} and there is no CAST,
-//   * every operand is a 16-byte aligned unit-stride vector (S_VEC) of T, or a scalar of T,
-//   * the traversal is flat: map with rankA==1; fold-inner with rankA==1 (any kept rows); fold-outer with rankA==rankB==1.
+// The planner (plan.cc: match_static) picks a specialisation when the canonical program equals a table entry (opcodes,
+// types, roles) and every operand is a 16-byte aligned unit-step vector (forward or reversed), one value per row, or a
+// scalar; maps may have up to 4 uncollapsible axes, fold-inner any kept rows, fold-outer one folded axis.
+//
+// NOTE (measured): any RUN-TIME choice between load instruction forms inside the unrolled load loop makes the compiler load
+// into temporaries and select right after each load, which serialises the loads on their latency (dot 7.0 -> 3.0 TB/s).
+// Operand kinds that change the load form are therefore compile-time template switches (GENERAL, REUSE).
 #include <cuda_runtime.h>
 #include "kbody.h"
 #include "launch.h"
@@ -17,153 +20,176 @@
 
 namespace racu {
 
-template <class T> struct VecOf;
-template <> struct VecOf<float> { using type = float4; static constexpr int V = 4; };
-template <> struct VecOf<int32_t> { using type = int4; static constexpr int V = 4; };
-template <> struct VecOf<double> { using type = double2; static constexpr int V = 2; };
+template <int ID> struct SPT
+{
+    static constexpr SProg P = static_prog(ID);
+    static constexpr bool wide = prog_wide(P);
+    using W = std::conditional_t<wide, uint64_t, uint32_t>;
+};
 
-template <class T> __device__ __forceinline__ void
-ld16(T * out, void const * p) // streaming 128-bit load: read once, do not keep in L1
+__host__ __device__ constexpr int es_of(int t) { return t==RACU_BOOL ? 1 : (t==RACU_I32 || t==RACU_F32) ? 4 : 8; }
+
+enum LdForm { LD_STREAM = 0, LD_REUSED = 1, LD_RW = 2 };
+
+template <int FORM> __device__ __forceinline__ uint4
+ld16(void const * p)
 {
-    uint32_t a, b, c, d;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
-    uint32_t w[4] = {a, b, c, d};
-    memcpy(out, w, 16);
-}
-template <class T> __device__ __forceinline__ void
-ld16_reused(T * out, void const * p) // operand re-read by every kept row (the vector of gemv): let L1 keep it
-{
-    uint32_t a, b, c, d;
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
-    uint32_t w[4] = {a, b, c, d};
-    memcpy(out, w, 16);
-}
-template <class T> __device__ __forceinline__ void
-ld16_rw(T * out, void const * p) // destination operand (read-modify-write): ordinary load
-{
-    uint4 q = *reinterpret_cast<uint4 const *>(p);
-    memcpy(out, &q, 16);
-}
-template <class T> __device__ __forceinline__ void
-st16(void * p, T const * v)
-{
-    uint4 q;
-    memcpy(&q, v, 16);
-    *reinterpret_cast<uint4 *>(p) = q;
+    uint4 r;
+    if constexpr (FORM==LD_STREAM) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if constexpr (FORM==LD_REUSED) asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else r = *reinterpret_cast<uint4 const *>(p);
+    return r;
 }
 
-// The constexpr postfix evaluator. x[k][j]: lane j of input k (role SP_Y is the destination's old value).
-template <class T, int ID> __device__ __forceinline__ void
-eval_static(T const (*x)[VecOf<T>::V], T * out)
+// 64-bit lanes are loaded as 64-bit registers: packing two 32-bit halves after the load is an ALU op that depends on the load
+// and stalls on it, which serialises the loads.
+template <int FORM> __device__ __forceinline__ void
+ld16x2(uint64_t & a, uint64_t & b, void const * p)
 {
-    constexpr int V = VecOf<T>::V;
-    constexpr SProg P = static_prog(ID);
-    T st[P.n>0 ? P.n : 1][V];
+    if constexpr (FORM==LD_STREAM) asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+    else if constexpr (FORM==LD_REUSED) asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+    else { ulonglong2 q = *reinterpret_cast<ulonglong2 const *>(p); a = q.x; b = q.y; }
+}
+
+// Operand vectors are held as RAW 32-bit words exactly as loaded (4 words for SV 4-byte elements, 8 for 8-byte ones, 1 for
+// bools); they become typed slot values only at PUSH time inside the evaluator. Anything computed from a loaded register
+// right after the load (packing halves, widening) would stall on that load and serialise the loads.
+template <int FORM> __device__ __forceinline__ void
+load_words(uint32_t * x, unsigned char const * p, int t)
+{
+    int const es = es_of(t);
+    if (4==es) { uint4 q = ld16<FORM>(p); x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w; }
+    else if (8==es) {
+        uint4 q0 = ld16<FORM>(p), q1 = ld16<FORM>(p+16);
+        x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w; x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+    } else { x[0] = *reinterpret_cast<uint32_t const *>(p); }
+}
+// one element broadcast to every lane, in raw words
+__device__ __forceinline__ void
+splat_words(uint32_t * x, unsigned char const * p, int t)
+{
+    int const es = es_of(t);
+    if (4==es) { uint32_t v = *reinterpret_cast<uint32_t const *>(p); x[0] = v; x[1] = v; x[2] = v; x[3] = v; }
+    else if (8==es) { uint2 v = *reinterpret_cast<uint2 const *>(p); x[0] = v.x; x[1] = v.y; x[2] = v.x; x[3] = v.y; x[4] = v.x; x[5] = v.y; x[6] = v.x; x[7] = v.y; }
+    else { uint32_t v = *p ? 0x01010101u : 0u; x[0] = v; }
+}
+__device__ __forceinline__ void
+splat_bits(uint32_t * x, uint64_t bits, int t)
+{
+    int const es = es_of(t);
+    if (4==es) { uint32_t v = uint32_t(bits); x[0] = v; x[1] = v; x[2] = v; x[3] = v; }
+    else if (8==es) { uint32_t lo = uint32_t(bits), hi = uint32_t(bits>>32); x[0] = lo; x[1] = hi; x[2] = lo; x[3] = hi; x[4] = lo; x[5] = hi; x[6] = lo; x[7] = hi; }
+    else { x[0] = bits ? 0x01010101u : 0u; }
+}
+template <class W> __device__ __forceinline__ W
+word_lane(uint32_t const * x, int j, int t) // lane j of a raw vector as slot bits
+{
+    int const es = es_of(t);
+    if (4==es) return W(x[j]);
+    if (8==es) { if constexpr (sizeof(W)==8) return uint64_t(x[2*j]) | (uint64_t(x[2*j+1])<<32); else return W(0); }
+    return W((x[0]>>(8*j))&0xffu ? 1 : 0);
+}
+template <class W> __device__ __forceinline__ void
+store_vec(unsigned char * p, W const * v, int t)
+{
+    int const es = es_of(t);
+    if (4==es) { uint4 q; q.x = uint32_t(v[0]); q.y = uint32_t(v[1]); q.z = uint32_t(v[2]); q.w = uint32_t(v[3]); *reinterpret_cast<uint4 *>(p) = q; }
+    else if (8==es) {
+        if constexpr (sizeof(W)==8) {
+            ulonglong2 q0, q1;
+            q0.x = v[0]; q0.y = v[1]; q1.x = v[2]; q1.y = v[3];
+            *reinterpret_cast<ulonglong2 *>(p) = q0; *reinterpret_cast<ulonglong2 *>(p+16) = q1;
+        }
+    } else { *reinterpret_cast<uint32_t *>(p) = (uint32_t(v[0])&1u) | ((uint32_t(v[1])&1u)<<8) | ((uint32_t(v[2])&1u)<<16) | ((uint32_t(v[3])&1u)<<24); }
+}
+
+// words per raw operand vector, and vectors in flight per thread: about 48 registers of operand data
+template <int ID> struct SPX
+{
+    static constexpr int XW = SPT<ID>::wide ? 2*SV : SV;
+    static constexpr int words() { int w = 0; for (int r=0; r<SPT<ID>::P.nin; ++r) w += SV*es_of(SPT<ID>::P.rtype[r])/4 + (es_of(SPT<ID>::P.rtype[r])<4); return w>0 ? w : 1; }
+    static constexpr int UNR = 48/words()>=4 ? 4 : 48/words()>=2 ? 48/words() : 1;
+};
+
+// The constexpr typed postfix evaluator. x[k]: raw words of role k's vector.
+template <int ID> __device__ __forceinline__ void
+eval_static(uint32_t const (*x)[SPX<ID>::XW], typename SPT<ID>::W * out)
+{
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    W st[P.n>0 ? P.n : 1][SV];
     int sp = 0;
 #pragma unroll
     for (int pc=0; pc<P.n; ++pc) {
-        int const op = P.ins[pc].op, arg = P.ins[pc].arg;
+        int const op = P.ins[pc].op, arg = P.ins[pc].arg, type = P.ins[pc].type, aux = P.ins[pc].aux;
         if (op==RACU_OP_PUSH) {
 #pragma unroll
-            for (int j=0; j<V; ++j) st[sp][j] = x[arg][j];
+            for (int j=0; j<SV; ++j) st[sp][j] = word_lane<W>(x[arg], j, type);
             ++sp;
-        } else if (op==RACU_OP_NEG || op==RACU_OP_SQR || op==RACU_OP_ABS) {
+        } else if (op==RACU_OP_CAST) {
 #pragma unroll
-            for (int j=0; j<V; ++j) { T a = st[sp-1][j]; st[sp-1][j] = op==RACU_OP_NEG ? T(-a) : op==RACU_OP_SQR ? T(a*a) : t_abs<T>(a); }
-        } else {
+            for (int j=0; j<SV; ++j) st[sp-1][j] = cast_any<W>(aux, type, st[sp-1][j]);
+        } else if (op>=RACU_OP_NEG && op<=RACU_OP_NOT) {
 #pragma unroll
-            for (int j=0; j<V; ++j) {
-                T a = st[sp-2][j], b = st[sp-1][j];
-                st[sp-2][j] = op==RACU_OP_ADD ? T(a+b) : op==RACU_OP_SUB ? T(a-b) : op==RACU_OP_MUL ? T(a*b) : op==RACU_OP_DIV ? T(a/b)
-                    : op==RACU_OP_MIN ? (b<a ? b : a) : (a<b ? b : a);
-            }
+            for (int j=0; j<SV; ++j) st[sp-1][j] = un_any<W>(op, type, st[sp-1][j]);
+        } else if (op==RACU_OP_FMA) {
+#pragma unroll
+            for (int j=0; j<SV; ++j) st[sp-3][j] = fma_any<W>(type, st[sp-3][j], st[sp-2][j], st[sp-1][j]);
+            sp -= 2;
+        } else { // binary
+#pragma unroll
+            for (int j=0; j<SV; ++j) st[sp-2][j] = bin_any<W>(op, type, st[sp-2][j], st[sp-1][j]);
             --sp;
         }
     }
 #pragma unroll
-    for (int j=0; j<V; ++j) out[j] = st[0][j];
+    for (int j=0; j<SV; ++j) out[j] = st[0][j];
 }
 
-template <class T, int FOLD> __device__ __forceinline__ T
-comb(T c, T x)
+// role k of the vector at (e0, off) -> raw words. kd is the operand kind (compile-time constant when !GENERAL).
+template <int ID, bool GENERAL, int FORM> __device__ __forceinline__ void
+fetch_role(SParams const & p, int k, uint32_t * x, int64_t off, int64_t e0)
 {
-    if constexpr (FOLD==RACU_ASSIGN_ADD || FOLD==RACU_ASSIGN_SUB) return T(c+x);
-    else if constexpr (FOLD==RACU_ASSIGN_MUL || FOLD==RACU_ASSIGN_DIV) return T(c*x);
-    else if constexpr (FOLD==RACU_ASSIGN_AMIN) return x<c ? x : c;
-    else return c<x ? x : c;
+    constexpr SProg P = SPT<ID>::P;
+    int const t = P.rtype[k], es = es_of(t);
+    int const kd = GENERAL ? int(p.kind[k]) : (SK_SCALAR==p.kind[k] ? int(SK_SCALAR) : int(SK_VEC));
+    unsigned char const * base = reinterpret_cast<unsigned char const *>(p.in[k]);
+    if (SK_SCALAR==kd) splat_bits(x, p.in[k], t);
+    else if (!GENERAL || SK_VEC==kd) {
+        if (k==P.yrole) load_words<LD_RW>(x, base + (off+e0)*es, t); else load_words<FORM>(x, base + (off+e0)*es, t);
+    } else if (SK_VECREV==kd) { // lanes reversed: swap whole elements
+        uint32_t r[SPX<ID>::XW];
+        load_words<FORM>(r, base + (off-e0-(SV-1))*es, t);
+        if (4==es) { x[0] = r[3]; x[1] = r[2]; x[2] = r[1]; x[3] = r[0]; }
+        else if (8==es) { x[0] = r[6]; x[1] = r[7]; x[2] = r[4]; x[3] = r[5]; x[4] = r[2]; x[5] = r[3]; x[6] = r[0]; x[7] = r[1]; }
+        else { x[0] = __byte_perm(r[0], 0, 0x0123); }
+    } else splat_words(x, base + off*es, t); // SK_ROW
 }
 
-template <class T> __device__ __forceinline__ T from_bits(uint64_t b);
-template <> __device__ __forceinline__ float from_bits<float>(uint64_t b) { return __uint_as_float(uint32_t(b)); }
-template <> __device__ __forceinline__ int32_t from_bits<int32_t>(uint64_t b) { return int32_t(uint32_t(b)); }
-template <> __device__ __forceinline__ double from_bits<double>(uint64_t b) { return __longlong_as_double((long long)b); }
-template <class T> __device__ __forceinline__ uint64_t to_bits(T v);
-template <> __device__ __forceinline__ uint64_t to_bits<float>(float v) { return __float_as_uint(v); }
-template <> __device__ __forceinline__ uint64_t to_bits<int32_t>(int32_t v) { return uint32_t(v); }
-template <> __device__ __forceinline__ uint64_t to_bits<double>(double v) { return uint64_t(__double_as_longlong(v)); }
-
-constexpr int SUNR = 4; // vectors in flight per thread per input
-
-// Fill x[k] for one vector at byte offset `off` from each input's base (+ rowoff[k]). Scalars are pre-broadcast in xs.
-// REUSE is a compile-time switch: a run-time choice between the two load forms makes the compiler load into temporaries
-// and select right after each load, which serialises the loads on their latency (measured: 7.0 -> 3.0 TB/s on dot).
-template <class T, int ID, bool REUSE=false> __device__ __forceinline__ void
-load_inputs(SParams const & p, T (*x)[VecOf<T>::V], T const (*xs)[VecOf<T>::V], int64_t const * rowoff, int64_t off)
-{
-    constexpr int V = VecOf<T>::V;
-    constexpr SProg P = static_prog(ID);
-#pragma unroll
-    for (int k=0; k<P.nin; ++k) {
-        if (p.scalar[k]) {
-#pragma unroll
-            for (int j=0; j<V; ++j) x[k][j] = xs[k][j];
-        } else if (SK_ROW==p.kind[k]) { // step 0 along the vectorised axis: one value per row (gevm: c(j) += a(i)*b(i,j))
-            T v = __ldg(reinterpret_cast<T const *>(reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k]));
-#pragma unroll
-            for (int j=0; j<V; ++j) x[k][j] = v;
-        } else if (k==P.yrole) {
-            ld16_rw<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
-        } else {
-            if constexpr (REUSE) {
-                if (p.reused[k]) ld16_reused<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
-                else ld16<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
-            } else {
-                ld16<T>(x[k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[k] + off);
-            }
-        }
-    }
-}
-
-// ---- map: dst[...] = P(inputs[...]) over up to KGR uncollapsible axes; axis 0 is vectorised (16 bytes per access).
+// ---- map: dst[...] = P(inputs[...]) over up to KGR uncollapsible axes; axis 0 is vectorised (SV elements per access).
 // Inputs per role: aligned unit-step vectors (forward or reversed), one value per row (prefix rank extension: the
 // `v` of B += A*C + v, examples/read-me.cc:32), or scalars. A flat traversal (rankA==1) may have a scalar tail.
-// GENERAL=false: every non-scalar input is a forward unit-step vector. The kind is then known at compile time, which matters:
-// a run-time choice between load forms makes the compiler select right after each load and serialises them.
-template <class T, int ID, bool GENERAL> __global__ void __launch_bounds__(KBLOCK)
-sflat_map_kernel(const __grid_constant__ SParams p)
+// GENERAL=false: every non-scalar input is a forward unit-step vector.
+template <int ID, bool GENERAL> __global__ void __launch_bounds__(KBLOCK)
+smap_kernel(const __grid_constant__ SParams p)
 {
-    constexpr int V = VecOf<T>::V;
-    constexpr SProg P = static_prog(ID);
-    T xs[P.nin][V];
-#pragma unroll
-    for (int k=0; k<P.nin; ++k) {
-#pragma unroll
-        for (int j=0; j<V; ++j) xs[k][j] = from_bits<T>(p.in[k]);
-    }
-    int64_t const per = int64_t(KBLOCK)*SUNR;
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    constexpr int des = es_of(P.otype), UNR = SPX<ID>::UNR, XW = SPX<ID>::XW;
+    int64_t const per = int64_t(KBLOCK)*UNR;
     for (int64_t g0 = int64_t(blockIdx.x)*per + threadIdx.x; g0<p.nvec; g0 += int64_t(gridDim.x)*per) {
-        T x[SUNR][P.nin][V];
-        int64_t doff[SUNR];
+        uint32_t x[UNR][P.nin][XW];
+        int64_t doff[UNR];
 #pragma unroll
-        for (int u=0; u<SUNR; ++u) {
+        for (int u=0; u<UNR; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK;
             if (g<p.nvec) {
                 int64_t e0;
                 uint32_t i1 = 0, i2 = 0, i3 = 0;
-                if (1==p.rankA) { e0 = g*V; }
+                if (1==p.rankA) { e0 = g*SV; }
                 else {
                     uint32_t n = uint32_t(g), q = fastdiv(n, p.vprdiv);
-                    e0 = int64_t(n-q*uint32_t(p.vpr))*V; n = q;
+                    e0 = int64_t(n-q*uint32_t(p.vpr))*SV; n = q;
                     if (2==p.rankA) i1 = n;
                     else { q = fastdiv(n, p.dA[1]); i1 = n-q*p.dA[1].len; n = q;
                         if (3==p.rankA) i2 = n; else { q = fastdiv(n, p.dA[2]); i2 = n-q*p.dA[2].len; i3 = q; } }
@@ -171,87 +197,88 @@ sflat_map_kernel(const __grid_constant__ SParams p)
                 doff[u] = e0 + int64_t(i1)*p.dsA[1] + int64_t(i2)*p.dsA[2] + int64_t(i3)*p.dsA[3];
 #pragma unroll
                 for (int k=0; k<P.nin; ++k) {
-                    int const kd = GENERAL ? int(p.kind[k]) : (p.scalar[k] ? int(SK_SCALAR) : int(SK_VEC));
-                    if (SK_SCALAR==kd) {
-#pragma unroll
-                        for (int j=0; j<V; ++j) x[u][k][j] = xs[k][j];
-                    } else {
-                        int64_t off = int64_t(i1)*p.sA[k][1] + int64_t(i2)*p.sA[k][2] + int64_t(i3)*p.sA[k][3];
-                        T const * base = reinterpret_cast<T const *>(p.in[k]);
-                        if (!GENERAL || SK_VEC==kd) {
-                            if (k==P.yrole) ld16_rw<T>(x[u][k], base + off + e0); else ld16<T>(x[u][k], base + off + e0);
-                        } else if (SK_VECREV==kd) {
-                            T r[V];
-                            ld16<T>(r, base + off - e0 - (V-1));
-#pragma unroll
-                            for (int j=0; j<V; ++j) x[u][k][j] = r[V-1-j];
-                        } else { // SK_ROW
-                            T v = __ldg(base + off);
-#pragma unroll
-                            for (int j=0; j<V; ++j) x[u][k][j] = v;
-                        }
-                    }
+                    int64_t off = int64_t(i1)*p.sA[k][1] + int64_t(i2)*p.sA[k][2] + int64_t(i3)*p.sA[k][3];
+                    fetch_role<ID, GENERAL, LD_STREAM>(p, k, x[u][k], off, e0);
                 }
             }
         }
 #pragma unroll
-        for (int u=0; u<SUNR; ++u) {
+        for (int u=0; u<UNR; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK;
-            if (g<p.nvec) { T out[V]; eval_static<T, ID>(x[u], out); st16<T>(static_cast<T *>(p.dst) + doff[u], out); }
+            if (g<p.nvec) { W out[SV]; eval_static<ID>(x[u], out); store_vec<W>(static_cast<unsigned char *>(p.dst) + doff[u]*des, out, P.otype); }
         }
     }
-    if (1==p.rankA && 0==blockIdx.x && 0==threadIdx.x) { // tail elements of a flat traversal, scalar
-        for (int64_t e = p.nvec*V; e<p.n; ++e) {
-            T x[P.nin][V], out[V];
+    if (1==p.rankA && 0==blockIdx.x && 0==threadIdx.x) { // tail elements of a flat traversal, one at a time
+        for (int64_t e = p.nvec*SV; e<p.n; ++e) {
+            uint32_t x[P.nin][XW];
+            W out[SV];
 #pragma unroll
             for (int k=0; k<P.nin; ++k) {
-                T const * base = reinterpret_cast<T const *>(p.in[k]);
-                x[k][0] = SK_SCALAR==p.kind[k] ? xs[k][0] : SK_VEC==p.kind[k] ? base[e] : SK_VECREV==p.kind[k] ? base[-e] : base[0];
+                int const es = es_of(P.rtype[k]);
+                unsigned char const * base = reinterpret_cast<unsigned char const *>(p.in[k]);
+                if (SK_SCALAR==p.kind[k]) splat_bits(x[k], p.in[k], P.rtype[k]);
+                else splat_words(x[k], base + (SK_VEC==p.kind[k] ? e : SK_VECREV==p.kind[k] ? -e : 0)*es, P.rtype[k]);
             }
-#pragma unroll
-            for (int k=0; k<P.nin; ++k) { for (int j=1; j<V; ++j) x[k][j] = x[k][0]; }
-            eval_static<T, ID>(x, out);
-            static_cast<T *>(p.dst)[e] = out[0];
+            eval_static<ID>(x, out);
+            store_elem<W>(static_cast<unsigned char *>(p.dst) + e*des, P.otype, out[0]);
         }
     }
 }
 
-template <class T, int FOLD> __device__ __forceinline__ T
-block_comb(T r, T * red)
+template <class W> __device__ __forceinline__ W shfl_xor_w(W v, int o);
+template <> __device__ __forceinline__ uint32_t shfl_xor_w<uint32_t>(uint32_t v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+template <> __device__ __forceinline__ uint64_t shfl_xor_w<uint64_t>(uint64_t v, int o) { return __shfl_xor_sync(0xffffffffu, (unsigned long long)v, o); }
+
+template <class W, int FOLD, int TYPE> __device__ __forceinline__ W
+block_comb(W r, W * red)
 {
-    for (int o=16; o>0; o>>=1) { T other = __shfl_xor_sync(0xffffffffu, r, o); r = comb<T, FOLD>(r, other); }
+    for (int o=16; o>0; o>>=1) { W other = shfl_xor_w<W>(r, o); r = combine<W>(FOLD, TYPE, r, other); }
     int const lane = threadIdx.x&31, warp = threadIdx.x>>5;
     if (0==lane) red[warp] = r;
     __syncthreads();
     if (0==threadIdx.x) {
         r = red[0];
-        for (int w=1; w<KBLOCK/32; ++w) r = comb<T, FOLD>(r, red[w]);
+        for (int w=1; w<KBLOCK/32; ++w) r = combine<W>(FOLD, TYPE, r, red[w]);
     }
     return r;
 }
 
-// ---- fold-inner, flat rows: CTA = (RB consecutive rows starting at kb*RB, chunk c); row length len0 (multiple of V unless
-// there is a single row). RB > 1 (rankB == 1 only) blocks rows in registers so that operands that do not move along the
-// kept axis (the vector of gemv: c(i) += a(i,j)*b(j), ra/ra.hh:418) are loaded once per RB rows instead of once per row.
-template <class T, int ID, int FOLD, bool REUSE> __global__ void __launch_bounds__(KBLOCK)
-sflat_fold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f)
+template <class W> __device__ __forceinline__ void
+emit_partial(SParams const & p, FinishParams const & f, int64_t chunk, int64_t n, W v)
 {
-    using W = std::conditional_t<sizeof(T)==8, uint64_t, uint32_t>;
-    constexpr int V = VecOf<T>::V;
-    constexpr SProg P = static_prog(ID);
-    constexpr int RB = 1;               // (register row blocking measured slower than L1 reuse: kept at 1)
-    constexpr int UN = SUNR;            // vectors in flight per input per row
-    __shared__ T red[KBLOCK/32];
-    // chunk-major order (gemv): CTAs resident together work on the SAME column chunk of consecutive rows, so the operand
-    // every row re-reads stays in L1; row-major order otherwise
-    uint32_t kb, c;
-    if (p.chunk_major) { c = blockIdx.x/uint32_t(p.nk/RB); kb = blockIdx.x-c*uint32_t(p.nk/RB); }
-    else { kb = blockIdx.x/uint32_t(p.nchunks); c = blockIdx.x-kb*uint32_t(p.nchunks); }
-    T xs[P.nin][V];
-    int64_t rowoff[RB][P.nin];
+    if (p.nchunks>1) {
+        if (p.wide_partials) static_cast<uint64_t *>(p.partial)[chunk*p.nk+n] = uint64_t(v);
+        else static_cast<uint32_t *>(p.partial)[chunk*p.nk+n] = uint32_t(v);
+    } else {
+        if (p.wide_partials) finish_apply<uint64_t>(f, n, uint64_t(v)); else finish_apply<uint32_t>(f, n, uint32_t(v));
+    }
+}
+
+// fold kernels: role k of vector g of the row at byte offset rowoff -> raw words
+template <int ID, int FORM> __device__ __forceinline__ void
+fetch_fold_role(SParams const & p, int k, uint32_t * x, unsigned char const * rowbase, int64_t g)
+{
+    constexpr SProg P = SPT<ID>::P;
+    int const t = P.rtype[k], es = es_of(t);
+    if (SK_SCALAR==p.kind[k]) splat_bits(x, p.in[k], t);
+    else if (SK_ROW==p.kind[k]) splat_words(x, rowbase, t);
+    else load_words<FORM>(x, rowbase + g*SV*es, t);
+}
+
+// ---- fold-inner, flat rows: CTA = (row kb, chunk c); row length n (multiple of SV unless there is a single row).
+// REUSE: some input does not move along the kept rows (the vector of gemv, ra/ra.hh:418): loads allocate in L1.
+template <int ID, int FOLD, bool REUSE> __global__ void __launch_bounds__(KBLOCK)
+sfold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f)
+{
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    constexpr int AT = P.otype, UNR = SPX<ID>::UNR, XW = SPX<ID>::XW;
+    __shared__ W red[KBLOCK/32];
+    uint32_t const kb = blockIdx.x/uint32_t(p.nchunks), c = blockIdx.x-kb*uint32_t(p.nchunks);
+    unsigned char const * rowbase[P.nin];
     {
         // row kb -> group-B position -> per input byte offset
-        uint32_t n = kb*RB, q, ib[KGR] = {0, 0, 0, 0};
+        uint32_t n = kb, q, ib[KGR] = {0, 0, 0, 0};
         if (p.rankB<=1) ib[0] = n;
         else {
             q = fastdiv(n, p.dB[0]); ib[0] = n-q*p.dB[0].len; n = q;
@@ -264,194 +291,174 @@ sflat_fold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant
             int64_t off = 0;
 #pragma unroll
             for (int j=0; j<KGR; ++j) { if (j<p.rankB) off += int64_t(ib[j])*p.sB[k][j]; }
-#pragma unroll
-            for (int r=0; r<RB; ++r) rowoff[r][k] = (off + int64_t(r)*p.sB[k][0])*int64_t(sizeof(T));
-#pragma unroll
-            for (int j=0; j<V; ++j) xs[k][j] = from_bits<T>(p.in[k]);
+            rowbase[k] = reinterpret_cast<unsigned char const *>(p.in[k]) + off*int64_t(es_of(P.rtype[k]));
         }
     }
-    int64_t const nfull = p.n/V;
+    int64_t const nfull = p.n/SV;
     int64_t const start = int64_t(c)*p.chunk_len;
     int64_t const end = start+p.chunk_len<nfull ? start+p.chunk_len : nfull;
-    T acc[RB][V];
+    W acc[SV];
 #pragma unroll
-    for (int r=0; r<RB; ++r)
-#pragma unroll
-        for (int j=0; j<V; ++j) acc[r][j] = from_bits<T>(p.identity);
-    int64_t const per = int64_t(KBLOCK)*UN;
+    for (int j=0; j<SV; ++j) acc[j] = W(p.identity);
+    int64_t const per = int64_t(KBLOCK)*UNR;
     for (int64_t g0 = start + threadIdx.x; g0<end; g0 += per) {
-        T x[RB][UN][P.nin][V];
+        uint32_t x[UNR][P.nin][XW];
 #pragma unroll
-        for (int u=0; u<UN; ++u) {
+        for (int u=0; u<UNR; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK;
             if (g<end) {
 #pragma unroll
-                for (int r=0; r<RB; ++r) {
-                    if (0==r) load_inputs<T, ID, REUSE>(p, x[0][u], xs, rowoff[0], g*16);
-                    else {
-#pragma unroll
-                        for (int k=0; k<P.nin; ++k) {
-                            if (0==p.sB[k][0] || p.scalar[k]) { // does not move along the kept axis: reuse row 0's registers
-#pragma unroll
-                                for (int j=0; j<V; ++j) x[r][u][k][j] = x[0][u][k][j];
-                            } else if (SK_ROW==p.kind[k]) {
-                                T v = __ldg(reinterpret_cast<T const *>(reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[r][k]));
-#pragma unroll
-                                for (int j=0; j<V; ++j) x[r][u][k][j] = v;
-                            } else {
-                                ld16<T>(x[r][u][k], reinterpret_cast<unsigned char const *>(p.in[k]) + rowoff[r][k] + g*16);
-                            }
-                        }
-                    }
-                }
+                for (int k=0; k<P.nin; ++k) fetch_fold_role<ID, REUSE ? LD_REUSED : LD_STREAM>(p, k, x[u][k], rowbase[k], g);
             }
         }
 #pragma unroll
-        for (int u=0; u<UN; ++u) {
+        for (int u=0; u<UNR; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK;
             if (g<end) {
+                W out[SV];
+                eval_static<ID>(x[u], out);
 #pragma unroll
-                for (int r=0; r<RB; ++r) {
-                    T out[V];
-                    eval_static<T, ID>(x[r][u], out);
-#pragma unroll
-                    for (int j=0; j<V; ++j) acc[r][j] = comb<T, FOLD>(acc[r][j], out[j]);
-                }
+                for (int j=0; j<SV; ++j) acc[j] = combine<W>(FOLD, AT, acc[j], out[j]);
             }
         }
     }
+    W r = acc[0];
 #pragma unroll
-    for (int r=0; r<RB; ++r) {
-        T v = acc[r][0];
+    for (int j=1; j<SV; ++j) r = combine<W>(FOLD, AT, r, acc[j]);
+    if (c+1==uint32_t(p.nchunks) && 0==threadIdx.x) { // tail elements of the row (single flat row only)
+        for (int64_t e = nfull*SV; e<p.n; ++e) {
+            uint32_t x[P.nin][XW];
+            W out[SV];
 #pragma unroll
-        for (int j=1; j<V; ++j) v = comb<T, FOLD>(v, acc[r][j]);
-        if (1==RB && c+1==uint32_t(p.nchunks) && 0==threadIdx.x) { // tail elements of the row (single flat row only)
-            for (int64_t e = nfull*V; e<p.n; ++e) {
-                T x[P.nin][V], out[V];
-#pragma unroll
-                for (int k=0; k<P.nin; ++k) x[k][0] = p.scalar[k] ? xs[k][0] : reinterpret_cast<T const *>(reinterpret_cast<unsigned char const *>(p.in[k])+rowoff[0][k])[SK_ROW==p.kind[k] ? 0 : e];
-#pragma unroll
-                for (int k=0; k<P.nin; ++k) { for (int j=1; j<V; ++j) x[k][j] = x[k][0]; }
-                eval_static<T, ID>(x, out);
-                v = comb<T, FOLD>(v, out[0]);
+            for (int k=0; k<P.nin; ++k) {
+                if (SK_SCALAR==p.kind[k]) splat_bits(x[k], p.in[k], P.rtype[k]);
+                else splat_words(x[k], rowbase[k] + (SK_ROW==p.kind[k] ? 0 : e)*es_of(P.rtype[k]), P.rtype[k]);
             }
-        }
-        if (r>0) __syncthreads(); // red[] reuse
-        v = block_comb<T, FOLD>(v, red);
-        if (0==threadIdx.x) {
-            int64_t const row = int64_t(kb)*RB + r;
-            if (p.nchunks>1) static_cast<W *>(p.partial)[int64_t(c)*p.nk+row] = W(to_bits<T>(v));
-            else finish_apply<W>(f, row, W(to_bits<T>(v)));
+            eval_static<ID>(x, out);
+            r = combine<W>(FOLD, AT, r, out[0]);
         }
     }
+    r = block_comb<W, FOLD, AT>(r, red);
+    if (0==threadIdx.x) emit_partial<W>(p, f, c, kb, r);
 }
 
 // ---- fold-outer, flat: thread = kept vector g (lanes are kept elements), blockIdx.y = chunk of the folded rows
-template <class T, int ID, int FOLD> __global__ void __launch_bounds__(KBLOCK)
-sflat_fold_outer_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f)
+template <int ID, int FOLD> __global__ void __launch_bounds__(KBLOCK)
+sfold_outer_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f)
 {
-    using W = std::conditional_t<sizeof(T)==8, uint64_t, uint32_t>;
-    constexpr int V = VecOf<T>::V;
-    constexpr SProg P = static_prog(ID);
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    constexpr int AT = P.otype, UNR = SPX<ID>::UNR, XW = SPX<ID>::XW;
     int64_t const g = int64_t(blockIdx.x)*KBLOCK + threadIdx.x;
-    if (g>=p.n/V) return;
+    if (g>=p.n/SV) return;
     uint32_t const c = blockIdx.y;
     int64_t const r0 = int64_t(c)*p.chunk_len;
     int64_t const r1 = r0+p.chunk_len<p.nB ? r0+p.chunk_len : p.nB;
-    T xs[P.nin][V];
+    W acc[SV];
 #pragma unroll
-    for (int k=0; k<P.nin; ++k) {
+    for (int j=0; j<SV; ++j) acc[j] = W(p.identity);
+    for (int64_t r = r0; r<r1; r += UNR) {
+        uint32_t x[UNR][P.nin][XW];
 #pragma unroll
-        for (int j=0; j<V; ++j) xs[k][j] = from_bits<T>(p.in[k]);
-    }
-    T acc[V];
-#pragma unroll
-    for (int j=0; j<V; ++j) acc[j] = from_bits<T>(p.identity);
-    for (int64_t r = r0; r<r1; r += SUNR) {
-        T x[SUNR][P.nin][V];
-#pragma unroll
-        for (int u=0; u<SUNR; ++u) {
+        for (int u=0; u<UNR; ++u) {
             if (r+u<r1) {
-                int64_t rowoff[P.nin];
 #pragma unroll
-                for (int k=0; k<P.nin; ++k) rowoff[k] = (r+u)*p.sB[k][0]*int64_t(sizeof(T));
-                load_inputs<T, ID>(p, x[u], xs, rowoff, g*16);
+                for (int k=0; k<P.nin; ++k) { // gevm: c(j) += a(i)*b(i,j): a is one value per folded row (SK_ROW)
+                    unsigned char const * rowbase = reinterpret_cast<unsigned char const *>(p.in[k]) + (r+u)*p.sB[k][0]*es_of(P.rtype[k]);
+                    fetch_fold_role<ID, LD_STREAM>(p, k, x[u][k], rowbase, g);
+                }
             }
         }
 #pragma unroll
-        for (int u=0; u<SUNR; ++u) {
+        for (int u=0; u<UNR; ++u) {
             if (r+u<r1) {
-                T out[V];
-                eval_static<T, ID>(x[u], out);
+                W out[SV];
+                eval_static<ID>(x[u], out);
 #pragma unroll
-                for (int j=0; j<V; ++j) acc[j] = comb<T, FOLD>(acc[j], out[j]);
+                for (int j=0; j<SV; ++j) acc[j] = combine<W>(FOLD, AT, acc[j], out[j]);
             }
         }
     }
 #pragma unroll
-    for (int j=0; j<V; ++j) {
-        if (p.nchunks>1) static_cast<W *>(p.partial)[int64_t(c)*p.nk+g*V+j] = W(to_bits<T>(acc[j]));
-        else finish_apply<W>(f, g*V+j, W(to_bits<T>(acc[j])));
-    }
+    for (int j=0; j<SV; ++j) emit_partial<W>(p, f, c, g*SV+j, acc[j]);
 }
 
 // ---------------- dispatch ----------------
 
-template <class T, int ID> static cudaError_t
+template <int ID> static cudaError_t
 launch_one(Plan const & plan, dim3 grid, cudaStream_t stream)
 {
     SParams const & p = plan.sp;
-    constexpr SProg P = static_prog(ID);
+    constexpr SProg P = SPT<ID>::P;
     if (p.mode==K_MAP) {
         if constexpr (!P.fold) {
-            bool general = false;
-            for (int k=0; k<P.nin; ++k) general = general || p.kind[k]==SK_VECREV || p.kind[k]==SK_ROW;
-            if (general) sflat_map_kernel<T, ID, true><<<grid, KBLOCK, 0, stream>>>(p); else sflat_map_kernel<T, ID, false><<<grid, KBLOCK, 0, stream>>>(p);
+            if (p.general) smap_kernel<ID, true><<<grid, KBLOCK, 0, stream>>>(p); else smap_kernel<ID, false><<<grid, KBLOCK, 0, stream>>>(p);
         }
     } else if constexpr (P.fold) {
+        bool any = false;
+        for (int k=0; k<SP_MAXIN; ++k) any = any || p.reused[k];
 #define RACU_SF(KERNEL, ...) \
         switch (p.fold_op) { \
-        case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: KERNEL<T, ID, RACU_ASSIGN_ADD __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        case RACU_ASSIGN_AMIN: KERNEL<T, ID, RACU_ASSIGN_AMIN __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        case RACU_ASSIGN_AMAX: KERNEL<T, ID, RACU_ASSIGN_AMAX __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        default: KERNEL<T, ID, RACU_ASSIGN_MUL __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
+        case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: KERNEL<ID, RACU_ASSIGN_ADD __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
+        case RACU_ASSIGN_AMIN: KERNEL<ID, RACU_ASSIGN_AMIN __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
+        case RACU_ASSIGN_AMAX: KERNEL<ID, RACU_ASSIGN_AMAX __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
+        default: KERNEL<ID, RACU_ASSIGN_MUL __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
         }
         if (p.mode==K_FOLD_INNER) {
-            bool any = false;
-            for (int k=0; k<SP_MAXIN; ++k) any = any || p.reused[k];
-            if (any) { RACU_SF(sflat_fold_inner_kernel, , true) } else { RACU_SF(sflat_fold_inner_kernel, , false) }
-        } else { RACU_SF(sflat_fold_outer_kernel) }
+            if (any) { RACU_SF(sfold_inner_kernel, , true) } else { RACU_SF(sfold_inner_kernel, , false) }
+        } else { RACU_SF(sfold_outer_kernel) }
 #undef RACU_SF
     }
     return cudaGetLastError();
 }
 
-template <int ID> static cudaError_t
-launch_typed(Plan const & plan, dim3 grid, cudaStream_t stream)
-{
-    switch (plan.sp.dtype) {
-    case RACU_F32: return launch_one<float, ID>(plan, grid, stream);
-    case RACU_F64: return launch_one<double, ID>(plan, grid, stream);
-    default: return launch_one<int32_t, ID>(plan, grid, stream);
-    }
-}
+// The table is compiled in SP_NPART translation units (ids congruent to SP_PART), in parallel: build.py.
+#ifndef SP_NPART
+#define SP_NPART 1
+#define SP_PART 0
+#endif
 
-template <int ID=0> static cudaError_t
+template <int ID=SP_PART> static cudaError_t
 launch_id(Plan const & plan, dim3 grid, cudaStream_t stream)
 {
     if constexpr (ID<SP_COUNT) {
-        if (plan.sp.id==ID) return launch_typed<ID>(plan, grid, stream);
-        return launch_id<ID+1>(plan, grid, stream);
+        if (plan.sp.id==ID) return launch_one<ID>(plan, grid, stream);
+        return launch_id<ID+SP_NPART>(plan, grid, stream);
     } else {
         return cudaErrorInvalidValue;
     }
 }
 
+#define RACU_CAT_(a, b) a##b
+#define RACU_CAT(a, b) RACU_CAT_(a, b)
+cudaError_t
+RACU_CAT(launch_static_part, SP_PART)(Plan const & plan, cudaStream_t stream)
+{
+    dim3 grid(plan.grid_x, plan.grid_y);
+    return launch_id<>(plan, grid, stream);
+}
+
+#if SP_PART==0
+cudaError_t launch_static_part1(Plan const & plan, cudaStream_t stream);
+cudaError_t launch_static_part2(Plan const & plan, cudaStream_t stream);
+cudaError_t launch_static_part3(Plan const & plan, cudaStream_t stream);
 cudaError_t
 launch_static(Plan const & plan, cudaStream_t stream)
 {
-    dim3 grid(plan.grid_x, plan.grid_y);
-    return launch_id<0>(plan, grid, stream);
+    switch (plan.sp.id % SP_NPART) {
+    case 0: return launch_static_part0(plan, stream);
+#if SP_NPART>1
+    case 1: return launch_static_part1(plan, stream);
+#endif
+#if SP_NPART>2
+    case 2: return launch_static_part2(plan, stream);
+#endif
+#if SP_NPART>3
+    case 3: return launch_static_part3(plan, stream);
+#endif
+    default: return cudaErrorInvalidValue;
+    }
 }
+#endif
 
 } // namespace racu

@@ -1,83 +1,139 @@
 // static_progs.h - the table of program shapes that have compile-time specialised kernels (static_kernels.cu), and the
 // parameters those kernels take. Plain C++: included by the planner (g++) and by the kernels (nvcc).
-// A program is a postfix sequence over ROLES: role r = the r-th distinct operand in order of first appearance;
-// `yrole` says which role (if any) is the destination's own old value (`dst OP= rhs` puts it first).
+//
+// A static program is the planner's canonical postfix program with operand indices replaced by ROLES: role r = the r-th
+// distinct operand in order of first appearance; `yrole` says which role (if any) is the destination's own old value
+// (`dst OP= rhs` puts it first). Instructions and roles are TYPED, so mixed-type expressions (float arrays with a double
+// vector, comparisons, casts) can be specialised exactly like the single-type ones.
 #pragma once
 #include "kcore.h"
 
 namespace racu {
 
-constexpr int SP_MAXINS = 8, SP_MAXIN = 4;
-struct SIns { uint8_t op, arg; };
-struct SProg { int n; SIns ins[SP_MAXINS]; int nin; int yrole; bool fold; };
+constexpr int SP_MAXINS = 12, SP_MAXIN = 4;
+struct SIns { uint8_t op, arg, type, aux; };
+struct SProg
+{
+    int n;
+    SIns ins[SP_MAXINS];
+    int nin;
+    int yrole;
+    bool fold;
+    uint8_t rtype[SP_MAXIN]; // element type of each role
+    uint8_t otype;           // maps: destination dtype (== type of the program result). folds: accumulator type
+};
 
+// shapes; each is instantiated for the element types listed in static_prog()
+enum SShape {
+    SH_COPY = 0,      // y = a
+    SH_NEG,           // y = -a
+    SH_YADD, SH_YSUB, SH_YMUL, SH_YDIV,   // y OP= a
+    SH_ADD, SH_SUB, SH_MUL, SH_DIV,       // y = a OP b
+    SH_YFMA, SH_YFMS,                     // y += a*b, y -= a*b      (B += A*C; cghs: x += t*r, g -= t*p)
+    SH_MULADD, SH_YMULADD,                // y = a*b + c ; y = y*b + c (cghs: r = r*gam + g)
+    SH_YFMA_ADD,                          // y += a*b + c             (examples/read-me.cc:32 shape: B += A*C + v)
+    SH_F_ID, SH_F_SQR, SH_F_MUL, SH_F_SQRDIFF, // folds of a, a*a, a*b, (a-b)^2  (sum, reduce_sqrm, dot, reduce_sqrm(a-b))
+    SH_NSHAPE
+};
+constexpr int SP_NUNIFORM = SH_NSHAPE*3; // every shape x {f32, f64, i32}
+// mixed-type programs, after the uniform ones
 enum {
-    SP_COPY = 0,      // y = a
-    SP_NEG,           // y = -a
-    SP_YADD, SP_YSUB, SP_YMUL, SP_YDIV,   // y OP= a
-    SP_ADD, SP_SUB, SP_MUL, SP_DIV,       // y = a OP b
-    SP_YFMA, SP_YFMS,                     // y += a*b, y -= a*b      (B += A*C; cghs: x += t*r, g -= t*p)
-    SP_MULADD, SP_YMULADD,                // y = a*b + c ; y = y*b + c (cghs: r = r*gam + g)
-    SP_YFMA_ADD,                          // y += a*b + c             (examples/read-me.cc:32 shape: B += A*C + v)
-    SF_ID, SF_SQR, SF_MUL, SF_SQRDIFF,    // folds of a, a*a, a*b, (a-b)^2  (sum, reduce_sqrm, dot, reduce_sqrm(a-b))
+    SPM_YFMA_ADD_F32_VD = SP_NUNIFORM, // float y += float a * float b + double v      (examples/read-me.cc:32 with std::vector<double>)
+    SPM_YADD_F32_SD_MUL,               // float y += double s * float a                 (B += 2.5*A with a double literal)
+    SPM_YSUB_F32_SD_MUL,               // float y -= double s * float a
+    SPM_F_SUM_F32_D,                   // double acc += float a                         (double c += float array)
     SP_COUNT
 };
 
-constexpr SIns sP(int r) { return SIns {RACU_OP_PUSH, uint8_t(r)}; }
-constexpr SIns sO(int op) { return SIns {uint8_t(op), 0}; }
+constexpr SIns sP(int r, int t) { return SIns {RACU_OP_PUSH, uint8_t(r), uint8_t(t), 0}; }
+constexpr SIns sO(int op, int t) { return SIns {uint8_t(op), 0, uint8_t(t), 0}; }
+constexpr SIns sC(int from, int to) { return SIns {RACU_OP_CAST, 0, uint8_t(to), uint8_t(from)}; }
+
+constexpr SProg
+uniform_prog(int shape, int T)
+{
+    uint8_t const t = uint8_t(T);
+    switch (shape) {
+    case SH_COPY: return SProg {1, {sP(0, T)}, 1, -1, false, {t}, t};
+    case SH_NEG: return SProg {2, {sP(0, T), sO(RACU_OP_NEG, T)}, 1, -1, false, {t}, t};
+    case SH_YADD: return SProg {3, {sP(0, T), sP(1, T), sO(RACU_OP_ADD, T)}, 2, 0, false, {t, t}, t};
+    case SH_YSUB: return SProg {3, {sP(0, T), sP(1, T), sO(RACU_OP_SUB, T)}, 2, 0, false, {t, t}, t};
+    case SH_YMUL: return SProg {3, {sP(0, T), sP(1, T), sO(RACU_OP_MUL, T)}, 2, 0, false, {t, t}, t};
+    case SH_YDIV: return SProg {3, {sP(0, T), sP(1, T), sO(RACU_OP_DIV, T)}, 2, 0, false, {t, t}, t};
+    case SH_ADD: return SProg {3, {sP(0, T), sP(1, T), sO(RACU_OP_ADD, T)}, 2, -1, false, {t, t}, t};
+    case SH_SUB: return SProg {3, {sP(0, T), sP(1, T), sO(RACU_OP_SUB, T)}, 2, -1, false, {t, t}, t};
+    case SH_MUL: return SProg {3, {sP(0, T), sP(1, T), sO(RACU_OP_MUL, T)}, 2, -1, false, {t, t}, t};
+    case SH_DIV: return SProg {3, {sP(0, T), sP(1, T), sO(RACU_OP_DIV, T)}, 2, -1, false, {t, t}, t};
+    case SH_YFMA: return SProg {5, {sP(0, T), sP(1, T), sP(2, T), sO(RACU_OP_MUL, T), sO(RACU_OP_ADD, T)}, 3, 0, false, {t, t, t}, t};
+    case SH_YFMS: return SProg {5, {sP(0, T), sP(1, T), sP(2, T), sO(RACU_OP_MUL, T), sO(RACU_OP_SUB, T)}, 3, 0, false, {t, t, t}, t};
+    case SH_MULADD: return SProg {5, {sP(0, T), sP(1, T), sO(RACU_OP_MUL, T), sP(2, T), sO(RACU_OP_ADD, T)}, 3, -1, false, {t, t, t}, t};
+    case SH_YMULADD: return SProg {5, {sP(0, T), sP(1, T), sO(RACU_OP_MUL, T), sP(2, T), sO(RACU_OP_ADD, T)}, 3, 0, false, {t, t, t}, t};
+    case SH_YFMA_ADD: return SProg {7, {sP(0, T), sP(1, T), sP(2, T), sO(RACU_OP_MUL, T), sP(3, T), sO(RACU_OP_ADD, T), sO(RACU_OP_ADD, T)}, 4, 0, false, {t, t, t, t}, t};
+    case SH_F_ID: return SProg {1, {sP(0, T)}, 1, -1, true, {t}, t};
+    case SH_F_SQR: return SProg {2, {sP(0, T), sO(RACU_OP_SQR, T)}, 1, -1, true, {t}, t};
+    case SH_F_MUL: return SProg {3, {sP(0, T), sP(1, T), sO(RACU_OP_MUL, T)}, 2, -1, true, {t, t}, t};
+    case SH_F_SQRDIFF: return SProg {4, {sP(0, T), sP(1, T), sO(RACU_OP_SUB, T), sO(RACU_OP_SQR, T)}, 2, -1, true, {t, t}, t};
+    default: return SProg {0, {}, 0, -1, false, {}, 0};
+    }
+}
 
 constexpr SProg
 static_prog(int id)
 {
+    constexpr int F = RACU_F32, D = RACU_F64;
+    if (id<SP_NUNIFORM) {
+        constexpr int types[3] = {RACU_F32, RACU_F64, RACU_I32};
+        return uniform_prog(id/3, types[id%3]);
+    }
     switch (id) {
-    case SP_COPY: return SProg {1, {sP(0)}, 1, -1, false};
-    case SP_NEG: return SProg {2, {sP(0), sO(RACU_OP_NEG)}, 1, -1, false};
-    case SP_YADD: return SProg {3, {sP(0), sP(1), sO(RACU_OP_ADD)}, 2, 0, false};
-    case SP_YSUB: return SProg {3, {sP(0), sP(1), sO(RACU_OP_SUB)}, 2, 0, false};
-    case SP_YMUL: return SProg {3, {sP(0), sP(1), sO(RACU_OP_MUL)}, 2, 0, false};
-    case SP_YDIV: return SProg {3, {sP(0), sP(1), sO(RACU_OP_DIV)}, 2, 0, false};
-    case SP_ADD: return SProg {3, {sP(0), sP(1), sO(RACU_OP_ADD)}, 2, -1, false};
-    case SP_SUB: return SProg {3, {sP(0), sP(1), sO(RACU_OP_SUB)}, 2, -1, false};
-    case SP_MUL: return SProg {3, {sP(0), sP(1), sO(RACU_OP_MUL)}, 2, -1, false};
-    case SP_DIV: return SProg {3, {sP(0), sP(1), sO(RACU_OP_DIV)}, 2, -1, false};
-    case SP_YFMA: return SProg {5, {sP(0), sP(1), sP(2), sO(RACU_OP_MUL), sO(RACU_OP_ADD)}, 3, 0, false};
-    case SP_YFMS: return SProg {5, {sP(0), sP(1), sP(2), sO(RACU_OP_MUL), sO(RACU_OP_SUB)}, 3, 0, false};
-    case SP_MULADD: return SProg {5, {sP(0), sP(1), sO(RACU_OP_MUL), sP(2), sO(RACU_OP_ADD)}, 3, -1, false};
-    case SP_YMULADD: return SProg {5, {sP(0), sP(1), sO(RACU_OP_MUL), sP(2), sO(RACU_OP_ADD)}, 3, 0, false};
-    case SP_YFMA_ADD: return SProg {7, {sP(0), sP(1), sP(2), sO(RACU_OP_MUL), sP(3), sO(RACU_OP_ADD), sO(RACU_OP_ADD)}, 4, 0, false};
-    case SF_ID: return SProg {1, {sP(0)}, 1, -1, true};
-    case SF_SQR: return SProg {2, {sP(0), sO(RACU_OP_SQR)}, 1, -1, true};
-    case SF_MUL: return SProg {3, {sP(0), sP(1), sO(RACU_OP_MUL)}, 2, -1, true};
-    case SF_SQRDIFF: return SProg {4, {sP(0), sP(1), sO(RACU_OP_SUB), sO(RACU_OP_SQR)}, 2, -1, true};
-    default: return SProg {0, {}, 0, -1, false};
+    case SPM_YFMA_ADD_F32_VD: // y(f32) -> f64 ; a*b in f32 -> f64 ; + v(f64) ; + ; -> f32
+        return SProg {10, {sP(0, F), sC(F, D), sP(1, F), sP(2, F), sO(RACU_OP_MUL, F), sC(F, D), sP(3, D), sO(RACU_OP_ADD, D), sO(RACU_OP_ADD, D), sC(D, F)},
+                      4, 0, false, {F, F, F, D}, F};
+    case SPM_YADD_F32_SD_MUL: // y(f32) -> f64 ; s(f64) * f64(a) ; + ; -> f32
+        return SProg {8, {sP(0, F), sC(F, D), sP(1, D), sP(2, F), sC(F, D), sO(RACU_OP_MUL, D), sO(RACU_OP_ADD, D), sC(D, F)}, 3, 0, false, {F, D, F}, F};
+    case SPM_YSUB_F32_SD_MUL:
+        return SProg {8, {sP(0, F), sC(F, D), sP(1, D), sP(2, F), sC(F, D), sO(RACU_OP_MUL, D), sO(RACU_OP_SUB, D), sC(D, F)}, 3, 0, false, {F, D, F}, F};
+    case SPM_F_SUM_F32_D: // fold: a(f32) -> f64 accumulator
+        return SProg {2, {sP(0, F), sC(F, D)}, 1, -1, true, {F}, D};
+    default: return SProg {0, {}, 0, -1, false, {}, 0};
     }
 }
 
+constexpr bool
+prog_wide(SProg const & P)
+{
+    bool w = P.otype==RACU_I64 || P.otype==RACU_F64;
+    for (int i=0; i<P.n; ++i) w = w || P.ins[i].type==RACU_I64 || P.ins[i].type==RACU_F64 || (P.ins[i].op==RACU_OP_CAST && (P.ins[i].aux==RACU_I64 || P.ins[i].aux==RACU_F64));
+    for (int r=0; r<P.nin; ++r) w = w || P.rtype[r]==RACU_I64 || P.rtype[r]==RACU_F64;
+    return w;
+}
+
+constexpr int SV = 4; // elements per static vector (16 bytes of 4-byte elements, 32 bytes of 8-byte ones)
+
+enum { SK_SCALAR = 0, SK_VEC = 1, SK_VECREV = 2 /* unit step backwards: aligned loads, lanes reversed */, SK_ROW = 3 /* step 0 on axis 0: one value per row */ };
+
 struct SParams
 {
-    int32_t id, dtype, mode, fold_op, nchunks, rankB;
-    uint64_t identity;
-    int64_t n;            // elements along the flat axis (row length)
-    int64_t nB;           // fold-outer: folded rows
-    int64_t chunk_len, nk;
+    int32_t id, mode, fold_op, nchunks, rankB, rankA;
+    int32_t wide_partials;        // folds: partial / finish slots are 64-bit
+    int32_t general;              // maps: some input is SK_VECREV / SK_ROW
+    uint64_t identity;            // accumulator start, slot bits
+    int64_t n;                    // elements along the flat axis (row length)
+    int64_t nB;                   // fold-outer: folded rows
+    int64_t chunk_len, nk;        // fold-inner: vectors per chunk; kept elements
     void * dst;
     void * partial;
-    uint64_t in[SP_MAXIN];        // role -> base address (vector inputs) or value bits (scalars)
-    uint8_t scalar[SP_MAXIN];
-    uint8_t kind[SP_MAXIN];       // maps: SK_* below
+    uint64_t in[SP_MAXIN];        // role -> base address (vector inputs) or value bits in the role's type (scalars)
+    uint8_t kind[SP_MAXIN];       // SK_*
     uint8_t reused[SP_MAXIN];     // folds: the operand does not move along the kept rows (every row re-reads it): cache in L1
     int64_t sB[SP_MAXIN][KGR];    // role -> element strides over group B
     KDim dB[KGR];
     // maps over up to KGR uncollapsible axes (axis 0 vectorised)
-    int32_t rankA, rb;            // rb: rows blocked per CTA in fold-inner (1 or 4)
-    int32_t chunk_major, pad2;    // fold-inner CTA order: blockIdx = chunk*nk + row instead of row*nchunks + chunk
     int64_t nvec, vpr;            // vectors in total, vectors per row
     KDim vprdiv;
     KDim dA[KGR];
     int64_t sA[SP_MAXIN][KGR];    // role -> element strides over group A (sA[.][0] is 1, -1 or 0)
     int64_t dsA[KGR];             // destination strides (dsA[0] == 1)
 };
-
-enum { SK_SCALAR = 0, SK_VEC = 1, SK_VECREV = 2 /* unit step backwards: aligned 16-byte load, lanes reversed */, SK_ROW = 3 /* step 0 on axis 0: one value per row */ };
 
 } // namespace racu

@@ -524,3 +524,49 @@ def laplace2d_stiff_and_mass(ex):
     w(i, j).assign(ra.sqrm(h) * (v(i, j) / 2. + (v(i - 1, j) + v(i, j - 1) + v(i + 1, j) + v(i, j + 1) + v(i + 1, j + 1) + v(i - 1, j - 1)) / 12.))
     ref[1:-1, 1:-1] = (h * h) * (c / 2. + (((((v0[:-2, 1:-1] + v0[1:-1, :-2]) + v0[2:, 1:-1]) + v0[1:-1, 2:]) + v0[2:, 2:]) + v0[:-2, :-2]) / 12.)
     eq(w, ref)
+
+
+@case
+def laplace2d_cghs_end_to_end(ex):
+    """examples/laplace2d.cc:60-91 + examples/cghs.hh:15-45: -laplace u = f on (N+1)^2 by conjugate gradients, every array op on
+    the executor. Pinned by the reference: max |u - g| <= 0.00463 and <= 67 iterations at N = 50, eps = 1e-5."""
+    N, EPS = 50, 1e-5
+    h = 1. / N
+    x = np.arange(N + 1) * h
+    PI = np.pi
+    g = np.zeros((N + 1, N + 1))
+    f = np.zeros((N + 1, N + 1))
+    g[1:-1, 1:-1] = np.sin(2 * PI * x[1:-1])[:, None] * np.sin(2 * PI * x[1:-1])[None, :]
+    f[1:-1, 1:-1] = 8 * PI * PI * g[1:-1, 1:-1]
+    v, w = ex.from_numpy(g), ex.from_numpy(f)
+    u, b = zeros(ex, (N + 1, N + 1), np.float64), zeros(ex, (N + 1, N + 1), np.float64)
+    i, j = ra.iota(N - 1, 1), ra.iota(N - 1, 1)
+
+    def mult_stiff(vv, ww):  # laplace2d.cc:36
+        ww(i, j).assign(4 * vv(i, j) - vv(i - 1, j) - vv(i, j - 1) - vv(i + 1, j) - vv(i, j + 1))
+
+    def mult_mass(vv, ww):  # laplace2d.cc:48
+        ww(i, j).assign(ra.sqrm(h) * (vv(i, j) / 2. + (vv(i - 1, j) + vv(i, j - 1) + vv(i + 1, j) + vv(i, j + 1)
+                                                       + vv(i + 1, j + 1) + vv(i - 1, j - 1)) / 12.))
+    mult_mass(w, b)
+    work = zeros(ex, (3, N + 1, N + 1), np.float64)
+    gg, r, p = work(0), work(1), work(2)
+    err = EPS * EPS * ra.reduce_sqrm(b)
+    mult_stiff(u, gg)
+    gg.assign(b - gg)
+    r.assign(gg)
+    its = 0
+    while ra.reduce_sqrm(gg) > err and its < 200:
+        mult_stiff(r, p)
+        rho = ra.reduce_sqrm(p)
+        sig = ra.dot(r, p)
+        tau = ra.dot(gg, r)
+        t = tau / sig
+        gam = (t * t * rho - tau) / tau
+        u += float(t) * r
+        gg -= float(t) * p
+        r.assign(r * float(gam) + gg)
+        its += 1
+    mx = ra.amax(ra.abs(u - v))
+    assert mx <= 0.00463, mx
+    assert its <= 67, its
