@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-log2n", type=int, default=27, help="bounded CPU sample size")
     ap.add_argument("--n3", type=int, default=1024, help="global grid edge for --workload stencil")
     ap.add_argument("--no-overlap", action="store_true", help="stencil: exchange then sweep, no stream overlap")
+    ap.add_argument("--halo", default="push", choices=["push", "nccl"],
+                    help="stencil at N>1: 'push' = one kernel per step, the sweep stores its edge planes into the neighbours' ghosts over "
+                         "NVLink peer memory (racu_stencil_push); 'nccl' = ncclSend/Recv exchange overlapped with the interior sweep")
     ap.add_argument("--graph", action="store_true", help="stencil: replay a CUDA graph of two steps instead of launching every step from the host (experimental)")
     return ap.parse_args()
 
@@ -364,14 +367,34 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local)
     sl = parallel.SlabStencil3D((n, n, n), world, rank)
     g = torch.Generator(device=dev)
     g.manual_seed(0x5EED0041 + rank)
-    A = torch.empty(sl.local_shape, device=dev, dtype=torch.float32).uniform_(-1, 1, generator=g)
-    An = torch.zeros_like(A)
+    push = world > 1 and args.halo == "push"
+    slab = None
+    if push:
+        # buffers from racu_alloc (exportable with CUDA IPC); every rank fills its own slab, ghosts included, from one global
+        # counter-based field so that the ghosts agree with the neighbours' owned planes at step 0
+        slab = cuda.PeerSlab(dist, world, rank, sl.local_shape, abi.F32)
+        A, An = slab.bufs
+        gs = sl.global_slice()
+        idx = torch.arange(gs.start * sl.plane, gs.stop * sl.plane, device=dev, dtype=torch.int64).view(sl.local_shape)
+        A.copy_(((idx * 2654435761 % 2000003).float() / 1000001.5) - 1.0)
+        del idx
+        torch.cuda.synchronize()
+        dist.barrier()
+    else:
+        A = torch.empty(sl.local_shape, device=dev, dtype=torch.float32).uniform_(-1, 1, generator=g)
+        An = torch.zeros_like(A)
     bufs = [A, An]
     sweep = cuda.stencil_sweep(abi.STENCIL_3D7, abi.F32)
-    exch = parallel.RacuCommExchanger(lib, comm, abi.F32, cuda.stream_ptr, cuda.check) if world > 1 else None
-    overlap = cuda.StreamOverlap() if world > 1 and not args.no_overlap else None
+    sweep_push = cuda.stencil_sweep_push(abi.STENCIL_3D7, abi.F32)
+    exch = parallel.RacuCommExchanger(lib, comm, abi.F32, cuda.stream_ptr, cuda.check) if world > 1 and not push else None
+    overlap = cuda.StreamOverlap() if world > 1 and not push and not args.no_overlap else None
+    tcount = [0]
 
     def step():
+        if push:
+            sl.step_push(tcount[0], slab.ptrs[:2], slab.ptrs[2], slab.peers, 4, sweep_push)
+            tcount[0] += 1
+            return
         sl.step(bufs[0].data_ptr(), bufs[1].data_ptr(), 4, sweep, exch, overlap)
         bufs.reverse()
 
@@ -386,7 +409,7 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local)
     # fast enough, so two steps (an even number: the buffers are back in place) are captured once and replayed.
     graph = None
     launches_per_step = None
-    if args.graph:
+    if args.graph and not push:  # (the push step carries its step number: not replayable)
         lib.racu_launch_count_reset()
         graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream()
@@ -434,14 +457,19 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local)
             "metric": "laplace3d Gcells/s", "value": gcells, "unit": "Gcells/s", "n_gpus": world, "steps": nsteps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[3] 7-point stencil f32 {n}^3 global grid, slab-sharded along axis 0, NCCL halo "
-                                   f"exchange per step, overlap={'off' if overlap is None else 'interior/edges on two streams'}, "
-                                   f"{'host launches' if graph is None else 'CUDA graph of 2 steps replayed'}",
+            "config": {"workload": f"configs[3] 7-point stencil f32 {n}^3 global grid, slab-sharded along axis 0, " + (
+                                   "one kernel per step: sweep + halo push into the neighbours' ghost planes over NVLink peer memory "
+                                   "(CUDA IPC), flag lock step" if push else
+                                   f"NCCL halo exchange per step, overlap={'off' if overlap is None else 'interior/edges on two streams'}") +
+                                   f", {'host launches' if graph is None else 'CUDA graph of 2 steps replayed'}",
                        "l2": "4 GiB per buffer, larger than L2"},
-            "roofline": {"bound": "hbm", "kernel": "stencil_tma<3D7>", "achieved": 8 * cells / world / (ms * 1e-3) / 1e9, "peak": peak,
+            "halo_timeouts": slab.timed_out() if push else None,
+            "roofline": {"bound": "hbm", "kernel": lib.racu_last_kernel().decode(), "achieved": 8 * cells / world / (ms * 1e-3) / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": 8 * cells / world / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                          "note": "per GPU: 8 B/cell algorithmic x cells per GPU / step time (includes exchange when N>1)"},
             "gpu_launches": launches, "clocks": sampler.summary()}))
+    if slab is not None:
+        slab.close()
     if world > 1:
         cuda.check(lib.racu_comm_destroy(comm))
         dist.destroy_process_group()

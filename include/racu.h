@@ -263,6 +263,37 @@ int racu_allreduce(racu_comm * comm, void * buf_dev, size_t count, int dtype, in
 int racu_halo_exchange(racu_comm * comm, const void * send_lo, void * recv_lo, const void * send_hi, void * recv_hi,
                        size_t count, int dtype, void * stream);
 
+
+/* ---- slab-sharded stencil step as ONE kernel: sweep + halo push over NVLink peer memory ----
+ * One process per GPU. Each rank keeps its two slab buffers (A / Anext, ghost planes included) and one flag block in
+ * memory from racu_alloc, exports them with racu_ipc_export, and maps its two neighbours' with racu_ipc_open (the
+ * handles travel over any control plane: torch.distributed, MPI, a file). Replaces, for the slab owner, the sequence
+ * "racu_halo_exchange; racu_stencil" and has no counterpart in the reference (single process, README.md:81).
+ *
+ * racu_stencil_push sweeps the whole local interior src -> dst like racu_stencil and, in the same kernel, stores the
+ * first / last owned plane it produces into the neighbour's ghost plane of ITS dst buffer (push_lo / push_hi). Lock step:
+ * flags[0] / flags[1] hold the number of steps the lower / higher neighbour has completed on the shared edge; the CTAs that
+ * read a ghost plane (or overwrite the neighbour's) first wait for flag >= step, and the last of them to finish sets the
+ * neighbour's flag to step+1 (system-scope release after the pushes). Only those edge CTAs wait, and they are scheduled in
+ * the middle of the grid, so the exchange hides behind the interior. flags[4] != 0 after a sync means a neighbour did
+ * not arrive within 20 s (the kernel gives up instead of hanging).
+ * Call with step = 0, 1, 2, ... and swapped buffers; ghost planes of the first src must hold the neighbours' data. */
+#define RACU_IPC_HANDLE_BYTES 64
+#define RACU_HALO_FLAG_WORDS 8
+int racu_ipc_export(void * dev_ptr, void * handle_out /* RACU_IPC_HANDLE_BYTES */);
+int racu_ipc_open(const void * handle, void ** dev_ptr_out);
+int racu_ipc_close(void * dev_ptr);
+typedef struct {
+    void * push_lo;        /* lower neighbour's HIGH ghost plane in its dst buffer (peer mapping), NULL at the global end */
+    void * push_hi;        /* higher neighbour's LOW ghost plane in its dst buffer, NULL at the global end */
+    uint32_t * flags;      /* local, RACU_HALO_FLAG_WORDS words, zeroed once before step 0 */
+    uint32_t * signal_lo;  /* &flags[1] of the lower neighbour (peer mapping) */
+    uint32_t * signal_hi;  /* &flags[0] of the higher neighbour (peer mapping) */
+    uint32_t step;         /* steps already completed */
+    uint32_t reserved;
+} racu_halo_push;
+int racu_stencil_push(const racu_stencil_desc * s, const racu_halo_push * h, void * stream);
+
 #ifdef __cplusplus
 }
 #endif

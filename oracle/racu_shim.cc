@@ -66,4 +66,25 @@ int racu_comm_init_rank(racu_comm **, const void *, int, int) { return RACU_ERR_
 int racu_comm_destroy(racu_comm *) { return RACU_ERR_UNSUPPORTED; }
 int racu_allreduce(racu_comm *, void *, size_t, int, int, void *) { return RACU_ERR_UNSUPPORTED; }
 int racu_halo_exchange(racu_comm *, const void *, void *, const void *, void *, size_t, int, void *) { return RACU_ERR_UNSUPPORTED; }
+int racu_ipc_export(void *, void *) { return RACU_ERR_UNSUPPORTED; }
+int racu_ipc_open(const void *, void **) { return RACU_ERR_UNSUPPORTED; }
+int racu_ipc_close(void *) { return RACU_ERR_UNSUPPORTED; }
+// Host-memory meaning of the fused step (all "ranks" live in one process and are stepped one after the other): sweep, then
+// copy the interior of the first / last owned plane into the neighbour's ghost plane and raise its flag.
+int racu_stencil_push(const racu_stencil_desc * s, const racu_halo_push * h, void *)
+{
+    if (int e = oracle_stencil_raw(s)) return e;
+    size_t const es = s->dtype==RACU_F32 ? 4 : 8;
+    for (int side=0; side<2; ++side) {
+        char * peer = static_cast<char *>(side ? h->push_hi : h->push_lo);
+        if (!peer) continue;
+        int64_t const i = side ? s->len[0]-2 : 1;
+        char const * src = static_cast<char const *>(s->dst) + i*s->dst_stride[0]*es;
+        for (int64_t j=1; j<s->len[1]-1; ++j)
+            for (int64_t k=1; k<s->len[2]-1; ++k)
+                std::memcpy(peer + (j*s->dst_stride[1]+k*s->dst_stride[2])*es, src + (j*s->dst_stride[1]+k*s->dst_stride[2])*es, es);
+        *(side ? h->signal_hi : h->signal_lo) = h->step+1;
+    }
+    return RACU_OK;
+}
 }

@@ -32,6 +32,8 @@ RED_SUM, RED_PROD, RED_AMIN, RED_AMAX = 1, 3, 5, 6
 STENCIL_3D7, STENCIL_2D5, STENCIL_1D3, STENCIL_2D5_STIFF = 1, 2, 3, 4
 
 UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
+HALO_FLAG_WORDS = 8
 
 
 class Base(C.Union):
@@ -97,6 +99,18 @@ class GemmDesc(C.Structure):
     ]
 
 
+class HaloPush(C.Structure):
+    _fields_ = [
+        ("push_lo", C.c_void_p),
+        ("push_hi", C.c_void_p),
+        ("flags", C.c_void_p),
+        ("signal_lo", C.c_void_p),
+        ("signal_hi", C.c_void_p),
+        ("step", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
 # Every symbol include/racu.h declares: (name, restype, argtypes). tests/test_abi.py checks the built
 # library exports each of them.
 _P = C.c_void_p
@@ -129,6 +143,10 @@ SYMBOLS = [
     ("racu_comm_destroy", C.c_int, [_P]),
     ("racu_allreduce", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int, _P]),
     ("racu_halo_exchange", C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_int, _P]),
+    ("racu_ipc_export", C.c_int, [_P, _P]),
+    ("racu_ipc_open", C.c_int, [_P, C.POINTER(_P)]),
+    ("racu_ipc_close", C.c_int, [_P]),
+    ("racu_stencil_push", C.c_int, [C.POINTER(StencilDesc), C.POINTER(HaloPush), _P]),
 ]
 
 

@@ -149,4 +149,34 @@ int racu_halo_exchange(racu_comm * comm, const void * send_lo, void * recv_lo, c
     return RACU_OK;
 }
 
+// ---- peer memory for racu_stencil_push: CUDA IPC handles of racu_alloc'ed buffers
+
+static_assert(sizeof(cudaIpcMemHandle_t)<=RACU_IPC_HANDLE_BYTES, "ipc handle size");
+
+int racu_ipc_export(void * dev_ptr, void * handle_out)
+{
+    if (!dev_ptr || !handle_out) return fail(RACU_ERR_BAD_DESC, "null argument");
+    cudaIpcMemHandle_t h;
+    if (cudaError_t e = cudaIpcGetMemHandle(&h, dev_ptr)) return cuda_fail(e, "cudaIpcGetMemHandle");
+    std::memset(handle_out, 0, RACU_IPC_HANDLE_BYTES);
+    std::memcpy(handle_out, &h, sizeof(h));
+    return RACU_OK;
+}
+
+int racu_ipc_open(const void * handle, void ** dev_ptr_out)
+{
+    if (!handle || !dev_ptr_out) return fail(RACU_ERR_BAD_DESC, "null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    if (cudaError_t e = cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess)) return cuda_fail(e, "cudaIpcOpenMemHandle");
+    return RACU_OK;
+}
+
+int racu_ipc_close(void * dev_ptr)
+{
+    if (!dev_ptr) return RACU_OK;
+    if (cudaError_t e = cudaIpcCloseMemHandle(dev_ptr)) return cuda_fail(e, "cudaIpcCloseMemHandle");
+    return RACU_OK;
+}
+
 } // extern "C"

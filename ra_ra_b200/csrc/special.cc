@@ -94,6 +94,12 @@ int racu_stencil(const racu_stencil_desc * s, void * stream)
     return racu_map(&d, stream);
 }
 
+int racu_stencil_push(const racu_stencil_desc * s, const racu_halo_push * h, void * stream)
+{
+    if (!s || !h || !s->src || !s->dst) return fail(RACU_ERR_BAD_DESC, "bad stencil descriptor");
+    return stencil_push(s, h, cudaStream_t(stream));
+}
+
 // c(all, insert<1>) += a * b(insert<1>): expression axes (i, k, j). ra/ra.hh:407.
 int racu_gemm(const racu_gemm_desc * g, void * stream)
 {

@@ -12,6 +12,11 @@
 // column live in registers, the j and k neighbours come from the current stage. Each input cell is therefore read from
 // L2/HBM once per CTA (plus halo), each output written once: 8 B / cell algorithmic for f32.
 // 2-D stencils are the same kernel with a single plane (no marching).
+//
+// Slab-sharded sweeps (one process per GPU, racu_stencil_push): the FUSED instantiation of the same kernel also stores the
+// first / last owned plane it produces into the neighbour's ghost plane (peer memory mapped with CUDA IPC, plain 16-byte
+// stores that travel over NVLink) and keeps the two neighbours in lock step with one flag word per side, so a step is ONE
+// kernel launch with no separate exchange. See the protocol comment at racu_stencil_push.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -47,7 +52,30 @@ struct StParams
     int32_t i_lo, i_hi;      // output planes [i_lo, i_hi) (3-D); ignored for 2-D
     int32_t ci;              // planes per CTA chunk
     int32_t vec_store;       // destination allows aligned 16-byte stores
+    // FUSED only (racu_stencil_push)
+    void * push_lo, * push_hi;           // neighbour's ghost plane (element [.,0,0]) mirroring my plane 1 / plane n0-2, or null
+    uint32_t * flags;                    // local: [0] lower neighbour's completed steps, [1] higher's, [2]/[3] CTA counters, [4] timeout
+    uint32_t * signal_lo, * signal_hi;   // the neighbours' flag words this rank sets (peer memory)
+    uint32_t step;                       // steps completed before this launch
+    int32_t edge_ctas;                   // CTAs per edge chunk (gridDim.x*gridDim.y)
 };
+
+// ---- system-scope flag helpers for the fused halo push
+__device__ __forceinline__ uint32_t ld_acquire_sys(uint32_t const * p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys(uint32_t * p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint64_t globaltimer_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+constexpr uint64_t ST_WAIT_TIMEOUT_NS = 20ull*1000*1000*1000; // a neighbour that never arrives sets flags[4] instead of hanging the GPU
+
+__device__ __forceinline__ void
+wait_neighbour(uint32_t * flags, int side, uint32_t want)
+{
+    if (int32_t(ld_acquire_sys(flags+side)-want)>=0) return;
+    uint64_t const t0 = globaltimer_ns();
+    while (int32_t(ld_acquire_sys(flags+side)-want)<0) {
+        __nanosleep(64);
+        if (globaltimer_ns()-t0>ST_WAIT_TIMEOUT_NS) { atomicExch(flags+4, 1u+side); break; }
+    }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(void const * p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t * bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
@@ -81,7 +109,7 @@ stencil_value(T c, T ip, T jp, T kp, T im, T jm, T km)
     else return ((((T(4)*c) - jm) - km) - jp) - kp;                                                     // STIFF
 }
 
-template <class T, int KIND> __global__ void __launch_bounds__(ST_THREADS)
+template <class T, int KIND, bool FUSED> __global__ void __launch_bounds__(ST_THREADS)
 stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StParams p)
 {
     using TL = StTile<T>;
@@ -95,8 +123,17 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     int const tk = tid % (TK/VT), tj = tid / (TK/VT);          // tj in [0, ST_TR)
     int const k0 = blockIdx.x*TK, j0 = 1 + blockIdx.y*ST_TJ;   // first output k of the tile (vector aligned), first output j
     int const k = k0 + tk*VT, j = j0 + tj;
-    int const ilo = is3d ? p.i_lo + int(blockIdx.z)*p.ci : 0;
+    // FUSED: the two edge chunks (0 and gz-1: they read a ghost plane and feed the neighbours) are scheduled in the middle
+    // of the grid, so that the neighbours' flags have long arrived when they start and the pushed planes have long landed
+    // when the kernel ends; every other chunk keeps its order.
+    int chunk = int(blockIdx.z);
+    if constexpr (FUSED) {
+        int const gz = int(gridDim.z), e = (gz-2)/2;
+        if (gz>2) chunk = chunk<e ? chunk+1 : (chunk==e ? 0 : (chunk==e+1 ? gz-1 : chunk-1));
+    }
+    int const ilo = is3d ? p.i_lo + chunk*p.ci : 0;
     int const ihi = is3d ? min(p.i_hi, ilo + p.ci) : 1;
+    bool const touch_lo = FUSED && p.push_lo && 1==ilo, touch_hi = FUSED && p.push_hi && ihi==p.n0-1;
     int const nplanes = is3d ? (ihi-ilo+2) : 1;                // input planes ilo-1 .. ihi
     constexpr uint32_t plane_bytes = (ST_TJ+2)*TKB*sizeof(T); // bytes one TMA box delivers
 
@@ -104,6 +141,13 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
         for (int s=0; s<ST_STAGES; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if constexpr (FUSED) {
+            // The neighbour has finished step p.step-1: its pushes into my ghost plane of the source have landed, and it no
+            // longer reads the ghost plane of ITS destination that this CTA is about to overwrite.
+            if (touch_lo) wait_neighbour(p.flags, 0, p.step);
+            if (touch_hi) wait_neighbour(p.flags, 1, p.step);
+            if (touch_lo || touch_hi) asm volatile("fence.proxy.async;" ::: "memory"); // remote generic-proxy writes -> my TMA reads
+        }
     }
     __syncthreads();
     auto issue = [&](int q) { // input plane q of this chunk -> stage q % STAGES
@@ -134,6 +178,19 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         else {
 #pragma unroll
             for (int l=0; l<VT; ++l) { if (lane_ok[r][l]) d[int64_t(l)*p.ds2] = o[l]; }
+        }
+        if constexpr (FUSED) { // the same values into the neighbours' ghost planes (same inner strides)
+#pragma unroll
+            for (int side=0; side<2; ++side) {
+                void * const peer = side ? p.push_hi : p.push_lo;
+                if (!peer || i!=(side ? p.n0-2 : 1)) continue;
+                T * g = static_cast<T *>(peer) + int64_t(j+r*ST_TR)*p.ds1 + int64_t(k)*p.ds2;
+                if (all_ok[r] && p.vec_store) { uint4 q; memcpy(&q, o, 16); *reinterpret_cast<uint4 *>(g) = q; }
+                else {
+#pragma unroll
+                    for (int l=0; l<VT; ++l) { if (lane_ok[r][l]) g[int64_t(l)*p.ds2] = o[l]; }
+                }
+            }
         }
     };
 
@@ -188,6 +245,23 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             __syncthreads();                                  // plane q is no longer read by anyone
             if (0==tid && q+ST_STAGES<nplanes) issue(q+ST_STAGES);
         }
+        if constexpr (FUSED) {
+            // Edge CTAs count themselves; the last one of an edge chunk tells that neighbour "step p.step+1 done on my side":
+            // every push has been made visible system wide (fence after the CTA barrier, cumulative) and every read of my
+            // ghost plane has completed (each TMA stage was waited for).
+            if ((touch_lo || touch_hi) && 0==tid) {
+                __threadfence_system();
+#pragma unroll
+                for (int side=0; side<2; ++side) {
+                    if (!(side ? touch_hi : touch_lo)) continue;
+                    if (atomicAdd(p.flags+2+side, 1u)==uint32_t(p.edge_ctas-1)) {
+                        p.flags[2+side] = 0;
+                        __threadfence_system();
+                        st_release_sys(side ? p.signal_hi : p.signal_lo, p.step+1);
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -212,7 +286,7 @@ encode_fn()
 }
 
 template <class T, int KIND> static int
-launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled)
+launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled, racu_halo_push const * h = nullptr)
 {
     using TL = StTile<T>;
     constexpr bool is3d = KIND==RACU_STENCIL_3D7;
@@ -260,12 +334,19 @@ launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled)
         if (gz>65535) { p.ci = int32_t((planes+65534)/65535); gz = unsigned((planes+p.ci-1)/p.ci); }
     }
     size_t smem = size_t(ST_STAGES)*TL::PLANE*sizeof(T);
-    auto kernel = stencil_tma_kernel<T, KIND>;
+    auto kernel = stencil_tma_kernel<T, KIND, false>;
+    if constexpr (is3d) {
+        if (h) {
+            kernel = stencil_tma_kernel<T, KIND, true>;
+            p.push_lo = h->push_lo; p.push_hi = h->push_hi; p.flags = h->flags; p.signal_lo = h->signal_lo; p.signal_hi = h->signal_hi;
+            p.step = h->step; p.edge_ctas = int32_t(gx*gy);
+        }
+    }
     if (smem>32*1024) { if (cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return cuda_fail(e, "stencil smem"); }
     kernel<<<dim3(gx, gy, gz), ST_THREADS, smem, stream>>>(tmap, p);
     launch_count_add(1);
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "stencil_tma");
-    set_kernel(is3d ? "stencil_tma<3D7>" : (KIND==RACU_STENCIL_2D5 ? "stencil_tma<2D5>" : "stencil_tma<2D5_STIFF>"));
+    set_kernel(is3d ? (h ? "stencil_tma<3D7, halo push>" : "stencil_tma<3D7>") : (KIND==RACU_STENCIL_2D5 ? "stencil_tma<2D5>" : "stencil_tma<2D5_STIFF>"));
     *handled = 1;
     return RACU_OK;
 }
@@ -284,6 +365,22 @@ try_special_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * hand
     default: return RACU_OK;
     }
 #undef RACU_ST
+}
+
+// One step of a slab-sharded 7-point sweep as ONE launch: sweep + halo push + neighbour lock step (see include/racu.h).
+int
+stencil_push(racu_stencil_desc const * s, racu_halo_push const * h, cudaStream_t stream)
+{
+    if (s->kind!=RACU_STENCIL_3D7 || 3!=s->rank) return fail(RACU_ERR_UNSUPPORTED, "racu_stencil_push: 3-D 7-point stencil only");
+    if (s->dtype!=RACU_F32 && s->dtype!=RACU_F64) return fail(RACU_ERR_UNSUPPORTED, "stencil dtype must be f32 or f64");
+    if (0!=s->lo0 || 0!=s->hi0) return fail(RACU_ERR_BAD_DESC, "racu_stencil_push sweeps the whole local interior");
+    if (!h->flags || (h->push_lo && !h->signal_lo) || (h->push_hi && !h->signal_hi)) return fail(RACU_ERR_BAD_DESC, "racu_stencil_push: missing flag words");
+    if (s->len[0]<3) return fail(RACU_ERR_BAD_DESC, "racu_stencil_push: a slab needs at least one owned plane between its ghosts");
+    int handled = 0;
+    int e = s->dtype==RACU_F32 ? launch_stencil<float, RACU_STENCIL_3D7>(s, stream, &handled, h) : launch_stencil<double, RACU_STENCIL_3D7>(s, stream, &handled, h);
+    if (e) return e;
+    if (!handled) return fail(RACU_ERR_UNSUPPORTED, "racu_stencil_push: the slab is not expressible as a TMA tensor map (innermost stride 1, 16-byte aligned rows)");
+    return RACU_OK;
 }
 
 // racu_map pattern recognition: is this descriptor one of the reference's stencil slice expressions? (special.cc builds the

@@ -107,3 +107,79 @@ def stencil_sweep(kind=abi.STENCIL_3D7, dtype=abi.F32):
         s.lo0, s.hi0 = lo0, hi0
         check(lib.racu_stencil(C.byref(s), stream_ptr()))
     return sweep
+
+
+def stencil_sweep_push(kind=abi.STENCIL_3D7, dtype=abi.F32):
+    """sweep_push(...) through racu_stencil_push, for parallel.SlabStencil3D.step_push."""
+    def sweep_push(src_ptr, dst_ptr, shape, strides, push_lo, push_hi, flags, signal_lo, signal_hi, step):
+        s = abi.StencilDesc()
+        s.kind, s.dtype, s.rank = kind, dtype, len(shape)
+        s.src, s.dst = src_ptr, dst_ptr
+        for k in range(len(shape)):
+            s.len[k], s.src_stride[k], s.dst_stride[k] = shape[k], strides[k], strides[k]
+        h = abi.HaloPush()
+        h.push_lo, h.push_hi, h.flags, h.signal_lo, h.signal_hi, h.step = push_lo, push_hi, flags, signal_lo, signal_hi, step
+        check(lib.racu_stencil_push(C.byref(s), C.byref(h), stream_ptr()))
+    return sweep_push
+
+
+class _RawCuda:
+    """Zero-copy torch view of a racu_alloc'ed buffer (through __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerSlab:
+    """The two slab buffers (A / Anext, ghosts included) and the flag block of one rank, allocated with racu_alloc so that
+    they can be exported with CUDA IPC, plus the mappings of the two neighbours' (racu_ipc_open). `dist` is only the control
+    plane that carries the 64-byte handles."""
+
+    def __init__(self, dist, world, rank, local_shape, dtype=abi.F32):
+        self.dist, self.world, self.rank = dist, world, rank
+        es = abi.DTYPE_SIZE[dtype]
+        nbytes = int(np.prod(local_shape)) * es
+        self.ptrs = []
+        for nb in (nbytes, nbytes, abi.HALO_FLAG_WORDS * 4):
+            p = C.c_void_p()
+            check(lib.racu_alloc(C.byref(p), nb))
+            self.ptrs.append(p.value)
+        typestr = "<f4" if dtype == abi.F32 else "<f8"
+        self.bufs = [torch.as_tensor(_RawCuda(p, local_shape, typestr), device="cuda") for p in self.ptrs[:2]]
+        self.flags = torch.as_tensor(_RawCuda(self.ptrs[2], (abi.HALO_FLAG_WORDS,), "<i4"), device="cuda")
+        self.flags.zero_()
+        for b in self.bufs:
+            b.zero_()
+        torch.cuda.synchronize()
+        mine = []
+        for p in self.ptrs:
+            h = (C.c_ubyte * abi.IPC_HANDLE_BYTES)()
+            check(lib.racu_ipc_export(C.c_void_p(p), h))
+            mine.append(bytes(h))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        self.peers, self._opened = {}, []
+        for r in (rank - 1, rank + 1):
+            if 0 <= r < world:
+                mapped = []
+                for h in everyone[r]:
+                    q = C.c_void_p()
+                    check(lib.racu_ipc_open(h, C.byref(q)))
+                    mapped.append(q.value)
+                    self._opened.append(q.value)
+                self.peers[r] = tuple(mapped)
+        dist.barrier()
+
+    def timed_out(self):
+        return int(self.flags[4].item())
+
+    def close(self):
+        torch.cuda.synchronize()
+        for q in self._opened:
+            check(lib.racu_ipc_close(C.c_void_p(q)))
+        self._opened = []
+        self.bufs, self.flags = [], None
+        self.dist.barrier()  # nobody frees a buffer a neighbour still maps
+        for p in self.ptrs:
+            check(lib.racu_free(C.c_void_p(p)))
+        self.ptrs = []

@@ -8,6 +8,12 @@ kernels + NCCL through racu_comm_*) and in CPU tests (gloo + the oracle as the s
 
     sweep(src_ptr, dst_ptr, shape, strides, lo0, hi0)   one 7-point sweep over planes [lo0, hi0) of a local slab
     exchanger.exchange(send_lo, recv_lo, send_hi, recv_hi, count)   neighbour planes, non periodic ends
+
+Two schedules for the stencil: `step` (exchange the halo planes of the source with NCCL send/recv, sweep the interior
+meanwhile, edges last) and `step_push` (ONE kernel per step: the sweep stores its edge planes straight into the neighbours'
+ghost planes over NVLink peer memory and keeps the neighbours in lock step with flags, racu_stencil_push):
+
+    sweep_push(src_ptr, dst_ptr, shape, strides, push_lo, push_hi, flags, signal_lo, signal_hi, step)
 """
 
 
@@ -93,6 +99,33 @@ class SlabStencil3D:
             sweep(src_ptr, dst_ptr, self.local_shape, strides, 1, min(2, n0 - 1))
         if self.g_hi and n0 - 2 >= lo_edge and (n0 - 2 > 1 or not self.g_lo):
             sweep(src_ptr, dst_ptr, self.local_shape, strides, n0 - 2, n0 - 1)
+
+
+    def push_targets(self, t, itemsize, peers):
+        """Where step t (src = buffer t % 2, dst = buffer (t+1) % 2) pushes its edge planes and raises its flags.
+
+        `peers` maps a neighbour's rank to (buffer0_ptr, buffer1_ptr, flags_ptr) as addressable from this rank. The lower
+        neighbour's HIGH ghost is the last plane of its slab, the higher neighbour's LOW ghost is its plane 0; flag word 0 of
+        a rank is written by its lower neighbour, word 1 by its higher one (include/racu.h, racu_halo_push).
+        Returns (push_lo, push_hi, signal_lo, signal_hi), None where there is no neighbour."""
+        d = (t + 1) % 2
+        push_lo = push_hi = sig_lo = sig_hi = None
+        if self.g_lo:
+            lo = SlabStencil3D(self.shape, self.world, self.rank - 1)
+            push_lo = peers[self.rank - 1][d] + (lo.local_n0 - 1) * self.plane * itemsize
+            sig_lo = peers[self.rank - 1][2] + 4
+        if self.g_hi:
+            push_hi = peers[self.rank + 1][d]
+            sig_hi = peers[self.rank + 1][2]
+        return push_lo, push_hi, sig_lo, sig_hi
+
+    def step_push(self, t, bufs, flags_ptr, peers, itemsize, sweep_push):
+        """Step t as one fused launch: sweep bufs[t % 2] -> bufs[(t+1) % 2] over the whole local interior, edge planes pushed
+        into the neighbours' ghosts of THEIR destination buffer. Needs no exchange before it: the ghosts of the source were
+        pushed by the neighbours during step t-1 (for t = 0 they come with the initial data)."""
+        n0, n1, n2 = self.local_shape
+        push_lo, push_hi, sig_lo, sig_hi = self.push_targets(t, itemsize, peers)
+        sweep_push(bufs[t % 2], bufs[(t + 1) % 2], self.local_shape, (n1 * n2, n2, 1), push_lo, push_hi, flags_ptr, sig_lo, sig_hi, t)
 
 
 class TorchDistExchanger:

@@ -23,7 +23,7 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, shape, steps, out_dir):
+def _worker(rank, world, port, shape, steps, out_dir, mode="nccl"):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -34,16 +34,31 @@ def _worker(rank, world, port, shape, steps, out_dir):
     comm = parallel.make_comm(lib, cuda.check, dist, world, rank)
     a0 = np.random.default_rng(41).uniform(-1, 1, shape).astype(np.float32)
     sl = parallel.SlabStencil3D(shape, world, rank)
-    A = torch.from_numpy(a0[sl.global_slice()].copy()).cuda()
-    An = torch.zeros_like(A)
-    bufs = [A, An]
-    sweep = cuda.stencil_sweep()
-    exch = parallel.RacuCommExchanger(lib, comm, abi.F32, cuda.stream_ptr, cuda.check)
-    ov = cuda.StreamOverlap()
-    for _ in range(steps):
-        sl.step(bufs[0].data_ptr(), bufs[1].data_ptr(), 4, sweep, exch, ov)
-        bufs.reverse()
-    torch.cuda.synchronize()
+    if mode == "push":  # one kernel per step: sweep + halo push into the neighbours' ghosts over peer memory
+        slab = cuda.PeerSlab(dist, world, rank, sl.local_shape, abi.F32)
+        slab.bufs[0].copy_(torch.from_numpy(a0[sl.global_slice()].copy()))
+        torch.cuda.synchronize()
+        dist.barrier()
+        sweep_push = cuda.stencil_sweep_push()
+        for t in range(steps):
+            sl.step_push(t, slab.ptrs[:2], slab.ptrs[2], slab.peers, 4, sweep_push)
+        torch.cuda.synchronize()
+        assert slab.timed_out() == 0
+        assert cuda.lib.racu_last_kernel() == b"stencil_tma<3D7, halo push>"
+        dist.barrier()
+        bufs = [slab.bufs[steps % 2].clone()]
+        slab.close()
+    else:
+        A = torch.from_numpy(a0[sl.global_slice()].copy()).cuda()
+        An = torch.zeros_like(A)
+        bufs = [A, An]
+        sweep = cuda.stencil_sweep()
+        exch = parallel.RacuCommExchanger(lib, comm, abi.F32, cuda.stream_ptr, cuda.check)
+        ov = cuda.StreamOverlap()
+        for _ in range(steps):
+            sl.step(bufs[0].data_ptr(), bufs[1].data_ptr(), 4, sweep, exch, ov)
+            bufs.reverse()
+        torch.cuda.synchronize()
     np.save(os.path.join(out_dir, f"A_{rank}.npy"), bufs[0][sl.owned_local()].cpu().numpy())
     # sharded fold: local partial + racu_allreduce
     ex = cuda.CudaExecutor(rank)
@@ -59,14 +74,15 @@ def _worker(rank, world, port, shape, steps, out_dir):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("shape", [(64, 40, 132), (33, 64, 64)])
-def test_sharded_stencil_equals_single_gpu(shape, tmp_path):
+@pytest.mark.parametrize("mode", ["nccl", "push"])
+@pytest.mark.parametrize("shape", [(64, 40, 132), (33, 64, 64), (8, 300, 260)])
+def test_sharded_stencil_equals_single_gpu(shape, mode, tmp_path):
     import torch
     import torch.multiprocessing as mp
     from ra_ra_b200 import cuda
-    world, steps = min(_ngpu(), 4), 6
-    port = 29900 + (os.getpid() + shape[0]) % 90
-    mp.spawn(_worker, args=(world, port, shape, steps, str(tmp_path)), nprocs=world, join=True)
+    world, steps = min(_ngpu(), 4), 7
+    port = 29900 + (os.getpid() + shape[0] + (40 if mode == "push" else 0)) % 90
+    mp.spawn(_worker, args=(world, port, shape, steps, str(tmp_path), mode), nprocs=world, join=True)
     a0 = np.random.default_rng(41).uniform(-1, 1, shape).astype(np.float32)
     A = torch.from_numpy(a0).cuda()
     An = torch.zeros_like(A)

@@ -95,3 +95,41 @@ def test_shard_bounds_cover_axis():
             b = [parallel.shard_bounds(n, world, r) for r in range(world)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+@pytest.mark.parametrize("world,shape", [(2, (12, 7, 9)), (3, (11, 6, 8)), (4, (9, 5, 6)), (3, (5, 6, 7)), (8, (16, 5, 5))])
+def test_push_schedule_matches_single_process(world, shape):
+    """parallel.SlabStencil3D.step_push (the one-kernel-per-step schedule of racu_stencil_push): every pointer it derives
+    - neighbour ghost planes in the right buffer, flag words - is exercised on host memory with all ranks in this process,
+    stepped one after the other, through the host-memory stand-in of the ABI (oracle/libracu_oracle.so, tests only)."""
+    shim = C.CDLL(os.path.join(os.path.dirname(HERE), "oracle", "libracu_oracle.so"))
+    shim.racu_stencil_push.argtypes = [C.POINTER(abi.StencilDesc), C.POINTER(abi.HaloPush), C.c_void_p]
+    steps, dt = 5, np.float32
+    a0 = np.random.default_rng(43).uniform(-1, 1, shape).astype(dt)
+    slabs = [parallel.SlabStencil3D(shape, world, r) for r in range(world)]
+    bufs = [[a0[sl.global_slice()].copy(), np.zeros(sl.local_shape, dt)] for sl in slabs]
+    flags = [np.zeros(abi.HALO_FLAG_WORDS, np.uint32) for _ in range(world)]
+    ptrs = [(b[0].ctypes.data, b[1].ctypes.data, f.ctypes.data) for b, f in zip(bufs, flags)]
+
+    def sweep_push(src, dst, lshape, strides, push_lo, push_hi, fl, sig_lo, sig_hi, step):
+        s = abi.StencilDesc()
+        s.kind, s.dtype, s.rank, s.src, s.dst = abi.STENCIL_3D7, abi.F32, 3, src, dst
+        for k in range(3):
+            s.len[k], s.src_stride[k], s.dst_stride[k] = lshape[k], strides[k], strides[k]
+        h = abi.HaloPush()
+        h.push_lo, h.push_hi, h.flags, h.signal_lo, h.signal_hi, h.step = push_lo, push_hi, fl, sig_lo, sig_hi, step
+        assert shim.racu_stencil_push(C.byref(s), C.byref(h), None) == 0
+
+    for t in range(steps):
+        for r, sl in enumerate(slabs):
+            # the lock-step condition the kernel waits for: both neighbours have completed t steps on the shared edge
+            assert (not sl.g_lo or flags[r][0] >= t) and (not sl.g_hi or flags[r][1] >= t)
+            peers = {q: ptrs[q] for q in (r - 1, r + 1) if 0 <= q < world}
+            sl.step_push(t, ptrs[r][:2], ptrs[r][2], peers, 4, sweep_push)
+    A, An = _reference(a0, steps, dt)
+    cur, oth = steps % 2, (steps + 1) % 2
+    gotA = np.concatenate([bufs[r][cur][sl.owned_local()] for r, sl in enumerate(slabs)])
+    gotAn = np.concatenate([bufs[r][oth][sl.owned_local()] for r, sl in enumerate(slabs)])
+    assert np.array_equal(gotA, A) and np.array_equal(gotAn, An)
+    for r, sl in enumerate(slabs):
+        assert flags[r][0] == (steps if sl.g_lo else 0) and flags[r][1] == (steps if sl.g_hi else 0)
