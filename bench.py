@@ -241,8 +241,9 @@ def main():
     b_t = torch.rand(N, generator=g, device=dev, dtype=torch.float32)
     a, b = ex.wrap(a_t), ex.wrap(b_t)
     A2 = ex.wrap(a_t.view(m, n))
-    scal = torch.zeros(4, device=dev, dtype=torch.float32)  # sum, sqrm, dot
-    rows_t = torch.zeros(n, device=dev, dtype=torch.float32)
+    # sum-rows output and the three scalars (sum, sqrm, dot) share one allocation: one allreduce combines them at N>1
+    shared_t = torch.zeros(n + 4, device=dev, dtype=torch.float32)
+    rows_t, scal = shared_t[:n], shared_t[n:]
     cols_t = torch.zeros(m, device=dev, dtype=torch.float32)
     rows, cols = ex.wrap(rows_t), ex.wrap(cols_t)
 
@@ -262,8 +263,7 @@ def main():
         cuda.check(lib.racu_map(C.byref(d_rows), sp()))
         cuda.check(lib.racu_map(C.byref(d_cols), sp()))
         if world > 1:  # partials of the sharded leading axis: one allreduce each (sum-cols outputs stay sharded)
-            cuda.check(lib.racu_allreduce(comm, C.c_void_p(scal.data_ptr()), 3, abi.F32, abi.RED_SUM, sp()))
-            cuda.check(lib.racu_allreduce(comm, C.c_void_p(rows_t.data_ptr()), n, abi.F32, abi.RED_SUM, sp()))
+            cuda.check(lib.racu_allreduce(comm, C.c_void_p(shared_t.data_ptr()), n + 3, abi.F32, abi.RED_SUM, sp()))
 
     bytes_step = 4 * N * 6 + 4 * (n + m)  # per GPU, algorithmic
     sampler = ClockSampler(local)
@@ -385,15 +385,13 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local)
         An = torch.zeros_like(A)
     bufs = [A, An]
     sweep = cuda.stencil_sweep(abi.STENCIL_3D7, abi.F32)
-    sweep_push = cuda.stencil_sweep_push(abi.STENCIL_3D7, abi.F32)
     exch = parallel.RacuCommExchanger(lib, comm, abi.F32, cuda.stream_ptr, cuda.check) if world > 1 and not push else None
     overlap = cuda.StreamOverlap() if world > 1 and not push and not args.no_overlap else None
-    tcount = [0]
+    stepper = cuda.PushStepper(sl, slab, abi.STENCIL_3D7, abi.F32) if push else None
 
     def step():
         if push:
-            sl.step_push(tcount[0], slab.ptrs[:2], slab.ptrs[2], slab.peers, 4, sweep_push)
-            tcount[0] += 1
+            stepper.step()
             return
         sl.step(bufs[0].data_ptr(), bufs[1].data_ptr(), 4, sweep, exch, overlap)
         bufs.reverse()

@@ -123,6 +123,31 @@ def stencil_sweep_push(kind=abi.STENCIL_3D7, dtype=abi.F32):
     return sweep_push
 
 
+class PushStepper:
+    """Steps of parallel.SlabStencil3D.step_push with everything but the step number prepared once: the two (descriptor,
+    halo) pairs for even / odd steps. One call = one racu_stencil_push launch."""
+
+    def __init__(self, sl, slab, kind=abi.STENCIL_3D7, dtype=abi.F32):
+        self.t, self.pairs = 0, []
+        es = abi.DTYPE_SIZE[dtype]
+        for par in (0, 1):
+            got = []
+            sl.step_push(par, slab.ptrs[:2], slab.ptrs[2], slab.peers, es, lambda *a: got.append(a))
+            src, dst, shape, strides, push_lo, push_hi, flags, sig_lo, sig_hi, _ = got[0]
+            s, h = abi.StencilDesc(), abi.HaloPush()
+            s.kind, s.dtype, s.rank, s.src, s.dst = kind, dtype, 3, src, dst
+            for k in range(3):
+                s.len[k], s.src_stride[k], s.dst_stride[k] = shape[k], strides[k], strides[k]
+            h.push_lo, h.push_hi, h.flags, h.signal_lo, h.signal_hi = push_lo, push_hi, flags, sig_lo, sig_hi
+            self.pairs.append((s, h, C.byref(s), C.byref(h)))
+
+    def step(self):
+        s, h, ps, ph = self.pairs[self.t & 1]
+        h.step = self.t
+        check(lib.racu_stencil_push(ps, ph, stream_ptr()))
+        self.t += 1
+
+
 class _RawCuda:
     """Zero-copy torch view of a racu_alloc'ed buffer (through __cuda_array_interface__)."""
 
