@@ -202,6 +202,13 @@ typedef enum {
 int racu_reduce(const racu_desc * d, int redop, void * out_host, void * stream);
 /* Same, result left in device memory (asynchronous). */
 int racu_reduce_dev(const racu_desc * d, int redop, void * out_dev, void * stream);
+/* Plan d exactly as racu_map would (redop == 0) or racu_reduce (redop != 0) and make sure its kernel exists, WITHOUT
+ * launching anything. A program that is not in the pre-compiled table is specialised now (NVRTC) and cached in memory and
+ * on disk ($RACU_JIT_CACHE, default: jit_cache/ next to the library), so the first real call does not pay for it. Needs
+ * no GPU: on a build host only the disk cache is filled. *kernel_out (optional) = the kernel family that will run.
+ * The device analogue of the reference instantiating ply_ravel for an expression type at compile time. */
+int racu_prepare(const racu_desc * d, int redop, const char ** kernel_out);
+
 /* Kernel configuration introspection for tests/bench: how many of this library's kernels were
  * launched by this thread since the last reset. */
 int64_t racu_launch_count(void);

@@ -44,6 +44,7 @@ int racu_agree(const racu_desc * d, int32_t * r, int64_t * l) { return oracle_ag
 int racu_map(const racu_desc * d, void *) { return oracle_map(d); }
 int racu_reduce(const racu_desc * d, int redop, void * out, void *) { return oracle_reduce(d, redop, out); }
 int racu_reduce_dev(const racu_desc * d, int redop, void * out, void *) { return oracle_reduce(d, redop, out); }
+int racu_prepare(const racu_desc *, int, const char ** k) { if (k) *k = "oracle"; return RACU_OK; }
 int64_t racu_launch_count(void) { return 0; }
 void racu_launch_count_reset(void) {}
 const char * racu_last_kernel(void) { return "oracle"; }

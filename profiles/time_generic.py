@@ -25,3 +25,10 @@ run("B = sqrt(A*A + C*C)", lambda: B.assign(ra.sqrt(A * A + Cc * Cc)), 12 * E)
 run("B = (A - C)*(A + C) + A*0.5f - C", lambda: B.assign((A - Cc) * (A + Cc) + A * ra.np.float32(0.5) - Cc), 12 * E)
 run("sum(where(A > 0.5f, A, 0f))", lambda: ra.sum(ra.where(A > ra.np.float32(0.5), A, ra.np.float32(0))), 4 * E)
 run("B = A(reversed rows) * C  [int idx]", lambda: B.assign(ra.reverse(A, 0) * Cc + ra._1), 12 * E)
+I32 = ex.wrap(torch.randint(-5, 6, (n, n), device=dev, dtype=torch.int32))
+D = ex.wrap(torch.rand(n // 2, n, device=dev, dtype=torch.float64))
+Ah = ex.wrap(A.owner[: n // 2])
+run("B = pick(int(A>.5)+int(C>.5), A, C, A+C)", lambda: B.assign(ra.pick(ra.cast(abi.I32, A > 0.5) + ra.cast(abi.I32, Cc > 0.5), A, Cc, A + Cc)), 12 * E)
+run("I = (I*3 - I%4) & 7", lambda: I32.assign((I32 * 3 - I32 % 4) & 7), 8 * E)
+run("D(f64) = A(f32)*D + 1", lambda: D.assign(Ah * D + 1.0), (4 + 8 + 8) * E // 2)
+run("amax(abs(A - C))", lambda: ra.amax(ra.abs(A - Cc)), 8 * E)

@@ -132,6 +132,7 @@ SYMBOLS = [
     ("racu_map", C.c_int, [C.POINTER(Desc), _P]),
     ("racu_reduce", C.c_int, [C.POINTER(Desc), C.c_int, _P, _P]),
     ("racu_reduce_dev", C.c_int, [C.POINTER(Desc), C.c_int, _P, _P]),
+    ("racu_prepare", C.c_int, [C.POINTER(Desc), C.c_int, C.POINTER(C.c_char_p)]),
     ("racu_launch_count", C.c_int64, []),
     ("racu_launch_count_reset", None, []),
     ("racu_last_kernel", C.c_char_p, []),

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libracu.so")
 STATIC_PARTS = 4  # the static program table is compiled in this many parallel translation units
-SOURCES = ["ply_kernels.cu"] + [f"static_kernels.cu#{k}" for k in range(STATIC_PARTS)] + [ "stencil.cu", "transpose.cu", "gemm.cu", "plan.cc", "api.cc", "special.cc", "comm.cc"]
+SOURCES = ["ply_kernels.cu"] + [f"static_kernels.cu#{k}" for k in range(STATIC_PARTS)] + [ "stencil.cu", "transpose.cu", "gemm.cu", "plan.cc", "api.cc", "special.cc", "comm.cc", "jit.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O3", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
 
@@ -26,17 +26,60 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+# Sources the run-time specialiser (jit.cc) hands to NVRTC, embedded in the library as text. The last four stand in for
+# the host headers kcore.h / racu.h include: NVRTC has the fixed-width types and math built in, nothing else is used.
+JIT_HEADERS = ["static_device.h", "kbody.h", "kcore.h", "static_progs.h", "../../include/racu.h"]
+JIT_STUBS = {
+    "stdint.h": """#pragma once
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;
+typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;
+typedef unsigned long uintptr_t; typedef long intptr_t;
+""",
+    "stddef.h": "#pragma once\n",
+    "math.h": "#pragma once\n",
+    "type_traits": """#pragma once
+namespace std {
+template <class A, class B> struct is_same { static constexpr bool value = false; };
+template <class A> struct is_same<A, A> { static constexpr bool value = true; };
+template <class A, class B> inline constexpr bool is_same_v = is_same<A, B>::value;
+template <bool C, class A, class B> struct conditional { using type = A; };
+template <class A, class B> struct conditional<false, A, B> { using type = B; };
+template <bool C, class A, class B> using conditional_t = typename conditional<C, A, B>::type;
+}
+""",
+}
+
+
+def _write_jit_sources(bdir):
+    parts = []
+    for name in JIT_HEADERS:
+        parts.append((name, open(os.path.join(CSRC, name)).read()))
+    parts += list(JIT_STUBS.items())
+    out = []
+    for name, text in parts:
+        assert ')RACUSRC"' not in text
+        # string literals are capped at 64 KiB by some compilers: concatenate adjacent raw literals of <= 16 KiB
+        chunks = [text[i:i + 16000] for i in range(0, len(text), 16000)] or [""]
+        out.append('{"%s",\n%s},\n' % (name, "\n".join('R"RACUSRC(%s)RACUSRC"' % c for c in chunks)))
+    path = os.path.join(bdir, "jit_sources.inc")
+    new = "".join(out)
+    if not os.path.exists(path) or open(path).read() != new:
+        open(path, "w").write(new)
+    return path
+
+
 def build_lib(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     bdir = os.path.join(CSRC, "build")
     os.makedirs(bdir, exist_ok=True)
+    jit_inc = _write_jit_sources(bdir)
     hdrs = _headers()
     jobs = []
     for s in SOURCES:
         name, _, part = s.partition("#")
         src = os.path.join(CSRC, name)
         obj = os.path.join(bdir, s.replace("#", "_") + ".o")
-        if force or _stale(obj, [src] + hdrs):
+        if force or _stale(obj, [src] + hdrs + ([jit_inc] if name == "jit.cc" else [])):
             if name.endswith(".cc"):  # host-only translation units
                 cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++20", "-fPIC", "-Wall", "-Wno-unknown-pragmas",
                        "-I", os.path.join(os.path.dirname(os.path.dirname(nvcc)), "include"), "-c", src, "-o", obj]

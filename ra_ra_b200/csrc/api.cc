@@ -128,6 +128,27 @@ int racu_map(const racu_desc * d, void * stream)
     return run_plan(d, 0, nullptr, cudaStream_t(stream));
 }
 
+int racu_prepare(const racu_desc * d, int redop, const char ** kernel_out)
+{
+    if (!d) return fail(RACU_ERR_BAD_DESC, "null descriptor");
+    Plan plan;
+    std::string err;
+    racu_desc sub;
+    racu_desc const * cur = d;
+    void * const out = redop ? reinterpret_cast<void *>(uintptr_t(256)) : nullptr; // planning only looks at its alignment
+    for (int depth=0; depth<RACU_MAX_RANK; ++depth) {
+        int e = make_plan(cur, redop, out, plan, err);
+        if (RACU_OK==e) break;
+        if (e!=RACU_ERR_PEEL) return fail(e, err);
+        if (!can_peel(cur, out!=nullptr)) return fail(RACU_ERR_UNSUPPORTED, err);
+        racu_desc next;
+        peel_axis0(*cur, 0, next); // every slice of the peeled axis runs the same program
+        sub = next; cur = &sub;
+    }
+    if (kernel_out) *kernel_out = plan.empty ? "none (empty)" : plan.kernel;
+    return RACU_OK;
+}
+
 int racu_reduce_dev(const racu_desc * d, int redop, void * out_dev, void * stream)
 {
     if (!d || !out_dev) return fail(RACU_ERR_BAD_DESC, "null argument");

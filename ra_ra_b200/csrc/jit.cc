@@ -1,0 +1,292 @@
+// jit.cc - run-time specialisation of the ply kernels for programs that are not in the pre-compiled table.
+//
+// The reference fuses every expression at COMPILE time: `B += A*C + v` is one template instantiation of ply_ravel's loop
+// (ra/ply.hh:58-68) with the op inlined (ra/expr.hh:661). A C-ABI library cannot see the caller's templates, so the device
+// analogue is done when the expression first arrives: the planner's canonical typed postfix program (static_progs.h, SProg)
+// is handed to NVRTC as a constexpr (RACU_JIT_PROG) together with the SAME hand-written kernel bodies the pre-compiled table
+// uses (static_device.h, embedded in the library as text), compiled for sm_100a with -fmad=false, and cached: in memory per
+// device, and as a cubin on disk keyed by program + variant + a hash of the embedded sources. Same ops, same order, same
+// types as the interpreter and the oracle, so results stay bit-identical; only the instruction stream is specialised.
+//
+// NVRTC is bound with dlopen at first use. If it is not there the planner keeps the interpreted kernels (ply_kernels.cu) -
+// still the GPU, only slower; there is no CPU path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+#include "special.h"
+
+namespace racu {
+
+struct JitSource { char const * name; char const * text; };
+static JitSource const jit_sources[] = {
+#include "build/jit_sources.inc"
+};
+
+// ---- NVRTC, bound lazily
+using nvrtcProgram = struct _nvrtcProgram *;
+static struct Nvrtc
+{
+    int (*CreateProgram)(nvrtcProgram *, char const *, char const *, int, char const * const *, char const * const *) = nullptr;
+    int (*CompileProgram)(nvrtcProgram, int, char const * const *) = nullptr;
+    int (*GetCUBINSize)(nvrtcProgram, size_t *) = nullptr;
+    int (*GetCUBIN)(nvrtcProgram, char *) = nullptr;
+    int (*GetProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
+    int (*GetProgramLog)(nvrtcProgram, char *) = nullptr;
+    int (*DestroyProgram)(nvrtcProgram *) = nullptr;
+    bool ok = false;
+} nvrtc;
+
+static bool
+nvrtc_load()
+{
+    static std::once_flag once;
+    std::call_once(once, []{
+        void * h = nullptr;
+        for (char const * name : {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"}) { if ((h = dlopen(name, RTLD_NOW | RTLD_LOCAL))) break; }
+        if (!h) return;
+        bool all = true;
+#define RACU_SYM(NAME) do { nvrtc.NAME = reinterpret_cast<decltype(nvrtc.NAME)>(dlsym(h, "nvrtc" #NAME)); all = all && nvrtc.NAME; } while (0)
+        RACU_SYM(CreateProgram); RACU_SYM(CompileProgram); RACU_SYM(GetCUBINSize); RACU_SYM(GetCUBIN); RACU_SYM(GetProgramLogSize);
+        RACU_SYM(GetProgramLog); RACU_SYM(DestroyProgram);
+#undef RACU_SYM
+        nvrtc.ok = all;
+    });
+    return nvrtc.ok;
+}
+
+// ---- driver entry points (module load / launch), through the runtime like stencil.cu does for the tensor-map encoder
+static struct Drv
+{
+    CUresult (*ModuleLoadData)(CUmodule *, void const *) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, char const *) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **) = nullptr;
+    bool ok = false;
+} drv;
+
+static bool
+drv_load()
+{
+    static std::once_flag once;
+    std::call_once(once, []{
+        auto get = [](char const * name) -> void * {
+            void * p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaSuccess==cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) && q==cudaDriverEntryPointSuccess) return p;
+            cudaGetLastError();
+            return nullptr;
+        };
+        drv.ModuleLoadData = reinterpret_cast<decltype(drv.ModuleLoadData)>(get("cuModuleLoadData"));
+        drv.ModuleGetFunction = reinterpret_cast<decltype(drv.ModuleGetFunction)>(get("cuModuleGetFunction"));
+        drv.LaunchKernel = reinterpret_cast<decltype(drv.LaunchKernel)>(get("cuLaunchKernel"));
+        drv.ok = drv.ModuleLoadData && drv.ModuleGetFunction && drv.LaunchKernel;
+    });
+    return drv.ok;
+}
+
+// ---- keys and source text
+
+static uint64_t
+fnv1a(void const * data, size_t n, uint64_t h = 1469598103934665603ull)
+{
+    unsigned char const * p = static_cast<unsigned char const *>(data);
+    for (size_t i=0; i<n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+static uint64_t
+sources_hash()
+{
+    static uint64_t h = []{
+        uint64_t x = fnv1a("racu-jit-1", 10);
+        for (JitSource const & s : jit_sources) x = fnv1a(s.text, std::strlen(s.text), x);
+        return x;
+    }();
+    return h;
+}
+
+// variant: maps 0/1 = GENERAL; fold-inner 0/1 = REUSE; fold-outer 0
+static int
+fold_class(int fold_op)
+{
+    switch (fold_op) {
+    case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: return RACU_ASSIGN_ADD;
+    case RACU_ASSIGN_AMIN: return RACU_ASSIGN_AMIN;
+    case RACU_ASSIGN_AMAX: return RACU_ASSIGN_AMAX;
+    default: return RACU_ASSIGN_MUL;
+    }
+}
+
+std::string
+jit_prog_text(SProg const & P)
+{
+    std::string s = "SProg {" + std::to_string(P.n) + ", {";
+    for (int i=0; i<P.n; ++i) {
+        SIns const & in = P.ins[i];
+        s += "SIns {" + std::to_string(in.op) + ", " + std::to_string(in.arg) + ", " + std::to_string(in.type) + ", " + std::to_string(in.aux) + "}";
+        if (i+1<P.n) s += ", ";
+    }
+    s += "}, " + std::to_string(P.nin) + ", " + std::to_string(P.yrole) + ", " + (P.fold ? "true" : "false") + ", {";
+    for (int r=0; r<P.nin; ++r) { s += std::to_string(P.rtype[r]); if (r+1<P.nin) s += ", "; }
+    s += "}, " + std::to_string(P.otype) + "}";
+    return s;
+}
+
+std::string
+jit_kernel_text(SProg const & P, int mode, int variant, int fold_op)
+{
+    std::string s = "#define RACU_JIT_PROG " + jit_prog_text(P) + "\n#include \"static_device.h\"\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(racu::KBLOCK)\nracu_jit_kernel(const __grid_constant__ racu::SParams p";
+    if (mode==K_MAP) s += std::string(")\n{ racu::smap_body<racu::SP_JIT, ") + (variant ? "true" : "false") + ">(p); }\n";
+    else if (mode==K_FOLD_INNER) s += ", const __grid_constant__ racu::FinishParams f)\n{ racu::sfold_inner_body<racu::SP_JIT, " + std::to_string(fold_class(fold_op)) + ", " + (variant ? "true" : "false") + ">(p, f); }\n";
+    else s += ", const __grid_constant__ racu::FinishParams f)\n{ racu::sfold_outer_body<racu::SP_JIT, " + std::to_string(fold_class(fold_op)) + ">(p, f); }\n";
+    return s;
+}
+
+static std::string
+cache_dir()
+{
+    if (char const * e = std::getenv("RACU_JIT_CACHE")) return e;
+    Dl_info info;
+    if (dladdr(reinterpret_cast<void *>(&sources_hash), &info) && info.dli_fname) { // next to libracu.so
+        std::string p = info.dli_fname;
+        size_t k = p.rfind('/');
+        return (k==std::string::npos ? std::string(".") : p.substr(0, k)) + "/jit_cache";
+    }
+    return "jit_cache";
+}
+
+static bool
+read_file(std::string const & path, std::vector<char> & out)
+{
+    FILE * f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    long n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    out.resize(n>0 ? size_t(n) : 0);
+    bool ok = n>0 && std::fread(out.data(), 1, size_t(n), f)==size_t(n);
+    std::fclose(f);
+    return ok;
+}
+
+static void
+write_file(std::string const & dir, std::string const & path, std::vector<char> const & data)
+{
+    mkdir(dir.c_str(), 0755);
+    std::string tmp = path + ".tmp" + std::to_string(long(getpid()));
+    FILE * f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    bool ok = std::fwrite(data.data(), 1, data.size(), f)==data.size();
+    std::fclose(f);
+    if (ok) std::rename(tmp.c_str(), path.c_str()); else std::remove(tmp.c_str());
+}
+
+// Compile (or fetch from the disk cache) the cubin of one specialisation. Needs no GPU.
+static bool
+jit_cubin(SProg const & P, int mode, int variant, int fold_op, std::vector<char> & cubin, std::string & err)
+{
+    std::string const src = jit_kernel_text(P, mode, variant, fold_op);
+    uint64_t const key = fnv1a(src.data(), src.size(), sources_hash());
+    char name[40];
+    std::snprintf(name, sizeof(name), "%016llx.cubin", static_cast<unsigned long long>(key));
+    std::string const dir = cache_dir(), path = dir + "/" + name;
+    bool const use_disk = !std::getenv("RACU_JIT_NO_DISK");
+    if (use_disk && read_file(path, cubin)) return true;
+    if (!nvrtc_load()) { err = "NVRTC (libnvrtc.so.12) is not available"; return false; }
+    constexpr int nh = int(sizeof(jit_sources)/sizeof(jit_sources[0]));
+    char const * names[nh]; char const * texts[nh];
+    for (int i=0; i<nh; ++i) { names[i] = jit_sources[i].name; texts[i] = jit_sources[i].text; }
+    nvrtcProgram prog = nullptr;
+    if (nvrtc.CreateProgram(&prog, src.c_str(), "racu_jit.cu", nh, texts, names)) { err = "nvrtcCreateProgram failed"; return false; }
+    char const * opts[] = {"--gpu-architecture=sm_100a", "-std=c++20", "-fmad=false", "-default-device", "-lineinfo"};
+    int const rc = nvrtc.CompileProgram(prog, int(sizeof(opts)/sizeof(opts[0])), opts);
+    if (rc) {
+        size_t n = 0;
+        nvrtc.GetProgramLogSize(prog, &n);
+        std::string log(n, ' ');
+        if (n) nvrtc.GetProgramLog(prog, log.data());
+        err = "nvrtcCompileProgram failed:\n" + log.substr(0, 4000);
+        nvrtc.DestroyProgram(&prog);
+        return false;
+    }
+    size_t n = 0;
+    if (nvrtc.GetCUBINSize(prog, &n) || 0==n) { err = "nvrtcGetCUBINSize failed"; nvrtc.DestroyProgram(&prog); return false; }
+    cubin.resize(n);
+    int const r2 = nvrtc.GetCUBIN(prog, cubin.data());
+    nvrtc.DestroyProgram(&prog);
+    if (r2) { err = "nvrtcGetCUBIN failed"; return false; }
+    if (use_disk) write_file(dir, path, cubin);
+    return true;
+}
+
+// ---- per-device kernel cache
+
+static std::mutex jit_mutex;
+static std::map<std::string, CUfunction> jit_loaded;   // key: device + kernel text
+static int64_t jit_compiles = 0;
+
+static int
+variant_of(Plan const & plan)
+{
+    SParams const & sp = plan.sp;
+    if (sp.mode==K_MAP) return sp.general ? 1 : 0;
+    if (sp.mode==K_FOLD_INNER) { bool any = false; for (int k=0; k<SP_MAXIN; ++k) any = any || sp.reused[k]; return any ? 1 : 0; }
+    return 0;
+}
+
+// Planner hook (plan.cc: g_jit_prepare): make sure the specialisation of plan.jit_prog exists. With a device, the kernel is
+// loaded and plan.jit_fn set; without one (racu_prepare on a build host) the cubin is only compiled into the disk cache.
+static bool
+jit_prepare(Plan & plan, std::string & err)
+{
+    int const variant = variant_of(plan);
+    int dev = -1;
+    bool const have_dev = cudaSuccess==cudaGetDevice(&dev) && dev>=0 && cudaSuccess==cudaFree(nullptr);
+    if (!have_dev) cudaGetLastError();
+    std::string const src = jit_kernel_text(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op);
+    std::string const key = std::to_string(dev) + "|" + src;
+    std::lock_guard<std::mutex> lock(jit_mutex);
+    auto it = jit_loaded.find(key);
+    if (it!=jit_loaded.end()) { plan.jit_fn = it->second; return true; }
+    std::vector<char> cubin;
+    if (!jit_cubin(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op, cubin, err)) return false;
+    ++jit_compiles;
+    if (!have_dev) { plan.jit_fn = nullptr; return true; }
+    if (!drv_load()) { err = "driver entry points for module loading are not available"; return false; }
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    if (CUresult r = drv.ModuleLoadData(&mod, cubin.data())) { err = "cuModuleLoadData failed: " + std::to_string(int(r)); return false; }
+    if (CUresult r = drv.ModuleGetFunction(&fn, mod, "racu_jit_kernel")) { err = "cuModuleGetFunction failed: " + std::to_string(int(r)); return false; }
+    jit_loaded.emplace(key, fn);
+    plan.jit_fn = fn;
+    return true;
+}
+
+cudaError_t
+launch_jit(Plan const & plan, cudaStream_t stream)
+{
+    if (!plan.jit_fn || !drv_load()) return cudaErrorInvalidDeviceFunction;
+    void * args[2] = {const_cast<SParams *>(&plan.sp), const_cast<FinishParams *>(&plan.fp)};
+    CUresult r = drv.LaunchKernel(static_cast<CUfunction>(plan.jit_fn), plan.grid_x, plan.grid_y, 1, KBLOCK, 1, 1, 0, stream, args, nullptr);
+    if (CUDA_SUCCESS!=r) return cudaErrorLaunchFailure;
+    return cudaSuccess;
+}
+
+int64_t jit_compile_count() { return jit_compiles; }
+
+extern bool (*g_jit_prepare)(Plan &, std::string &);
+static struct JitInstall { JitInstall() { g_jit_prepare = &jit_prepare; } } jit_install;
+
+} // namespace racu

@@ -7,6 +7,7 @@
 namespace racu {
 cudaError_t launch_plan(Plan const & plan, cudaStream_t stream);
 cudaError_t launch_static(Plan const & plan, cudaStream_t stream);
+cudaError_t launch_jit(Plan const & plan, cudaStream_t stream);
 bool try_transpose(Plan const & plan, cudaStream_t stream, cudaError_t & err);
 cudaError_t launch_fill(void * dst, int dtype, racu_base v, size_t n, cudaStream_t stream);
 int64_t launch_count();

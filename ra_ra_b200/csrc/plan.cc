@@ -12,6 +12,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -284,7 +285,7 @@ peel_axis0(racu_desc const & d, int64_t i, racu_desc & out)
 
 // Does the canonical program have a compile-time specialised kernel (static_progs.h)? Fills plan.sp if so.
 static void
-match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold)
+match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold)
 {
     KParams & kp = plan.kp;
     plan.is_static = false;
@@ -317,7 +318,6 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
     uint8_t rtype[SP_MAXIN] = {};
     for (size_t pc=0; pc<prog.size(); ++pc) {
         racu_ins const & i = prog[pc];
-        if (i.op==RACU_OP_PICK) return;
         if (i.op==RACU_OP_PUSH) {
             if (role_of[i.arg]<0) {
                 if (nrole>=SP_MAXIN) return;
@@ -330,7 +330,7 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
             }
             seq[pc] = SIns {RACU_OP_PUSH, uint8_t(role_of[i.arg]), i.type, 0};
         } else {
-            seq[pc] = SIns {i.op, 0, i.type, uint8_t(i.op==RACU_OP_CAST ? i.aux : 0)};
+            seq[pc] = SIns {i.op, uint8_t(i.op==RACU_OP_PICK ? i.arg : 0), i.type, uint8_t(i.op==RACU_OP_CAST || i.op==RACU_OP_PICK ? i.aux : 0)};
         }
     }
     int const otype = fold ? kp.acc_type : kp.opnd[dst].dtype;
@@ -343,7 +343,15 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
         for (int pc=0; pc<P.n && same; ++pc) same = P.ins[pc].op==seq[pc].op && P.ins[pc].type==seq[pc].type && P.ins[pc].aux==seq[pc].aux && P.ins[pc].arg==seq[pc].arg;
         if (same) id = c;
     }
-    if (id<0) return;
+    if (id<0) { // not in the table: specialise at run time (jit.cc) if the library carries the specialiser
+        if (!g_jit_prepare || std::getenv("RACU_NO_JIT")) return;
+        SProg & P = plan.jit_prog;
+        P = SProg {};
+        P.n = int(prog.size()); P.nin = nrole; P.yrole = yrole; P.fold = fold; P.otype = uint8_t(otype);
+        for (int pc=0; pc<P.n; ++pc) P.ins[pc] = seq[pc];
+        for (int r=0; r<nrole; ++r) P.rtype[r] = rtype[r];
+        id = SP_JIT;
+    }
     SParams & sp = plan.sp;
     std::memset(&sp, 0, sizeof(sp));
     int64_t const nvec0 = kp.len0/SV;
@@ -419,9 +427,25 @@ match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold
             sp.reused[r] = sp.kind[r]==SK_VEC && !moves;
         }
     }
+    if (SP_JIT==id) {
+        std::string err;
+        if (!g_jit_prepare(plan, err)) { if (std::getenv("RACU_JIT_VERBOSE")) std::fprintf(stderr, "racu jit: %s\n", err.c_str()); return; }
+    }
     plan.is_static = true;
-    static const char * names[3] = {"sflat_map", "sflat_fold_inner", "sflat_fold_outer"};
-    plan.kernel = names[kp.mode];
+    static const char * names[6] = {"sflat_map", "sflat_fold_inner", "sflat_fold_outer", "jit_map", "jit_fold_inner", "jit_fold_outer"};
+    plan.kernel = names[kp.mode + (SP_JIT==id ? 3 : 0)];
+}
+
+bool (*g_jit_prepare)(Plan &, std::string &) = nullptr;
+
+// The static / run-time specialised kernels use their own launch geometry: if no specialisation applies in the end (or the
+// specialiser fails), the interpreter's plan must come back untouched.
+static void
+match_static(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fold)
+{
+    Plan const saved = plan;
+    match_static_(plan, prog, dst, fold);
+    if (!plan.is_static) plan = saved;
 }
 
 int

@@ -22,7 +22,12 @@ struct Plan
     const char * kernel = "";
     bool is_static = false;      // a compile-time specialised kernel matched (static_kernels.cu)
     SParams sp;
+    SProg jit_prog {};           // sp.id == SP_JIT: the program the kernel is specialised for at run time (jit.cc)
+    void * jit_fn = nullptr;     // its loaded kernel (CUfunction)
 };
+
+// Set by jit.cc when the library carries the run-time specialiser (never in the CPU plan simulator).
+extern bool (*g_jit_prepare)(Plan &, std::string &);
 
 // What the expression computes, before any layout decision.
 struct Shape { int rank; int64_t len[KMAXR]; };

@@ -1,0 +1,385 @@
+// static_device.h - device side of the specialised ply kernels: the compile-time typed postfix evaluator and the map /
+// fold-inner / fold-outer bodies built on it. Included by static_kernels.cu (the table of pre-compiled program shapes, nvcc)
+// and, verbatim, by the run-time specialiser (jit.cc: the same bodies instantiated by NVRTC for a program that is not in
+// the table). Device code only: no host headers beyond what kcore.h needs.
+#pragma once
+#include "kbody.h"
+#include "static_progs.h"
+
+namespace racu {
+
+template <int ID> struct SPT
+{
+    static constexpr SProg P = static_prog(ID);
+    static constexpr bool wide = prog_wide(P);
+    using W = std::conditional_t<wide, uint64_t, uint32_t>;
+};
+
+__host__ __device__ constexpr int es_of(int t) { return t==RACU_BOOL ? 1 : (t==RACU_I32 || t==RACU_F32) ? 4 : 8; }
+
+enum LdForm { LD_STREAM = 0, LD_REUSED = 1, LD_RW = 2 };
+
+template <int FORM> __device__ __forceinline__ uint4
+ld16(void const * p)
+{
+    uint4 r;
+    if constexpr (FORM==LD_STREAM) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if constexpr (FORM==LD_REUSED) asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else r = *reinterpret_cast<uint4 const *>(p);
+    return r;
+}
+
+// 64-bit lanes are loaded as 64-bit registers: packing two 32-bit halves after the load is an ALU op that depends on the load
+// and stalls on it, which serialises the loads.
+template <int FORM> __device__ __forceinline__ void
+ld16x2(uint64_t & a, uint64_t & b, void const * p)
+{
+    if constexpr (FORM==LD_STREAM) asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+    else if constexpr (FORM==LD_REUSED) asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+    else { ulonglong2 q = *reinterpret_cast<ulonglong2 const *>(p); a = q.x; b = q.y; }
+}
+
+// Operand vectors are held as RAW 32-bit words exactly as loaded (4 words for SV 4-byte elements, 8 for 8-byte ones, 1 for
+// bools); they become typed slot values only at PUSH time inside the evaluator. Anything computed from a loaded register
+// right after the load (packing halves, widening) would stall on that load and serialise the loads.
+template <int FORM> __device__ __forceinline__ void
+load_words(uint32_t * x, unsigned char const * p, int t)
+{
+    int const es = es_of(t);
+    if (4==es) { uint4 q = ld16<FORM>(p); x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w; }
+    else if (8==es) {
+        uint4 q0 = ld16<FORM>(p), q1 = ld16<FORM>(p+16);
+        x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w; x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+    } else { x[0] = *reinterpret_cast<uint32_t const *>(p); }
+}
+// one element broadcast to every lane, in raw words
+__device__ __forceinline__ void
+splat_words(uint32_t * x, unsigned char const * p, int t)
+{
+    int const es = es_of(t);
+    if (4==es) { uint32_t v = *reinterpret_cast<uint32_t const *>(p); x[0] = v; x[1] = v; x[2] = v; x[3] = v; }
+    else if (8==es) { uint2 v = *reinterpret_cast<uint2 const *>(p); x[0] = v.x; x[1] = v.y; x[2] = v.x; x[3] = v.y; x[4] = v.x; x[5] = v.y; x[6] = v.x; x[7] = v.y; }
+    else { uint32_t v = *p ? 0x01010101u : 0u; x[0] = v; }
+}
+__device__ __forceinline__ void
+splat_bits(uint32_t * x, uint64_t bits, int t)
+{
+    int const es = es_of(t);
+    if (4==es) { uint32_t v = uint32_t(bits); x[0] = v; x[1] = v; x[2] = v; x[3] = v; }
+    else if (8==es) { uint32_t lo = uint32_t(bits), hi = uint32_t(bits>>32); x[0] = lo; x[1] = hi; x[2] = lo; x[3] = hi; x[4] = lo; x[5] = hi; x[6] = lo; x[7] = hi; }
+    else { x[0] = bits ? 0x01010101u : 0u; }
+}
+template <class W> __device__ __forceinline__ W
+word_lane(uint32_t const * x, int j, int t) // lane j of a raw vector as slot bits
+{
+    int const es = es_of(t);
+    if (4==es) return W(x[j]);
+    if (8==es) { if constexpr (sizeof(W)==8) return uint64_t(x[2*j]) | (uint64_t(x[2*j+1])<<32); else return W(0); }
+    return W((x[0]>>(8*j))&0xffu ? 1 : 0);
+}
+template <class W> __device__ __forceinline__ void
+store_vec(unsigned char * p, W const * v, int t)
+{
+    int const es = es_of(t);
+    if (4==es) { uint4 q; q.x = uint32_t(v[0]); q.y = uint32_t(v[1]); q.z = uint32_t(v[2]); q.w = uint32_t(v[3]); *reinterpret_cast<uint4 *>(p) = q; }
+    else if (8==es) {
+        if constexpr (sizeof(W)==8) {
+            ulonglong2 q0, q1;
+            q0.x = v[0]; q0.y = v[1]; q1.x = v[2]; q1.y = v[3];
+            *reinterpret_cast<ulonglong2 *>(p) = q0; *reinterpret_cast<ulonglong2 *>(p+16) = q1;
+        }
+    } else { *reinterpret_cast<uint32_t *>(p) = (uint32_t(v[0])&1u) | ((uint32_t(v[1])&1u)<<8) | ((uint32_t(v[2])&1u)<<16) | ((uint32_t(v[3])&1u)<<24); }
+}
+
+// words per raw operand vector, and vectors in flight per thread: about 48 registers of operand data
+template <int ID> struct SPX
+{
+    static constexpr int XW = SPT<ID>::wide ? 2*SV : SV;
+    static constexpr int words() { int w = 0; for (int r=0; r<SPT<ID>::P.nin; ++r) w += SV*es_of(SPT<ID>::P.rtype[r])/4 + (es_of(SPT<ID>::P.rtype[r])<4); return w>0 ? w : 1; }
+    static constexpr int UNR = 48/words()>=4 ? 4 : 48/words()>=2 ? 48/words() : 1;
+};
+
+// The constexpr typed postfix evaluator. x[k]: raw words of role k's vector.
+template <int ID> __device__ __forceinline__ void
+eval_static(uint32_t const (*x)[SPX<ID>::XW], typename SPT<ID>::W * out)
+{
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    W st[P.n>0 ? P.n : 1][SV];
+    int sp = 0;
+#pragma unroll
+    for (int pc=0; pc<P.n; ++pc) {
+        int const op = P.ins[pc].op, arg = P.ins[pc].arg, type = P.ins[pc].type, aux = P.ins[pc].aux;
+        if (op==RACU_OP_PUSH) {
+#pragma unroll
+            for (int j=0; j<SV; ++j) st[sp][j] = word_lane<W>(x[arg], j, type);
+            ++sp;
+        } else if (op==RACU_OP_CAST) {
+#pragma unroll
+            for (int j=0; j<SV; ++j) st[sp-1][j] = cast_any<W>(aux, type, st[sp-1][j]);
+        } else if (op>=RACU_OP_NEG && op<=RACU_OP_NOT) {
+#pragma unroll
+            for (int j=0; j<SV; ++j) st[sp-1][j] = un_any<W>(op, type, st[sp-1][j]);
+        } else if (op==RACU_OP_PICK) { // stack: sel a0 .. a(n-1) -> a(sel); n = arg, selector type = aux (ra/expr.hh:686-728)
+#pragma unroll
+            for (int j=0; j<SV; ++j) {
+                W sel = st[sp-1-arg][j];
+                if (aux==RACU_BOOL) sel = W(uint32_t(sel)&0xffu); else if (aux==RACU_I32) sel = W(uint32_t(sel));
+                W r = st[sp-arg][j];             // out of contract selectors take branch 0, like the oracle
+#pragma unroll
+                for (int b=1; b<arg; ++b) r = sel==W(b) ? st[sp-arg+b][j] : r;
+                st[sp-1-arg][j] = r;
+            }
+            sp -= arg;
+        } else if (op==RACU_OP_FMA) {
+#pragma unroll
+            for (int j=0; j<SV; ++j) st[sp-3][j] = fma_any<W>(type, st[sp-3][j], st[sp-2][j], st[sp-1][j]);
+            sp -= 2;
+        } else { // binary
+#pragma unroll
+            for (int j=0; j<SV; ++j) st[sp-2][j] = bin_any<W>(op, type, st[sp-2][j], st[sp-1][j]);
+            --sp;
+        }
+    }
+#pragma unroll
+    for (int j=0; j<SV; ++j) out[j] = st[0][j];
+}
+
+// role k of the vector at (e0, off) -> raw words. kd is the operand kind (compile-time constant when !GENERAL).
+template <int ID, bool GENERAL, int FORM> __device__ __forceinline__ void
+fetch_role(SParams const & p, int k, uint32_t * x, int64_t off, int64_t e0)
+{
+    constexpr SProg P = SPT<ID>::P;
+    int const t = P.rtype[k], es = es_of(t);
+    int const kd = GENERAL ? int(p.kind[k]) : (SK_SCALAR==p.kind[k] ? int(SK_SCALAR) : int(SK_VEC));
+    unsigned char const * base = reinterpret_cast<unsigned char const *>(p.in[k]);
+    if (SK_SCALAR==kd) splat_bits(x, p.in[k], t);
+    else if (!GENERAL || SK_VEC==kd) {
+        if (k==P.yrole) load_words<LD_RW>(x, base + (off+e0)*es, t); else load_words<FORM>(x, base + (off+e0)*es, t);
+    } else if (SK_VECREV==kd) { // lanes reversed: swap whole elements
+        uint32_t r[SPX<ID>::XW];
+        load_words<FORM>(r, base + (off-e0-(SV-1))*es, t);
+        if (4==es) { x[0] = r[3]; x[1] = r[2]; x[2] = r[1]; x[3] = r[0]; }
+        else if (8==es) { x[0] = r[6]; x[1] = r[7]; x[2] = r[4]; x[3] = r[5]; x[4] = r[2]; x[5] = r[3]; x[6] = r[0]; x[7] = r[1]; }
+        else { x[0] = __byte_perm(r[0], 0, 0x0123); }
+    } else splat_words(x, base + off*es, t); // SK_ROW
+}
+
+// ---- map: dst[...] = P(inputs[...]) over up to KGR uncollapsible axes; axis 0 is vectorised (SV elements per access).
+// Inputs per role: aligned unit-step vectors (forward or reversed), one value per row (prefix rank extension: the
+// `v` of B += A*C + v, examples/read-me.cc:32), or scalars. A flat traversal (rankA==1) may have a scalar tail.
+// GENERAL=false: every non-scalar input is a forward unit-step vector.
+template <int ID, bool GENERAL> __device__ __forceinline__ void
+smap_body(SParams const & p)
+{
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    constexpr int des = es_of(P.otype), UNR = SPX<ID>::UNR, XW = SPX<ID>::XW;
+    int64_t const per = int64_t(KBLOCK)*UNR;
+    for (int64_t g0 = int64_t(blockIdx.x)*per + threadIdx.x; g0<p.nvec; g0 += int64_t(gridDim.x)*per) {
+        uint32_t x[UNR][P.nin][XW];
+        int64_t doff[UNR];
+#pragma unroll
+        for (int u=0; u<UNR; ++u) {
+            int64_t g = g0 + int64_t(u)*KBLOCK;
+            if (g<p.nvec) {
+                int64_t e0;
+                uint32_t i1 = 0, i2 = 0, i3 = 0;
+                if (1==p.rankA) { e0 = g*SV; }
+                else {
+                    uint32_t n = uint32_t(g), q = fastdiv(n, p.vprdiv);
+                    e0 = int64_t(n-q*uint32_t(p.vpr))*SV; n = q;
+                    if (2==p.rankA) i1 = n;
+                    else { q = fastdiv(n, p.dA[1]); i1 = n-q*p.dA[1].len; n = q;
+                        if (3==p.rankA) i2 = n; else { q = fastdiv(n, p.dA[2]); i2 = n-q*p.dA[2].len; i3 = q; } }
+                }
+                doff[u] = e0 + int64_t(i1)*p.dsA[1] + int64_t(i2)*p.dsA[2] + int64_t(i3)*p.dsA[3];
+#pragma unroll
+                for (int k=0; k<P.nin; ++k) {
+                    int64_t off = int64_t(i1)*p.sA[k][1] + int64_t(i2)*p.sA[k][2] + int64_t(i3)*p.sA[k][3];
+                    fetch_role<ID, GENERAL, LD_STREAM>(p, k, x[u][k], off, e0);
+                }
+            }
+        }
+#pragma unroll
+        for (int u=0; u<UNR; ++u) {
+            int64_t g = g0 + int64_t(u)*KBLOCK;
+            if (g<p.nvec) { W out[SV]; eval_static<ID>(x[u], out); store_vec<W>(static_cast<unsigned char *>(p.dst) + doff[u]*des, out, P.otype); }
+        }
+    }
+    if (1==p.rankA && 0==blockIdx.x && 0==threadIdx.x) { // tail elements of a flat traversal, one at a time
+        for (int64_t e = p.nvec*SV; e<p.n; ++e) {
+            uint32_t x[P.nin][XW];
+            W out[SV];
+#pragma unroll
+            for (int k=0; k<P.nin; ++k) {
+                int const es = es_of(P.rtype[k]);
+                unsigned char const * base = reinterpret_cast<unsigned char const *>(p.in[k]);
+                if (SK_SCALAR==p.kind[k]) splat_bits(x[k], p.in[k], P.rtype[k]);
+                else splat_words(x[k], base + (SK_VEC==p.kind[k] ? e : SK_VECREV==p.kind[k] ? -e : 0)*es, P.rtype[k]);
+            }
+            eval_static<ID>(x, out);
+            store_elem<W>(static_cast<unsigned char *>(p.dst) + e*des, P.otype, out[0]);
+        }
+    }
+}
+
+template <class W> __device__ __forceinline__ W shfl_xor_w(W v, int o);
+template <> __device__ __forceinline__ uint32_t shfl_xor_w<uint32_t>(uint32_t v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+template <> __device__ __forceinline__ uint64_t shfl_xor_w<uint64_t>(uint64_t v, int o) { return __shfl_xor_sync(0xffffffffu, (unsigned long long)v, o); }
+
+template <class W, int FOLD, int TYPE> __device__ __forceinline__ W
+block_comb(W r, W * red)
+{
+    for (int o=16; o>0; o>>=1) { W other = shfl_xor_w<W>(r, o); r = combine<W>(FOLD, TYPE, r, other); }
+    int const lane = threadIdx.x&31, warp = threadIdx.x>>5;
+    if (0==lane) red[warp] = r;
+    __syncthreads();
+    if (0==threadIdx.x) {
+        r = red[0];
+        for (int w=1; w<KBLOCK/32; ++w) r = combine<W>(FOLD, TYPE, r, red[w]);
+    }
+    return r;
+}
+
+template <class W> __device__ __forceinline__ void
+emit_partial(SParams const & p, FinishParams const & f, int64_t chunk, int64_t n, W v)
+{
+    if (p.nchunks>1) {
+        if (p.wide_partials) static_cast<uint64_t *>(p.partial)[chunk*p.nk+n] = uint64_t(v);
+        else static_cast<uint32_t *>(p.partial)[chunk*p.nk+n] = uint32_t(v);
+    } else {
+        if (p.wide_partials) finish_apply<uint64_t>(f, n, uint64_t(v)); else finish_apply<uint32_t>(f, n, uint32_t(v));
+    }
+}
+
+// fold kernels: role k of vector g of the row at byte offset rowoff -> raw words
+template <int ID, int FORM> __device__ __forceinline__ void
+fetch_fold_role(SParams const & p, int k, uint32_t * x, unsigned char const * rowbase, int64_t g)
+{
+    constexpr SProg P = SPT<ID>::P;
+    int const t = P.rtype[k], es = es_of(t);
+    if (SK_SCALAR==p.kind[k]) splat_bits(x, p.in[k], t);
+    else if (SK_ROW==p.kind[k]) splat_words(x, rowbase, t);
+    else load_words<FORM>(x, rowbase + g*SV*es, t);
+}
+
+// ---- fold-inner, flat rows: CTA = (row kb, chunk c); row length n (multiple of SV unless there is a single row).
+// REUSE: some input does not move along the kept rows (the vector of gemv, ra/ra.hh:418): loads allocate in L1.
+template <int ID, int FOLD, bool REUSE> __device__ __forceinline__ void
+sfold_inner_body(SParams const & p, FinishParams const & f)
+{
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    constexpr int AT = P.otype, UNR = SPX<ID>::UNR, XW = SPX<ID>::XW;
+    __shared__ W red[KBLOCK/32];
+    uint32_t const kb = blockIdx.x/uint32_t(p.nchunks), c = blockIdx.x-kb*uint32_t(p.nchunks);
+    unsigned char const * rowbase[P.nin];
+    {
+        // row kb -> group-B position -> per input byte offset
+        uint32_t n = kb, q, ib[KGR] = {0, 0, 0, 0};
+        if (p.rankB<=1) ib[0] = n;
+        else {
+            q = fastdiv(n, p.dB[0]); ib[0] = n-q*p.dB[0].len; n = q;
+            if (2==p.rankB) ib[1] = n;
+            else { q = fastdiv(n, p.dB[1]); ib[1] = n-q*p.dB[1].len; n = q;
+                if (3==p.rankB) ib[2] = n; else { q = fastdiv(n, p.dB[2]); ib[2] = n-q*p.dB[2].len; ib[3] = q; } }
+        }
+#pragma unroll
+        for (int k=0; k<P.nin; ++k) {
+            int64_t off = 0;
+#pragma unroll
+            for (int j=0; j<KGR; ++j) { if (j<p.rankB) off += int64_t(ib[j])*p.sB[k][j]; }
+            rowbase[k] = reinterpret_cast<unsigned char const *>(p.in[k]) + off*int64_t(es_of(P.rtype[k]));
+        }
+    }
+    int64_t const nfull = p.n/SV;
+    int64_t const start = int64_t(c)*p.chunk_len;
+    int64_t const end = start+p.chunk_len<nfull ? start+p.chunk_len : nfull;
+    W acc[SV];
+#pragma unroll
+    for (int j=0; j<SV; ++j) acc[j] = W(p.identity);
+    int64_t const per = int64_t(KBLOCK)*UNR;
+    for (int64_t g0 = start + threadIdx.x; g0<end; g0 += per) {
+        uint32_t x[UNR][P.nin][XW];
+#pragma unroll
+        for (int u=0; u<UNR; ++u) {
+            int64_t g = g0 + int64_t(u)*KBLOCK;
+            if (g<end) {
+#pragma unroll
+                for (int k=0; k<P.nin; ++k) fetch_fold_role<ID, REUSE ? LD_REUSED : LD_STREAM>(p, k, x[u][k], rowbase[k], g);
+            }
+        }
+#pragma unroll
+        for (int u=0; u<UNR; ++u) {
+            int64_t g = g0 + int64_t(u)*KBLOCK;
+            if (g<end) {
+                W out[SV];
+                eval_static<ID>(x[u], out);
+#pragma unroll
+                for (int j=0; j<SV; ++j) acc[j] = combine<W>(FOLD, AT, acc[j], out[j]);
+            }
+        }
+    }
+    W r = acc[0];
+#pragma unroll
+    for (int j=1; j<SV; ++j) r = combine<W>(FOLD, AT, r, acc[j]);
+    if (c+1==uint32_t(p.nchunks) && 0==threadIdx.x) { // tail elements of the row (single flat row only)
+        for (int64_t e = nfull*SV; e<p.n; ++e) {
+            uint32_t x[P.nin][XW];
+            W out[SV];
+#pragma unroll
+            for (int k=0; k<P.nin; ++k) {
+                if (SK_SCALAR==p.kind[k]) splat_bits(x[k], p.in[k], P.rtype[k]);
+                else splat_words(x[k], rowbase[k] + (SK_ROW==p.kind[k] ? 0 : e)*es_of(P.rtype[k]), P.rtype[k]);
+            }
+            eval_static<ID>(x, out);
+            r = combine<W>(FOLD, AT, r, out[0]);
+        }
+    }
+    r = block_comb<W, FOLD, AT>(r, red);
+    if (0==threadIdx.x) emit_partial<W>(p, f, c, kb, r);
+}
+
+// ---- fold-outer, flat: thread = kept vector g (lanes are kept elements), blockIdx.y = chunk of the folded rows
+template <int ID, int FOLD> __device__ __forceinline__ void
+sfold_outer_body(SParams const & p, FinishParams const & f)
+{
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    constexpr int AT = P.otype, UNR = SPX<ID>::UNR, XW = SPX<ID>::XW;
+    int64_t const g = int64_t(blockIdx.x)*KBLOCK + threadIdx.x;
+    if (g>=p.n/SV) return;
+    uint32_t const c = blockIdx.y;
+    int64_t const r0 = int64_t(c)*p.chunk_len;
+    int64_t const r1 = r0+p.chunk_len<p.nB ? r0+p.chunk_len : p.nB;
+    W acc[SV];
+#pragma unroll
+    for (int j=0; j<SV; ++j) acc[j] = W(p.identity);
+    for (int64_t r = r0; r<r1; r += UNR) {
+        uint32_t x[UNR][P.nin][XW];
+#pragma unroll
+        for (int u=0; u<UNR; ++u) {
+            if (r+u<r1) {
+#pragma unroll
+                for (int k=0; k<P.nin; ++k) { // gevm: c(j) += a(i)*b(i,j): a is one value per folded row (SK_ROW)
+                    unsigned char const * rowbase = reinterpret_cast<unsigned char const *>(p.in[k]) + (r+u)*p.sB[k][0]*es_of(P.rtype[k]);
+                    fetch_fold_role<ID, LD_STREAM>(p, k, x[u][k], rowbase, g);
+                }
+            }
+        }
+#pragma unroll
+        for (int u=0; u<UNR; ++u) {
+            if (r+u<r1) {
+                W out[SV];
+                eval_static<ID>(x[u], out);
+#pragma unroll
+                for (int j=0; j<SV; ++j) acc[j] = combine<W>(FOLD, AT, acc[j], out[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j=0; j<SV; ++j) emit_partial<W>(p, f, c, g*SV+j, acc[j]);
+}
+
+} // namespace racu

@@ -10,7 +10,7 @@
 
 namespace racu {
 
-constexpr int SP_MAXINS = 12, SP_MAXIN = 4;
+constexpr int SP_MAXINS = 32, SP_MAXIN = 8;
 struct SIns { uint8_t op, arg, type, aux; };
 struct SProg
 {
@@ -42,7 +42,8 @@ enum {
     SPM_YADD_F32_SD_MUL,               // float y += double s * float a                 (B += 2.5*A with a double literal)
     SPM_YSUB_F32_SD_MUL,               // float y -= double s * float a
     SPM_F_SUM_F32_D,                   // double acc += float a                         (double c += float array)
-    SP_COUNT
+    SP_COUNT,
+    SP_JIT = SP_COUNT                  // a program specialised at run time (jit.cc): static_prog(SP_JIT) is RACU_JIT_PROG
 };
 
 constexpr SIns sP(int r, int t) { return SIns {RACU_OP_PUSH, uint8_t(r), uint8_t(t), 0}; }
@@ -81,6 +82,9 @@ constexpr SProg
 static_prog(int id)
 {
     constexpr int F = RACU_F32, D = RACU_F64;
+#ifdef RACU_JIT_PROG
+    if (id==SP_JIT) return RACU_JIT_PROG;
+#endif
     if (id<SP_NUNIFORM) {
         constexpr int types[3] = {RACU_F32, RACU_F64, RACU_I32};
         return uniform_prog(id/3, types[id%3]);

@@ -51,6 +51,8 @@ struct StParams
     int32_t n0, n1, n2;      // full array extents (marching axis first). 2-D: n0 = 1
     int32_t i_lo, i_hi;      // output planes [i_lo, i_hi) (3-D); ignored for 2-D
     int32_t ci;              // planes per CTA chunk
+    int32_t gz;              // chunks along the marching axis; gridDim.z = gz * bands
+    int32_t gyb;             // tile rows per band (gridDim.y)
     int32_t vec_store;       // destination allows aligned 16-byte stores
     // FUSED only (racu_stencil_push)
     void * push_lo, * push_hi;           // neighbour's ghost plane (element [.,0,0]) mirroring my plane 1 / plane n0-2, or null
@@ -121,14 +123,19 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 
     int const tid = threadIdx.x;
     int const tk = tid % (TK/VT), tj = tid / (TK/VT);          // tj in [0, ST_TR)
-    int const k0 = blockIdx.x*TK, j0 = 1 + blockIdx.y*ST_TJ;   // first output k of the tile (vector aligned), first output j
+    // Bands: blockIdx.z = band*gz + chunk. A band (all of k, gyb tile rows of j) is marched through completely before the next
+    // one starts, so that the CTAs resident together - consecutive chunks of one band - find each other's halo planes in L2
+    // whatever the plane size (2048^2 planes: a whole plane's worth of tiles per chunk is 4x what the GPU holds at once).
+    int const band = is3d ? int(blockIdx.z)/p.gz : 0;
+    int const k0 = blockIdx.x*TK, j0 = 1 + (band*p.gyb + int(blockIdx.y))*ST_TJ; // first output k of the tile (vector aligned), first output j
+    if (j0>=p.n1-1) return;                                    // last band may be short (whole CTA leaves before any barrier)
     int const k = k0 + tk*VT, j = j0 + tj;
     // FUSED: the two edge chunks (0 and gz-1: they read a ghost plane and feed the neighbours) are scheduled in the middle
     // of the grid, so that the neighbours' flags have long arrived when they start and the pushed planes have long landed
     // when the kernel ends; every other chunk keeps its order.
-    int chunk = int(blockIdx.z);
+    int chunk = is3d ? int(blockIdx.z) - band*p.gz : 0;
     if constexpr (FUSED) {
-        int const gz = int(gridDim.z), e = (gz-2)/2;
+        int const gz = p.gz, e = (gz-2)/2;
         if (gz>2) chunk = chunk<e ? chunk+1 : (chunk==e ? 0 : (chunk==e+1 ? gz-1 : chunk-1));
     }
     int const ilo = is3d ? p.i_lo + chunk*p.ci : 0;
@@ -333,13 +340,23 @@ launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled, 
         gz = unsigned((planes+p.ci-1)/p.ci);
         if (gz>65535) { p.ci = int32_t((planes+65534)/65535); gz = unsigned((planes+p.ci-1)/p.ci); }
     }
+    p.gz = int32_t(gz); p.gyb = int32_t(gy);
+    unsigned const tiles_y = gy;                 // valid tile rows (edge CTA count of the fused step)
+    if (is3d) {
+        // bands of about 512 tiles (the 1024^2 plane this was tuned on: 8 x 64 tiles per chunk)
+        int64_t band_tiles = 512;
+        if (char const * e = std::getenv("RACU_ST_BAND")) band_tiles = std::max(1, std::atoi(e)); // tuning knob
+        unsigned gyb = unsigned(std::max<int64_t>(1, band_tiles/gx));
+        unsigned nb = (gy+gyb-1)/gyb;
+        if (nb>1 && uint64_t(nb)*gz<=65535) { p.gyb = int32_t(gyb); gy = gyb; gz *= nb; }
+    }
     size_t smem = size_t(ST_STAGES)*TL::PLANE*sizeof(T);
     auto kernel = stencil_tma_kernel<T, KIND, false>;
     if constexpr (is3d) {
         if (h) {
             kernel = stencil_tma_kernel<T, KIND, true>;
             p.push_lo = h->push_lo; p.push_hi = h->push_hi; p.flags = h->flags; p.signal_lo = h->signal_lo; p.signal_hi = h->signal_hi;
-            p.step = h->step; p.edge_ctas = int32_t(gx*gy);
+            p.step = h->step; p.edge_ctas = int32_t(gx*tiles_y);
         }
     }
     if (smem>32*1024) { if (cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return cuda_fail(e, "stencil smem"); }
