@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GIB = 1 << 30
+DOT_TRAFFIC_BYTES = 8_590_148_000 + 5_600_000  # ncu: dram read + write of sflat_fold_inner<f32, dot> at 2^30 elements (profiles/r01_dot_full_summary.md)
 
 
 def parse():
@@ -108,6 +109,33 @@ def cpu_baseline(log2n, runs=3):
             "seconds": t}
 
 
+def cpu_all_cores(log2n=24, max_threads=64):
+    """Not the reference (which is single threaded, README.md:81): the same loops on disjoint shards, one per host core,
+    to show what the box's cores deliver together when a user shards by hand. ctypes releases the GIL during the calls."""
+    L = baseline_lib()
+    T = max(1, min(os.cpu_count() or 1, max_threads))
+    N = 1 << log2n
+    m = 1 << (log2n // 2)
+    n = N // m
+    rng = np.random.default_rng(0x5EED0013)
+    shards = [(rng.random(N, dtype=np.float32), rng.random(N, dtype=np.float32), np.zeros(n, np.float32), np.zeros(m, np.float32))
+              for _ in range(T)]
+    reps = 4
+
+    def work(sh):
+        for _ in range(reps):
+            cpu_reduce_step(L, sh[0], sh[1], m, n, sh[2], sh[3])
+    ths = [threading.Thread(target=work, args=(sh,)) for sh in shards]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return {"value": T * reps * 4 * N * 6 / dt / 1e9, "unit": "GB/s", "cores": T,
+            "sample": f"{T} threads x {reps} passes over private 2^{log2n}-element shards (not the reference: it is single threaded)"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (port) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -137,7 +165,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "l2": "inputs larger than L2"},
-        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
+                         "all_cores_sharded_by_hand": cpu_all_cores()},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -254,10 +283,16 @@ def main():
     d_cols, k5 = ra.flatten(ra.as_expr(A2), dst=cols, assign=abi.ASSIGN_ADD, ex=ex)
     sp = cuda.stream_ptr
 
+    dot_events = []  # CUDA events around the dominant kernel (dot: 8 B / element) inside the timed steps
+
     def step():
         cuda.check(lib.racu_reduce_dev(C.byref(d_sum), abi.RED_SUM, C.c_void_p(scal.data_ptr()), sp()))
         cuda.check(lib.racu_reduce_dev(C.byref(d_sqrm), abi.RED_SUM, C.c_void_p(scal.data_ptr() + 4), sp()))
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
         cuda.check(lib.racu_reduce_dev(C.byref(d_dot), abi.RED_SUM, C.c_void_p(scal.data_ptr() + 8), sp()))
+        eb.record()
+        dot_events.append((ea, eb))
         rows_t.zero_()
         cols_t.zero_()
         cuda.check(lib.racu_map(C.byref(d_rows), sp()))
@@ -282,10 +317,10 @@ def main():
                  "dot_rel_err": abs(float(scal[2]) - float((ref * b_t.double()).sum())) / float((ref * b_t.double()).sum())}
         del ref
 
-    # ---- roofline of the dominant kernel: ply_fold_inner<u32> running dot (8 B / element), timed alone
-    def dot_only():
-        cuda.check(lib.racu_reduce_dev(C.byref(d_dot), abi.RED_SUM, C.c_void_p(scal.data_ptr() + 8), sp()))
-    ms_dot = timed(dot_only, max(args.steps, 10), 3)
+    # ---- roofline of the dominant kernel: sflat_fold_inner running dot (8 B / element) + its ply_finish, average launch
+    # duration over the timed steps (CUDA events recorded around it on the launching stream, inside the timed region)
+    ms_dot = sum(a.elapsed_time(b) for a, b in dot_events[-args.steps:]) / args.steps
+    cuda.check(lib.racu_reduce_dev(C.byref(d_dot), abi.RED_SUM, C.c_void_p(scal.data_ptr() + 8), sp()))  # (names the kernel below)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -294,7 +329,8 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = 8.0 * N / (ms_dot * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": lib.racu_last_kernel().decode() + "<f32, dot> + ply_finish", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": DOT_TRAFFIC_BYTES if args.log2n == 30 else None,
+                "traffic_source": "profiles/r01_dot_full_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at 2^30 elements",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": 8 * N, "ms_per_launch": ms_dot}
 
@@ -338,6 +374,8 @@ def main():
         extra = run_extras(args, torch, ex, lib, cuda, ra, abi, timed, peak)
 
     cpu = cpu_baseline(args.cpu_log2n) if rank == 0 and world == 1 else None
+    if cpu is not None:
+        cpu["all_cores_sharded_by_hand"] = cpu_all_cores()
     sampler.join(timeout=2)
     if rank == 0:
         out = {
