@@ -1,5 +1,5 @@
 """Small driver for ncu: a few launches of each ply kernel family on one GPU (sizes > L2, short enough for ncu's replays).
-Usage: python profiles/prof_ply.py [which ...]   which in: dot sum map mapv cols rows stencil"""
+Usage: python profiles/prof_ply.py [which ...]   which in: dot sum map mapv mapvf cols rows jit dgemm sgemm stencil"""
 import ctypes as C
 import os
 import sys
@@ -42,6 +42,18 @@ for w in which:
         elif w == "rows":
             r = ex.wrap(rows_t)(ra.insert(1))
             r += A2
+        elif w == "jit":      # a program outside the table: run-time specialised map (where + sqrt)
+            B2.assign(ra.where(A2 < B2, A2 * B2, ra.sqrt(A2)) + 0.5)
+        elif w == "dgemm":    # FP64 DMMA contraction, 4096^3
+            ng = 4096
+            ga, gb = (ex.wrap(torch.rand(ng, ng, device=dev, dtype=torch.float64)) for _ in range(2))
+            gc = ex.wrap(torch.zeros(ng, ng, device=dev, dtype=torch.float64))
+            ra.gemm(ga, gb, gc)
+        elif w == "sgemm":    # 3xTF32 contraction, 4096^3
+            ng = 4096
+            ga, gb = (ex.wrap(torch.rand(ng, ng, device=dev, dtype=torch.float32)) for _ in range(2))
+            gc = ex.wrap(torch.zeros(ng, ng, device=dev, dtype=torch.float32))
+            ra.gemm(ga, gb, gc)
         elif w == "stencil":
             n3 = 512
             A3 = torch.rand(n3, n3, n3, device=dev)

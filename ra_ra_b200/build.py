@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libracu.so")
 STATIC_PARTS = 4  # the static program table is compiled in this many parallel translation units
-SOURCES = ["ply_kernels.cu"] + [f"static_kernels.cu#{k}" for k in range(STATIC_PARTS)] + [ "stencil.cu", "transpose.cu", "gemm.cu", "plan.cc", "api.cc", "special.cc", "comm.cc", "jit.cc"]
+SOURCES = ["ply_kernels.cu"] + [f"static_kernels.cu#{k}" for k in range(STATIC_PARTS)] + [ "stencil.cu", "transpose.cu", "gemm.cu", "gemm_tc5.cu", "plan.cc", "api.cc", "special.cc", "comm.cc", "jit.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O3", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
 

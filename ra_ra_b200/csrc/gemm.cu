@@ -206,6 +206,10 @@ try_special_gemm(racu_gemm_desc const * gd, cudaStream_t stream, int * handled)
     int const bk = f64 ? DK : SK;
     size_t const es = f64 ? 8 : 4;
     if (gd->M<=0 || gd->N<=0 || gd->K<=0) { *handled = 1; return RACU_OK; } // nothing to add (test/reduction.cc:300-310: 0x0 corner)
+    if (!f64) { // f32: tcgen05 / TMEM kernel first (gemm_tc5.cu, any shape); the mma.sync 3xTF32 kernel below is the second choice
+        if (int e = try_tcgen05_sgemm(gd, stream, handled)) return e;
+        if (*handled) return RACU_OK;
+    }
     // tile multiples and 16-byte rows only; anything else runs as a fold on the ply kernels
     if (0!=gd->M%GM || 0!=gd->N%GN || 0!=gd->K%bk) return RACU_OK;
     if (gd->M>=(int64_t(1)<<31) || gd->N>=(int64_t(1)<<31) || gd->K>=(int64_t(1)<<31)) return RACU_OK;

@@ -263,6 +263,8 @@ jit_prepare(Plan & plan, std::string & err)
     std::vector<char> cubin;
     if (!jit_cubin(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op, cubin, err)) return false;
     ++jit_compiles;
+    if (std::getenv("RACU_JIT_VERBOSE")) std::fprintf(stderr, "racu jit: specialised %s (mode %d variant %d fold %d) for device %d, %zu bytes\n",
+                                                      jit_prog_text(plan.jit_prog).c_str(), plan.sp.mode, variant, plan.sp.fold_op, dev, cubin.size());
     if (!have_dev) { plan.jit_fn = nullptr; return true; }
     if (!drv_load()) { err = "driver entry points for module loading are not available"; return false; }
     CUmodule mod = nullptr;

@@ -304,6 +304,7 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
     };
     auto kind_of = [&](KOpnd const & k) -> int {
         if (k.kind==RACU_SCALAR) return SK_SCALAR;
+        if (k.kind==RACU_SEQ) return k.dtype==RACU_BOOL ? -1 : SK_SEQ;
         if (k.kind!=RACU_MEM) return -1;
         int64_t const es = k.esize;
         if (1==k.sA[0]) return (0==k.base%16 && aligned_outer(k)) ? SK_VEC : -1;
@@ -407,7 +408,7 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
         if (r<0) continue;
         KOpnd const & k = kp.opnd[o];
         sp.kind[r] = uint8_t(kind_of(k));
-        if (sp.kind[r]==SK_VECREV || (map && sp.kind[r]==SK_ROW)) sp.general = 1;
+        if (sp.kind[r]==SK_VECREV || sp.kind[r]==SK_SEQ || (map && sp.kind[r]==SK_ROW)) sp.general = 1;
         if (k.kind==RACU_SCALAR) { // value bits in the role's type
             switch (k.dtype) {
             case RACU_F32: sp.in[r] = f32_bits(float(bits_f64(k.base))); break;

@@ -69,6 +69,19 @@ splat_bits(uint32_t * x, uint64_t bits, int t)
     else if (8==es) { uint32_t lo = uint32_t(bits), hi = uint32_t(bits>>32); x[0] = lo; x[1] = hi; x[2] = lo; x[3] = hi; x[4] = lo; x[5] = hi; x[6] = lo; x[7] = hi; }
     else { x[0] = bits ? 0x01010101u : 0u; }
 }
+// SEQ role: lane j holds origin + (off + j*s0) computed in the role's type, exactly like seq_value (kcore.h) / Seq (ra/expr.hh:86-91)
+__device__ __forceinline__ void
+seq_words(uint32_t * x, uint64_t org, int64_t off, int64_t s0, int t)
+{
+#pragma unroll
+    for (int j=0; j<SV; ++j) {
+        int64_t const o = off + j*s0;
+        if (t==RACU_I32) x[j] = uint32_t(int32_t(int32_t(int64_t(org)) + int32_t(o)));
+        else if (t==RACU_F32) x[j] = __float_as_uint(float(__longlong_as_double((long long)org)) + float(o));
+        else if (t==RACU_I64) { uint64_t const v = uint64_t(int64_t(org) + o); x[2*j] = uint32_t(v); x[2*j+1] = uint32_t(v>>32); }
+        else if (t==RACU_F64) { uint64_t const v = uint64_t(__double_as_longlong(__longlong_as_double((long long)org) + double(o))); x[2*j] = uint32_t(v); x[2*j+1] = uint32_t(v>>32); }
+    }
+}
 template <class W> __device__ __forceinline__ W
 word_lane(uint32_t const * x, int j, int t) // lane j of a raw vector as slot bits
 {
@@ -154,6 +167,7 @@ fetch_role(SParams const & p, int k, uint32_t * x, int64_t off, int64_t e0)
     int const kd = GENERAL ? int(p.kind[k]) : (SK_SCALAR==p.kind[k] ? int(SK_SCALAR) : int(SK_VEC));
     unsigned char const * base = reinterpret_cast<unsigned char const *>(p.in[k]);
     if (SK_SCALAR==kd) splat_bits(x, p.in[k], t);
+    else if (GENERAL && SK_SEQ==kd) seq_words(x, p.in[k], off + e0*p.sA[k][0], p.sA[k][0], t);
     else if (!GENERAL || SK_VEC==kd) {
         if (k==P.yrole) load_words<LD_RW>(x, base + (off+e0)*es, t); else load_words<FORM>(x, base + (off+e0)*es, t);
     } else if (SK_VECREV==kd) { // lanes reversed: swap whole elements
@@ -216,6 +230,7 @@ smap_body(SParams const & p)
                 int const es = es_of(P.rtype[k]);
                 unsigned char const * base = reinterpret_cast<unsigned char const *>(p.in[k]);
                 if (SK_SCALAR==p.kind[k]) splat_bits(x[k], p.in[k], P.rtype[k]);
+                else if (SK_SEQ==p.kind[k]) seq_words(x[k], p.in[k], e*p.sA[k][0], 0, P.rtype[k]);
                 else splat_words(x[k], base + (SK_VEC==p.kind[k] ? e : SK_VECREV==p.kind[k] ? -e : 0)*es, P.rtype[k]);
             }
             eval_static<ID>(x, out);
@@ -260,6 +275,7 @@ fetch_fold_role(SParams const & p, int k, uint32_t * x, unsigned char const * ro
     constexpr SProg P = SPT<ID>::P;
     int const t = P.rtype[k], es = es_of(t);
     if (SK_SCALAR==p.kind[k]) splat_bits(x, p.in[k], t);
+    else if (SK_SEQ==p.kind[k]) seq_words(x, p.in[k], int64_t(reinterpret_cast<intptr_t>(rowbase)) + g*SV*p.sA[k][0], p.sA[k][0], t); // rowbase: the row's offset
     else if (SK_ROW==p.kind[k]) splat_words(x, rowbase, t);
     else load_words<FORM>(x, rowbase + g*SV*es, t);
 }
@@ -290,7 +306,8 @@ sfold_inner_body(SParams const & p, FinishParams const & f)
             int64_t off = 0;
 #pragma unroll
             for (int j=0; j<KGR; ++j) { if (j<p.rankB) off += int64_t(ib[j])*p.sB[k][j]; }
-            rowbase[k] = reinterpret_cast<unsigned char const *>(p.in[k]) + off*int64_t(es_of(P.rtype[k]));
+            if (SK_SEQ==p.kind[k]) rowbase[k] = reinterpret_cast<unsigned char const *>(intptr_t(off)); // no memory: carry the offset itself
+            else rowbase[k] = reinterpret_cast<unsigned char const *>(p.in[k]) + off*int64_t(es_of(P.rtype[k]));
         }
     }
     int64_t const nfull = p.n/SV;
@@ -331,6 +348,7 @@ sfold_inner_body(SParams const & p, FinishParams const & f)
 #pragma unroll
             for (int k=0; k<P.nin; ++k) {
                 if (SK_SCALAR==p.kind[k]) splat_bits(x[k], p.in[k], P.rtype[k]);
+                else if (SK_SEQ==p.kind[k]) seq_words(x[k], p.in[k], int64_t(reinterpret_cast<intptr_t>(rowbase[k])) + e*p.sA[k][0], 0, P.rtype[k]);
                 else splat_words(x[k], rowbase[k] + (SK_ROW==p.kind[k] ? 0 : e)*es_of(P.rtype[k]), P.rtype[k]);
             }
             eval_static<ID>(x, out);
@@ -363,7 +381,8 @@ sfold_outer_body(SParams const & p, FinishParams const & f)
             if (r+u<r1) {
 #pragma unroll
                 for (int k=0; k<P.nin; ++k) { // gevm: c(j) += a(i)*b(i,j): a is one value per folded row (SK_ROW)
-                    unsigned char const * rowbase = reinterpret_cast<unsigned char const *>(p.in[k]) + (r+u)*p.sB[k][0]*es_of(P.rtype[k]);
+                    unsigned char const * rowbase = SK_SEQ==p.kind[k] ? reinterpret_cast<unsigned char const *>(intptr_t((r+u)*p.sB[k][0]))
+                        : reinterpret_cast<unsigned char const *>(p.in[k]) + (r+u)*p.sB[k][0]*es_of(P.rtype[k]);
                     fetch_fold_role<ID, LD_STREAM>(p, k, x[u][k], rowbase, g);
                 }
             }

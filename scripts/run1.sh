@@ -1,5 +1,3 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; tail -15 gpurun_out/pytest_gpu.log
-RACU_NO_JIT=1 timeout 300 python profiles/time_generic.py > gpurun_out/generic_nojit.log 2>&1; cat gpurun_out/generic_nojit.log
-timeout 300 python profiles/time_generic.py > gpurun_out/generic_jit.log 2>&1; cat gpurun_out/generic_jit.log
-ls ra_ra_b200/jit_cache | wc -l
+timeout 300 python profiles/check_sgemm_tc5.py > gpurun_out/tc5.log 2>&1; echo "rc=$?" >> gpurun_out/tc5.log; tail -60 gpurun_out/tc5.log
+RACU_JIT_VERBOSE=1 timeout 200 python profiles/time_folds_percall.py > gpurun_out/folds_percall.log 2>&1; cat gpurun_out/folds_percall.log

@@ -40,6 +40,12 @@ CASES = {
     "reversed_rows": ("map", lambda q: (ra.max(_rev(q["A"]), q["C"]) - q["w"], q["B"], abi.ASSIGN_MUL, 0)),
     "five_operands": ("map", lambda q: ((q["A"] + q["C"]) * (q["B"] - q["D"]) / (ra.abs(q["I"]) + 1), q["B"], abi.ASSIGN_SET, 0)),
     "flat_axpby": ("map", lambda q: (q["x"] * 0.5 - q["y"] * 0.25 + ra.min(q["x"], q["y"]), q["y"], abi.ASSIGN_SET, 0)),
+    "index_init_i64": ("map", lambda q: (ra.tindex(0, abi.I64) * N + ra.tindex(1, abi.I64), q["L"], abi.ASSIGN_SET, 0)),       # A = _0*n + _1
+    "index_mixed_f32": ("map", lambda q: (q["A"] * ra.tindex(1, abi.I32) - ra.tindex(0, abi.I32), q["B"], abi.ASSIGN_SET, 0)),
+    "index_flat_iota": ("map", lambda q: (q["x"] + ra.iota(M * N, 3, 2), q["y"], abi.ASSIGN_ADD, 0)),
+    "fold_index_weighted": ("fold", lambda q: (q["x"] * (ra.as_expr(ra.iota(M * N, 1, 1, abi.I32)) % 8), None, 0, abi.RED_SUM)),
+    "fold_rows_index": ("foldto", lambda q: (q["A"] * ra.tindex(1, abi.I32) + ra.tindex(0, abi.I32), q["rows"], abi.ASSIGN_ADD, 0)),
+    "fold_cols_index": ("foldto", lambda q: (q["C"] * ra.tindex(0, abi.I32) + ra.tindex(1, abi.I32), q["cols"](ra.insert(1)), abi.ASSIGN_ADD, 0)),
     "fold_sum_abs_diff_mul": ("fold", lambda q: (ra.abs(q["A"] - q["C"]) * q["C"], None, 0, abi.RED_SUM)),
     "fold_amax_where": ("fold", lambda q: (ra.where(q["A"] > 0, q["A"], -q["C"]), None, 0, abi.RED_AMAX)),
     "fold_rows_inner": ("foldto", lambda q: (q["A"] * q["C"] - q["D"], q["rows"], abi.ASSIGN_ADD, 0)),          # c(i) += f(i,j): fold-inner per row
