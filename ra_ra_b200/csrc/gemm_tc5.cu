@@ -6,16 +6,17 @@
 //     a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,   x_hi = x with the low 13 mantissa bits cleared (a TF32 value), x_lo = x - x_hi (exact)
 // accumulated in fp32 in this order (small terms first). Dropped: a_lo*b_lo (~2^-22 |a||b|) and the TF32 truncation of x_lo.
 //
-// One CTA per 128x128 tile of c, 256 threads in three roles (one warp per role, not a warpgroup: tcgen05.mma is issued by ONE
+// One CTA per 128x128 tile of c, 384 threads in three roles (one warp per role, not a warpgroup: tcgen05.mma is issued by ONE
 // thread on behalf of the CTA):
 //   warp 0    TMA producer: per k-block (32 k = one 128-byte swizzle row) the a tile [128 m][32 k] lands 128B-swizzled
 //             (K-major, ready for the MMA) and the b tile [32 k][128 n] lands as it lies in memory (N contiguous).
-//   warps 4-7 split: a -> a_hi (masked in place) and a_lo (same swizzled positions); b is TRANSPOSED on the way to K-major
+//   warps 4-11 split: a -> a_hi (masked in place) and a_lo (same swizzled positions); b is TRANSPOSED on the way to K-major
 //             b_hi / b_lo tiles [128 n][32 k] (16-byte chunk c of row n goes to chunk c ^ (n & 7): the 128B swizzle), then
-//             fence.proxy.async + arrive. The same four warps run the epilogue (warp w reads TMEM lanes 32*(w%4)..+31).
+//             fence.proxy.async + arrive. The same eight warps run the epilogue (warp w reads TMEM lanes 32*(w%4)..+31, half of the columns).
 //   warp 1    MMA issuer: 4 k-steps (UMMA_K = 8) x 3 MMAs M128 N128 per k-block into 128 TMEM columns; tcgen05.commit hands the
 //             stage back to the producer and, after the last k-block, the accumulator to the epilogue.
-// Two 80 KiB stages; 1 CTA / SM. Tiles are rasterised in groups of 16 tile rows so that co-resident CTAs share a / b panels in L2.
+// Three 64 KiB operand stages (a_hi a_lo b_hi b_lo) + a two-slot ring for the raw b tile: the TMA runs up to three k-blocks ahead
+// of the MMA, the split of k-block kb+1 overlaps the MMAs of kb. 1 CTA / SM. Tiles are rasterised in groups of 16 tile rows so that co-resident CTAs share a / b panels in L2.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -30,10 +31,11 @@ namespace racu {
 namespace tc5 {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 2, THREADS = 256, SPLIT_THREADS = 128, GROUP_M = 16;
-constexpr uint32_t TILE = BM*BK*4;  // 16 KiB, every tile of a stage
-constexpr uint32_t OFF_AHI = 0, OFF_ALO = TILE, OFF_BST = 2*TILE, OFF_BHI = 3*TILE, OFF_BLO = 4*TILE, STAGE_BYTES = 5*TILE;
-constexpr uint32_t SMEM_BYTES = STAGES*STAGE_BYTES + 1024; // + slack for the manual 1024-byte alignment (swizzle atoms)
+constexpr int STAGES = 3 /* operand ring */, BSTAGES = 2 /* raw b ring */, THREADS = 384, SPLIT_THREADS = 256, GROUP_M = 16;
+constexpr uint32_t TILE = BM*BK*4;  // 16 KiB, every tile
+// operand stage: a_hi (the TMA lands here, 128B-swizzled) | a_lo | b_hi | b_lo ; then the raw b ring (TMA, plain [BK][BN])
+constexpr uint32_t OFF_AHI = 0, OFF_ALO = TILE, OFF_BHI = 2*TILE, OFF_BLO = 3*TILE, STAGE_BYTES = 4*TILE, OFF_BRAW = STAGES*STAGE_BYTES;
+constexpr uint32_t SMEM_BYTES = STAGES*STAGE_BYTES + BSTAGES*TILE + 1024; // + slack for the manual 1024-byte alignment (swizzle atoms)
 constexpr uint32_t TMEM_COLS = 128;
 // instruction descriptor (upper 32 bits of the 64-bit idesc): D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N>>3, M>>4
 constexpr uint32_t IDESC = (1u<<4) | (2u<<7) | (2u<<10) | (uint32_t(BN>>3)<<17) | (uint32_t(BM>>4)<<24);
@@ -93,10 +95,11 @@ __device__ __forceinline__ void split4(float4 v, float4 & hi, float4 & lo)
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float * C, int64_t ldc, int M, int N, int K, int vec_c)
+sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float * C, int64_t ldc, int M, int N, int K, int vec_c, int mask_hi)
 {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full[STAGES], ready[STAGES], empty[STAGES], tmem_full;
+    // a_full: TMA -> split, MMA.  b_full / b_empty: raw b ring, TMA <-> split.  ready: split -> MMA.  empty: MMA (commit) -> TMA.
+    __shared__ __align__(8) uint64_t a_full[STAGES], ready[STAGES], empty[STAGES], b_full[BSTAGES], b_empty[BSTAGES], tmem_full;
     __shared__ uint32_t tmem_holder;
     uint32_t const base = (s32(smem_raw)+1023u) & ~1023u;          // shared-space address of stage 0
     unsigned char * const gen = smem_raw + (base-s32(smem_raw));   // the same place, generic pointer
@@ -110,7 +113,9 @@ sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (0==threadIdx.x) {
 #pragma unroll
-        for (int s=0; s<STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
+        for (int s=0; s<STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&ready[s], SPLIT_THREADS); mbar_init(&empty[s], 1); }
+#pragma unroll
+        for (int r=0; r<BSTAGES; ++r) { mbar_init(&b_full[r], 1); mbar_init(&b_empty[r], SPLIT_THREADS); }
         mbar_init(&tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -126,12 +131,13 @@ sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (0==warp) {
         if (0==lane) { // ---- TMA producer
             for (int kb=0; kb<nkb; ++kb) {
-                int const s = kb%STAGES;
-                uint32_t const ph = uint32_t(kb/STAGES)&1u;
-                mbar_wait(&empty[s], ph^1u);                          // the MMAs that read this stage have completed
-                mbar_expect_tx(&full[s], 2*TILE);
-                tma_load_2d(base + s*STAGE_BYTES + OFF_AHI, &tmA, kb*BK, m0, &full[s]);
-                tma_load_2d(base + s*STAGE_BYTES + OFF_BST, &tmB, n0, kb*BK, &full[s]);
+                int const s = kb%STAGES, r = kb%BSTAGES;
+                mbar_wait(&b_empty[r], (uint32_t(kb/BSTAGES)&1u)^1u); // the split warps have read this raw b slot
+                mbar_expect_tx(&b_full[r], TILE);
+                tma_load_2d(base + OFF_BRAW + r*TILE, &tmB, n0, kb*BK, &b_full[r]);
+                mbar_wait(&empty[s], (uint32_t(kb/STAGES)&1u)^1u);    // the MMAs that read this operand stage have completed
+                mbar_expect_tx(&a_full[s], TILE);
+                tma_load_2d(base + s*STAGE_BYTES + OFF_AHI, &tmA, kb*BK, m0, &a_full[s]);
             }
         }
     } else if (1==warp) {
@@ -139,7 +145,7 @@ sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int kb=0; kb<nkb; ++kb) {
                 int const s = kb%STAGES;
                 uint32_t const ph = uint32_t(kb/STAGES)&1u;
-                mbar_wait(&full[s], ph);
+                mbar_wait(&a_full[s], ph);
                 mbar_wait(&ready[s], ph);                             // hi / lo tiles written and fenced by the split warps
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t const st = base + s*STAGE_BYTES;
@@ -156,11 +162,11 @@ sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             umma_commit(&tmem_full);
         }
     } else if (warp>=4) {
-        int const t = int(threadIdx.x)-(THREADS-SPLIT_THREADS);      // 0..127
+        int const t = int(threadIdx.x)-(THREADS-SPLIT_THREADS);      // 0..255
+        int const bn = t&(BN-1), bh = t>>7;                          // b: row n of the K-major tiles, and which half of its 8 chunks
         for (int kb=0; kb<nkb; ++kb) { // ---- split
-            int const s = kb%STAGES;
-            uint32_t const ph = uint32_t(kb/STAGES)&1u;
-            mbar_wait(&full[s], ph);
+            int const s = kb%STAGES, r = kb%BSTAGES;
+            mbar_wait(&a_full[s], uint32_t(kb/STAGES)&1u);           // (a_full follows empty[s]: a_lo / b_hi / b_lo of this stage are free too)
             unsigned char * const st = gen + s*STAGE_BYTES;
             // a: hi in place, lo at the same (swizzled) position of its own tile
 #pragma unroll
@@ -168,29 +174,31 @@ sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 int const idx = (t + SPLIT_THREADS*j)*16;
                 float4 v = *reinterpret_cast<float4 const *>(st+OFF_AHI+idx), hi, lo;
                 split4(v, hi, lo);
-                *reinterpret_cast<float4 *>(st+OFF_AHI+idx) = hi;
+                if (mask_hi) *reinterpret_cast<float4 *>(st+OFF_AHI+idx) = hi; // default off: kind::tf32 ignores the low 13 mantissa bits itself (measured: identical results)
                 *reinterpret_cast<float4 *>(st+OFF_ALO+idx) = lo;
             }
-            // b: staging [BK k][BN n] -> K-major [BN n][BK k] with the 128-byte swizzle; this thread owns row n = t
-            float const * const bs = reinterpret_cast<float const *>(st+OFF_BST) + t;
+            // b: staging [BK k][BN n] -> K-major [BN n][BK k] with the 128-byte swizzle; this thread owns half of row n = t % 128
+            mbar_wait(&b_full[r], uint32_t(kb/BSTAGES)&1u);
+            float const * const bs = reinterpret_cast<float const *>(gen+OFF_BRAW+r*TILE) + bn;
 #pragma unroll
-            for (int kc=0; kc<BK/4; ++kc) {
+            for (int kc=bh*(BK/8); kc<(bh+1)*(BK/8); ++kc) {
                 float4 v {bs[(4*kc+0)*BN], bs[(4*kc+1)*BN], bs[(4*kc+2)*BN], bs[(4*kc+3)*BN]}, hi, lo;
                 split4(v, hi, lo);
-                int const off = t*128 + ((kc ^ (t&7))<<4);
-                *reinterpret_cast<float4 *>(st+OFF_BHI+off) = hi;
+                int const off = bn*128 + ((kc ^ (bn&7))<<4);
+                *reinterpret_cast<float4 *>(st+OFF_BHI+off) = mask_hi ? hi : v;
                 *reinterpret_cast<float4 *>(st+OFF_BLO+off) = lo;
             }
+            mbar_arrive(&b_empty[r]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> tensor-core (async proxy) reads
             mbar_arrive(&ready[s]);
         }
         // ---- epilogue: TMEM -> registers -> c += acc
         mbar_wait(&tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        int const q = warp&3;
+        int const q = warp&3, half = (warp-4)>>2;                    // TMEM lane quarter of this warp (warp % 4), column half
         int const row = m0 + q*32 + lane;
 #pragma unroll 1
-        for (int c0=0; c0<BN; c0+=32) {
+        for (int c0=half*(BN/2); c0<(half+1)*(BN/2); c0+=32) {
             uint32_t v[32];
             tmem_ld32(tmem + (uint32_t(q*32)<<16) + uint32_t(c0), v);
             if (row<M) {
@@ -264,7 +272,7 @@ try_tcgen05_sgemm(racu_gemm_desc const * gd, cudaStream_t stream, int * handled)
     int const vec_c = 0==(uintptr_t(gd->c)%16) && 0==(gd->ldc*4)%16;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(sgemm3x_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)))) return cuda_fail(e, "sgemm tcgen05 smem");
-    sgemm3x_tc5_kernel<<<unsigned(tiles), THREADS, SMEM_BYTES, stream>>>(tmA, tmB, static_cast<float *>(gd->c), gd->ldc, int(gd->M), int(gd->N), int(gd->K), vec_c);
+    sgemm3x_tc5_kernel<<<unsigned(tiles), THREADS, SMEM_BYTES, stream>>>(tmA, tmB, static_cast<float *>(gd->c), gd->ldc, int(gd->M), int(gd->N), int(gd->K), vec_c, std::getenv("RACU_TC5_MASK") ? 1 : 0);
     launch_count_add(1);
     if ((e = cudaGetLastError())) return cuda_fail(e, "sgemm tcgen05");
     set_kernel("sgemm_3xtf32_tcgen05");

@@ -253,7 +253,7 @@ jit_prepare(Plan & plan, std::string & err)
 {
     int const variant = variant_of(plan);
     int dev = -1;
-    bool const have_dev = cudaSuccess==cudaGetDevice(&dev) && dev>=0 && cudaSuccess==cudaFree(nullptr);
+    bool have_dev = cudaSuccess==cudaGetDevice(&dev) && dev>=0; // (cheap: no context work on the per-call path)
     if (!have_dev) cudaGetLastError();
     std::string const src = jit_kernel_text(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op);
     std::string const key = std::to_string(dev) + "|" + src;
@@ -263,6 +263,7 @@ jit_prepare(Plan & plan, std::string & err)
     std::vector<char> cubin;
     if (!jit_cubin(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op, cubin, err)) return false;
     ++jit_compiles;
+    if (have_dev && cudaSuccess!=cudaFree(nullptr)) { cudaGetLastError(); have_dev = false; } // make the primary context current before loading
     if (std::getenv("RACU_JIT_VERBOSE")) std::fprintf(stderr, "racu jit: specialised %s (mode %d variant %d fold %d) for device %d, %zu bytes\n",
                                                       jit_prog_text(plan.jit_prog).c_str(), plan.sp.mode, variant, plan.sp.fold_op, dev, cubin.size());
     if (!have_dev) { plan.jit_fn = nullptr; return true; }

@@ -324,7 +324,7 @@ def test_gemm_tensor_core_path(mnk, dt, exc):
     b.assign((ra._1 - 2 * ra._0) % 5)
     c = exc.from_numpy(np.ones((m, n), dtype=dt))
     ra.gemm(a, b, c)
-    assert exc.last_kernel() in ("dgemm_dmma884", "sgemm_3xtf32"), exc.last_kernel()
+    assert exc.last_kernel() in ("dgemm_dmma884", "sgemm_3xtf32_tcgen05"), exc.last_kernel()
     ref = np.ones((m, n)) + a.numpy().astype(np.float64) @ b.numpy().astype(np.float64)
     assert np.array_equal(c.numpy().astype(np.float64), ref)
     # (ii) random, through views of larger buffers (lda/ldb/ldc > extents)
@@ -335,7 +335,7 @@ def test_gemm_tensor_core_path(mnk, dt, exc):
     Av, Bv, Cv = exc.from_numpy(A)(ra.all, ra.iota(k)), exc.from_numpy(B)(ra.all, ra.iota(n)), exc.from_numpy(C0)
     Cs = Cv(ra.all, ra.iota(n))
     ra.gemm(Av, Bv, Cs)
-    assert exc.last_kernel() in ("dgemm_dmma884", "sgemm_3xtf32")
+    assert exc.last_kernel() in ("dgemm_dmma884", "sgemm_3xtf32_tcgen05")
     got = Cv.numpy().astype(np.float64)
     A64, B64 = A[:, :k].astype(np.float64), B[:, :n].astype(np.float64)
     ref = C0.astype(np.float64)
