@@ -10,6 +10,9 @@ ok_all = True
 if len(sys.argv) > 1 and sys.argv[1] == "mask":
     os.environ["RACU_TC5_MASK"] = "1"
     print("RACU_TC5_MASK=1: hi operands are masked explicitly (default: raw fp32 words, the tensor core drops the low 13 bits itself)")
+if len(sys.argv) > 1 and sys.argv[1] == "ss":
+    os.environ["RACU_TC5_SS"] = "1"
+    print("RACU_TC5_SS=1: a operand from shared memory (SS form)")
 for (m, n, k) in [(128, 128, 32), (128, 128, 64), (128, 128, 256), (256, 384, 96), (100, 72, 40), (384, 128, 1000), (1024, 1024, 1024)]:
     a = torch.rand(m, k, device="cuda") * 2 - 1
     b = torch.rand(k, n, device="cuda") * 2 - 1

@@ -31,12 +31,21 @@ namespace racu {
 namespace tc5 {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 3 /* operand ring */, BSTAGES = 2 /* raw b ring */, THREADS = 384, SPLIT_THREADS = 256, GROUP_M = 16;
+constexpr int BSTAGES = 2 /* raw b ring */, THREADS = 384, SPLIT_THREADS = 256, GROUP_M = 16;
 constexpr uint32_t TILE = BM*BK*4;  // 16 KiB, every tile
-// operand stage: a_hi (the TMA lands here, 128B-swizzled) | a_lo | b_hi | b_lo ; then the raw b ring (TMA, plain [BK][BN])
-constexpr uint32_t OFF_AHI = 0, OFF_ALO = TILE, OFF_BHI = 2*TILE, OFF_BLO = 3*TILE, STAGE_BYTES = 4*TILE, OFF_BRAW = STAGES*STAGE_BYTES;
-constexpr uint32_t SMEM_BYTES = STAGES*STAGE_BYTES + BSTAGES*TILE + 1024; // + slack for the manual 1024-byte alignment (swizzle atoms)
-constexpr uint32_t TMEM_COLS = 128;
+// Two forms of the a operand:
+//   TS = false  a_hi / a_lo are shared-memory tiles (tcgen05.mma SS form). Stage: a_hi (TMA target) | a_lo | b_hi | b_lo, 3 stages.
+//   TS = true   a_hi / a_lo live in TENSOR MEMORY (TS form): the split warps read the raw a tile once and tcgen05.st both halves
+//               into 2 x 32 TMEM columns per stage; the MMA then reads only b from shared memory, which halves the operand traffic
+//               on the shared-memory port - the limiter of this kernel. Stage: a raw (TMA target) | b_hi | b_lo, 4 stages.
+template <bool TS> struct Cfg
+{
+    static constexpr int STAGES = TS ? 4 : 3;
+    static constexpr uint32_t OFF_AHI = 0, OFF_ALO = TILE /* SS only */, OFF_BHI = TS ? TILE : 2*TILE, OFF_BLO = OFF_BHI+TILE, STAGE_BYTES = OFF_BLO+TILE;
+    static constexpr uint32_t OFF_BRAW = STAGES*STAGE_BYTES;
+    static constexpr uint32_t SMEM_BYTES = STAGES*STAGE_BYTES + BSTAGES*TILE + 1024; // + slack for the manual 1024-byte alignment (swizzle atoms)
+    static constexpr uint32_t TMEM_COLS = TS ? 512 : 128;   // accumulator: columns 0..127; TS: a_hi / a_lo of stage s at 128 + 64 s (+32)
+};
 // instruction descriptor (upper 32 bits of the 64-bit idesc): D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N>>3, M>>4
 constexpr uint32_t IDESC = (1u<<4) | (2u<<7) | (2u<<10) | (uint32_t(BN>>3)<<17) | (uint32_t(BM>>4)<<24);
 
@@ -72,6 +81,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                  :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
 }
+// TS form: a from tensor memory (lane = row m, one tf32 per 32-bit column = k), b from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, uint32_t const (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                    "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t * bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(s32(bar)) : "memory");
@@ -94,9 +115,13 @@ __device__ __forceinline__ void split4(float4 v, float4 & hi, float4 & lo)
     lo.x = v.x-hi.x; lo.y = v.y-hi.y; lo.z = v.z-hi.z; lo.w = v.w-hi.w;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool TS> __global__ void __launch_bounds__(THREADS, 1)
 sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float * C, int64_t ldc, int M, int N, int K, int vec_c, int mask_hi)
 {
+    using CF = Cfg<TS>;
+    constexpr int STAGES = CF::STAGES;
+    constexpr uint32_t OFF_AHI = CF::OFF_AHI, OFF_ALO = CF::OFF_ALO, OFF_BHI = CF::OFF_BHI, OFF_BLO = CF::OFF_BLO, STAGE_BYTES = CF::STAGE_BYTES,
+                       OFF_BRAW = CF::OFF_BRAW, TMEM_COLS = CF::TMEM_COLS;
     extern __shared__ unsigned char smem_raw[];
     // a_full: TMA -> split, MMA.  b_full / b_empty: raw b ring, TMA <-> split.  ready: split -> MMA.  empty: MMA (commit) -> TMA.
     __shared__ __align__(8) uint64_t a_full[STAGES], ready[STAGES], empty[STAGES], b_full[BSTAGES], b_empty[BSTAGES], tmem_full;
@@ -149,13 +174,25 @@ sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_wait(&ready[s], ph);                             // hi / lo tiles written and fenced by the split warps
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t const st = base + s*STAGE_BYTES;
-                uint64_t const ahi = umma_desc(st+OFF_AHI), alo = umma_desc(st+OFF_ALO), bhi = umma_desc(st+OFF_BHI), blo = umma_desc(st+OFF_BLO);
+                uint64_t const bhi = umma_desc(st+OFF_BHI), blo = umma_desc(st+OFF_BLO);
+                if constexpr (TS) {
+                    uint32_t const ahi = tmem + 128u + uint32_t(s)*64u, alo = ahi + 32u;
 #pragma unroll
-                for (int k4=0; k4<BK/8; ++k4) {                       // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
-                    uint64_t const o = uint64_t(k4*2);
-                    umma_tf32(tmem, alo+o, bhi+o, (kb|k4)>0);
-                    umma_tf32(tmem, ahi+o, blo+o, 1);
-                    umma_tf32(tmem, ahi+o, bhi+o, 1);
+                    for (int k4=0; k4<BK/8; ++k4) {                   // a: +8 TMEM columns per k-step; b: +32 bytes inside the swizzle row
+                        uint64_t const o = uint64_t(k4*2);
+                        umma_tf32_ts(tmem, alo+8u*k4, bhi+o, (kb|k4)>0);
+                        umma_tf32_ts(tmem, ahi+8u*k4, blo+o, 1);
+                        umma_tf32_ts(tmem, ahi+8u*k4, bhi+o, 1);
+                    }
+                } else {
+                    uint64_t const ahi = umma_desc(st+OFF_AHI), alo = umma_desc(st+OFF_ALO);
+#pragma unroll
+                    for (int k4=0; k4<BK/8; ++k4) {                   // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
+                        uint64_t const o = uint64_t(k4*2);
+                        umma_tf32(tmem, alo+o, bhi+o, (kb|k4)>0);
+                        umma_tf32(tmem, ahi+o, blo+o, 1);
+                        umma_tf32(tmem, ahi+o, bhi+o, 1);
+                    }
                 }
                 umma_commit(&empty[s]);                               // (implies tcgen05.fence::before_thread_sync)
             }
@@ -168,6 +205,22 @@ sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int const s = kb%STAGES, r = kb%BSTAGES;
             mbar_wait(&a_full[s], uint32_t(kb/STAGES)&1u);           // (a_full follows empty[s]: a_lo / b_hi / b_lo of this stage are free too)
             unsigned char * const st = gen + s*STAGE_BYTES;
+            if constexpr (TS) {
+                // a: this thread owns row m = 32 (warp % 4) + lane (its TMEM lane) and 16 of the 32 k: four 16-byte chunks out of the
+                // swizzled tile (chunk c of row m sits at c ^ (m & 7): conflict free across a quarter warp), hi and lo to TMEM
+                int const m = (warp&3)*32 + lane, h = (warp-4)>>2;
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int c=0; c<4; ++c) {
+                    float4 v = *reinterpret_cast<float4 const *>(st+OFF_AHI + m*128 + (((4*h+c) ^ (m&7))<<4)), vh, vl;
+                    split4(v, vh, vl);
+                    hi[4*c] = __float_as_uint(v.x); hi[4*c+1] = __float_as_uint(v.y); hi[4*c+2] = __float_as_uint(v.z); hi[4*c+3] = __float_as_uint(v.w);
+                    lo[4*c] = __float_as_uint(vl.x); lo[4*c+1] = __float_as_uint(vl.y); lo[4*c+2] = __float_as_uint(vl.z); lo[4*c+3] = __float_as_uint(vl.w);
+                }
+                uint32_t const ta = tmem + (uint32_t((warp&3)*32)<<16) + 128u + uint32_t(s)*64u + uint32_t(16*h);
+                tmem_st16(ta, hi);
+                tmem_st16(ta+32u, lo);
+            } else
             // a: hi in place, lo at the same (swizzled) position of its own tile
 #pragma unroll
             for (int j=0; j<int(TILE/16)/SPLIT_THREADS; ++j) {
@@ -189,6 +242,10 @@ sgemm3x_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 *reinterpret_cast<float4 *>(st+OFF_BLO+off) = lo;
             }
             mbar_arrive(&b_empty[r]);
+            if constexpr (TS) {
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> tensor-core (async proxy) reads
             mbar_arrive(&ready[s]);
         }
@@ -271,8 +328,14 @@ try_tcgen05_sgemm(racu_gemm_desc const * gd, cudaStream_t stream, int * handled)
     if (tiles>=(int64_t(1)<<31)) return RACU_OK;
     int const vec_c = 0==(uintptr_t(gd->c)%16) && 0==(gd->ldc*4)%16;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(sgemm3x_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)))) return cuda_fail(e, "sgemm tcgen05 smem");
-    sgemm3x_tc5_kernel<<<unsigned(tiles), THREADS, SMEM_BYTES, stream>>>(tmA, tmB, static_cast<float *>(gd->c), gd->ldc, int(gd->M), int(gd->N), int(gd->K), vec_c, std::getenv("RACU_TC5_MASK") ? 1 : 0);
+    int const mask = std::getenv("RACU_TC5_MASK") ? 1 : 0;
+    if (std::getenv("RACU_TC5_SS")) { // a operand from shared memory (the first version of this kernel; kept for comparison)
+        if ((e = cudaFuncSetAttribute(sgemm3x_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<false>::SMEM_BYTES)))) return cuda_fail(e, "sgemm tcgen05 smem");
+        sgemm3x_tc5_kernel<false><<<unsigned(tiles), THREADS, Cfg<false>::SMEM_BYTES, stream>>>(tmA, tmB, static_cast<float *>(gd->c), gd->ldc, int(gd->M), int(gd->N), int(gd->K), vec_c, mask);
+    } else {
+        if ((e = cudaFuncSetAttribute(sgemm3x_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<true>::SMEM_BYTES)))) return cuda_fail(e, "sgemm tcgen05 smem");
+        sgemm3x_tc5_kernel<true><<<unsigned(tiles), THREADS, Cfg<true>::SMEM_BYTES, stream>>>(tmA, tmB, static_cast<float *>(gd->c), gd->ldc, int(gd->M), int(gd->N), int(gd->K), vec_c, mask);
+    }
     launch_count_add(1);
     if ((e = cudaGetLastError())) return cuda_fail(e, "sgemm tcgen05");
     set_kernel("sgemm_3xtf32_tcgen05");
