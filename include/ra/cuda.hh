@@ -502,6 +502,50 @@ template <class A, class B> requires (tomap<A, B>) auto dot(A const & a, B const
 template <class A> requires (is_ra<A>) auto reduce_sqrm(A const & a) { return reduce(sqrm(a), RACU_RED_SUM); }
 template <class A> requires (is_ra<A>) auto norm2(A const & a) { return std::sqrt(reduce_sqrm(a)); }
 
+// any / every / index / lexical_compare: ra/ra.hh:279-304. The reference short-circuits a sequential traversal (early(),
+// ra/ply.hh:169); the order of traversal is unspecified (docs/ra-ra.texi:3143-3148), so on the device they are max / min
+// folds over the truth values and over the position of the first hit. Empty: false / true / -1 / false, like the reference's
+// defaults.
+template <class A> requires (is_ra<A>) bool any(A const & a) { return reduce(cast<int>(cast<bool>(a)), RACU_RED_AMAX)>0; }
+template <class A> requires (is_ra<A>) bool every(A const & a) { return reduce(cast<int>(cast<bool>(a)), RACU_RED_AMIN)>0; }
+// index of the first true element along axis 0 (the reference matches a rank-1 iota() against axis 0: rank > 1 "checks
+// elements but only returns the first index", test/early.cc:77-82): the smallest axis-0 index that holds a true element.
+template <class A> requires (is_ra<A>) dim_t index(A const & a)
+{
+    constexpr dim_t none = std::numeric_limits<dim_t>::max();
+    dim_t const i = reduce(where(a, _0, none), RACU_RED_AMIN);
+    return none==i ? dim_t(-1) : i;
+}
+// first position, in row-major order, where a != b decides: a < b there (false if there is none).
+// key = 2 * (row-major position) + (a < b ? 0 : 1) where a != b: the smallest key is the first difference.
+template <int R, class A, class B> bool lexical_compare_rank(A const & a, B const & b, std::vector<dim_t> const & sh)
+{
+    constexpr dim_t none = std::numeric_limits<dim_t>::max();
+    auto lt01 = where(a<b, dim_t(0), dim_t(1));
+    if constexpr (0==R) {
+        return reduce(where(a!=b, lt01, none), RACU_RED_AMIN)==0;
+    } else {
+        dim_t st[R], acc = 1;
+        for (int k=R-1; k>=0; --k) { st[k] = acc; acc *= sh[k]; }
+        auto pos = [&]<int ... k>(std::integer_sequence<int, k ...>) { return ((TIndex<k> {}*st[k]) + ...); }(std::make_integer_sequence<int, R> {});
+        dim_t const key = reduce(where(a!=b, pos*dim_t(2) + lt01, none), RACU_RED_AMIN);
+        return none!=key && 0==key%2;
+    }
+}
+template <class A, class B> requires (tomap<A, B>) bool lexical_compare(A const & a, B const & b)
+{
+    auto const sh = shape(a!=b);
+    switch (sh.size()) {
+    case 0: return lexical_compare_rank<0>(a, b, sh);
+    case 1: return lexical_compare_rank<1>(a, b, sh);
+    case 2: return lexical_compare_rank<2>(a, b, sh);
+    case 3: return lexical_compare_rank<3>(a, b, sh);
+    case 4: return lexical_compare_rank<4>(a, b, sh);
+    case 5: return lexical_compare_rank<5>(a, b, sh);
+    default: RACU_ASSERT(false, RACU_ERR_UNSUPPORTED, std::string("lexical_compare: rank > 5")); return false;
+    }
+}
+
 
 // ---------------------
 // views: ra/arrays.hh:84-149; ViewBig ra/expr.hh:233

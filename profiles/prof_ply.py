@@ -54,6 +54,17 @@ for w in which:
             ga, gb = (ex.wrap(torch.rand(ng, ng, device=dev, dtype=torch.float32)) for _ in range(2))
             gc = ex.wrap(torch.zeros(ng, ng, device=dev, dtype=torch.float32))
             ra.gemm(ga, gb, gc)
+        elif w in ("gemv32", "gevm32", "gemv64", "gevm64"):   # bench-gemv shapes, 16384^2
+            gdt = torch.float32 if w.endswith("32") else torch.float64
+            ng = 16384
+            gm = ex.wrap(torch.rand(ng, ng, device=dev, dtype=gdt))
+            gx = ex.wrap(torch.rand(ng, device=dev, dtype=gdt))
+            gy = ex.wrap(torch.zeros(ng, device=dev, dtype=gdt))
+            if w.startswith("gemv"):
+                ra.gemv(gm, gx, gy)
+            else:
+                ra.gevm(gx, gm, gy)
+            del gm
         elif w == "stencil":
             n3 = 512
             A3 = torch.rand(n3, n3, n3, device=dev)

@@ -657,6 +657,47 @@ def amin(a): return _reduce(a, abi.RED_AMIN)
 def amax(a): return _reduce(a, abi.RED_AMAX)
 
 
+# any / every / index / lexical_compare (ra/ra.hh:279-304). The reference short-circuits a sequential traversal (early(),
+# ra/ply.hh:169); the order is unspecified (docs/ra-ra.texi:3143-3148), so here they are max / min folds over the truth values
+# and over the position of the first hit. Empty: False / True / -1 / False, like the reference's defaults.
+_NONE = (1 << 63) - 1
+
+
+def any(a):  # noqa: A001
+    return bool(_reduce(cast(I32, cast(BOOL, a)), abi.RED_AMAX) > 0)
+
+
+def every(a):
+    return bool(_reduce(cast(I32, cast(BOOL, a)), abi.RED_AMIN) > 0)
+
+
+def index(a):
+    """First true element along axis 0 (a rank-1 iota() matched against axis 0: for rank > 1 the reference "checks elements
+    but only returns the first index", test/early.cc:77-82): the smallest axis-0 index holding a true element, or -1."""
+    i = int(_reduce(where(a, tindex(0, I64), np.int64(_NONE)), abi.RED_AMIN))
+    return -1 if i == _NONE else i
+
+
+def lexical_compare(a, b):
+    """a < b at the first position, in row-major order, where they differ; False if they do not."""
+    a, b = as_expr(a), as_expr(b)
+    ne = a.ne(b)
+    ex = _find_ex(ne)
+    d, keep = flatten(ne, ex=ex)
+    shape = ex.agree(d)
+    del keep
+    lt01 = where(a < b, np.int64(0), np.int64(1))
+    if _builtins.len(shape) == 0:
+        return int(_reduce(where(ne, lt01, np.int64(_NONE)), abi.RED_AMIN)) == 0
+    pos, acc = None, 1
+    for k in range(_builtins.len(shape) - 1, -1, -1):
+        term = tindex(k, I64) * np.int64(acc)
+        pos = term if pos is None else pos + term
+        acc *= shape[k]
+    key = int(_reduce(where(ne, pos * np.int64(2) + lt01, np.int64(_NONE)), abi.RED_AMIN))
+    return key != _NONE and key % 2 == 0
+
+
 def dot(a, b):
     """ra/ra.hh:379-385 with RA_FMA=0: c += a*b."""
     return _reduce(as_expr(a) * b, abi.RED_SUM)

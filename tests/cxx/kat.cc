@@ -264,5 +264,28 @@ int main()
         tr.test_eq(ref, A);
         tr.test_eq(refn, Anext);
     }
+    tr.section("any / every / index / lexical_compare: test/early.cc:17-82, ra/ra.hh:279-304");
+    {
+        rc::Big<int, 0> a0({}, 99);
+        tr.test(rc::any(a0==99)); tr.test(rc::every(a0==99));
+        rc::Big<int, 2> a({2, 3}, rc::_0*2 + rc::_1*10);
+        tr.test(!rc::any(a%2!=0)); tr.test(rc::every(a%2==0));
+        rc::Big<int, 2> b({2, 3}, 1);
+        b(1, 1) = 0;
+        tr.test(!rc::every(1==b)); tr.test(rc::any(0==b));
+        auto bt = rc::transpose<1, 0>(b);
+        tr.test(!rc::every(1==bt)); tr.test(rc::any(0==bt));
+        rc::Big<int, 1> d {1, 3, -1, 9};
+        tr.test(2==rc::index(d<0)); tr.test(-1==rc::index(d>10));
+        rc::Big<int, 2> e({2, 2}, 0);
+        e(0, 0) = 1; e(0, 1) = 3; e(1, 0) = -1; e(1, 1) = 9;
+        tr.test(1==rc::index(e<0), "index with rank 2 returns the first axis-0 index"); tr.test(-1==rc::index(e>10));
+        rc::Big<int, 1> z({0}, 0);
+        tr.test(!rc::any(z==0)); tr.test(rc::every(z==1)); tr.test(-1==rc::index(z==0));
+        rc::Big<int, 2> x({2, 3}, rc::_0*3 + rc::_1), y({2, 3}, rc::_0*3 + rc::_1);
+        tr.test(!rc::lexical_compare(x, y));
+        y(1, 1) = 7; y(1, 2) = 0;
+        tr.test(rc::lexical_compare(x, y)); tr.test(!rc::lexical_compare(y, x));
+    }
     return tr.summary();
 }

@@ -570,3 +570,38 @@ def laplace2d_cghs_end_to_end(ex):
     mx = ra.amax(ra.abs(u - v))
     assert mx <= 0.00463, mx
     assert its <= 67, its
+
+
+@case
+def early_any_every_index(ex):
+    """test/early.cc:17-82: any / every over rank 0, static and dynamic rank; index() incl. rank 2 ("only returns first index")."""
+    a0 = arr(ex, 99, np.int32)                                     # rank 0 (:18-22)
+    assert ra.any(a0.eq(99)) and ra.every(a0.eq(99))
+    a = zeros(ex, (2, 3), np.int32)                                # a = _0*2 + _1*10 (:53-57): no odd element
+    a.assign(ra.tindex(0, abi.I32) * 2 + ra.tindex(1, abi.I32) * 10)
+    assert not ra.any((a % 2).ne(0)) and ra.every((a % 2).eq(0))
+    b = arr(ex, [[1, 1, 1], [1, 0, 1]], np.int32)                  # :36-43, also through a transposed view
+    assert not ra.every(b.eq(1)) and ra.any(b.eq(0))
+    bt = ra.transpose(b, (1, 0))
+    assert not ra.every(bt.eq(1)) and ra.any(bt.eq(0))
+    c = zeros(ex, (9,), np.int32)                                  # a = iota(9)*2 (:59-63)
+    c.assign(ra.iota(9) * 2)
+    assert not ra.any((c % 2).ne(0)) and ra.every((c % 2).eq(0))
+    d = arr(ex, [1, 3, -1, 9], np.int32)                           # :65-69
+    assert ra.index(d < 0) == 2 and ra.index(d > 10) == -1
+    e = arr(ex, [[1, 3], [-1, 9]], np.int32)                       # :77-82
+    assert ra.index(e < 0) == 1 and ra.index(e > 10) == -1
+    z = zeros(ex, (0,), np.int32)                                  # defaults of early() on an empty traversal (ra/ra.hh:282,288,297)
+    assert not ra.any(z.eq(0)) and ra.every(z.eq(1)) and ra.index(z.eq(0)) == -1
+
+
+@case
+def lexical_compare_first_difference(ex):
+    """ra/ra.hh:299-304: a < b at the first differing position in row-major order, False when equal."""
+    a = arr(ex, [[1, 2, 3], [4, 5, 6]], np.int32)
+    b = arr(ex, [[1, 2, 3], [4, 7, 0]], np.int32)
+    assert ra.lexical_compare(a, b) and not ra.lexical_compare(b, a) and not ra.lexical_compare(a, a)
+    c = arr(ex, [[1, 2, 4], [0, 0, 0]], np.int32)                  # differs earlier, the other way: later elements do not matter
+    assert ra.lexical_compare(a, c) and not ra.lexical_compare(c, a)
+    x, y = arr(ex, [0.5, 2.5], np.float64), arr(ex, [0.5, -1.], np.float64)
+    assert not ra.lexical_compare(x, y) and ra.lexical_compare(y, x)
