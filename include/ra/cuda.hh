@@ -23,6 +23,7 @@
 // Written for g++ >= 13 -std=c++23 (no deducing-this, <print> or ranges::to). Include only this file and link libracu.so.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstddef>
@@ -160,6 +161,7 @@ class Builder
 public:
     racu_desc d;
     std::vector<void *> temps; // device copies of host vectors, freed after the traversal
+    int shift = 0;             // leaves flattened now are placed `shift` axes further in (dead leading axes): index arrays of a(i ...)
 
     Builder() { std::memset(&d, 0, sizeof(d)); d.dst = -1; }
     Builder(Builder const &) = delete;
@@ -187,9 +189,21 @@ public:
         RACU_CK(rank<=RACU_MAX_RANK, "Rank too large.");
         racu_operand o;
         std::memset(&o, 0, sizeof(o));
-        o.kind = RACU_MEM; o.dtype = dtype_of<std::remove_cv_t<T>>; o.rank = rank;
+        RACU_CK(rank+shift<=RACU_MAX_RANK, "Rank too large.");
+        o.kind = RACU_MEM; o.dtype = dtype_of<std::remove_cv_t<T>>; o.rank = rank+shift;
         o.base.ptr = const_cast<std::remove_cv_t<T> *>(p);
-        for (rank_t k=0; k<rank; ++k) { o.len[k] = dv[k].len; o.stride[k] = dv[k].step; }
+        for (rank_t k=0; k<shift; ++k) { o.len[k] = UNB; o.stride[k] = 0; }
+        for (rank_t k=0; k<rank; ++k) { o.len[shift+k] = dv[k].len; o.stride[shift+k] = dv[k].step; }
+        return operand(o);
+    }
+    // an array addressed by computed offsets (RACU_OP_LOAD): base = element at offset 0, [lo, hi] = valid element offsets
+    template <class T> int ptr(T const * p, dim_t lo, dim_t hi)
+    {
+        racu_operand o;
+        std::memset(&o, 0, sizeof(o));
+        o.kind = RACU_PTR; o.dtype = dtype_of<std::remove_cv_t<T>>; o.rank = 0;
+        o.base.ptr = const_cast<std::remove_cv_t<T> *>(p);
+        o.len[0] = lo; o.len[1] = hi;
         return operand(o);
     }
     template <class T> int scalar(T v)
@@ -204,9 +218,11 @@ public:
     {
         racu_operand o;
         std::memset(&o, 0, sizeof(o));
-        o.kind = RACU_SEQ; o.dtype = dtype_of<T>; o.rank = rank;
+        RACU_CK(rank+shift<=RACU_MAX_RANK, "Rank too large.");
+        o.kind = RACU_SEQ; o.dtype = dtype_of<T>; o.rank = rank+shift;
         if constexpr (std::is_floating_point_v<T>) o.base.f = double(org); else o.base.i = int64_t(org);
-        for (rank_t k=0; k<rank; ++k) { o.len[k] = len[k]; o.stride[k] = step[k]; }
+        for (rank_t k=0; k<shift; ++k) { o.len[k] = UNB; o.stride[k] = 0; }
+        for (rank_t k=0; k<rank; ++k) { o.len[shift+k] = len[k]; o.stride[shift+k] = step[k]; }
         return operand(o);
     }
 };
@@ -463,6 +479,33 @@ template <class A, class B> requires (tomap<A, B>)
 constexpr auto operator||(A && a, B && b) { return where(std::forward<A>(a), true, cast<bool>(std::forward<B>(b))); }
 
 
+// a(i ...) with unbeaten subscripts (index arrays / index expressions): ra/ply.hh:461-499,531-549. The reference maps
+// a-as-a-function over the subscripts, each on its own axes (fromu_loop / wrank); here the element offset
+// sum(index_k * step_k) is an ordinary I64 expression and RACU_OP_LOAD reads a[offset]. Offsets are clamped to the array
+// (the reference asserts on a bad index, ra/ply.hh:395). Rvalue only: scatter through index arrays is not on the device path.
+template <class T> struct Gather: node_tag
+{
+    using value_type = T;
+    struct Term { std::function<void (Builder &)> flat; int shift; dim_t step; }; // flat pushes the index as I64
+    T const * base = nullptr;
+    dim_t lo = 0, hi = 0;
+    std::vector<Term> terms;
+    void flatten(Builder & b) const
+    {
+        if (terms.empty()) b.emit(RACU_OP_PUSH, dtype_of<dim_t>, b.scalar<dim_t>(0));
+        for (std::size_t q=0; q<terms.size(); ++q) {
+            int const old = b.shift;
+            b.shift += terms[q].shift;
+            terms[q].flat(b);
+            b.shift = old;
+            b.emit(RACU_OP_PUSH, dtype_of<dim_t>, b.scalar<dim_t>(terms[q].step));
+            b.emit(RACU_OP_MUL, dtype_of<dim_t>);
+            if (q>0) b.emit(RACU_OP_ADD, dtype_of<dim_t>);
+        }
+        b.emit(RACU_OP_LOAD, dtype_of<T>, b.ptr<T>(base, lo, hi), dtype_of<dim_t>);
+    }
+};
+
 // ---------------------
 // ply: flatten and launch (replaces ra::ply, ra/ply.hh:157-166, for device resident expressions)
 // ---------------------
@@ -599,8 +642,74 @@ struct View: node_tag
 
     void flatten(Builder & b) const { b.emit(RACU_OP_PUSH, dtype_of<value_type>, b.template mem<T>(cp, dimv.data(), rank())); }
 
-    // ---- beaten subscripts: from() / fromb(), ra/ply.hh:367-435,503-551
+    // ---- unbeaten subscripts (index arrays, index expressions, std::vector<int>): from() -> fromu(), ra/ply.hh:461-499
+    template <class I0> static constexpr bool is_unbeaten = (is_ra<I0> && !is_iota<std::decay_t<I0>>) || is_fov<std::decay_t<I0>>;
     template <class ... I>
+    Gather<value_type> gather(I const & ... i) const
+    {
+        std::vector<Dim> bv;                                   // the source after its beaten subscripts; gathered axes kept whole
+        std::vector<std::function<void (Builder &)>> fl;       // per axis of bv: the index expression (empty: the axis is traversed)
+        std::vector<int> rk;                                   // per axis of bv: expression axes it takes
+        dim_t pl = 0;
+        int ak = 0, seen = 0;
+        int const nstatic = (0 + ... + (int(UNB)==fsrc<std::decay_t<I>> ? 0 : fsrc<std::decay_t<I>>));
+        auto one = [&](auto const & i0) {
+            using I0 = std::decay_t<decltype(i0)>;
+            if constexpr (std::integral<I0> || is_lenlike<I0>) {
+                RACU_CK(ak<rank(), "Too many subscripts.");
+                dim_t la = len(ak), ii = lenx(i0)(la);
+                RACU_CK(0<=ii && ii<la, "Bad index " + std::to_string(ii) + " in len[" + std::to_string(ak) + "]=" + std::to_string(la) + ".");
+                pl += ii*dimv[ak].step;
+                ++ak;
+            } else if constexpr (is_iota<I0>) {
+                RACU_CK(ak<rank(), "Too many subscripts.");
+                dim_t la = len(ak), n = i0.n(la), o = i0.o(la), s = i0.s(la);
+                RACU_ASSERT(UNB!=n, RACU_ERR_UNSUPPORTED, "unbounded iota subscripts are not beatable (ra/ply.hh:341)");
+                RACU_CK(0==n || (0<=o && o<la && 0<=o+(n-1)*s && o+(n-1)*s<la), "Bad iota subscript.");
+                bv.push_back(Dim {n, s*dimv[ak].step}); fl.emplace_back(); rk.push_back(1);
+                pl += o*dimv[ak].step;
+                ++ak;
+            } else if constexpr (requires { []<int N>(dots_t<N>){}(i0); }) {
+                int n = I0::N;
+                if (int(UNB)==n) n = rank()-ak-(nstatic-seen);
+                RACU_CK(n>=0 && ak+n<=rank(), "Too many subscripts.");
+                for (int q=0; q<n; ++q) { bv.push_back(dimv[ak++]); fl.emplace_back(); rk.push_back(1); }
+            } else if constexpr (is_unbeaten<I0>) {
+                RACU_CK(ak<rank(), "Too many subscripts.");
+                auto node = iter(i0);
+                using N = std::decay_t<decltype(node)>;
+                static_assert(std::is_integral_v<typename N::value_type> && !std::is_same_v<typename N::value_type, bool>, "subscripts must be integers");
+                int r = 1;
+                if constexpr (!is_fov<I0>) r = int(ra::cuda::shape(node).size());
+                fl.emplace_back([node](Builder & b) { node.flatten(b); b.template cast<typename N::value_type, dim_t>(); });
+                bv.push_back(dimv[ak]); rk.push_back(r);
+                ++ak;
+            } else {
+                static_assert(std::integral<I0>, "this subscript cannot be combined with index arrays on the device path");
+            }
+            if constexpr (int(UNB)!=fsrc<I0>) seen += fsrc<I0>;
+        };
+        (one(i), ...);
+        for (; ak<rank(); ++ak) { bv.push_back(dimv[ak]); fl.emplace_back(); rk.push_back(1); } // trailing axes implied
+        Gather<value_type> g;
+        g.base = cp+pl;
+        int pos = 0;
+        for (std::size_t q=0; q<bv.size(); ++q) {
+            dim_t const ln = bv[q].len, st = bv[q].step;
+            RACU_ASSERT(ln>=0, RACU_ERR_UNSUPPORTED, "dead axes next to an index array subscript");
+            if (fl[q]) g.terms.push_back({fl[q], pos, st});
+            else g.terms.push_back({[ln](Builder & b) { dim_t one_ = 1; b.emit(RACU_OP_PUSH, dtype_of<dim_t>, b.seq<dim_t>(0, 1, &ln, &one_)); }, pos, st});
+            pos += rk[q];
+            if (ln>0) { g.lo += std::min<dim_t>(0, (ln-1)*st); g.hi += std::max<dim_t>(0, (ln-1)*st); }
+        }
+        RACU_CK(pos<=RACU_MAX_RANK, "Rank too large.");
+        return g;
+    }
+
+    // ---- beaten subscripts: from() / fromb(), ra/ply.hh:367-435,503-551
+    template <class ... I> requires ((is_unbeaten<I> || ...))
+    auto operator()(I const & ... i) const { return gather(i ...); }
+    template <class ... I> requires (!(is_unbeaten<I> || ...))
     auto operator()(I const & ... i) const
     {
         constexpr rank_t BR = frombrank<R, std::decay_t<I> ...>();

@@ -69,7 +69,11 @@ typedef enum {
 typedef enum {
     RACU_MEM = 0,    /* Cell over memory: base.ptr + sum idx[k]*stride[k] (elements). ra/expr.hh:266-312 */
     RACU_SEQ = 1,    /* Cell over Seq (iota, tindex): value = base + T(sum idx[k]*stride[k]). ra/expr.hh:79-100 */
-    RACU_SCALAR = 2  /* Scalar<C>: rank 0, step 0. ra/expr.hh:104-120 */
+    RACU_SCALAR = 2, /* Scalar<C>: rank 0, step 0. ra/expr.hh:104-120 */
+    RACU_PTR = 3     /* An array addressed by COMPUTED element offsets (RACU_OP_LOAD): the unbeaten subscripts A(I, J) of
+                        ra/ply.hh:461-499 and at(A, I) (ra/ra.hh:228-250). rank 0, takes no part in shape agreement.
+                        base.ptr = element at offset 0; len[0] / len[1] = smallest / largest valid element offset. Offsets
+                        are clamped into that range (the reference asserts on a bad index, RA_CK ra/ply.hh:395). */
 } racu_kind;
 
 typedef union {
@@ -130,9 +134,12 @@ typedef enum {
     RACU_OP_GE = 37,
     /* other */
     RACU_OP_FMA = 40,  /* a b c -> fma(a,b,c) */
-    RACU_OP_PICK = 41  /* sel x0 .. x(n-1) -> x[sel]; arg = n, aux = selector type, type = T of branches.
+    RACU_OP_PICK = 41, /* sel x0 .. x(n-1) -> x[sel]; arg = n, aux = selector type, type = T of branches.
                           ra::pick ra/expr.hh:686-728; where(w,t,f) = pick(bool(w), f, t) ra/ra.hh:255-256.
                           Only the chosen branch is observable: the opcode set is side-effect free. */
+    RACU_OP_LOAD = 42  /* off -> opnd[arg][off]: gather. arg = index of a RACU_PTR operand, type = its element dtype,
+                          aux = integer type of the offset (I32 or I64). The host writes A(I, J) as
+                          LOAD(A, I*step0 + J*step1) with I and J placed on their own expression axes (ra/ply.hh:461-499). */
 } racu_opcode;
 
 typedef struct {

@@ -126,6 +126,10 @@ check_program(racu_desc const * d)
             if (sel!=in.aux || sel==RACU_F32 || sel==RACU_F64) return -1;
             sp -= n; st[sp-1] = in.type; break;
         }
+        case RACU_OP_LOAD:
+            if (in.arg>=d->nopnd || d->opnd[in.arg].kind!=RACU_PTR || d->opnd[in.arg].dtype!=in.type) return -1;
+            if (sp<1 || st[sp-1]!=in.aux || (in.aux!=RACU_I32 && in.aux!=RACU_I64)) return -1;
+            st[sp-1] = in.type; break;
         default: return -1;
         }
     }
@@ -292,6 +296,13 @@ eval(racu_desc const * d, Leaf const * leaf)
             if (sel<0 || sel>=n) { sel = 0; } // RA_CK "Bad pick" ra/expr.hh:708: out of contract
             st[sp-1-n] = st[sp-n+sel];
             sp -= n; break;
+        }
+        case RACU_OP_LOAD: { // unbeaten subscripts: *frompl(a.data(), a, i ...) (ra/ply.hh:531-549) with the offset already summed
+            racu_operand const & a = d->opnd[in.arg];
+            int64_t off = with_type(in.aux, [&](auto s) { return int64_t(get<decltype(s)>(st[sp-1])); });
+            off = off<a.len[0] ? a.len[0] : off>a.len[1] ? a.len[1] : off; // out of contract (RA_CK "Bad index", ra/ply.hh:395): clamp
+            st[sp-1] = with_type(in.type, [&](auto t) { return mk<decltype(t)>(static_cast<decltype(t) const *>(a.base.ptr)[off]); });
+            break;
         }
         default:
             st[sp-2] = with_type(in.type, [&](auto t) { return binary<decltype(t)>(in.op, get<decltype(t)>(st[sp-2]), get<decltype(t)>(st[sp-1])); });

@@ -18,13 +18,13 @@ BOOL, I32, I64, F32, F64 = range(5)
 DTYPE_NAMES = ["bool", "i32", "i64", "f32", "f64"]
 DTYPE_SIZE = [1, 4, 8, 4, 8]
 
-MEM, SEQ, SCALAR = range(3)
+MEM, SEQ, SCALAR, PTR = range(4)
 
 OP_PUSH, OP_CAST = 0, 1
 OP_NEG, OP_ABS, OP_SQRT, OP_SQR, OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_NOT = range(2, 11)
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_MOD, OP_MIN, OP_MAX, OP_POW, OP_ATAN2, OP_BAND, OP_BOR, OP_BXOR = range(16, 28)
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE = range(32, 38)
-OP_FMA, OP_PICK = 40, 41
+OP_FMA, OP_PICK, OP_LOAD = 40, 41, 42
 
 ASSIGN_SET, ASSIGN_ADD, ASSIGN_SUB, ASSIGN_MUL, ASSIGN_DIV, ASSIGN_AMIN, ASSIGN_AMAX = range(7)
 RED_SUM, RED_PROD, RED_AMIN, RED_AMAX = 1, 3, 5, 6

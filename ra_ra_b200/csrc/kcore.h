@@ -591,6 +591,16 @@ interp(KParams const & p, unsigned char const * stage, unsigned char * stack, in
             }
             break;
         }
+        case RACU_OP_LOAD: { // gather: t = opnd[arg][clamp(t)] (unbeaten subscripts, ra/ply.hh:461-499); lanes past the end hold
+            KOpnd const & o = p.opnd[in.arg]; // anything, the clamp keeps every access inside the array
+            unsigned char const * const gb = reinterpret_cast<unsigned char const *>(o.base);
+            RACU_LANES {
+                int64_t off = in.aux==RACU_I32 ? int64_t(int32_t(uint32_t(t[u][j]))) : int64_t(t[u][j]);
+                off = off<o.sA[0] ? o.sA[0] : off>o.sA[1] ? o.sA[1] : off;
+                t[u][j] = load_elem<W>(gb + off*int64_t(o.esize), o.dtype);
+            }
+            break;
+        }
         case RACU_OP_PICK: {
             int n = in.arg;
             RACU_LANES {

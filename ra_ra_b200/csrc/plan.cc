@@ -48,7 +48,7 @@ check_ins(racu_ins const * ins, int nins, racu_operand const * opnd, int nopnd, 
         auto need = [&](int n) { if (sp<n) return false; for (int j=0; j<n; ++j) { if (st[sp-1-j]!=in.type) return false; } return true; };
         switch (in.op) {
         case RACU_OP_PUSH:
-            if (in.arg>=nopnd || opnd[in.arg].dtype!=in.type) return bad(pc, "push");
+            if (in.arg>=nopnd || opnd[in.arg].dtype!=in.type || opnd[in.arg].kind==RACU_PTR) return bad(pc, "push");
             st[sp++] = in.type; break;
         case RACU_OP_CAST:
             if (sp<1 || st[sp-1]!=in.aux || in.aux>=RACU_NDTYPE) return bad(pc, "cast");
@@ -82,6 +82,10 @@ check_ins(racu_ins const * ins, int nins, racu_operand const * opnd, int nopnd, 
             if (sel!=in.aux || is_float(sel)) return bad(pc, "pick selector");
             sp -= n; st[sp-1] = in.type; break;
         }
+        case RACU_OP_LOAD: // gather: integer offset -> element of a RACU_PTR operand
+            if (in.arg>=nopnd || opnd[in.arg].kind!=RACU_PTR || opnd[in.arg].dtype!=in.type) return bad(pc, "load operand");
+            if (sp<1 || st[sp-1]!=in.aux || (in.aux!=RACU_I32 && in.aux!=RACU_I64)) return bad(pc, "load offset");
+            st[sp-1] = in.type; break;
         default: return bad(pc, "opcode");
         }
     }
@@ -95,7 +99,8 @@ check_program(racu_desc const * d, std::string & err)
     if (d->nopnd<=0 || d->nopnd>RACU_MAX_OPND) { err = "bad operand count"; return -1; }
     for (int o=0; o<d->nopnd; ++o) {
         racu_operand const & p = d->opnd[o];
-        if (p.dtype<0 || p.dtype>=RACU_NDTYPE || p.kind<RACU_MEM || p.kind>RACU_SCALAR) { err = "bad operand kind/dtype"; return -1; }
+        if (p.dtype<0 || p.dtype>=RACU_NDTYPE || p.kind<RACU_MEM || p.kind>RACU_PTR) { err = "bad operand kind/dtype"; return -1; }
+        if (p.kind==RACU_PTR && (0!=p.rank || p.len[0]>p.len[1] || !p.base.ptr)) { err = "bad pointer operand"; return -1; }
     }
     return check_ins(d->ins, d->nins, d->opnd, d->nopnd, err);
 }
@@ -170,8 +175,9 @@ namespace {
 struct WOp // working operand
 {
     int kind, dtype;
-    uint64_t base;   // MEM: byte address; else value bits
+    uint64_t base;   // MEM / PTR: byte address; else value bits
     int64_t st[KMAXR];
+    int64_t lo = 0, hi = 0; // PTR: valid element offsets
 };
 
 struct Work
@@ -304,6 +310,7 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
     };
     auto kind_of = [&](KOpnd const & k) -> int {
         if (k.kind==RACU_SCALAR) return SK_SCALAR;
+        if (k.kind==RACU_PTR) return SK_PTR;
         if (k.kind==RACU_SEQ) return k.dtype==RACU_BOOL ? -1 : SK_SEQ;
         if (k.kind!=RACU_MEM) return -1;
         int64_t const es = k.esize;
@@ -330,6 +337,13 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
                 role_of[i.arg] = nrole++;
             }
             seq[pc] = SIns {RACU_OP_PUSH, uint8_t(role_of[i.arg]), i.type, 0};
+        } else if (i.op==RACU_OP_LOAD) { // the gathered array is a role of kind SK_PTR (never fetched as a vector)
+            if (role_of[i.arg]<0) {
+                if (nrole>=SP_MAXIN) return;
+                rtype[nrole] = kp.opnd[i.arg].dtype;
+                role_of[i.arg] = nrole++;
+            }
+            seq[pc] = SIns {RACU_OP_LOAD, uint8_t(role_of[i.arg]), i.type, i.aux};
         } else {
             seq[pc] = SIns {i.op, uint8_t(i.op==RACU_OP_PICK ? i.arg : 0), i.type, uint8_t(i.op==RACU_OP_CAST || i.op==RACU_OP_PICK ? i.aux : 0)};
         }
@@ -408,7 +422,7 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
         if (r<0) continue;
         KOpnd const & k = kp.opnd[o];
         sp.kind[r] = uint8_t(kind_of(k));
-        if (sp.kind[r]==SK_VECREV || sp.kind[r]==SK_SEQ || (map && sp.kind[r]==SK_ROW)) sp.general = 1;
+        if (sp.kind[r]==SK_VECREV || sp.kind[r]==SK_SEQ || sp.kind[r]==SK_PTR || (map && sp.kind[r]==SK_ROW)) sp.general = 1;
         if (k.kind==RACU_SCALAR) { // value bits in the role's type
             switch (k.dtype) {
             case RACU_F32: sp.in[r] = f32_bits(float(bits_f64(k.base))); break;
@@ -420,6 +434,7 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
             sp.in[r] = k.base;
         }
         for (int j=0; j<KGR; ++j) { sp.sB[r][j] = j<kp.rankB ? k.sB[j] : 0; sp.sA[r][j] = j<kp.rankA ? k.sA[j] : 0; }
+        if (k.kind==RACU_PTR) { sp.sA[r][0] = k.sA[0]; sp.sA[r][1] = k.sA[1]; } // valid offsets of a gathered array
     }
     if (fold && kp.mode==K_FOLD_INNER && kp.rankB>=1 && kp.nk>1) {
         for (int r=0; r<nrole; ++r) {
@@ -486,10 +501,11 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
         racu_operand const & p = d->opnd[o];
         WOp x {};
         x.kind = p.kind; x.dtype = p.dtype;
-        if (p.kind==RACU_MEM) x.base = uint64_t(uintptr_t(p.base.ptr));
+        if (p.kind==RACU_MEM || p.kind==RACU_PTR) x.base = uint64_t(uintptr_t(p.base.ptr));
         else if (is_float(p.dtype)) x.base = f64_bits(p.base.f);
         else x.base = uint64_t(p.base.i);
         for (int k=0; k<KMAXR; ++k) x.st[k] = (k<p.rank && p.kind!=RACU_SCALAR) ? p.stride[k] : 0; // Cell::step ra/expr.hh:294-295
+        if (p.kind==RACU_PTR) { x.lo = p.len[0]; x.hi = p.len[1]; }
         w.op.push_back(x);
     }
     w.ins.assign(d->ins, d->ins+d->nins);
@@ -528,6 +544,11 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     {
         uint64_t dlo, dhi; extent(w, w.op[dst], dlo, dhi);
         for (int o=0; o<int(w.op.size()); ++o) {
+            if (o!=dst && w.op[o].kind==RACU_PTR) { // a gathered array: everything it may address
+                uint64_t const es = dtype_size(w.op[o].dtype), lo = w.op[o].base + uint64_t(w.op[o].lo*int64_t(es)), hi = w.op[o].base + uint64_t((w.op[o].hi+1)*int64_t(es));
+                if (lo<dhi && dlo<hi) alias_other = true;
+                continue;
+            }
             if (o==dst || w.op[o].kind!=RACU_MEM) continue;
             uint64_t lo, hi; extent(w, w.op[o], lo, hi);
             if (lo<dhi && dlo<hi) { if (same_view(w, w.op[o], w.op[dst])) alias_same = true; else alias_other = true; }
@@ -692,7 +713,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     // ---- slot width
     bool wide = dtype_size(A)==8;
     for (auto const & o: w.op) wide |= dtype_size(o.dtype)==8;
-    for (auto const & i: prog) wide |= dtype_size(i.type)==8 || (i.op==RACU_OP_CAST && dtype_size(i.aux)==8) || (i.op==RACU_OP_PICK && dtype_size(i.aux)==8);
+    for (auto const & i: prog) wide |= dtype_size(i.type)==8 || (i.op==RACU_OP_CAST && dtype_size(i.aux)==8) || ((i.op==RACU_OP_PICK || i.op==RACU_OP_LOAD) && dtype_size(i.aux)==8);
     int const V = wide ? 2 : 4;
 
     if (nA>KGR || nB>KGR) { err = "more than 4 uncollapsible axes in one group"; return RACU_ERR_PEEL; }
@@ -724,6 +745,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
         for (int j=0; j<nA; ++j) k.sA[j] = x.st[j];
         for (int j=0; j<nB; ++j) k.sB[j] = x.st[nA+j];
         if (x.kind==RACU_SCALAR) { k.stage = S_NONE; continue; }
+        if (x.kind==RACU_PTR) { k.stage = S_NONE; k.sA[0] = x.lo; k.sA[1] = x.hi; continue; } // addressed by RACU_OP_LOAD only
         if (x.kind==RACU_SEQ) { k.stage = S_SEQ; continue; }
         if (0==x.st[0]) { k.stage = S_BCAST; continue; }
         bool vec = 1==x.st[0] && 0==(x.base % uint64_t(V*k.esize));
@@ -750,7 +772,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
         switch (i.op) {
         case RACU_OP_PUSH: if (sd>=1) { k.lvl = uint8_t(sd-1); depth = std::max(depth, sd); } ++sd; break;
         case RACU_OP_CAST: case RACU_OP_NEG: case RACU_OP_ABS: case RACU_OP_SQRT: case RACU_OP_SQR: case RACU_OP_EXP:
-        case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS: case RACU_OP_NOT: break;
+        case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS: case RACU_OP_NOT: case RACU_OP_LOAD: break;
         case RACU_OP_FMA: k.lvl = uint8_t(sd-3); sd -= 2; break;
         case RACU_OP_PICK: k.lvl = uint8_t(sd-1-i.arg); sd -= i.arg; break;
         default: k.lvl = uint8_t(sd-2); --sd; break;

@@ -114,7 +114,7 @@ template <int ID> struct SPX
 
 // The constexpr typed postfix evaluator. x[k]: raw words of role k's vector.
 template <int ID> __device__ __forceinline__ void
-eval_static(uint32_t const (*x)[SPX<ID>::XW], typename SPT<ID>::W * out)
+eval_static(SParams const & p, uint32_t const (*x)[SPX<ID>::XW], typename SPT<ID>::W * out)
 {
     using W = typename SPT<ID>::W;
     constexpr SProg P = SPT<ID>::P;
@@ -133,6 +133,14 @@ eval_static(uint32_t const (*x)[SPX<ID>::XW], typename SPT<ID>::W * out)
         } else if (op>=RACU_OP_NEG && op<=RACU_OP_NOT) {
 #pragma unroll
             for (int j=0; j<SV; ++j) st[sp-1][j] = un_any<W>(op, type, st[sp-1][j]);
+        } else if (op==RACU_OP_LOAD) { // gather (ra/ply.hh:461-499): role arg is the array (SK_PTR), the offset is clamped to its valid range
+            unsigned char const * const gb = reinterpret_cast<unsigned char const *>(p.in[arg]);
+#pragma unroll
+            for (int j=0; j<SV; ++j) {
+                int64_t off = aux==RACU_I32 ? int64_t(int32_t(uint32_t(st[sp-1][j]))) : int64_t(st[sp-1][j]);
+                off = off<p.sA[arg][0] ? p.sA[arg][0] : off>p.sA[arg][1] ? p.sA[arg][1] : off;
+                st[sp-1][j] = load_elem<W>(gb + off*es_of(type), type);
+            }
         } else if (op==RACU_OP_PICK) { // stack: sel a0 .. a(n-1) -> a(sel); n = arg, selector type = aux (ra/expr.hh:686-728)
 #pragma unroll
             for (int j=0; j<SV; ++j) {
@@ -167,6 +175,7 @@ fetch_role(SParams const & p, int k, uint32_t * x, int64_t off, int64_t e0)
     int const kd = GENERAL ? int(p.kind[k]) : (SK_SCALAR==p.kind[k] ? int(SK_SCALAR) : int(SK_VEC));
     unsigned char const * base = reinterpret_cast<unsigned char const *>(p.in[k]);
     if (SK_SCALAR==kd) splat_bits(x, p.in[k], t);
+    else if (GENERAL && SK_PTR==kd) {} // addressed by RACU_OP_LOAD inside the evaluator
     else if (GENERAL && SK_SEQ==kd) seq_words(x, p.in[k], off + e0*p.sA[k][0], p.sA[k][0], t);
     else if (!GENERAL || SK_VEC==kd) {
         if (k==P.yrole) load_words<LD_RW>(x, base + (off+e0)*es, t); else load_words<FORM>(x, base + (off+e0)*es, t);
@@ -218,7 +227,7 @@ smap_body(SParams const & p)
 #pragma unroll
         for (int u=0; u<UNR; ++u) {
             int64_t g = g0 + int64_t(u)*KBLOCK;
-            if (g<p.nvec) { W out[SV]; eval_static<ID>(x[u], out); store_vec<W>(static_cast<unsigned char *>(p.dst) + doff[u]*des, out, P.otype); }
+            if (g<p.nvec) { W out[SV]; eval_static<ID>(p, x[u], out); store_vec<W>(static_cast<unsigned char *>(p.dst) + doff[u]*des, out, P.otype); }
         }
     }
     if (1==p.rankA && 0==blockIdx.x && 0==threadIdx.x) { // tail elements of a flat traversal, one at a time
@@ -230,10 +239,11 @@ smap_body(SParams const & p)
                 int const es = es_of(P.rtype[k]);
                 unsigned char const * base = reinterpret_cast<unsigned char const *>(p.in[k]);
                 if (SK_SCALAR==p.kind[k]) splat_bits(x[k], p.in[k], P.rtype[k]);
+                else if (SK_PTR==p.kind[k]) {}
                 else if (SK_SEQ==p.kind[k]) seq_words(x[k], p.in[k], e*p.sA[k][0], 0, P.rtype[k]);
                 else splat_words(x[k], base + (SK_VEC==p.kind[k] ? e : SK_VECREV==p.kind[k] ? -e : 0)*es, P.rtype[k]);
             }
-            eval_static<ID>(x, out);
+            eval_static<ID>(p, x, out);
             store_elem<W>(static_cast<unsigned char *>(p.dst) + e*des, P.otype, out[0]);
         }
     }
@@ -275,6 +285,7 @@ fetch_fold_role(SParams const & p, int k, uint32_t * x, unsigned char const * ro
     constexpr SProg P = SPT<ID>::P;
     int const t = P.rtype[k], es = es_of(t);
     if (SK_SCALAR==p.kind[k]) splat_bits(x, p.in[k], t);
+    else if (SK_PTR==p.kind[k]) {}
     else if (SK_SEQ==p.kind[k]) seq_words(x, p.in[k], int64_t(reinterpret_cast<intptr_t>(rowbase)) + g*SV*p.sA[k][0], p.sA[k][0], t); // rowbase: the row's offset
     else if (SK_ROW==p.kind[k]) splat_words(x, rowbase, t);
     else load_words<FORM>(x, rowbase + g*SV*es, t);
@@ -332,7 +343,7 @@ sfold_inner_body(SParams const & p, FinishParams const & f)
             int64_t g = g0 + int64_t(u)*KBLOCK;
             if (g<end) {
                 W out[SV];
-                eval_static<ID>(x[u], out);
+                eval_static<ID>(p, x[u], out);
 #pragma unroll
                 for (int j=0; j<SV; ++j) acc[j] = combine<W>(FOLD, AT, acc[j], out[j]);
             }
@@ -348,10 +359,11 @@ sfold_inner_body(SParams const & p, FinishParams const & f)
 #pragma unroll
             for (int k=0; k<P.nin; ++k) {
                 if (SK_SCALAR==p.kind[k]) splat_bits(x[k], p.in[k], P.rtype[k]);
+                else if (SK_PTR==p.kind[k]) {}
                 else if (SK_SEQ==p.kind[k]) seq_words(x[k], p.in[k], int64_t(reinterpret_cast<intptr_t>(rowbase[k])) + e*p.sA[k][0], 0, P.rtype[k]);
                 else splat_words(x[k], rowbase[k] + (SK_ROW==p.kind[k] ? 0 : e)*es_of(P.rtype[k]), P.rtype[k]);
             }
-            eval_static<ID>(x, out);
+            eval_static<ID>(p, x, out);
             r = combine<W>(FOLD, AT, r, out[0]);
         }
     }
@@ -391,7 +403,7 @@ sfold_outer_body(SParams const & p, FinishParams const & f)
         for (int u=0; u<UNR; ++u) {
             if (r+u<r1) {
                 W out[SV];
-                eval_static<ID>(x[u], out);
+                eval_static<ID>(p, x[u], out);
 #pragma unroll
                 for (int j=0; j<SV; ++j) acc[j] = combine<W>(FOLD, AT, acc[j], out[j]);
             }

@@ -107,7 +107,7 @@ constexpr bool
 prog_wide(SProg const & P)
 {
     bool w = P.otype==RACU_I64 || P.otype==RACU_F64;
-    for (int i=0; i<P.n; ++i) w = w || P.ins[i].type==RACU_I64 || P.ins[i].type==RACU_F64 || (P.ins[i].op==RACU_OP_CAST && (P.ins[i].aux==RACU_I64 || P.ins[i].aux==RACU_F64));
+    for (int i=0; i<P.n; ++i) w = w || P.ins[i].type==RACU_I64 || P.ins[i].type==RACU_F64 || ((P.ins[i].op==RACU_OP_CAST || P.ins[i].op==RACU_OP_LOAD) && (P.ins[i].aux==RACU_I64 || P.ins[i].aux==RACU_F64));
     for (int r=0; r<P.nin; ++r) w = w || P.rtype[r]==RACU_I64 || P.rtype[r]==RACU_F64;
     return w;
 }
@@ -115,7 +115,8 @@ prog_wide(SProg const & P)
 constexpr int SV = 4; // elements per static vector (16 bytes of 4-byte elements, 32 bytes of 8-byte ones)
 
 enum { SK_SCALAR = 0, SK_VEC = 1, SK_VECREV = 2 /* unit step backwards: aligned loads, lanes reversed */, SK_ROW = 3 /* step 0 on axis 0: one value per row */,
-       SK_SEQ = 4 /* iota / tindex (ra/expr.hh:79-100): value = origin + element offset, no memory */ };
+       SK_SEQ = 4 /* iota / tindex (ra/expr.hh:79-100): value = origin + element offset, no memory */,
+       SK_PTR = 5 /* gathered array (RACU_OP_LOAD): in[] = base address, sA[][0..1] = valid element offsets; never fetched */ };
 
 struct SParams
 {

@@ -66,7 +66,8 @@ class LenExpr:
         self.f = f
 
     def resolve(self, n):
-        return int(self.f(n))
+        v = self.f(n)
+        return v if isinstance(v, np.ndarray) else int(v)  # (len - std::array {...}: an unbeatable subscript, test/fromu.cc:26)
 
     def _bin(self, other, op):
         g = other.f if isinstance(other, LenExpr) else (lambda n, o=other: o)
@@ -258,6 +259,48 @@ class Op(Expr):
         self.op, self.args, self.optype, self.dtype, self.arg, self.aux = op, args, optype, rtype, arg, aux
 
 
+class Gather(Expr):
+    """a(i ...) with unbeaten subscripts (index arrays / index expressions): ra/ply.hh:461-499,531-549. `view` is the source after
+    its beaten subscripts, `off` the I64 element offset expression sum(index_k * step_k) with every index placed on its own
+    expression axes, [lo, hi] the valid offsets of `view` (the device clamps: the reference asserts, ra/ply.hh:395)."""
+
+    def __init__(self, view, off, lo, hi):
+        self.view, self.off, self.lo, self.hi, self.dtype = view, off, lo, hi, view.dtype
+
+    def assign(self, rhs):
+        raise RaError(abi.ERR_UNSUPPORTED, "a(i ...) with index arrays as an lvalue (scatter) is not on the device path yet")
+    __iadd__ = __isub__ = __imul__ = __itruediv__ = assign
+
+
+def _expr_rank(e):
+    if isinstance(e, Leaf):
+        return e.view.rank
+    if isinstance(e, SeqLeaf):
+        return builtins_len(e.lens)
+    if isinstance(e, HostVec):
+        return 1
+    if isinstance(e, Gather):
+        return _expr_rank(e.off)
+    if isinstance(e, Op):
+        return _builtins.max([_expr_rank(a) for a in e.args] + [0])
+    return 0
+
+
+def _shift_axes(e, n, ex):
+    """The same expression placed n axes further in: its first n axes are dead (len UNB, step 0), like insert<n>."""
+    if n == 0 or isinstance(e, ScalarLeaf):
+        return e
+    if isinstance(e, Leaf):
+        return Leaf(e.view(insert(n)))
+    if isinstance(e, HostVec):
+        return Leaf(ex.from_numpy(e.arr)(insert(n)))
+    if isinstance(e, SeqLeaf):
+        return SeqLeaf(e.dtype, e.org, [UNB] * n + e.lens, [0] * n + e.steps)
+    if isinstance(e, Gather):
+        return Gather(e.view, _shift_axes(e.off, n, ex), e.lo, e.hi)
+    return Op(e.op, [_shift_axes(a, n, ex) for a in e.args], e.optype, e.dtype, e.arg, e.aux)
+
+
 def tindex(w, dtype=I64):
     """ra::_0 .. : index along axis w, dead on the axes before it (Reframe, ra/expr.hh:402-455)."""
     return SeqLeaf(dtype, 0, [UNB] * (w + 1), [0] * w + [1])
@@ -440,6 +483,7 @@ class View:
     def __call__(self, *subs):
         a, ak, pl, bv = self.dims, 0, 0, []
         subs = list(subs)
+        gathers = {}  # position in bv -> integer index expression (unbeaten subscript)
 
         def fsrc(i):  # ra/ply.hh:344-348
             return i.n if isinstance(i, Dots) else 0 if isinstance(i, Insert) else 1
@@ -464,6 +508,15 @@ class View:
                 bv.append([n, s * st])
                 pl += o * st
                 ak += 1
+            elif isinstance(i0, (View, Expr, list, tuple, np.ndarray)) or (isinstance(i0, LenExpr) and ak < self.rank
+                                                                          and isinstance(_wlen(i0, a[ak][0]), np.ndarray)):
+                # unbeaten: the axis is kept whole in the beaten view and addressed through the index expression (:461-499)
+                _ck(ak < self.rank, "Too many subscripts.")
+                ie = as_expr(_wlen(i0, a[ak][0]) if isinstance(i0, LenExpr) else i0)
+                _ck(ie.dtype in (I32, I64), "subscripts must be integers", abi.ERR_BAD_DESC)
+                gathers[builtins_len(bv)] = ie
+                bv.append(list(a[ak]))
+                ak += 1
             elif isinstance(i0, (int, np.integer, LenExpr)):  # :390-398
                 _ck(ak < self.rank, "Too many subscripts.")
                 la, st = a[ak]
@@ -475,7 +528,24 @@ class View:
                 raise RaError(abi.ERR_UNSUPPORTED, "unbeaten (gather) subscripts are not on the device path yet")
         bv += [list(d) for d in a[ak:]]  # trailing axes implied, :374-381
         _ck(builtins_len(bv) <= abi.MAX_RANK, "Rank too large.")
-        return self._at(pl, bv)
+        if not gathers:
+            return self._at(pl, bv)
+        # fromu (:480-499): map(a-as-function, i ..., iota(len) for the other axes): every index gets its own expression axes
+        pos, off, lo, hi = 0, None, 0, 0
+        for q, (ln, st) in enumerate(bv):
+            if q in gathers:
+                ie = gathers[q]
+                term = cast(I64, _shift_axes(ie, pos, self.ex)) * np.int64(st)
+                pos += _expr_rank(ie)
+            else:
+                _ck(ln != UNB, "insert<> next to an index array subscript", abi.ERR_UNSUPPORTED)
+                term = SeqLeaf(I64, 0, [UNB] * pos + [ln], [0] * pos + [1]) * np.int64(st)
+                pos += 1
+            if ln > 0:
+                lo, hi = lo + _builtins.min(0, (ln - 1) * st), hi + _builtins.max(0, (ln - 1) * st)
+            off = term if off is None else off + term
+        _ck(pos <= abi.MAX_RANK, "Rank too large.")
+        return Gather(self._at(pl, bv), off if off is not None else ScalarLeaf(0, I64), lo, hi)
 
     def __getitem__(self, subs):
         if subs is Ellipsis:
@@ -574,6 +644,10 @@ def flatten(e, dst=None, assign=abi.ASSIGN_SET, ex=None):
         p.kind, p.dtype, p.rank = kind, dtype, rank
         if kind == MEM:
             p.base.ptr = base
+        elif kind == abi.PTR:
+            p.base.ptr = base
+            p.len[0], p.len[1] = lens  # smallest / largest valid element offset
+            lens = steps = []
         elif is_float(dtype):
             p.base.f = float(base)
         else:
@@ -614,6 +688,11 @@ def flatten(e, dst=None, assign=abi.ASSIGN_SET, ex=None):
                                             lambda: add_operand(SEQ, n.dtype, builtins_len(n.lens), n.org, n.lens, n.steps)))
         elif isinstance(n, ScalarLeaf):
             emit(abi.OP_PUSH, n.dtype, once(("scalar", n.dtype, repr(n.value)), lambda: add_operand(SCALAR, n.dtype, 0, n.value, [], [])))
+        elif isinstance(n, Gather):
+            walk(n.off)
+            keep.append(n.view.owner)
+            emit(abi.OP_LOAD, n.dtype, once(("ptr", n.view.ptr, n.dtype, n.lo, n.hi),
+                                            lambda: add_operand(abi.PTR, n.dtype, 0, n.view.ptr, [n.lo, n.hi], [])), I64)
         else:
             for a in n.args:
                 walk(a)
@@ -643,6 +722,8 @@ def _reduce(e, redop):
 def _find_ex(e):
     if isinstance(e, Leaf):
         return e.view.ex
+    if isinstance(e, Gather):
+        return e.view.ex
     if isinstance(e, Op):
         for a in e.args:
             x = _find_ex(a)
@@ -655,6 +736,20 @@ def sum(a): return _reduce(a, abi.RED_SUM)  # noqa: A001
 def prod(a): return _reduce(a, abi.RED_PROD)
 def amin(a): return _reduce(a, abi.RED_AMIN)
 def amax(a): return _reduce(a, abi.RED_AMAX)
+
+
+def at(a, i):
+    """ra::at(a, i) (ra/ra.hh:228-239): i holds index TUPLES along its last axis (rank(a) coordinates each); the result has the
+    shape of i without that axis: at(a, i)[...] = a[i[..., 0], i[..., 1], ...]."""
+    _ck(isinstance(a, View) and isinstance(i, View), "at(a, i) takes views", abi.ERR_BAD_DESC)
+    _ck(i.rank >= 1 and i.len(i.rank - 1) == a.rank, "at(): the last axis of i must hold rank(a) coordinates")
+    off, lo, hi = None, 0, 0
+    for k, (ln, st) in enumerate(a.dims):
+        term = cast(I64, Leaf(i(dots(i.rank - 1), k))) * np.int64(st)
+        off = term if off is None else off + term
+        if ln > 0:
+            lo, hi = lo + _builtins.min(0, (ln - 1) * st), hi + _builtins.max(0, (ln - 1) * st)
+    return Gather(a, off if off is not None else ScalarLeaf(0, I64), lo, hi)
 
 
 # any / every / index / lexical_compare (ra/ra.hh:279-304). The reference short-circuits a sequential traversal (early(),

@@ -287,5 +287,29 @@ int main()
         y(1, 1) = 7; y(1, 2) = 0;
         tr.test(rc::lexical_compare(x, y)); tr.test(!rc::lexical_compare(y, x));
     }
+    tr.section("unbeaten subscripts a(i ...): test/fromu.cc:46-67,70-83,107-121");
+    {
+        rc::Big<double, 1> v {7, 9, 3, 4};
+        std::vector<int> i3201 {3, 2, 0, 1};
+        tr.test_eq(vec<double> {4, 3, 7, 9}, v(i3201));
+        rc::Big<int, 2> ii({2, 2}, 0);
+        ii(0, 0) = 3; ii(0, 1) = 2; ii(1, 0) = 0; ii(1, 1) = 1;
+        tr.test_eq(vec<double> {4, 3, 7, 9}, v(ii));                                   // rank-2 index array: result 2x2
+        rc::Big<double, 2> m({2, 2}, rc::_0*2 + rc::_1 + 1);                          // {{1, 2}, {3, 4}}
+        std::vector<int> i01 {0, 1}, i10 {1, 0};
+        tr.test_eq(vec<double> {1, 2, 3, 4}, m(i01, i01));
+        tr.test_eq(vec<double> {2, 1, 4, 3}, m(i01, i10));
+        tr.test_eq(vec<double> {3, 4, 1, 2}, m(i10, i01));
+        tr.test_eq(vec<double> {4, 3, 2, 1}, m(i10, i10));
+        tr.test_eq(vec<double> {4, 2}, m(i10, 1));                                     // mixed unbeaten / scalar
+        tr.test_eq(vec<double> {4, 3}, m(1, i10));
+        rc::Big<int, 2> b({4, 3}, rc::_0*10 + rc::_1);
+        rc::Big<int, 1> rows {3, 0, 3};
+        tr.test_eq(vec<int> {30, 31, 32, 0, 1, 2, 30, 31, 32}, b(rows));               // other axis kept whole
+        std::vector<int> cols {2, 0};
+        tr.test_eq(vec<int> {2, 0, 12, 10, 22, 20, 32, 30}, b(rc::all, cols));
+        tr.test_eq(vec<int> {12*2+1, 10*2+1, 22*2+1, 20*2+1}, b(rc::iota(2, 1), cols)*2 + 1);
+        tr.test_eq(vec<int> {9, 8, 7, 6}, rc::Big<int, 1>({10}, rc::_0)(9 - rc::Big<int, 1> {0, 1, 2, 3})); // index EXPRESSION (test/fromu.cc:26)
+    }
     return tr.summary();
 }

@@ -21,6 +21,9 @@ def make_inputs(ex, seed=11):
         "x": ex.from_numpy(f(M * N)), "y": ex.from_numpy(f(M * N)),              # flat
         "rows": ex.from_numpy(np.zeros(M, np.float32)), "cols": ex.from_numpy(np.zeros(N, np.float32)),
         "mask": ex.from_numpy(np.zeros((M, N), bool)),
+        "ridx": ex.from_numpy(rng.integers(0, M, M).astype(np.int32)),        # row indices (with repeats)
+        "perm": ex.from_numpy(rng.permutation(M * N).astype(np.int64)),       # flat permutation
+        "cidx": ex.from_numpy(rng.integers(0, N, N).astype(np.int32)),
     }
 
 
@@ -46,6 +49,10 @@ CASES = {
     "fold_index_weighted": ("fold", lambda q: (q["x"] * (ra.as_expr(ra.iota(M * N, 1, 1, abi.I32)) % 8), None, 0, abi.RED_SUM)),
     "fold_rows_index": ("foldto", lambda q: (q["A"] * ra.tindex(1, abi.I32) + ra.tindex(0, abi.I32), q["rows"], abi.ASSIGN_ADD, 0)),
     "fold_cols_index": ("foldto", lambda q: (q["C"] * ra.tindex(0, abi.I32) + ra.tindex(1, abi.I32), q["cols"](ra.insert(1)), abi.ASSIGN_ADD, 0)),
+    "gather_rows": ("map", lambda q: (q["A"](q["ridx"]) + q["C"], q["B"], abi.ASSIGN_SET, 0)),                  # B = A(I) + C: whole rows by index (ra/ply.hh:461-499)
+    "gather_flat_perm": ("map", lambda q: (q["x"](q["perm"]) * 2, q["y"], abi.ASSIGN_ADD, 0)),
+    "gather_outer_product": ("map", lambda q: (q["D"](q["ridx"], q["cidx"]), q["B"], abi.ASSIGN_SET, 0)),         # B(i,j) = D(I(i), J(j))
+    "gather_fold": ("fold", lambda q: (q["x"](q["perm"]) * q["y"], None, 0, abi.RED_SUM)),
     "fold_sum_abs_diff_mul": ("fold", lambda q: (ra.abs(q["A"] - q["C"]) * q["C"], None, 0, abi.RED_SUM)),
     "fold_amax_where": ("fold", lambda q: (ra.where(q["A"] > 0, q["A"], -q["C"]), None, 0, abi.RED_AMAX)),
     "fold_rows_inner": ("foldto", lambda q: (q["A"] * q["C"] - q["D"], q["rows"], abi.ASSIGN_ADD, 0)),          # c(i) += f(i,j): fold-inner per row

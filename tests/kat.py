@@ -605,3 +605,33 @@ def lexical_compare_first_difference(ex):
     assert ra.lexical_compare(a, c) and not ra.lexical_compare(c, a)
     x, y = arr(ex, [0.5, 2.5], np.float64), arr(ex, [0.5, -1.], np.float64)
     assert not ra.lexical_compare(x, y) and ra.lexical_compare(y, x)
+
+
+@case
+def unbeaten_subscripts_gather(ex):
+    """test/fromu.cc:23-31,46-67,70-83,107-121: a(i ...) with index arrays is the outer product of the subscripts applied to a
+    (ra/ply.hh:461-499); scalars and iotas mix in; `len` resolves inside an unbeatable subscript."""
+    a = zeros(ex, (10,), np.int32)
+    a.assign(ra.tindex(0, abi.I32))
+    eq(concrete(ex, a(ra.len - np.array([1, 2, 3, 4])), (4,), np.int32), [9, 8, 7, 6])                   # :25-26
+    v = arr(ex, [7, 9, 3, 4], np.float64)
+    eq(concrete(ex, v(np.array([3, 2, 0, 1])), (4,), np.float64), [4, 3, 7, 9])                           # :50
+    eq(concrete(ex, v(arr(ex, [[3, 2], [0, 1]], np.int32)), (2, 2), np.float64), [[4, 3], [7, 9]])        # :63-64 rank-2 index
+    m = arr(ex, [[1, 2], [3, 4]], np.float64)
+    for i, j in (([0, 1], [0, 1]), ([0, 1], [1, 0]), ([1, 0], [0, 1]), ([1, 0], [1, 0])):                 # :75-82
+        eq(concrete(ex, m(np.array(i), np.array(j)), (2, 2), np.float64), m.numpy()[np.ix_(i, j)])
+    eq(concrete(ex, m(np.array([1, 0]), 1), (2,), np.float64), [4, 2])                                    # :111-118 mixed
+    eq(concrete(ex, m(1, np.array([1, 0])), (2,), np.float64), [4, 3])
+    eq(concrete(ex, m(np.array([0, 1]), 1), (2,), np.float64), [2, 4])
+    # index array on one axis, the other kept whole (beaten `all`, implied): rows picked whole
+    b = zeros(ex, (4, 3), np.int32)
+    b.assign(ra.tindex(0, abi.I32) * 10 + ra.tindex(1, abi.I32))
+    eq(concrete(ex, b(np.array([3, 0, 3])), (3, 3), np.int32), b.numpy()[[3, 0, 3]])
+    eq(concrete(ex, b(ra.all, np.array([2, 0])), (4, 2), np.int32), b.numpy()[:, [2, 0]])
+    eq(concrete(ex, b(ra.iota(2, 1), np.array([2, 0])), (2, 2), np.int32), b.numpy()[1:3][:, [2, 0]])
+    # through a transposed / reversed source and inside a larger expression
+    bt = ra.transpose(b, (1, 0))
+    eq(concrete(ex, bt(np.array([2, 0]), np.array([3, 1, 0])) * 2 + 1, (2, 3), np.int32), b.numpy().T[np.ix_([2, 0], [3, 1, 0])] * 2 + 1)
+    # at(a, i): index tuples (ra/ra.hh:228-239; examples/indirect.cc)
+    ij = arr(ex, [[0, 1], [3, 2], [1, 0]], np.int32)
+    eq(concrete(ex, ra.at(b, ij), (3,), np.int32), [1, 32, 10])

@@ -41,7 +41,12 @@ def random_view(rng, ex, shape, dtype, intvals=False):
 def random_expr(rng, ex, shape, depth):
     """Random expression whose operands have a random prefix of `shape` as their own shape."""
     if depth == 0 or rng.integers(0, 4) == 0:
-        kind = rng.integers(0, 6)
+        kind = rng.integers(0, 7)
+        if kind == 6:  # gather: a(i) with an index EXPRESSION of the frame's prefix shape (unbeaten subscript, ra/ply.hh:461-499)
+            r = int(rng.integers(0, len(shape) + 1))
+            iv, _ = random_view(rng, ex, shape[:r], DT[rng.integers(2, 4)])
+            src, _ = random_view(rng, ex, (7,), DT[rng.integers(0, 4)])
+            return src(((ra.as_expr(iv) % 7) + 7) % 7)
         if kind == 0:
             return ra.as_expr(int(rng.integers(-3, 4)))
         if kind == 1:
