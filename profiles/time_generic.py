@@ -32,3 +32,9 @@ run("B = pick(int(A>.5)+int(C>.5), A, C, A+C)", lambda: B.assign(ra.pick(ra.cast
 run("I = (I*3 - I%4) & 7", lambda: I32.assign((I32 * 3 - I32 % 4) & 7), 8 * E)
 run("D(f64) = A(f32)*D + 1", lambda: D.assign(Ah * D + 1.0), (4 + 8 + 8) * E // 2)
 run("amax(abs(A - C))", lambda: ra.amax(ra.abs(A - Cc)), 8 * E)
+# unbeaten subscripts (gather): whole rows by index (bandwidth bound), random flat permutation (32-byte sector per 4-byte element)
+ridx = ex.wrap(torch.randint(0, n, (n,), device=dev, dtype=torch.int32))
+perm = ex.wrap(torch.randperm(n * n, device=dev))
+flatA, flatB = ex.wrap(A.owner.view(-1)), ex.wrap(B.owner.view(-1))
+run("B = A(ridx)   [rows by index]", lambda: B.assign(A(ridx)), 8 * E)
+run("b = a(perm)   [random permutation]", lambda: flatB.assign(flatA(perm)), 16 * E)

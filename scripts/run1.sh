@@ -1,4 +1,3 @@
 set -x
-P="python profiles/prof_ply.py gemv32 gevm32 gevm64 sgemm"
-$P > gpurun_out/plain_prof2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'fold|tc5' -c 12 -o gpurun_out/r01c_gemv_full $P > gpurun_out/ncu_f2.log 2>&1
-tail -3 gpurun_out/ncu_f2.log; cat gpurun_out/plain_prof2.log | tail -5
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; tail -8 gpurun_out/pytest_gpu.log
+timeout 300 python profiles/time_generic.py > gpurun_out/generic_jit.log 2>&1; cat gpurun_out/generic_jit.log
