@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-log2n", type=int, default=27, help="bounded CPU sample size")
     ap.add_argument("--n3", type=int, default=1024, help="global grid edge for --workload stencil")
     ap.add_argument("--no-overlap", action="store_true", help="stencil: exchange then sweep, no stream overlap")
+    ap.add_argument("--laplace", type=int, default=1, help="reduce workload: also run the laplace3d 1024^3 strong-scaling leg (reported under 'laplace3d')")
     ap.add_argument("--halo", default="push", choices=["push", "nccl"],
                     help="stencil at N>1: 'push' = one kernel per step, the sweep stores its edge planes into the neighbours' ghosts over "
                          "NVLink peer memory (racu_stencil_push); 'nccl' = ncclSend/Recv exchange overlapped with the interior sweep")
@@ -373,6 +374,13 @@ def main():
     if args.extras and world == 1:
         extra = run_extras(args, torch, ex, lib, cuda, ra, abi, timed, peak)
 
+    # ---- the other half of BASELINE.json's metric at this N: laplace3d 1024^3, strong scaling, same process and communicator
+    laplace = None
+    if args.laplace:
+        a_t = b_t = a = b = A2 = None  # (the closures above see the rebinding: the 8 GiB of inputs are released)
+        torch.cuda.empty_cache()
+        laplace = run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local, emit=False, steps=50, warmup=6)
+
     cpu = cpu_baseline(args.cpu_log2n) if rank == 0 and world == 1 else None
     if cpu is not None:
         cpu["all_cores_sharded_by_hand"] = cpu_all_cores()
@@ -386,7 +394,7 @@ def main():
                        "bytes_per_step_per_gpu": bytes_step, "sharding": "leading axis, one process per GPU"},
             "frac_of_measured_hbm_peak": value / world / peak,
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "check": check,
-            "extra": extra,
+            "extra": extra, "laplace3d": laplace,
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
@@ -396,12 +404,18 @@ def main():
         dist.destroy_process_group()
 
 
-def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local):
+def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local, emit=True, steps=None, warmup=None):
     """configs[3]: 7-point sweep (bench/bench-stencil3.cc:55-64) on a GLOBAL f32 n^3 grid, slab-sharded along axis 0 with
     an NCCL halo exchange per step (strong scaling: the global grid is fixed as N grows). One step = one sweep + swap."""
     from ra_ra_b200 import parallel
     n = args.n3
     dev = ex.device
+    class _A:  # (steps / warmup of this leg; the other options as given)
+        pass
+    a2 = _A()
+    a2.__dict__.update(vars(args))
+    a2.steps, a2.warmup = steps or args.steps, warmup if warmup is not None else args.warmup
+    args = a2
     sl = parallel.SlabStencil3D((n, n, n), world, rank)
     g = torch.Generator(device=dev)
     g.manual_seed(0x5EED0041 + rank)
@@ -488,8 +502,9 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local)
     peak = float(peaks.get("hbm_gbs", 6650.0))
     gcells = cells / (ms * 1e-3) / 1e9
     sampler.join(timeout=2)
+    line = None
     if rank == 0:
-        print(json.dumps({
+        line = ({
             "metric": "laplace3d Gcells/s", "value": gcells, "unit": "Gcells/s", "n_gpus": world, "steps": nsteps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -503,9 +518,15 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local)
             "roofline": {"bound": "hbm", "kernel": lib.racu_last_kernel().decode(), "achieved": 8 * cells / world / (ms * 1e-3) / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": 8 * cells / world / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                          "note": "per GPU: 8 B/cell algorithmic x cells per GPU / step time (includes exchange when N>1)"},
-            "gpu_launches": launches, "clocks": sampler.summary()}))
+            "gpu_launches": launches, "clocks": sampler.summary()})
     if slab is not None:
         slab.close()
+    del bufs, A, An
+    torch.cuda.empty_cache()
+    if not emit:
+        return line
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         cuda.check(lib.racu_comm_destroy(comm))
         dist.destroy_process_group()
