@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-log2n", type=int, default=27, help="bounded CPU sample size")
     ap.add_argument("--n3", type=int, default=1024, help="global grid edge for --workload stencil")
+    ap.add_argument("--n0", type=int, default=0, help="stencil: extent of the sharded axis if not n3 (e.g. 512 at N=4 gives every GPU the slab it has at N=8 on 1024^3)")
     ap.add_argument("--no-overlap", action="store_true", help="stencil: exchange then sweep, no stream overlap")
     ap.add_argument("--laplace", type=int, default=1, help="reduce workload: also run the laplace3d 1024^3 strong-scaling leg (reported under 'laplace3d')")
     ap.add_argument("--halo", default="push", choices=["push", "nccl"],
@@ -416,7 +417,8 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local,
     a2.__dict__.update(vars(args))
     a2.steps, a2.warmup = steps or args.steps, warmup if warmup is not None else args.warmup
     args = a2
-    sl = parallel.SlabStencil3D((n, n, n), world, rank)
+    n0 = args.n0 or n
+    sl = parallel.SlabStencil3D((n0, n, n), world, rank)
     g = torch.Generator(device=dev)
     g.manual_seed(0x5EED0041 + rank)
     push = world > 1 and args.halo == "push"
@@ -493,7 +495,7 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local,
     sampler.stop_flag = True
     ms = float(ms.item()) / nsteps
     launches = int(lib.racu_launch_count()) if graph is None else launches_per_step * nsteps
-    cells = float(n) ** 3
+    cells = float(n0) * float(n) ** 2
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -508,7 +510,7 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local,
             "metric": "laplace3d Gcells/s", "value": gcells, "unit": "Gcells/s", "n_gpus": world, "steps": nsteps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[3] 7-point stencil f32 {n}^3 global grid, slab-sharded along axis 0, " + (
+            "config": {"workload": f"configs[3] 7-point stencil f32 {n0}x{n}x{n} global grid, slab-sharded along axis 0, " + (
                                    "one kernel per step: sweep + halo push into the neighbours' ghost planes over NVLink peer memory "
                                    "(CUDA IPC), flag lock step" if push else
                                    f"NCCL halo exchange per step, overlap={'off' if overlap is None else 'interior/edges on two streams'}") +
