@@ -891,6 +891,27 @@ transpose_dims(int const * s, rank_t ns, Dim const * src, Dim * dst, rank_t nd) 
 }
 
 // transpose<1, 0>(a): axis k of a goes to axis s[k] of the result; repeated targets give diagonals (:444-461).
+// at(a, i) (ra/ra.hh:228-239): i holds index TUPLES along its last axis (rank(a) coordinates each); the result has the shape of
+// i without that axis: at(a, i)[...] = a[i[..., 0], i[..., 1], ...].
+template <class T, rank_t R, class J, rank_t RI> requires (std::is_integral_v<J>)
+Gather<std::remove_cv_t<T>> at(View<T, R> const & a, View<J, RI> const & i)
+{
+    RACU_CK(i.rank()>=1 && i.len(i.rank()-1)==a.rank(), "at(): the last axis of i must hold rank(a) coordinates");
+    Gather<std::remove_cv_t<T>> g;
+    g.base = a.cp;
+    for (rank_t k=0; k<a.rank(); ++k) {
+        View<J, ANY> ik;                                     // i(dots, k): the k-th coordinate of every tuple
+        ik.cp = i.cp + k*i.dimv[i.rank()-1].step;
+        ik.dimv.assign(i.dimv.begin(), i.dimv.end()-1);
+        dim_t const ln = a.len(k), st = a.dimv[k].step;
+        g.terms.push_back({[ik](Builder & b) { ik.flatten(b); b.template cast<std::remove_cv_t<J>, dim_t>(); }, 0, st});
+        if (ln>0) { g.lo += std::min<dim_t>(0, (ln-1)*st); g.hi += std::max<dim_t>(0, (ln-1)*st); }
+    }
+    return g;
+}
+template <class A, class I> requires (requires (A const & a, I const & i) { a.view(); i.view(); })
+auto at(A const & a, I const & i) { return at(a.view(), i.view()); }
+
 template <int ... s, class T, rank_t R> requires (sizeof...(s)>0)
 auto transpose(View<T, R> const & a)
 {

@@ -54,9 +54,11 @@ check_ins(racu_ins const * ins, int nins, racu_operand const * opnd, int nopnd, 
             if (sp<1 || st[sp-1]!=in.aux || in.aux>=RACU_NDTYPE) return bad(pc, "cast");
             st[sp-1] = in.type; break;
         case RACU_OP_NEG: case RACU_OP_ABS: case RACU_OP_SQR:
-            if (!need(1) || isb) return bad(pc, "unary"); break;
+            if (!need(1) || isb) return bad(pc, "unary");
+            break;
         case RACU_OP_SQRT: case RACU_OP_EXP: case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS:
-            if (!need(1) || !isf) return bad(pc, "float unary"); break;
+            if (!need(1) || !isf) return bad(pc, "float unary");
+            break;
         case RACU_OP_NOT:
             if (!need(1)) return bad(pc, "not");
             st[sp-1] = RACU_BOOL; break;

@@ -309,6 +309,9 @@ int main()
         std::vector<int> cols {2, 0};
         tr.test_eq(vec<int> {2, 0, 12, 10, 22, 20, 32, 30}, b(rc::all, cols));
         tr.test_eq(vec<int> {12*2+1, 10*2+1, 22*2+1, 20*2+1}, b(rc::iota(2, 1), cols)*2 + 1);
+        rc::Big<int, 2> ij({3, 2}, 0);                                                 // at(a, i): index tuples (ra/ra.hh:228-239)
+        ij(0, 1) = 1; ij(1, 0) = 3; ij(1, 1) = 2; ij(2, 0) = 1;
+        tr.test_eq(vec<int> {1, 32, 10}, rc::at(b, ij));
         tr.test_eq(vec<int> {9, 8, 7, 6}, rc::Big<int, 1>({10}, rc::_0)(9 - rc::Big<int, 1> {0, 1, 2, 3})); // index EXPRESSION (test/fromu.cc:26)
     }
     return tr.summary();
