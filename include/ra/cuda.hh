@@ -891,6 +891,51 @@ transpose_dims(int const * s, rank_t ns, Dim const * src, Dim * dst, rank_t nd) 
 }
 
 // transpose<1, 0>(a): axis k of a goes to axis s[k] of the result; repeated targets give diagonals (:444-461).
+// Whole-expression reduction whose result STAYS on the device: dst is a rank-0 view of the expression's type. The reference
+// returns the scalar by value (ra/ra.hh:348-401); chains of reductions and maps then need no host round trip per scalar.
+template <class T, rank_t R, class E> requires (is_ra<E>)
+void reduce_into(View<T, R> const & dst, E const & e, int redop=RACU_RED_SUM)
+{
+    static_assert(std::is_same_v<std::remove_cv_t<T>, typename E::value_type>, "reduce_into: destination type must be the expression's");
+    RACU_CK(0==dst.rank(), "reduce_into needs a rank-0 destination.");
+    Builder b;
+    e.flatten(b);
+    ck_status(racu_reduce_dev(&b.d, redop, dst.cp, stream()));
+}
+
+// Conjugate gradient after Hestenes and Stiefel: examples/cghs.hh:15-45 with rho, sig, tau, t, gam resident on the device
+// (rank-0 views filled by reduce_into, combined by rank-0 maps): one host read per iteration, the convergence test the
+// reference makes at the top of the loop. mult(v, w): w = A v. work: 3 x shape(b). Returns the iteration count.
+template <class Mult, class B, class X, class W>
+int cghs(Mult && mult, B const & b, X & x, W & work, double eps, int max_its=std::numeric_limits<int>::max())
+{
+    Big<double, 1> scal({8}, 0.);
+    work = 0.;
+    auto g = work(0), r = work(1), p = work(2);
+    auto err = scal(0), gg = scal(1), rho = scal(2), sig = scal(3), tau = scal(4), t = scal(5), gam = scal(6);
+    reduce_into(err, sqrm(b));
+    err *= eps*eps;                                          // :26
+    mult(x, g);
+    g = b-g;
+    r = g;
+    int its = 0;
+    for (; its<max_its; ++its) {
+        reduce_into(gg, sqrm(g));
+        auto const e_gg = scal(iota(2)).to_host();           // reduce_sqrm(g) > err   (:33)
+        if (!(e_gg[1]>e_gg[0])) break;
+        mult(r, p);
+        reduce_into(rho, sqrm(p));                           // :35-37
+        reduce_into(sig, r*p);
+        reduce_into(tau, g*r);
+        t = tau/sig;                                         // :38
+        gam = (t*t*rho - tau)/tau;                           // :39
+        x += t*r;                                            // :40-42
+        g -= t*p;
+        r = r*gam + g;
+    }
+    return its;
+}
+
 // at(a, i) (ra/ra.hh:228-239): i holds index TUPLES along its last axis (rank(a) coordinates each); the result has the shape of
 // i without that axis: at(a, i)[...] = a[i[..., 0], i[..., 1], ...].
 template <class T, rank_t R, class J, rank_t RI> requires (std::is_integral_v<J>)

@@ -72,6 +72,10 @@ class CudaExecutor:
     def reduce_dev(self, d, redop, out_tensor):
         check(lib.racu_reduce_dev(C.byref(d), redop, C.c_void_p(out_tensor.data_ptr()), stream_ptr()))
 
+    def reduce_into(self, d, redop, ptr):
+        """Whole-expression reduction into device memory (no host round trip): racu_reduce_dev."""
+        check(lib.racu_reduce_dev(C.byref(d), redop, C.c_void_p(ptr), stream_ptr()))
+
     def last_kernel(self):
         return lib.racu_last_kernel().decode()
 

@@ -719,6 +719,18 @@ def _reduce(e, redop):
     return out
 
 
+def reduce_into(dst, e, redop=abi.RED_SUM):
+    """Whole-expression reduction whose result STAYS where the arrays live: dst is a rank-0 view of the expression's type.
+    The reference returns the scalar by value (ra/ra.hh:348-401); chains of reductions and maps (examples/cghs.hh) then need no
+    host round trip per scalar."""
+    e = as_expr(e)
+    _ck(isinstance(dst, View) and dst.rank == 0 and dst.dtype == e.dtype, "reduce_into needs a rank-0 destination of the expression's type", abi.ERR_BAD_DESC)
+    d, keep = flatten(e, ex=dst.ex)
+    dst.ex.reduce_into(d, redop, dst.ptr)
+    del keep
+    return dst
+
+
 def _find_ex(e):
     if isinstance(e, Leaf):
         return e.view.ex

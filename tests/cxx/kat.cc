@@ -314,5 +314,23 @@ int main()
         tr.test_eq(vec<int> {1, 32, 10}, rc::at(b, ij));
         tr.test_eq(vec<int> {9, 8, 7, 6}, rc::Big<int, 1>({10}, rc::_0)(9 - rc::Big<int, 1> {0, 1, 2, 3})); // index EXPRESSION (test/fromu.cc:26)
     }
+    tr.section("cghs with device resident scalars: examples/laplace2d.cc:60-91, examples/cghs.hh:15-45");
+    {
+        int const N = 50;
+        double const h = 1./N, PI = 3.14159265358979323846;
+        std::vector<double> gv((N+1)*(N+1), 0.), fv((N+1)*(N+1), 0.);
+        for (int i=1; i<N; ++i) for (int j=1; j<N; ++j) { gv[i*(N+1)+j] = std::sin(2*PI*i*h)*std::sin(2*PI*j*h); fv[i*(N+1)+j] = 8*PI*PI*gv[i*(N+1)+j]; }
+        rc::Big<double, 2> v({N+1, N+1}, 0.), w({N+1, N+1}, 0.), u({N+1, N+1}, 0.), b({N+1, N+1}, 0.);
+        rc::ck_status(racu_memcpy_h2d(v.data(), gv.data(), gv.size()*8, rc::stream()));
+        rc::ck_status(racu_memcpy_h2d(w.data(), fv.data(), fv.size()*8, rc::stream()));
+        auto i = rc::iota(N-1, 1), j = rc::iota(N-1, 1);
+        auto mult_stiff = [&](auto const & vv, auto const & ww) { ww(i, j) = 4*vv(i, j) - vv(i-1, j) - vv(i, j-1) - vv(i+1, j) - vv(i, j+1); };
+        b(i, j) = (h*h)*(w(i, j)/2. + (w(i-1, j) + w(i, j-1) + w(i+1, j) + w(i, j+1) + w(i+1, j+1) + w(i-1, j-1))/12.);
+        rc::Big<double, 3> work({3, N+1, N+1}, 0.);
+        int const its = rc::cghs(mult_stiff, b, u, work, 1e-5, 200);
+        double const mx = rc::amax(rc::abs(u-v));
+        tr.test(mx<=0.00463, "max error " + std::to_string(mx));
+        tr.test(its<=67, "iterations " + std::to_string(its));
+    }
     return tr.summary();
 }

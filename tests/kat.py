@@ -635,3 +635,31 @@ def unbeaten_subscripts_gather(ex):
     # at(a, i): index tuples (ra/ra.hh:228-239; examples/indirect.cc)
     ij = arr(ex, [[0, 1], [3, 2], [1, 0]], np.int32)
     eq(concrete(ex, ra.at(b, ij), (3,), np.int32), [1, 32, 10])
+
+
+@case
+def laplace2d_cghs_scalars_on_device(ex):
+    """The same solve as laplace2d_cghs_end_to_end (examples/laplace2d.cc:60-91), through ra_ra_b200.cg.cghs: rho, sig, tau, t and
+    gam never leave the executor's memory. Same pins: max |u - g| <= 0.00463, <= 67 iterations at N = 50, eps = 1e-5."""
+    from ra_ra_b200 import cg
+    N, EPS = 50, 1e-5
+    h = 1. / N
+    x = np.arange(N + 1) * h
+    PI = np.pi
+    g = np.zeros((N + 1, N + 1))
+    f = np.zeros((N + 1, N + 1))
+    g[1:-1, 1:-1] = np.sin(2 * PI * x[1:-1])[:, None] * np.sin(2 * PI * x[1:-1])[None, :]
+    f[1:-1, 1:-1] = 8 * PI * PI * g[1:-1, 1:-1]
+    v, w = ex.from_numpy(g), ex.from_numpy(f)
+    u, b = zeros(ex, (N + 1, N + 1), np.float64), zeros(ex, (N + 1, N + 1), np.float64)
+    i, j = ra.iota(N - 1, 1), ra.iota(N - 1, 1)
+
+    def mult_stiff(vv, ww):  # laplace2d.cc:36
+        ww(i, j).assign(4 * vv(i, j) - vv(i - 1, j) - vv(i, j - 1) - vv(i + 1, j) - vv(i, j + 1))
+    b(i, j).assign(ra.sqrm(h) * (w(i, j) / 2. + (w(i - 1, j) + w(i, j - 1) + w(i + 1, j) + w(i, j + 1) + w(i + 1, j + 1) + w(i - 1, j - 1)) / 12.))
+    work = zeros(ex, (3, N + 1, N + 1), np.float64)
+    scal = zeros(ex, (8,), np.float64)
+    its = cg.cghs(mult_stiff, b, u, work, EPS, scal, max_its=200)
+    mx = ra.amax(ra.abs(u - v))
+    assert mx <= 0.00463, mx
+    assert its <= 67, its

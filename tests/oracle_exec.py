@@ -74,6 +74,13 @@ class OracleExecutor:
         return out[0]
 
 
+def _oracle_reduce_into(self, d, redop, ptr):
+    _check(lib().oracle_reduce(C.byref(d), redop, C.c_void_p(ptr)))
+
+
+OracleExecutor.reduce_into = _oracle_reduce_into
+
+
 def oracle_reverse(dims, k):
     dv = (OracleDim * len(dims))(*[OracleDim(l, s) for l, s in dims])
     off = C.c_int64()

@@ -60,3 +60,8 @@ class SimExecutor(OracleExecutor):
         if st != abi.OK:
             raise ra.RaError(st, lib().racu_sim_last_error().decode())
         return out[0]
+
+    def reduce_into(self, d, redop, ptr):
+        st = lib().racu_sim_run(C.byref(d), redop, C.c_void_p(ptr))
+        if st != abi.OK:
+            raise ra.RaError(st, lib().racu_sim_last_error().decode())
