@@ -482,7 +482,7 @@ constexpr auto operator||(A && a, B && b) { return where(std::forward<A>(a), tru
 // a(i ...) with unbeaten subscripts (index arrays / index expressions): ra/ply.hh:461-499,531-549. The reference maps
 // a-as-a-function over the subscripts, each on its own axes (fromu_loop / wrank); here the element offset
 // sum(index_k * step_k) is an ordinary I64 expression and RACU_OP_LOAD reads a[offset]. Offsets are clamped to the array
-// (the reference asserts on a bad index, ra/ply.hh:395). Rvalue only: scatter through index arrays is not on the device path.
+// (the reference asserts on a bad index, ra/ply.hh:395).
 template <class T> struct Gather: node_tag
 {
     using value_type = T;
@@ -490,7 +490,9 @@ template <class T> struct Gather: node_tag
     T const * base = nullptr;
     dim_t lo = 0, hi = 0;
     std::vector<Term> terms;
-    void flatten(Builder & b) const
+    Gather() = default;
+    Gather(Gather const &) = default;
+    void flatten_offset(Builder & b) const
     {
         if (terms.empty()) b.emit(RACU_OP_PUSH, dtype_of<dim_t>, b.scalar<dim_t>(0));
         for (std::size_t q=0; q<terms.size(); ++q) {
@@ -502,8 +504,29 @@ template <class T> struct Gather: node_tag
             b.emit(RACU_OP_MUL, dtype_of<dim_t>);
             if (q>0) b.emit(RACU_OP_ADD, dtype_of<dim_t>);
         }
+    }
+    void flatten(Builder & b) const
+    {
+        flatten_offset(b);
         b.emit(RACU_OP_LOAD, dtype_of<T>, b.ptr<T>(base, lo, hi), dtype_of<dim_t>);
     }
+    // as an lvalue (test/fromu.cc:53-61,84-92): a[off] OP= x over the frame of the subscripts and x: a scatter. The program leaves
+    // [offset, value] and the destination is the RACU_PTR operand; repeated indices combine in an unspecified order.
+    template <class X> void assign(int op, X const & x) const
+    {
+        Builder b;
+        flatten_offset(b);
+        b.d.dst = b.ptr<T>(base, lo, hi);
+        b.d.assign = op;
+        iter(x).flatten(b);
+        ck_status(racu_map(&b.d, stream()));
+    }
+    Gather const & operator=(Gather const & x) const { assign(RACU_ASSIGN_SET, x); return *this; }
+#define RACU_ASSIGNOP(OP, CODE) \
+    template <class X> requires (is_operand<X>) Gather const & operator OP(X const & x) const { assign(CODE, x); return *this; }
+    RACU_ASSIGNOP(=, RACU_ASSIGN_SET) RACU_ASSIGNOP(+=, RACU_ASSIGN_ADD) RACU_ASSIGNOP(-=, RACU_ASSIGN_SUB)
+    RACU_ASSIGNOP(*=, RACU_ASSIGN_MUL) RACU_ASSIGNOP(/=, RACU_ASSIGN_DIV)
+#undef RACU_ASSIGNOP
 };
 
 // ---------------------

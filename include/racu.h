@@ -167,7 +167,10 @@ typedef enum {
 typedef struct {
     int32_t nopnd;
     int32_t nins;
-    int32_t dst;    /* index of the destination operand (kind MEM), or -1 for racu_reduce */
+    int32_t dst;    /* index of the destination operand (kind MEM), or -1 for racu_reduce. A RACU_PTR destination is a SCATTER
+                       (a(i ...) OP= x with index arrays, ra/ply.hh:461-499 used as an lvalue): the program then leaves TWO values,
+                       [element offset, value in the common type of dst and value]; repeated offsets combine atomically for
+                       += -= *= /= (in an unspecified order) and leave any one of the values for = */
     int32_t assign; /* racu_assign */
     racu_operand opnd[RACU_MAX_OPND];
     racu_ins ins[RACU_MAX_INS];

@@ -133,6 +133,8 @@ check_program(racu_desc const * d)
         default: return -1;
         }
     }
+    // scatter (dst is a RACU_PTR operand): the program leaves [element offset, value]
+    if (d->dst>=0 && d->dst<d->nopnd && d->opnd[d->dst].kind==RACU_PTR) return (2==sp && (st[0]==RACU_I32 || st[0]==RACU_I64)) ? st[1] : -1;
     return 1==sp ? st[0] : -1;
 }
 
@@ -266,7 +268,7 @@ binary(int op, T a, T b)
 
 // Map::operator* (ra/expr.hh:661): op(*leaf...). Pick::operator* (:720) and pick_star (:701-710).
 Val
-eval(racu_desc const * d, Leaf const * leaf)
+eval(racu_desc const * d, Leaf const * leaf, Val * second=nullptr)
 {
     Val st[RACU_MAX_INS+1];
     int sp = 0;
@@ -309,6 +311,7 @@ eval(racu_desc const * d, Leaf const * leaf)
             --sp; break;
         }
     }
+    if (second && sp>=2) *second = st[1];
     return st[0];
 }
 
@@ -354,7 +357,7 @@ check_desc(racu_desc const * d, bool need_dst)
     int rt = check_program(d);
     if (rt<0) return fail(RACU_ERR_BAD_DESC, "bad program");
     if (need_dst) {
-        if (d->dst<0 || d->dst>=d->nopnd || d->opnd[d->dst].kind!=RACU_MEM) return fail(RACU_ERR_BAD_DESC, "bad destination");
+        if (d->dst<0 || d->dst>=d->nopnd || (d->opnd[d->dst].kind!=RACU_MEM && d->opnd[d->dst].kind!=RACU_PTR)) return fail(RACU_ERR_BAD_DESC, "bad destination");
         if (d->assign<RACU_ASSIGN_SET || d->assign>RACU_ASSIGN_AMAX) return fail(RACU_ERR_BAD_DESC, "bad assign op");
         int dt = d->opnd[d->dst].dtype;
         if (d->assign>=RACU_ASSIGN_ADD && d->assign<=RACU_ASSIGN_DIV && (dt==RACU_BOOL || rt==RACU_BOOL))
@@ -429,6 +432,16 @@ oracle_map(racu_desc const * d)
     if (int e = check_desc(d, true)) return e;
     racu_operand const & y = d->opnd[d->dst];
     int dst = d->dst, as = d->assign;
+    if (y.kind==RACU_PTR) { // a(i ...) OP= x with index arrays (test/fromu.cc:53-61,84-92): y = a[offset], sequentially: repeated indices accumulate
+        std::vector<Leaf> leaf(d->nopnd);
+        return ply_ravel(d, [&](Leaf const * lf, Val const & off) {
+            Val x;
+            eval(d, lf, &x); // (the traversal's own eval returned only the bottom of the stack)
+            int64_t o = off.type==RACU_I32 ? int64_t(off.i32) : off.i64;
+            o = o<y.len[0] ? y.len[0] : o>y.len[1] ? y.len[1] : o;
+            assign(as, y.dtype, y.base.ptr, o, x);
+        });
+    }
     return ply_ravel(d, [&](Leaf const * leaf, Val const & x) { assign(as, y.dtype, y.base.ptr, leaf[dst].pos, x); });
 }
 

@@ -101,6 +101,42 @@ store_vector(KParams const & p, KIdx const & a, W const * t)
     }
 }
 
+// Scatter: a[off] OP= x for the live lanes of one vector (a(i ...) OP= x with index arrays, ra/ply.hh:461-499 as an lvalue).
+// Offsets may repeat: on the device the update is an atomic compare-and-swap loop on the element's own 4 or 8 bytes, computing
+// exactly what the sequential reference computes for one element - old -> value type, OP, -> element type - in an unspecified
+// order; `=` leaves any one of the values. Offsets are clamped into the array like RACU_OP_LOAD.
+template <class W> RACU_HD void
+scatter_vector(KParams const & p, W const * off, W const * x, int nvalid)
+{
+    constexpr int V = Lanes<W>::V;
+    KOpnd const & k = p.opnd[p.dst];
+    int const dt = k.dtype, vt = p.acc_type, es = k.esize;
+#pragma unroll
+    for (int j=0; j<V; ++j) {
+        if (j>=nvalid) continue;
+        int64_t o = int64_t(off[j]);
+        o = o<k.sA[0] ? k.sA[0] : o>k.sA[1] ? k.sA[1] : o;
+        unsigned char * const ptr = reinterpret_cast<unsigned char *>(k.base) + o*int64_t(es);
+        if (RACU_ASSIGN_SET==p.fold_op || 1==es) { store_elem<W>(ptr, dt, cast_any<W>(vt, dt, x[j])); continue; }
+        auto rmw = [&](W old) { return cast_any<W>(vt, dt, finish_op<W>(p.fold_op, vt, cast_any<W>(dt, vt, old), x[j])); };
+#if defined(__CUDA_ARCH__)
+        if (4==es) {
+            unsigned int * const w = reinterpret_cast<unsigned int *>(ptr);
+            unsigned int old = *w, assumed;
+            do { assumed = old; old = atomicCAS(w, assumed, (unsigned int)(rmw(W(assumed)))); } while (old!=assumed);
+        } else {
+            if constexpr (sizeof(W)==8) {
+                unsigned long long * const w = reinterpret_cast<unsigned long long *>(ptr);
+                unsigned long long old = *w, assumed;
+                do { assumed = old; old = atomicCAS(w, assumed, (unsigned long long)(rmw(W(assumed)))); } while (old!=assumed);
+            }
+        }
+#else
+        store_elem<W>(ptr, dt, rmw(load_elem<W>(ptr, dt)));
+#endif
+    }
+}
+
 // dst[kept n] = overwrite ? total : dst[kept n] OP total, with the accumulator <-> destination conversions.
 template <class W> RACU_HD void
 finish_apply(FinishParams const & f, int64_t n, W total)

@@ -67,6 +67,8 @@ struct KParams
     int32_t acc_type;         // racu_dtype of the accumulator
     int32_t overwrite;        // folds: result replaces dst instead of combining with its old value (racu_reduce)
     int32_t nchunks;
+    int32_t scatter;          // MAP with a RACU_PTR destination: the program leaves [I64 offset (stack level 0), value]; fold_op = the assign op,
+    int32_t pad0;             // acc_type = the value's type (common type of destination and right hand side)
     uint64_t identity;        // accumulator start value, slot bits
     int64_t len0;             // length of A dim 0 in elements
     int64_t vpr;              // vectors per row = ceil(len0 / V)

@@ -36,7 +36,7 @@ static int common_type(int a, int b)
 
 // Type-checks the postfix program by simulating its type stack. Returns the result dtype, or -1.
 static int
-check_ins(racu_ins const * ins, int nins, racu_operand const * opnd, int nopnd, std::string & err)
+check_ins(racu_ins const * ins, int nins, racu_operand const * opnd, int nopnd, std::string & err, bool scatter=false)
 {
     int st[RACU_MAX_INS+1], sp = 0;
     auto bad = [&](int pc, char const * what) { err = "bad program at instruction " + std::to_string(pc) + ": " + what; return -1; };
@@ -91,6 +91,10 @@ check_ins(racu_ins const * ins, int nins, racu_operand const * opnd, int nopnd, 
         default: return bad(pc, "opcode");
         }
     }
+    if (scatter) { // the destination is a RACU_PTR operand: [element offset, value]
+        if (2!=sp || st[0]!=RACU_I64) { err = "bad scatter program: it must leave an I64 element offset and a value"; return -1; }
+        return st[1];
+    }
     if (1!=sp) { err = "bad program: stack not reduced to one value"; return -1; }
     return st[0];
 }
@@ -104,7 +108,8 @@ check_program(racu_desc const * d, std::string & err)
         if (p.dtype<0 || p.dtype>=RACU_NDTYPE || p.kind<RACU_MEM || p.kind>RACU_PTR) { err = "bad operand kind/dtype"; return -1; }
         if (p.kind==RACU_PTR && (0!=p.rank || p.len[0]>p.len[1] || !p.base.ptr)) { err = "bad pointer operand"; return -1; }
     }
-    return check_ins(d->ins, d->nins, d->opnd, d->nopnd, err);
+    bool const scatter = d->dst>=0 && d->dst<d->nopnd && d->opnd[d->dst].kind==RACU_PTR;
+    return check_ins(d->ins, d->nins, d->opnd, d->nopnd, err, scatter);
 }
 
 // Match::rank / len / check: ra/expr.hh:529-608.
@@ -297,7 +302,7 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
 {
     KParams & kp = plan.kp;
     plan.is_static = false;
-    if (std::getenv("RACU_NO_STATIC")) return;
+    if (std::getenv("RACU_NO_STATIC") || kp.scatter) return; // (scatters run on the interpreting kernel)
     if (int(prog.size())>SP_MAXINS) return;
     bool const map = kp.mode==K_MAP;
     if (!map && kp.rankA!=1) return;
@@ -476,6 +481,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     if (int e = agree(d, sh, err)) return e;
 
     bool const reducing = reduce_out!=nullptr;
+    bool const scatter = !reducing && d->dst>=0 && d->dst<d->nopnd && d->opnd[d->dst].kind==RACU_PTR; // a(i ...) OP= x with index arrays
     int assign = d->assign;
     if (reducing) {
         if (d->dst!=-1) { err = "reduce needs dst = -1"; return RACU_ERR_BAD_DESC; }
@@ -488,7 +494,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
         }
         if (rt==RACU_BOOL && (assign==RACU_ASSIGN_ADD || assign==RACU_ASSIGN_MUL)) { err = "arithmetic reduction of bool"; return RACU_ERR_BAD_DESC; }
     } else {
-        if (d->dst<0 || d->dst>=d->nopnd || d->opnd[d->dst].kind!=RACU_MEM) { err = "bad destination"; return RACU_ERR_BAD_DESC; }
+        if (d->dst<0 || d->dst>=d->nopnd || (d->opnd[d->dst].kind!=RACU_MEM && d->opnd[d->dst].kind!=RACU_PTR)) { err = "bad destination"; return RACU_ERR_BAD_DESC; }
         if (assign<RACU_ASSIGN_SET || assign>RACU_ASSIGN_AMAX) { err = "bad assign op"; return RACU_ERR_BAD_DESC; }
         int dt = d->opnd[d->dst].dtype;
         if (assign>=RACU_ASSIGN_ADD && assign<=RACU_ASSIGN_DIV && (dt==RACU_BOOL || rt==RACU_BOOL)) { err = "arithmetic assign on bool"; return RACU_ERR_BAD_DESC; }
@@ -538,13 +544,14 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     // ---- destination with step 0 on a live axis => fold over those axes
     bool red[KMAXR];
     int nred = 0;
-    for (int k=0; k<w.rank; ++k) { red[k] = 0==w.op[dst].st[k]; nred += red[k]; }
+    for (int k=0; k<w.rank; ++k) { red[k] = !scatter && 0==w.op[dst].st[k]; nred += red[k]; }
     bool fold = nred>0 || reducing;
 
     // aliasing between dst and sources
     bool alias_same = false, alias_other = false;
     {
         uint64_t dlo, dhi; extent(w, w.op[dst], dlo, dhi);
+        if (scatter) { uint64_t const es = dtype_size(D); dlo = w.op[dst].base + uint64_t(w.op[dst].lo*int64_t(es)); dhi = w.op[dst].base + uint64_t((w.op[dst].hi+1)*int64_t(es)); }
         for (int o=0; o<int(w.op.size()); ++o) {
             if (o!=dst && w.op[o].kind==RACU_PTR) { // a gathered array: everything it may address
                 uint64_t const es = dtype_size(w.op[o].dtype), lo = w.op[o].base + uint64_t(w.op[o].lo*int64_t(es)), hi = w.op[o].base + uint64_t((w.op[o].hi+1)*int64_t(es));
@@ -627,7 +634,11 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     // ---- program: fold `dst OP= rhs` into it (maps) or end in the accumulator type (folds)
     std::vector<racu_ins> prog;
     int A = rt; // accumulator type
-    if (!fold) {
+    if (scatter) { // the kernel applies `a[off] OP= value` itself (atomically: offsets may repeat); value in the common type, C++ style
+        A = (assign==RACU_ASSIGN_SET || assign==RACU_ASSIGN_AMIN || assign==RACU_ASSIGN_AMAX) ? D : common_type(D, rt);
+        prog = w.ins;
+        emit_cast(prog, rt, A);
+    } else if (!fold) {
         if (assign==RACU_ASSIGN_SET) {
             prog = w.ins;
             emit_cast(prog, rt, D);
@@ -655,7 +666,21 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     for (int a=0, b=w.rank-1; a<b; ++a, --b) { w.swap(a, b); std::swap(red[a], red[b]); }
     int nA = 0, nB = 0; // group sizes after ordering: axes [0,nA) = group A, [nA, nA+nB) = group B
     int mode = K_MAP;
-    if (!fold) {
+    if (scatter) { // no destination strides: order the axes by the source that moves along most of them
+        int dom = -1, best = -1;
+        for (int o=0; o<int(w.op.size()); ++o) {
+            if (w.op[o].kind!=RACU_MEM) continue;
+            int c = 0; for (int k=0; k<w.rank; ++k) c += w.op[o].st[k]!=0;
+            if (c>best) { best = c; dom = o; }
+        }
+        if (dom>=0) {
+            for (int k=0; k<w.rank; ++k) { if (w.op[dom].st[k]<0) w.flip(k); }
+            sort_axes(w, 0, w.rank, [&](int k) -> int64_t { int64_t s = w.op[dom].st[k]; return 0==s ? std::numeric_limits<int64_t>::max() : s; });
+        }
+        nA = merge_axes(w, 0, w.rank);
+        nB = 0;
+        if (0==nA) { w.len[0] = 1; for (auto & o: w.op) o.st[0] = 0; w.rank = 1; nA = 1; }
+    } else if (!fold) {
         for (int k=0; k<w.rank; ++k) { if (w.op[dst].st[k]<0) w.flip(k); }
         sort_axes(w, 0, w.rank, [&](int k) { return w.op[dst].st[k]; });
         nA = merge_axes(w, 0, w.rank);
@@ -736,6 +761,7 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     // ---- operands: staging mode and slot
     kp.nopnd = int(w.op.size());
     kp.dst = dst;
+    kp.scatter = scatter;
     int nstage = 0, nasync = 0;
     bool used[RACU_MAX_OPND] = {};
     for (auto const & i: prog) { if (i.op==RACU_OP_PUSH) used[i.arg] = true; }

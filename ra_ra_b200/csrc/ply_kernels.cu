@@ -50,7 +50,11 @@ ply_map_kernel(const __grid_constant__ KParams p)
         W t[U][V];
         interp<W, U>(p, stage, stack, sstride, t);
 #pragma unroll
-        for (int u=0; u<U; ++u) { if (nvalid[u]>0) store_vector<W>(p, a[u], t[u]); }
+        for (int u=0; u<U; ++u) {
+            if (nvalid[u]<=0) continue;
+            if (p.scatter) scatter_vector<W>(p, reinterpret_cast<W const *>(stack + u*sstride), t[u], nvalid[u]); // stack level 0: the offsets
+            else store_vector<W>(p, a[u], t[u]);
+        }
     }
 }
 

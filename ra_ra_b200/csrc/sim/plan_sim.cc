@@ -40,7 +40,8 @@ sim_run(Plan & plan)
             { int nv = int(std::min<int64_t>(V, p.len0-a.e0)); stage_group<W, 1, 1, 1>(p, &a, &b, &nv, stage, ss, HostCopy {}); }
             W t[1][V];
             interp<W, 1>(p, stage, stack, ss, t);
-            store_vector<W>(p, a, t[0]);
+            if (p.scatter) scatter_vector<W>(p, reinterpret_cast<W const *>(stack), t[0], int(std::min<int64_t>(V, p.len0-a.e0)));
+            else store_vector<W>(p, a, t[0]);
         }
     } else if (p.mode==K_FOLD_INNER) {
         for (int64_t kb=0; kb<p.nk; ++kb) {

@@ -267,9 +267,19 @@ class Gather(Expr):
     def __init__(self, view, off, lo, hi):
         self.view, self.off, self.lo, self.hi, self.dtype = view, off, lo, hi, view.dtype
 
-    def assign(self, rhs):
-        raise RaError(abi.ERR_UNSUPPORTED, "a(i ...) with index arrays as an lvalue (scatter) is not on the device path yet")
-    __iadd__ = __isub__ = __imul__ = __itruediv__ = assign
+    # as an lvalue (test/fromu.cc:53-61,84-92): a[off] OP= x over the frame of the subscripts and x. Repeated indices combine in an
+    # unspecified order (the reference: sequentially), `=` then leaves any one of the values.
+    def _assign(self, op, rhs):
+        d, keep = flatten(as_expr(rhs), dst=self, assign=op, ex=self.view.ex)
+        self.view.ex.map(d)
+        del keep
+        return self
+
+    def assign(self, rhs): return self._assign(abi.ASSIGN_SET, rhs)
+    def __iadd__(self, rhs): return self._assign(abi.ASSIGN_ADD, rhs)
+    def __isub__(self, rhs): return self._assign(abi.ASSIGN_SUB, rhs)
+    def __imul__(self, rhs): return self._assign(abi.ASSIGN_MUL, rhs)
+    def __itruediv__(self, rhs): return self._assign(abi.ASSIGN_DIV, rhs)
 
 
 def _expr_rank(e):
@@ -556,6 +566,8 @@ class View:
         dst = self[subs]
         if isinstance(rhs, View) and rhs.ptr == dst.ptr and rhs.dims == dst.dims and rhs.owner is dst.owner:
             return  # result of `A[I] += x`
+        if isinstance(rhs, Gather) and isinstance(dst, Gather) and rhs.view.ptr == dst.view.ptr and rhs.view.dims == dst.view.dims:
+            return  # result of `A[I] += x` with index arrays: the scatter already happened
         dst.assign(rhs)
 
     # -- assignment ops: ra/expr.hh:50-60, ra/arrays.hh:131-135
@@ -698,7 +710,12 @@ def flatten(e, dst=None, assign=abi.ASSIGN_SET, ex=None):
                 walk(a)
             emit(n.op, n.optype, n.arg, n.aux)
 
-    if dst is not None:
+    if isinstance(dst, Gather):  # scatter: the program leaves [element offset, value]; the destination is the RACU_PTR operand
+        walk(dst.off)
+        keep.append(dst.view.owner)
+        d.dst = once(("ptr", dst.view.ptr, dst.dtype, dst.lo, dst.hi),
+                     lambda: add_operand(abi.PTR, dst.dtype, 0, dst.view.ptr, [dst.lo, dst.hi], []))
+    elif dst is not None:
         d.dst = once(view_key(dst), lambda: view_operand(dst))
     else:
         d.dst = -1

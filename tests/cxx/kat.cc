@@ -314,6 +314,30 @@ int main()
         tr.test_eq(vec<int> {1, 32, 10}, rc::at(b, ij));
         tr.test_eq(vec<int> {9, 8, 7, 6}, rc::Big<int, 1>({10}, rc::_0)(9 - rc::Big<int, 1> {0, 1, 2, 3})); // index EXPRESSION (test/fromu.cc:26)
     }
+    tr.section("a(i ...) with index arrays as an lvalue: test/fromu.cc:28-31,53-61,84-92");
+    {
+        rc::Big<double, 1> a({4}, 0.);
+        std::vector<int> i3201 {3, 2, 0, 1};
+        a(i3201) = std::vector<double> {9, 7, 1, 4};
+        tr.test_eq(vec<double> {1, 4, 7, 9}, a);
+        a(i3201) = 77.;
+        tr.test_eq(vec<double> {77, 77, 77, 77}, a);
+        rc::Big<double, 2> m({2, 2}, 0.), x({2, 2}, 0.);
+        x(0, 0) = 9; x(0, 1) = 7; x(1, 0) = 1; x(1, 1) = 4;
+        std::vector<int> i10 {1, 0};
+        m(i10, i10) = x;
+        tr.test_eq(vec<double> {4, 1, 7, 9}, m);
+        m(i10, i10) *= x;
+        tr.test_eq(vec<double> {16, 1, 49, 81}, m);
+        m(i10, i10) = std::vector<double> {9, 7};                                      // prefix matching of the right hand side
+        tr.test_eq(vec<double> {7, 7, 9, 9}, m);
+        rc::Big<int, 1> idx {0, 3, 3, 1, 3, 0, 2, 3}, h({5}, 0);
+        h(idx) += 1;                                                                   // repeated indices accumulate
+        tr.test_eq(vec<int> {2, 1, 1, 4, 0}, h);
+        rc::Big<double, 1> src {10, 20, 30, 40}, out({6}, 0.);
+        out(std::vector<int> {5, 0, 2}) = src(std::vector<int> {3, 3, 1})*2 + 1;
+        tr.test_eq(vec<double> {81, 0, 41, 0, 0, 81}, out);
+    }
     tr.section("cghs with device resident scalars: examples/laplace2d.cc:60-91, examples/cghs.hh:15-45");
     {
         int const N = 50;

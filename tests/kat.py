@@ -663,3 +663,49 @@ def laplace2d_cghs_scalars_on_device(ex):
     mx = ra.amax(ra.abs(u - v))
     assert mx <= 0.00463, mx
     assert its <= 67, its
+
+
+@case
+def unbeaten_subscripts_scatter(ex):
+    """test/fromu.cc:28-31,53-61,84-92: a(i ...) with index arrays as an lvalue; the right hand side matches the subscripts' frame by
+    prefix; repeated indices accumulate (sequential in the reference, atomic on the device: exact for integers)."""
+    a = zeros(ex, (4,), np.float64)
+    a(np.array([3, 2, 0, 1])).assign(np.array([9., 7., 1., 4.]))                       # :53-55
+    eq(a, [1, 4, 7, 9])
+    a.assign(0.)
+    a(np.array([3, 2, 0, 1])).assign(77.)                                              # :59-61 rank extension of the right hand side
+    eq(a, [77, 77, 77, 77])
+    m = zeros(ex, (2, 2), np.float64)
+    m(np.array([1, 0]), np.array([1, 0])).assign(arr(ex, [[9, 7], [1, 4]], np.float64))  # :84-86
+    eq(m, [[4, 1], [7, 9]])
+    g = m(np.array([1, 0]), np.array([1, 0]))
+    g *= arr(ex, [[9, 7], [1, 4]], np.float64)                                         # :87-88
+    eq(m, [[16, 1], [49, 81]])
+    m(np.array([1, 0]), np.array([1, 0])).assign(np.array([9., 7.]))                   # :90-91 prefix matching: rows of the frame
+    eq(m, [[7, 7], [9, 9]])
+    b = zeros(ex, (10, 10), np.int32)
+    b.assign(ra.tindex(0, abi.I32) - ra.tindex(1, abi.I32))
+    g = b(ra.len - np.array([1, 3, 4]))                                                # :28-31 whole rows 9, 7, 6
+    g += 100
+    ref = np.arange(10)[:, None] - np.arange(10)[None, :]
+    ref[[9, 7, 6]] += 100
+    eq(b, ref)
+    # repeated indices: a histogram (h(i) += 1), mixed types (float counts += int), and -= through a strided destination
+    idx = arr(ex, [0, 3, 3, 1, 3, 0, 2, 3], np.int32)
+    h = zeros(ex, (5,), np.int32)
+    g = h(idx)
+    g += 1
+    eq(h, [2, 1, 1, 4, 0])
+    hf = zeros(ex, (2, 5), np.float32)
+    g = hf(1)(idx)
+    g += arr(ex, [1, 2, 3, 4, 5, 6, 7, 8], np.int32)
+    eq(hf, [[0, 0, 0, 0, 0], [7, 4, 7, 18, 0]])
+    ht = ra.transpose(zeros(ex, (5, 2), np.float64), (1, 0))
+    g = ht(0)(idx)
+    g -= 0.5
+    eq(ht, [[-1, -.5, -.5, -2, 0], [0, 0, 0, 0, 0]])
+    # gather from one array, scatter into another, in one expression
+    src = arr(ex, [10., 20., 30., 40.], np.float64)
+    out = zeros(ex, (6,), np.float64)
+    out(np.array([5, 0, 2])).assign(src(np.array([3, 3, 1])) * 2 + 1)
+    eq(out, [81, 0, 41, 0, 0, 81])

@@ -79,3 +79,21 @@ def random_expr(rng, ex, shape, depth):
 
 
 SHAPES = [(), (1,), (7,), (4, 5), (3, 1, 6), (2, 3, 4), (5, 2, 3, 2), (9, 8), (2, 2, 2, 2, 3), (33, 5), (6, 130)]
+
+
+def random_scatter(rng, ex):
+    """dst(idx) OP= expr through index arrays (ra/ply.hh:461-499 as an lvalue). Distinct indices for every op (any order gives the
+    same result); repeated indices only for integer += / -= (exact in any order). Returns the destination buffer after the op."""
+    n = int(rng.integers(1, 40))
+    m = n + int(rng.integers(0, 9))
+    dt = DT[rng.integers(0, 4)]
+    dst, _ = random_view(rng, ex, (m,), dt, True)
+    rep = bool(rng.integers(0, 2)) and dt in (np.int32, np.int64)
+    idx = rng.integers(0, m, n) if rep else rng.permutation(m)[:n]
+    iv = ex.from_numpy(idx.astype([np.int32, np.int64][int(rng.integers(0, 2))]))
+    src, _ = random_view(rng, ex, (n,), np.int32 if rep else DT[rng.integers(0, 4)], True)
+    e = ra.as_expr(src) * 2 + ra.tindex(0, abi.I32)
+    op = ["__iadd__", "__isub__"][int(rng.integers(0, 2))] if rep else ["assign", "__iadd__", "__isub__", "__imul__"][int(rng.integers(0, 4))]
+    g = dst(iv)
+    getattr(g, op)(e)
+    return dst

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle_exec import OracleExecutor
-from randexpr import DT, SHAPES, random_expr, random_view
+from randexpr import DT, SHAPES, random_expr, random_scatter, random_view
 from ra_ra_b200 import abi, ra
 
 pytestmark = pytest.mark.gpu
@@ -43,6 +43,29 @@ def test_random_maps_cuda_vs_oracle(seed, exc):
         if outs is None:
             continue
         assert np.array_equal(outs[0], outs[1], equal_nan=True), (seed, assign)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_scatter_cuda_vs_oracle(seed, exc):
+    """a(i) OP= expr with index arrays: atomic read-modify-write on the device, sequential in the oracle; the generator keeps the
+    result independent of the order (distinct indices, or integer += / -= with repeats)."""
+    outs = []
+    for ex in (OracleExecutor(), exc):
+        rng = np.random.default_rng(9000 + seed)
+        outs.append(snapshot(ex, random_scatter(rng, ex)))
+    assert outs[0].dtype == outs[1].dtype and np.array_equal(outs[0], outs[1]), seed
+
+
+def test_scatter_histogram_large(exc):
+    """2^22 increments into 1000 bins (heavy contention on the compare-and-swap loop): counts are exact."""
+    import torch
+    n, bins = 1 << 22, 1000
+    idx_t = torch.randint(0, bins, (n,), device="cuda", dtype=torch.int32)
+    h_t = torch.zeros(bins, device="cuda", dtype=torch.int32)
+    g = exc.wrap(h_t)(exc.wrap(idx_t))
+    g += 1
+    assert exc.last_kernel().startswith("ply_map")
+    assert torch.equal(h_t.long(), torch.bincount(idx_t.long(), minlength=bins))
 
 
 @pytest.mark.parametrize("seed", range(40))

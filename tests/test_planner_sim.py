@@ -14,7 +14,16 @@ def test_kat_on_planner_sim(case):
     case(SimExecutor())
 
 
-from randexpr import DT, SHAPES, random_expr, random_view
+from randexpr import DT, SHAPES, random_expr, random_scatter, random_view
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_scatter_sim_vs_oracle(seed):
+    outs = []
+    for ex in (OracleExecutor(), SimExecutor()):
+        rng = np.random.default_rng(9000 + seed)
+        outs.append(np.array(random_scatter(rng, ex).owner, copy=True))
+    assert outs[0].dtype == outs[1].dtype and np.array_equal(outs[0], outs[1]), seed
 
 
 @pytest.mark.parametrize("seed", range(60))
