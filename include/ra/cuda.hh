@@ -914,6 +914,27 @@ transpose_dims(int const * s, rank_t ns, Dim const * src, Dim * dst, rank_t nd) 
 }
 
 // transpose<1, 0>(a): axis k of a goes to axis s[k] of the result; repeated targets give diagonals (:444-461).
+// ra::stencil(a, lo, hi) (ra/arrays.hh:615-630): a view of rank 2*rank(a) over the same memory; axes [0, r) run over the positions
+// whose neighbourhood [-lo, +hi] is inside a, axes [r, 2r) over the neighbourhood: s[i..., d...] = a[i+d ...].
+template <class T, rank_t R>
+View<T, ANY> stencil(View<T, R> const & a, dim_t lo, dim_t hi)
+{
+    RACU_CK(lo>=0 && hi>=0, "Bad stencil bounds.");
+    View<T, ANY> s;
+    s.cp = a.cp;
+    rank_t const r = a.rank();
+    RACU_CK(2*r<=RACU_MAX_RANK, "Rank too large.");
+    s.dimv.resize(2*r);
+    for (rank_t k=0; k<r; ++k) {
+        RACU_CK(a.len(k)>=lo+hi, "Stencil is too large for array.");
+        s.dimv[k] = Dim {a.len(k)-lo-hi, a.dimv[k].step};
+        s.dimv[r+k] = Dim {lo+hi+1, a.dimv[k].step};
+    }
+    return s;
+}
+template <class A> requires (requires (A const & a) { a.view(); })
+auto stencil(A const & a, dim_t lo, dim_t hi) { return stencil(a.view(), lo, hi); }
+
 // Whole-expression reduction whose result STAYS on the device: dst is a rank-0 view of the expression's type. The reference
 // returns the scalar by value (ra/ra.hh:348-401); chains of reductions and maps then need no host round trip per scalar.
 template <class T, rank_t R, class E> requires (is_ra<E>)

@@ -767,6 +767,20 @@ def amin(a): return _reduce(a, abi.RED_AMIN)
 def amax(a): return _reduce(a, abi.RED_AMAX)
 
 
+def stencil(a, lo, hi):
+    """ra::stencil(a, lo, hi) (ra/arrays.hh:615-630): a view of rank 2*rank(a) over the same memory. Axes [0, r) run over the
+    positions whose whole neighbourhood [-lo, +hi] is inside a, axes [r, 2r) over the neighbourhood: s[i..., d...] = a[i+d ...].
+    `Anext(I,J,K) += stencil(A,1,1) * mask(insert<3>)` is the f_sumprod form of bench/bench-stencil3.cc:94-105."""
+    r = a.rank
+    lo = [lo] * r if isinstance(lo, (int, np.integer)) else list(lo)
+    hi = [hi] * r if isinstance(hi, (int, np.integer)) else list(hi)
+    _ck(_builtins.all(x >= 0 for x in lo + hi), f"Bad stencil bounds lo {lo} hi {hi}.")
+    _ck(_builtins.all(a.len(k) >= lo[k] + hi[k] for k in range(r)), "Stencil is too large for array.")
+    dims = [[a.len(k) - lo[k] - hi[k], a.step(k)] for k in range(r)] + [[lo[k] + hi[k] + 1, a.step(k)] for k in range(r)]
+    _ck(builtins_len(dims) <= abi.MAX_RANK, "Rank too large.")
+    return a._at(0, dims)
+
+
 def at(a, i):
     """ra::at(a, i) (ra/ra.hh:228-239): i holds index TUPLES along its last axis (rank(a) coordinates each); the result has the
     shape of i without that axis: at(a, i)[...] = a[i[..., 0], i[..., 1], ...]."""

@@ -338,6 +338,18 @@ int main()
         out(std::vector<int> {5, 0, 2}) = src(std::vector<int> {3, 3, 1})*2 + 1;
         tr.test_eq(vec<double> {81, 0, 41, 0, 0, 81}, out);
     }
+    tr.section("stencil() view, f_sumprod form: ra/arrays.hh:615-630, bench/bench-stencil2.cc");
+    {
+        rc::Big<double, 2> B({6, 8}, rc::cast<double>((rc::_0*5 + rc::_1*3) % 7)), Bn({6, 8}, 0.), Br({6, 8}, 0.);
+        rc::Big<double, 2> mask({3, 3}, 0.);
+        mask(1, 1) = -4; mask(0, 1) = 1; mask(2, 1) = 1; mask(1, 0) = 1; mask(1, 2) = 1;
+        auto I = rc::iota(4, 1), J = rc::iota(6, 1);
+        Br(I, J) = -4*B(I, J) + B(I+1, J) + B(I, J+1) + B(I-1, J) + B(I, J-1);           // bench-stencil2.cc:53-55
+        auto S = rc::stencil(B, 1, 1);
+        tr.test(4==S.rank() && 4==S.len(0) && 6==S.len(1) && 3==S.len(2) && 3==S.len(3));
+        Bn(I, J) += S*mask(rc::insert<2>);
+        tr.test_eq(Br.to_host(), Bn);
+    }
     tr.section("cghs with device resident scalars: examples/laplace2d.cc:60-91, examples/cghs.hh:15-45");
     {
         int const N = 50;

@@ -709,3 +709,33 @@ def unbeaten_subscripts_scatter(ex):
     out = zeros(ex, (6,), np.float64)
     out(np.array([5, 0, 2])).assign(src(np.array([3, 3, 1])) * 2 + 1)
     eq(out, [81, 0, 41, 0, 0, 81])
+
+
+@case
+def stencil_view_sumprod_form(ex):
+    """ra::stencil (ra/arrays.hh:615-630) and the f_sumprod form of bench/bench-stencil3.cc:94-105,130: Anext(I,J,K) += Astencil * mask
+    with the mask on the neighbourhood axes gives the same sweep as the slice expression of :55-64 (the bench checks its variants
+    against each other); also the 2-D case of bench-stencil2.cc and test/wrank.cc:276."""
+    rng = np.random.default_rng(3)
+    n = (7, 6, 9)
+    a0 = rng.integers(-8, 9, n).astype(np.float64)
+    A, An1, An2 = ex.from_numpy(a0), zeros(ex, n, np.float64), zeros(ex, n, np.float64)
+    I, J, K = (ra.iota(m - 2, 1) for m in n)
+    An1(I, J, K).assign(-6 * A(I, J, K) + A(I + 1, J, K) + A(I, J + 1, K) + A(I, J, K + 1) + A(I - 1, J, K) + A(I, J - 1, K) + A(I, J, K - 1))
+    mask = np.zeros((3, 3, 3))
+    mask[1, 1, 1] = -6
+    for d in ((0, 1, 1), (2, 1, 1), (1, 0, 1), (1, 2, 1), (1, 1, 0), (1, 1, 2)):
+        mask[d] = 1
+    S = ra.stencil(A, 1, 1)
+    assert list(S.shape) == [5, 4, 7, 3, 3, 3], S.shape
+    eq(concrete(ex, S(0, 0, 0, ra.dots(3)), (3, 3, 3), np.float64), a0[:3, :3, :3])    # the neighbourhood of cell (1,1,1) (:141-142)
+    g = An2(I, J, K)
+    g += S * ex.from_numpy(mask)(ra.insert(3))
+    eq(An2, An1.numpy())
+    b0 = rng.integers(-8, 9, (6, 8)).astype(np.float64)
+    B, Bn = ex.from_numpy(b0), zeros(ex, (6, 8), np.float64)
+    g = Bn(ra.iota(4, 1), ra.iota(6, 1))
+    g += ra.stencil(B, 1, 1) * arr(ex, [[0, 1, 0], [1, -4, 1], [0, 1, 0]], np.float64)(ra.insert(2))
+    ref = np.zeros((6, 8))
+    ref[1:-1, 1:-1] = -4 * b0[1:-1, 1:-1] + b0[2:, 1:-1] + b0[1:-1, 2:] + b0[:-2, 1:-1] + b0[1:-1, :-2]
+    eq(Bn, ref)
