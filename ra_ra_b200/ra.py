@@ -258,6 +258,26 @@ class Op(Expr):
     def __init__(self, op, args, optype, rtype, arg=0, aux=0):
         self.op, self.args, self.optype, self.dtype, self.arg, self.aux = op, args, optype, rtype, arg, aux
 
+    # pick / where as an lvalue (test/where.cc:148-157, ra/expr.hh:686-728): `pick(sel, a0, a1, ...) OP= x` updates, per element, the
+    # branch the selector names. On the device: one masked assignment per branch, a_k = pick(sel, ..., a_k OP x at k, ...).
+    def _assign(self, assign_op, rhs):
+        _ck(self.op == abi.OP_PICK and _builtins.all(isinstance(b, Leaf) for b in self.args[1:]),
+            "only pick / where over arrays can be assigned to", abi.ERR_UNSUPPORTED)
+        sel, branches = self.args[0], self.args[1:]
+        binop_of = {abi.ASSIGN_ADD: abi.OP_ADD, abi.ASSIGN_SUB: abi.OP_SUB, abi.ASSIGN_MUL: abi.OP_MUL, abi.ASSIGN_DIV: abi.OP_DIV}
+        for k, b in enumerate(branches):
+            new = as_expr(rhs) if assign_op == abi.ASSIGN_SET else binop(binop_of[assign_op], b, rhs)
+            new = cast(b.dtype, new)
+            b.view.assign(Op(abi.OP_PICK, [sel] + [new if j == k else b for j in range(builtins_len(branches))], b.dtype, b.dtype,
+                             arg=builtins_len(branches), aux=sel.dtype))
+        return self
+
+    def assign(self, rhs): return self._assign(abi.ASSIGN_SET, rhs)
+    def __iadd__(self, rhs): return self._assign(abi.ASSIGN_ADD, rhs)
+    def __isub__(self, rhs): return self._assign(abi.ASSIGN_SUB, rhs)
+    def __imul__(self, rhs): return self._assign(abi.ASSIGN_MUL, rhs)
+    def __itruediv__(self, rhs): return self._assign(abi.ASSIGN_DIV, rhs)
+
 
 class Gather(Expr):
     """a(i ...) with unbeaten subscripts (index arrays / index expressions): ra/ply.hh:461-499,531-549. `view` is the source after
@@ -730,6 +750,7 @@ def flatten(e, dst=None, assign=abi.ASSIGN_SET, ex=None):
 def _reduce(e, redop):
     e = as_expr(e)
     ex = _find_ex(e)
+    _ck(ex is not None, "Bad shapes: the expression has no array operand, so no shape (examples/agreement.cc:56-61).", abi.ERR_SHAPE)
     d, keep = flatten(e, ex=ex)
     out = ex.reduce(d, redop, e.dtype)
     del keep

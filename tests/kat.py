@@ -739,3 +739,196 @@ def stencil_view_sumprod_form(ex):
     ref = np.zeros((6, 8))
     ref[1:-1, 1:-1] = -4 * b0[1:-1, 1:-1] + b0[2:, 1:-1] + b0[1:-1, 2:] + b0[:-2, 1:-1] + b0[1:-1, :-2]
     eq(Bn, ref)
+
+
+@case
+def maxwell_vector_potential(ex):
+    """examples/maxwell.cc:29-88: rank 5/6 slice assignments with `len`, shifted iotas, += on slices, transpose<0,1,2,3,5,4>,
+    the diagonal reduce divA += transpose<0,1,2,3,4,4>(DA). Pinned by the reference: amax(divA) == 0 and
+    F(19,0,0,0,2,1) == 0.3039588939177449 (exact where cos() is the host libm's; 1e-12 on the device's cos)."""
+    H, PI, delta = ra.all, np.pi, 1.
+    o, n, m, l = 20, 20, 2, 2
+    A = zeros(ex, (o, n, m, l, 4), np.float64)
+    DA, F = zeros(ex, (o, n, m, l, 4, 4), np.float64), zeros(ex, (o, n, m, l, 4, 4), np.float64)
+    divA = zeros(ex, (o, n, m, l), np.float64)
+    X, Y = zeros(ex, (n, m, l, 4), np.float64), zeros(ex, (n, m, l, 4), np.float64)
+    A(0, H, H, H, 2).assign(-ra.cos(ra.iota(n) * (2 * PI / n)) / (2 * PI / n))                     # :38
+    A(1, H, H, H, 2).assign(-ra.cos((ra.iota(n) - delta) * (2 * PI / n)) / (2 * PI / n))           # :39
+    L = ra.len
+    for t in range(1, o - 1):                                                                     # :43-60
+        X(ra.iota(L - 1)).assign(A(t, ra.iota(L - 1, 1)))
+        X(L - 1).assign(A(t, 0))
+        g = X(H, ra.iota(L - 1)); g += A(t, H, ra.iota(L - 1, 1))
+        g = X(H, L - 1); g += A(t, H, 0)
+        g = X(H, H, ra.iota(L - 1)); g += A(t, H, H, ra.iota(L - 1, 1))
+        g = X(H, H, L - 1); g += A(t, H, H, 0)
+        Y(ra.iota(L - 1, 1)).assign(A(t, ra.iota(L - 1)))
+        Y(0).assign(A(t, L - 1))
+        g = Y(H, ra.iota(L - 1, 1)); g += A(t, H, ra.iota(L - 1))
+        g = Y(H, 0); g += A(t, H, L - 1)
+        g = Y(H, H, ra.iota(L - 1, 1)); g += A(t, H, H, ra.iota(L - 1))
+        g = Y(H, H, 0); g += A(t, H, H, L - 1)
+        A(t + 1).assign(X + Y - A(t - 1) - 4 * A(t))
+    for k, factor in ((0, +1 / (2 * delta)), (1, -1 / (2 * delta)), (2, -1 / (2 * delta)), (3, -1 / (2 * delta))):   # diff, :64-71
+        if DA.len(k) >= 2:
+            hk, h4k = ra.dots(k), ra.dots(4 - k)
+            DA(hk, ra.iota(L - 2, 1), h4k, k).assign(A(hk, ra.iota(L - 2, 2)) - A(hk, ra.iota(L - 2, 0)))
+            DA(hk, 0, h4k, k).assign(A(hk, 1) - A(hk, L - 1))
+            DA(hk, L - 1, h4k, k).assign(A(hk, 0) - A(hk, L - 2))
+            g = DA(ra.dots(5), k); g *= factor
+    F.assign(ra.transpose(DA, (0, 1, 2, 3, 5, 4)) - DA)                                           # :80
+    divA += ra.transpose(DA, (0, 1, 2, 3, 4, 4))                                                   # :81 prefix matching reduces the last axis
+    assert ra.amax(divA) == 0.                                                                     # :83 Lorentz gauge
+    f = float(F(19, 0, 0, 0, 2, 1).numpy())
+    if ex.name == "cuda":
+        assert abs(f - 0.3039588939177449) <= 1e-12, f
+    else:
+        assert f == 0.3039588939177449, repr(f)                                                    # :88
+    Ey, Bz = F(ra.dots(1), H, 0, 0, 2, 0), F(ra.dots(1), H, 0, 0, 2, 1)                            # :90-92 fields stay within [-1, 1]
+    assert ra.amin(Ey) >= -1 and ra.amax(Ey) <= 1 and ra.amin(Bz) >= -1 and ra.amax(Bz) <= 1
+
+
+@case
+def checkply_reverse_transpose_combinations(ex):
+    """test/ra-1.cc:42-62,225-264: B -= A then B += A; B -= A for every reverse / transpose combination of source and destination."""
+    def check(mkA, mkB, shape):
+        a0 = np.arange(1, 1 + int(np.prod(shape)), dtype=np.int32).reshape(shape)
+        A0, B0 = ex.from_numpy(a0), ex.from_numpy(a0)
+        A, B = mkA(A0), mkB(B0)
+        c = B.numpy().copy()
+        an = A.numpy()
+        B -= A
+        eq(B, c - an)
+        B += A
+        B -= A
+        eq(B, c - an)
+    rev = lambda *ks: (lambda v: [v := ra.reverse(v, k) for k in ks][-1])  # noqa: E731
+    ident = lambda v: v  # noqa: E731
+    for mkA, mkB in ((ident, ident), (rev(0), ident), (ident, rev(0)), (rev(0), rev(0)), (rev(1), ident), (ident, rev(1)), (rev(1), rev(1)),
+                     (ident, rev(0, 1)), (rev(0, 1), ident), (rev(0, 1), rev(0, 1))):
+        check(mkA, mkB, (2, 3))
+    tr = lambda v: ra.transpose(v, (1, 0))  # noqa: E731
+    trr = lambda v: ra.reverse(ra.reverse(ra.transpose(v, (1, 0)), 1), 0)  # noqa: E731
+    for mkA, mkB in ((tr, ident), (ident, tr), (trr, ident), (ident, trr)):
+        check(mkA, mkB, (2, 2))
+
+
+@case
+def agreement_examples(ex):
+    """examples/agreement.cc:22-36,41-55,62-66,70-84: X = A+B-C with shapes [3 4 5], [3 4], [3]; B*7, B*C, B*B; i-j needs a shape;
+    A = b (prefix) against A = c(insert<1>) (skip an axis)."""
+    A, B, C = full(ex, (3, 4, 5), 1., np.float32), full(ex, (3, 4), 2., np.float32), full(ex, (3,), 3., np.float32)
+    X = full(ex, (3, 4, 5), 99., np.float32)
+    X.assign(A + B - C)
+    eq(X, np.zeros((3, 4, 5), np.float32))
+    eq(concrete(ex, B * 7., (3, 4), np.float32), np.full((3, 4), 14., np.float32))
+    c2 = arr(ex, [1, 2, 3], np.float32)
+    eq(concrete(ex, B * c2, (3, 4), np.float32), np.array([[2.] * 4, [4.] * 4, [6.] * 4], np.float32))
+    eq(concrete(ex, B * B, (3, 4), np.float32), np.full((3, 4), 4., np.float32))
+    ij = zeros(ex, (3, 4), np.float32)
+    ij.assign(ra.tindex(0) - ra.tindex(1))
+    eq(ij, (np.arange(3)[:, None] - np.arange(4)[None, :]).astype(np.float32))
+    A2, b, c = zeros(ex, (3, 4), np.float32), arr(ex, [0, 1, 2], np.float32), arr(ex, [0, 1, 2, 3], np.float32)
+    A2.assign(b)
+    eq(A2, np.repeat(np.arange(3, dtype=np.float32)[:, None], 4, 1))
+    A2.assign(c(ra.insert(1)))
+    eq(A2, np.repeat(np.arange(4, dtype=np.float32)[None, :], 3, 0))
+    try:
+        ra.sum(ra.tindex(0) - ra.tindex(1))                          # no shape anywhere: "the following would be invalid" (:60)
+        raise AssertionError("an expression without a shape must not evaluate")
+    except ra.RaError as e:
+        assert e.status == abi.ERR_SHAPE
+
+
+@case
+def frame_old_full_expression_only(ex):
+    """test/frame-old.cc:73-86 (c = b - a with a(3,2), b(3)) and :107-119: agreement is checked on the WHOLE expression: b - _1 has no
+    shape of its own along axis 1 but the destination gives it one."""
+    a = ex.from_numpy(np.arange(1, 7, dtype=np.float64).reshape(3, 2))
+    b = arr(ex, [1, 2, 3], np.float64)
+    c = zeros(ex, (3, 2), np.float64)
+    c.assign(a - b)
+    eq(c, [[0, 1], [1, 2], [2, 3]])
+    a2, b2 = zeros(ex, (2, 2), np.float64), arr(ex, [1., 2.], np.float64)
+    a2.assign(b2 - ra.tindex(1))
+    eq(a2, [[1, 0], [2, 1]])
+
+
+@case
+def where_as_lvalue(ex):
+    """test/where.cc:148-157 [raop01]: where(cond, a, b) = 7 writes a where cond holds and b elsewhere; += likewise."""
+    a, b = zeros(ex, (4,), np.int32), zeros(ex, (4,), np.int32)
+    i = ra.tindex(0, abi.I32)
+    ra.where(ra.logical_and(i > 0, i < 3), a, b).assign(7)
+    eq(a, [0, 7, 7, 0])
+    eq(b, [7, 0, 0, 7])
+    g = ra.where(ra.logical_or(i <= 0, i >= 3), a, b)
+    g += 2
+    eq(a, [2, 7, 7, 2])
+    eq(b, [7, 2, 2, 7])
+    m = arr(ex, [True, False], np.bool_)                              # :163-166 where with index operands as branches
+    eq(concrete(ex, ra.where(m, 3 * ra.tindex(0, abi.I32), 2 * ra.tindex(0, abi.I32)), (2,), np.int32), [0, 2])
+
+
+@case
+def unbounded_expression_raises(ex):
+    """test/checks.cc:159-193: a view with an inserted (unbounded) axis cannot be traversed on its own."""
+    z = zeros(ex, (10,), np.float64)
+    w = z(ra.insert(1), ra.all)
+    try:
+        w *= -1
+        raise AssertionError("w *= -1 over an unbounded axis must raise")
+    except ra.RaError as e:
+        assert e.status == abi.ERR_SHAPE and "unbounded" in str(e)
+    eq(z, np.zeros(10))
+
+
+@case
+def stencil2d_four_steps(ex):
+    """test/wrank.cc:230-280 / bench/bench-stencil2.cc:49-58,124: four sweeps of the 2-D 5-point stencil with buffer swap ("ts must be
+    even bc of swap"), slices against plain loops."""
+    n = 9
+    rng = np.random.default_rng(8)
+    a0 = rng.integers(-4, 5, (n, n)).astype(np.float64)
+    A, An = ex.from_numpy(a0), zeros(ex, (n, n), np.float64)
+    I, J = ra.iota(n - 2, 1), ra.iota(n - 2, 1)
+    ref, refn = a0.copy(), np.zeros((n, n))
+    for _ in range(4):
+        An(I, J).assign(-4 * A(I, J) + A(I + 1, J) + A(I, J + 1) + A(I - 1, J) + A(I, J - 1))
+        A, An = An, A
+        refn[1:-1, 1:-1] = -4 * ref[1:-1, 1:-1] + ref[2:, 1:-1] + ref[1:-1, 2:] + ref[:-2, 1:-1] + ref[1:-1, :-2]
+        ref, refn = refn, ref
+    eq(A, ref)
+    eq(An, refn)
+
+
+@case
+def bench_self_checks(ex):
+    """The exactness checks the reference's benches make on themselves: bench/bench-gemv.cc:87-92 (a = _0-_1, b = 1-2*_0), bench-sum-rows.cc:26-34
+    and bench-sum-cols.cc:23-31 (a = _0-_1: every spelling gives the same integers), bench-reduce-sqrm.cc:31 and bench-dot.cc (constant fills)."""
+    m, n = 37, 53
+    a = zeros(ex, (m, n), np.float64)
+    a.assign(ra.tindex(0) - ra.tindex(1))
+    an = np.arange(m)[:, None] - np.arange(n)[None, :] + 0.
+    b = zeros(ex, (n,), np.float64)
+    b.assign(1 - 2 * ra.tindex(0))
+    c = zeros(ex, (m,), np.float64)
+    ra.gemv(a, b, c)
+    eq(c, an @ (1. - 2 * np.arange(n)))
+    bt = zeros(ex, (m,), np.float64)
+    bt.assign(1 - 2 * ra.tindex(0))
+    c2 = zeros(ex, (n,), np.float64)
+    ra.gevm(bt, a, c2)
+    eq(c2, (1. - 2 * np.arange(m)) @ an)
+    rows, cols = zeros(ex, (n,), np.float64), zeros(ex, (m,), np.float64)
+    g = rows(ra.insert(1))
+    g += a
+    cols += a
+    eq(rows, an.sum(0))
+    eq(cols, an.sum(1))
+    N = 1000
+    x = full(ex, (N, 4), 1.5, np.float32)
+    y = full(ex, (N, 4), 2.0, np.float32)
+    assert ra.reduce_sqrm(x) == np.float32(2.25 * 4 * N)
+    assert ra.dot(x, y) == np.float32(3.0 * 4 * N)
+    assert ra.reduce_sqrm(x - y) == np.float32(0.25 * 4 * N)
