@@ -932,3 +932,65 @@ def bench_self_checks(ex):
     assert ra.reduce_sqrm(x) == np.float32(2.25 * 4 * N)
     assert ra.dot(x, y) == np.float32(3.0 * 4 * N)
     assert ra.reduce_sqrm(x - y) == np.float32(0.25 * 4 * N)
+
+
+def _laplace3d_fem(ex, n):
+    """examples/laplace3d.cc:24-176: trilinear FEM for -laplace u = f on [-1,1]^3; the operator is gather -> 8x8 element matrix
+    -> scatter-add over all elements (mult0, :60-68), written here as ONE fused fold (the gather feeds the element gemv) and ONE
+    scatter per product, then CG with device-resident scalars."""
+    from ra_ra_b200 import cg
+    d00, d16, d23 = 0., -1. / 6., 2. / 3.
+    SM = np.array([[d23, d00, d16, d00, d00, d16, d16, d16], [d00, d23, d00, d16, d16, d00, d16, d16],
+                   [d16, d00, d23, d00, d16, d16, d00, d16], [d00, d16, d00, d23, d16, d16, d16, d00],
+                   [d00, d16, d16, d16, d23, d00, d16, d00], [d16, d00, d16, d16, d00, d23, d00, d16],
+                   [d16, d16, d00, d16, d16, d00, d23, d00], [d16, d16, d16, d00, d00, d16, d00, d23]])
+    d827, d427, d227, d127 = 8. / 27., 4. / 27., 2. / 27., 1. / 27.
+    MM = np.array([[d827, d427, d227, d427, d427, d227, d127, d227], [d427, d827, d427, d227, d227, d427, d227, d127],
+                   [d227, d427, d827, d427, d127, d227, d427, d227], [d427, d227, d427, d827, d227, d127, d227, d427],
+                   [d427, d227, d127, d227, d827, d427, d227, d427], [d227, d427, d227, d127, d427, d827, d427, d227],
+                   [d127, d227, d427, d227, d227, d427, d827, d427], [d227, d127, d227, d427, d427, d227, d427, d827]])
+    ISF = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]])
+    h, PI = 1. / n, np.pi
+    pos = lambda m, i, j, k: m * (m * i + j) + k  # noqa: E731
+    gi = np.arange(n + 1)
+    X, Y, Z = np.meshgrid(-1. + 2. * gi * h, -1. + 2. * gi * h, -1. + 2. * gi * h, indexing="ij")   # V[pos(n+1,i,j,k)] (:113-116)
+    ei, ej, ek = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    EV = np.stack([pos(n + 1, ei + ISF[v][0], ej + ISF[v][1], ek + ISF[v][2]).ravel() for v in range(8)], 1).astype(np.int32)  # :119-122
+    bi, bj = np.meshgrid(gi, gi, indexing="ij")
+    Bnd = np.concatenate([pos(n + 1, 0, bi, bj).ravel(), pos(n + 1, n, bi, bj).ravel(), pos(n + 1, bi, 0, bj).ravel(),
+                          pos(n + 1, bi, n, bj).ravel(), pos(n + 1, bi, bj, 0).ravel(), pos(n + 1, bi, bj, n).ravel()]).astype(np.int32)  # :125-135
+    nv, ne = (n + 1) ** 3, n ** 3
+    ev, bnd = ex.from_numpy(EV), ex.from_numpy(Bnd)
+    T = zeros(ex, (ne, 8), np.float64)
+
+    def make_mult(M, scale):
+        Md = ex.from_numpy(M)
+
+        def mult(v, w):                                              # mult0 (:60-68)
+            T.assign(0.)
+            t = T
+            t += Md(ra.insert(1)) * v(ev(ra.all, ra.insert(1)))      # T(e,a) = sum_b M(a,b) v[EV(e,b)]: gather fused into the fold
+            w.assign(0.)
+            g = w(ev)
+            g += T                                                   # w(E.v) += M . v(E.v): scatter-add, vertices shared by 8 elements
+            w(bnd).assign(0.)                                        # set boundary
+            w *= scale                                               # scale factor
+        return mult
+    fx = .25 * 3. * PI * PI * np.cos(.5 * PI * X) * np.cos(.5 * PI * Y) * np.cos(.5 * PI * Z)
+    gx = np.cos(.5 * PI * X) * np.cos(.5 * PI * Y) * np.cos(.5 * PI * Z)
+    aux, c = ex.from_numpy(fx.ravel()), ex.from_numpy(gx.ravel())
+    b, x = zeros(ex, (nv,), np.float64), zeros(ex, (nv,), np.float64)
+    make_mult(MM, h * h * h)(aux, b)                                 # integral ~ product with the mass matrix (:147-149)
+    work, scal = zeros(ex, (3, nv), np.float64), zeros(ex, (8,), np.float64)
+    its = cg.cghs(make_mult(SM, h), b, x, work, 1e-5, scal, max_its=50)
+    return float(ra.amax(ra.abs(c - x))), its
+
+
+@case
+def laplace3d_fem_gather_scatter(ex):
+    """examples/laplace3d.cc:175-176 pins err <= 0.00033 and its <= 1 at n = 50 (cos cos cos is an eigenfunction of the discrete operator,
+    so CG converges at once). n = 50 on the oracle and on the device; n = 12 on the (slow) planner simulator, error bound scaled by (50/12)^2."""
+    n = 12 if ex.name == "sim" else 50
+    err, its = _laplace3d_fem(ex, n)
+    assert err <= 0.00033 * (50. / n) ** 2, err
+    assert its <= (2 if ex.name == "cuda" else 1), its             # (atomic scatter order: one extra iteration is tolerated on the device)
