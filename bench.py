@@ -51,7 +51,6 @@ def parse():
     ap.add_argument("--halo", default="push", choices=["push", "nccl"],
                     help="stencil at N>1: 'push' = one kernel per step, the sweep stores its edge planes into the neighbours' ghosts over "
                          "NVLink peer memory (racu_stencil_push); 'nccl' = ncclSend/Recv exchange overlapped with the interior sweep")
-    ap.add_argument("--graph", action="store_true", help="stencil: replay a CUDA graph of two steps instead of launching every step from the host (experimental)")
     return ap.parse_args()
 
 
@@ -457,35 +456,14 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local,
     for _ in range(args.warmup + (args.warmup % 2)):
         step()
     barrier()
-    # A step is a few short launches plus an NCCL group: at 8 GPUs (0.17 ms of sweep per step) the host cannot issue them
-    # fast enough, so two steps (an even number: the buffers are back in place) are captured once and replayed.
-    graph = None
-    launches_per_step = None
-    if args.graph and not push:  # (the push step carries its step number: not replayable)
-        lib.racu_launch_count_reset()
-        graph = torch.cuda.CUDAGraph()
-        cap = torch.cuda.Stream()
-        cap.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.graph(graph, stream=cap):
-            step()
-            step()
-        launches_per_step = int(lib.racu_launch_count()) // 2
-        torch.cuda.current_stream().wait_stream(cap)
-        for _ in range(2):
-            graph.replay()
-        barrier()
     nsteps = args.steps + (args.steps % 2)
     lib.racu_launch_count_reset()
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    if graph is not None:
-        for _ in range(nsteps // 2):
-            graph.replay()
-    else:
-        for _ in range(nsteps):
-            step()
+    for _ in range(nsteps):
+        step()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -494,7 +472,7 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local,
     barrier()
     sampler.stop_flag = True
     ms = float(ms.item()) / nsteps
-    launches = int(lib.racu_launch_count()) if graph is None else launches_per_step * nsteps
+    launches = int(lib.racu_launch_count())
     cells = float(n0) * float(n) ** 2
     peaks = {}
     try:
@@ -514,7 +492,7 @@ def run_stencil(args, torch, dist, ex, lib, cuda, abi, comm, world, rank, local,
                                    "one kernel per step: sweep + halo push into the neighbours' ghost planes over NVLink peer memory "
                                    "(CUDA IPC), flag lock step" if push else
                                    f"NCCL halo exchange per step, overlap={'off' if overlap is None else 'interior/edges on two streams'}") +
-                                   f", {'host launches' if graph is None else 'CUDA graph of 2 steps replayed'}",
+                                   ", launched step by step from the host",
                        "l2": "4 GiB per buffer, larger than L2"},
             "halo_timeouts": slab.timed_out() if push else None,
             "roofline": {"bound": "hbm", "kernel": lib.racu_last_kernel().decode(), "achieved": 8 * cells / world / (ms * 1e-3) / 1e9, "peak": peak,

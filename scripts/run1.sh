@@ -1,9 +1,2 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log; tail -6 gpurun_out/pytest_gpu.log
-timeout 500 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['roofline']['frac'], d['e2e'], d['laplace3d'] and {k:d['laplace3d'][k] for k in ('value','ms_per_step','n_gpus')}, d['clocks'])
-for k,v in d['extra'].items(): print(k, v)
-PY
+timeout 600 python -m pytest tests/test_gpu_kat.py tests/test_cxx_header.py -m gpu -x -q > gpurun_out/pytest_kat.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_kat.log; tail -25 gpurun_out/pytest_kat.log
