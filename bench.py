@@ -559,6 +559,52 @@ def run_extras(args, torch, ex, lib, cuda, ra, abi, timed, peak):
                                          "frac_of_measured_hbm_peak": 8 * cells / (ms * 1e-3) / 1e9 / peak,
                                          "kernel": lib.racu_last_kernel().decode()}
         del A, An, bufs
+    torch.cuda.empty_cache()
+    # configs[2]: strided views on f64 1024^3 (transpose, reverse, iota-slice assignment), 16 B per touched element; pure data movement
+    n3 = 1024
+    A_t = torch.empty(n3, n3, n3, device=dev, dtype=torch.float64)
+    A = ex.wrap(A_t)
+    A.assign(ra._0 * (n3 * n3) + ra._1 * n3 + ra._2)  # A[i,j,k] = i n^2 + j n + k: a misplaced element is detectable
+    B_t = torch.zeros_like(A_t)
+    B = ex.wrap(B_t)
+    views = [("B = transpose(A,{2,1,0})", ra.transpose(A, (2, 1, 0)), B, n3 ** 3), ("B = transpose(A,{0,2,1})", ra.transpose(A, (0, 2, 1)), B, n3 ** 3),
+             ("B = reverse(A,2)", ra.reverse(A, 2), B, n3 ** 3), ("B = reverse(A,0)", ra.reverse(A, 0), B, n3 ** 3),
+             ("B(iota(n/2,0,2), all, iota(n,n-1,-1)) = A(iota(n/2), all, all)", A(ra.iota(n3 // 2), ra.all, ra.all),
+              B(ra.iota(n3 // 2, 0, 2), ra.all, ra.iota(n3, n3 - 1, -1)), n3 ** 3 // 2)]
+    for name, src, dst, elems in views:
+        d, keep = ra.flatten(ra.as_expr(src), dst=dst, assign=abi.ASSIGN_SET, ex=ex)
+        ms = timed(lambda: cuda.check(lib.racu_map(C.byref(d), cuda.stream_ptr())), 5, 3)
+        gbs = 16.0 * elems / (ms * 1e-3) / 1e9
+        out["views f64 1024^3: " + name] = {"ms": ms, "GB/s": gbs, "frac_of_measured_hbm_peak": gbs / peak, "kernel": lib.racu_last_kernel().decode()}
+    out["views f64 1024^3: check"] = {"last assignment equals the index arithmetic": bool(torch.equal(B_t[0::2].flip(2), A_t[: n3 // 2]))}
+    del A_t, B_t, A, B, views
+    torch.cuda.empty_cache()
+    # configs[4]: dense contraction and gemv (bench-gemm / bench-gemv), f64 on DMMA and f32 as 3xTF32 on tcgen05; 8192^2 here to keep the
+    # default run short (16384^2 numbers: profiles/r01_sgemm_tcgen05.md)
+    ng = 8192
+    for dt, tname, es in ((torch.float64, "f64", 8), (torch.float32, "f32", 4)):
+        g.manual_seed(0x5EED0051)
+        a_t = torch.rand(ng, ng, generator=g, device=dev, dtype=dt) * 2 - 1
+        g.manual_seed(0x5EED0052)
+        b_t = torch.rand(ng, ng, generator=g, device=dev, dtype=dt) * 2 - 1
+        c_t = torch.zeros(ng, ng, device=dev, dtype=dt)
+        gd = abi.GemmDesc()
+        gd.dtype, gd.M, gd.N, gd.K = (abi.F64 if es == 8 else abi.F32), ng, ng, ng
+        gd.a, gd.lda, gd.b, gd.ldb, gd.c, gd.ldc = a_t.data_ptr(), ng, b_t.data_ptr(), ng, c_t.data_ptr(), ng
+        ms = timed(lambda: cuda.check(lib.racu_gemm(C.byref(gd), cuda.stream_ptr())), 3, 1)
+        kern = lib.racu_last_kernel().decode()
+        c_t.zero_()
+        cuda.check(lib.racu_gemm(C.byref(gd), cuda.stream_ptr()))
+        ref = a_t[:64].double() @ b_t.double()
+        err = float((c_t[:64].double() - ref).abs().max() / (a_t[:64].double().abs() @ b_t.double().abs()).max())
+        out[f"gemm {tname} {ng}^3"] = {"ms": ms, "TFLOP/s": 2.0 * ng ** 3 / (ms * 1e-3) / 1e12, "kernel": kern,
+                                       "max_err_over_sum_abs_products": err, "bound": "tensor pipe (f64: DMMA; f32: 3xTF32 on tcgen05, TMEM accumulator)"}
+        x_t, y_t = torch.rand(ng, device=dev, dtype=dt), torch.zeros(ng, device=dev, dtype=dt)
+        ms = timed(lambda: cuda.check(lib.racu_gemv(gd.dtype, 0, ng, ng, a_t.data_ptr(), ng, x_t.data_ptr(), 1, y_t.data_ptr(), 1, cuda.stream_ptr())), 20, 3)
+        gbs = es * ng * ng / (ms * 1e-3) / 1e9
+        out[f"gemv {tname} {ng}^2"] = {"ms": ms, "GB/s": gbs, "frac_of_measured_hbm_peak": gbs / peak, "kernel": lib.racu_last_kernel().decode(),
+                                       "l2": "matrix %d MiB > L2" % (es * ng * ng >> 20)}
+        del a_t, b_t, c_t, x_t, y_t
     return out
 
 
