@@ -24,6 +24,18 @@ def shard_bounds(n, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard0(view, world, rank):
+    """The slab of `view` this rank owns when an expression is sharded along its leading axis (maps, non-transposing view
+    copies and folds are independent per slab). By prefix matching every operand of rank >= 1 is sliced the same way - a row-broadcast
+    vector is split with the rows - and rank-0 operands are replicated. Transposes that move the sharded axis are not sharded
+    (replicas only): they would need an all-to-all."""
+    from . import ra
+    if view.rank == 0:
+        return view
+    lo, hi = shard_bounds(view.len(0), world, rank)
+    return view(ra.iota(hi - lo, lo))
+
+
 class SlabStencil3D:
     """bench/bench-stencil3.cc:55-64 on a global (n0, n1, n2) array sharded along axis 0.
 

@@ -133,3 +133,34 @@ def test_push_schedule_matches_single_process(world, shape):
     assert np.array_equal(gotA, A) and np.array_equal(gotAn, An)
     for r, sl in enumerate(slabs):
         assert flags[r][0] == (steps if sl.g_lo else 0) and flags[r][1] == (steps if sl.g_hi else 0)
+
+
+def test_shard0_map_and_fold_equal_the_unsharded_result():
+    """B += A*C + v and sum-rows / sum-cols / dot evaluated slab by slab (what each rank of an N-GPU job does) equal the whole-array
+    result; the per-slab partials of the folds add up (the allreduce)."""
+    sys.path.insert(0, HERE)
+    from oracle_exec import OracleExecutor
+    from ra_ra_b200 import ra
+    ex = OracleExecutor()
+    rng = np.random.default_rng(5)
+    m, n = 13, 8
+    a, b, c = (rng.integers(-4, 5, (m, n)).astype(np.float64) for _ in range(3))
+    v = rng.integers(-4, 5, m).astype(np.float64)
+    whole = b + a * c + v[:, None]
+    for world in (1, 2, 3, 5):
+        B = ex.from_numpy(b)
+        A, Cc, V = ex.from_numpy(a), ex.from_numpy(c), ex.from_numpy(v)
+        rows, dot = np.zeros(n), 0.
+        cols = ex.from_numpy(np.zeros(m))
+        for rank in range(world):
+            sA, sB, sC, sV = (parallel.shard0(x, world, rank) for x in (A, B, Cc, V))
+            sB += sA * sC + sV
+            part = ex.from_numpy(np.zeros(n))
+            pr = part(ra.insert(1))
+            pr += sA                                         # sum-rows: every rank holds a full-length partial -> allreduce
+            rows += part.numpy()
+            sc = parallel.shard0(cols, world, rank)          # sum-cols: outputs stay sharded
+            sc += sA
+            dot += float(ra.dot(sA, sC))
+        assert np.array_equal(B.numpy(), whole)
+        assert np.array_equal(rows, a.sum(0)) and np.array_equal(cols.numpy(), a.sum(1)) and dot == float((a * c).sum())
