@@ -559,6 +559,19 @@ typename E::value_type reduce(E const & e, int redop)
     }
 }
 
+// Plan an expression exactly as evaluating it would - a map when `dst` is given (dst OP= e), a whole-array reduction otherwise - and
+// make sure its kernel exists, without launching: a program outside the pre-compiled table is specialised and cached now
+// (racu_prepare). The device analogue of the compiler instantiating ply_ravel for the expression's type. Returns the kernel family.
+template <class E> requires (is_ra<E>)
+std::string prepare(E const & e, int redop=RACU_RED_SUM)
+{
+    Builder b;
+    e.flatten(b);
+    char const * k = "";
+    ck_status(racu_prepare(&b.d, redop, &k));
+    return k ? k : "";
+}
+
 // whole-array reductions: ra/ra.hh:306-322,348-401
 template <class A> requires (is_ra<A>) auto sum(A const & a) { return reduce(iter(a), RACU_RED_SUM); }
 template <class A> requires (is_ra<A>) auto prod(A const & a) { return reduce(iter(a), RACU_RED_PROD); }

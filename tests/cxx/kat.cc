@@ -350,6 +350,12 @@ int main()
         Bn(I, J) += S*mask(rc::insert<2>);
         tr.test_eq(Br.to_host(), Bn);
     }
+    tr.section("prepare: plan + specialise without launching (racu_prepare)");
+    {
+        rc::Big<float, 2> a({8, 16}, 1.f), c({8, 16}, 2.f);
+        tr.test(!rc::prepare(rc::where(a<c, a*c, rc::sqrt(c))).empty());
+        tr.test_eq(vec<float>(128, 1.f), a);                                           // nothing ran
+    }
     tr.section("cghs with device resident scalars: examples/laplace2d.cc:60-91, examples/cghs.hh:15-45");
     {
         int const N = 50;
