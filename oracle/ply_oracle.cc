@@ -416,11 +416,59 @@ ply_ravel(racu_desc const * d, Sink && sink)
     }
 }
 
+// ply_fixed / subply restated: ra/ply.hh:90-153. Same row-major order as ply_ravel but with NO collapsing of axes: a recursion
+// over the outer axes (subply, :105-118) and a flat loop over the innermost one only (:95-104). The reference selects it for static
+// shapes (:161-165) and its own tests run both traversals side by side (TEST(plier), test/ply.cc:35-44); so does this oracle
+// (oracle_set_traversal), which pins the collapse rule of ply_ravel against the traversal that does not need it.
+template <class Sink> int
+ply_fixed(racu_desc const * d, Sink && sink)
+{
+    int32_t rank;
+    dim_t len[RACU_MAX_RANK];
+    if (int e = agree(d, &rank, len)) return e; // validate(a) :131
+    std::vector<Leaf> leaf(d->nopnd);
+    for (int o=0; o<d->nopnd; ++o) { leaf[o].p = &d->opnd[o]; }
+    if (0==rank) { sink(leaf.data(), eval(d, leaf.data())); return RACU_OK; } // :134-139
+    auto order = [&](int k) { return rank-1-k; }; // inside first :142
+    std::vector<dim_t> ss0(d->nopnd);
+    for (int o=0; o<d->nopnd; ++o) { ss0[o] = leaf[o].step(order(0)); } // :145
+    auto subply = [&](auto && self, int k) -> void {
+        if (k<1) { // :94-104
+            std::vector<dim_t> place(d->nopnd);
+            for (int o=0; o<d->nopnd; ++o) { place[o] = leaf[o].pos; }
+            for (dim_t s=len[order(0)]; --s>=0;) {
+                sink(leaf.data(), eval(d, leaf.data()));
+                for (int o=0; o<d->nopnd; ++o) { leaf[o].mov(ss0[o]); }
+            }
+            for (int o=0; o<d->nopnd; ++o) { leaf[o].pos = place[o]; }
+        } else { // :105-118
+            dim_t const size = len[order(k)];
+            for (dim_t i=0; i<size; ++i) {
+                self(self, k-1);
+                for (auto & l: leaf) { l.adv(order(k), 1); }
+            }
+            for (auto & l: leaf) { l.adv(order(k), -size); }
+        }
+    };
+    subply(subply, rank-1);
+    return RACU_OK;
+}
+
+int g_traversal = 0; // 0: ply_ravel, 1: ply_fixed
+
+template <class Sink> int
+traverse(racu_desc const * d, Sink && sink)
+{
+    return g_traversal ? ply_fixed(d, sink) : ply_ravel(d, sink);
+}
+
 } // namespace
 
 extern "C" {
 
 const char * oracle_last_error_string(void) { return g_err; }
+// Which restated traversal the oracle uses: 0 = ply_ravel (ra/ply.hh:21-86, default), 1 = ply_fixed (ra/ply.hh:90-153).
+void oracle_set_traversal(int fixed) { g_traversal = fixed ? 1 : 0; }
 
 int oracle_agree(racu_desc const * d, int32_t * rank_out, int64_t * len_out) { return agree(d, rank_out, len_out); }
 
@@ -433,8 +481,7 @@ oracle_map(racu_desc const * d)
     racu_operand const & y = d->opnd[d->dst];
     int dst = d->dst, as = d->assign;
     if (y.kind==RACU_PTR) { // a(i ...) OP= x with index arrays (test/fromu.cc:53-61,84-92): y = a[offset], sequentially: repeated indices accumulate
-        std::vector<Leaf> leaf(d->nopnd);
-        return ply_ravel(d, [&](Leaf const * lf, Val const & off) {
+        return traverse(d, [&](Leaf const * lf, Val const & off) {
             Val x;
             eval(d, lf, &x); // (the traversal's own eval returned only the bottom of the stack)
             int64_t o = off.type==RACU_I32 ? int64_t(off.i32) : off.i64;
@@ -442,7 +489,7 @@ oracle_map(racu_desc const * d)
             assign(as, y.dtype, y.base.ptr, o, x);
         });
     }
-    return ply_ravel(d, [&](Leaf const * leaf, Val const & x) { assign(as, y.dtype, y.base.ptr, leaf[dst].pos, x); });
+    return traverse(d, [&](Leaf const * leaf, Val const & x) { assign(as, y.dtype, y.base.ptr, leaf[dst].pos, x); });
 }
 
 // sum / prod / amin / amax / dot / reduce_sqrm: ra/ra.hh:306-322,348-401. The accumulator has the program's result type
@@ -474,7 +521,7 @@ oracle_reduce(racu_desc const * d, int redop, void * out)
         }
         return 0;
     });
-    return ply_ravel(d, [&](Leaf const *, Val const & x) { assign(as, rt, out, 0, x); });
+    return traverse(d, [&](Leaf const *, Val const & x) { assign(as, rt, out, 0, x); });
 }
 
 // ---------------- view algebra (host only in the reference; O(rank)) ----------------

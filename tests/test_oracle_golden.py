@@ -13,6 +13,44 @@ def test_kat_on_oracle(case):
     case(OracleExecutor())
 
 
+@pytest.fixture
+def fixed_traversal():
+    from oracle_exec import lib
+    lib().oracle_set_traversal(1)
+    yield
+    lib().oracle_set_traversal(0)
+
+
+@pytest.mark.parametrize("case", kat.CASES, ids=lambda f: f.__name__)
+def test_kat_on_oracle_ply_fixed(case, fixed_traversal):
+    """The reference runs its traversal tests through ply_ravel AND ply_fixed (TEST(plier), test/ply.cc:35-44); so does the oracle:
+    the same known answers through the restated ply_fixed (ra/ply.hh:90-153: no collapsing of axes)."""
+    case(OracleExecutor())
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_ply_ravel_and_ply_fixed_agree_on_random_expressions(seed):
+    from oracle_exec import lib
+    from randexpr import DT, SHAPES, random_expr, random_view
+    outs = []
+    for fixed in (0, 1):
+        lib().oracle_set_traversal(fixed)
+        try:
+            rng = np.random.default_rng(2000 + seed)
+            ex = OracleExecutor()
+            shape = SHAPES[seed % len(SHAPES)]
+            dst, _ = random_view(rng, ex, shape, DT[rng.integers(0, 4)])
+            e = random_expr(rng, ex, shape, 2)
+            try:
+                dst += e
+            except ra.RaError as err:
+                assert err.status == abi.ERR_UNSUPPORTED, err
+            outs.append(np.array(dst.owner, copy=True))
+        finally:
+            lib().oracle_set_traversal(0)
+    assert np.array_equal(outs[0], outs[1], equal_nan=True)
+
+
 def test_view_algebra_matches_oracle():
     ex = OracleExecutor()
     a = ex.wrap(np.zeros((3, 4, 5, 6)))
