@@ -948,6 +948,39 @@ View<T, ANY> stencil(View<T, R> const & a, dim_t lo, dim_t hi)
 template <class A> requires (requires (A const & a) { a.view(); })
 auto stencil(A const & a, dim_t lo, dim_t hi) { return stencil(a.view(), lo, hi); }
 
+// refmin / refmax (ra/ra.hh:326-346): a REFERENCE to the first smallest / largest element in row-major order - here a rank-0 view of
+// it, assignable like the reference's `double &`. Two folds: the extreme value, then the smallest row-major position holding it.
+template <class T, rank_t R>
+View<T, 0> ref_extreme(View<T, R> const & a, int redop)
+{
+    RACU_CK(a.size()>0, "refmin requires nonempty argument.");
+    using V0 = std::remove_cv_t<T>;
+    V0 const m = reduce(a, redop);
+    rank_t const r = a.rank();
+    RACU_ASSERT(r<=5, RACU_ERR_UNSUPPORTED, std::string("refmin / refmax: rank > 5"));
+    constexpr dim_t none = std::numeric_limits<dim_t>::max();
+    dim_t st[5] = {0, 0, 0, 0, 0}, acc = 1, first = 0;
+    for (rank_t k=r-1; k>=0; --k) { st[k] = acc; acc *= a.len(k); }
+    auto hit = [&](auto const & pos) { return reduce(where(a==m, pos, none), RACU_RED_AMIN); };
+    switch (r) {
+    case 0: break;
+    case 1: first = hit(_0*st[0]); break;
+    case 2: first = hit(_0*st[0] + _1*st[1]); break;
+    case 3: first = hit(_0*st[0] + _1*st[1] + _2*st[2]); break;
+    case 4: first = hit(_0*st[0] + _1*st[1] + _2*st[2] + _3*st[3]); break;
+    default: first = hit(_0*st[0] + _1*st[1] + _2*st[2] + _3*st[3] + _4*st[4]); break;
+    }
+    View<T, 0> v;
+    dim_t off = 0;
+    for (rank_t k=0; k<r; ++k) { off += (first/st[k])*a.dimv[k].step; first %= st[k]; }
+    v.cp = a.cp + off;
+    return v;
+}
+template <class A> requires (requires (A const & a) { a.view(); }) auto refmin(A const & a) { return ref_extreme(a.view(), RACU_RED_AMIN); }
+template <class A> requires (requires (A const & a) { a.view(); }) auto refmax(A const & a) { return ref_extreme(a.view(), RACU_RED_AMAX); }
+template <class T, rank_t R> auto refmin(View<T, R> const & a) { return ref_extreme(a, RACU_RED_AMIN); }
+template <class T, rank_t R> auto refmax(View<T, R> const & a) { return ref_extreme(a, RACU_RED_AMAX); }
+
 // Whole-expression reduction whose result STAYS on the device: dst is a rank-0 view of the expression's type. The reference
 // returns the scalar by value (ra/ra.hh:348-401); chains of reductions and maps then need no host round trip per scalar.
 template <class T, rank_t R, class E> requires (is_ra<E>)

@@ -857,6 +857,32 @@ def lexical_compare(a, b):
     return key != _NONE and key % 2 == 0
 
 
+def _ref_extreme(a, redop):
+    """refmin / refmax (ra/ra.hh:326-346): a REFERENCE to the first smallest / largest element in row-major order, here a rank-0 view
+    of it (assignable like the reference's double &). Two folds: the extreme value, then the smallest row-major position holding it."""
+    _ck(isinstance(a, View), "refmin / refmax need an array (an lvalue), not an expression", abi.ERR_BAD_DESC)
+    _ck(a.size > 0, "refmin requires nonempty argument.")
+    m = _reduce(a, redop)
+    shape = a.shape
+    if builtins_len(shape) == 0:
+        return a
+    pos, acc = None, 1
+    for k in range(builtins_len(shape) - 1, -1, -1):
+        term = tindex(k, I64) * np.int64(acc)
+        pos = term if pos is None else pos + term
+        acc *= shape[k]
+    first = int(_reduce(where(as_expr(a).eq(RACU2NP[a.dtype].type(m)), pos, np.int64(_NONE)), abi.RED_AMIN))
+    idx = []
+    for k in range(builtins_len(shape) - 1, -1, -1):
+        idx.append(first % shape[k])
+        first //= shape[k]
+    return a(*reversed(idx))
+
+
+def refmin(a): return _ref_extreme(a, abi.RED_AMIN)
+def refmax(a): return _ref_extreme(a, abi.RED_AMAX)
+
+
 def dot(a, b):
     """ra/ra.hh:379-385 with RA_FMA=0: c += a*b."""
     return _reduce(as_expr(a) * b, abi.RED_SUM)

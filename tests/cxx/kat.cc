@@ -350,6 +350,25 @@ int main()
         Bn(I, J) += S*mask(rc::insert<2>);
         tr.test_eq(Br.to_host(), Bn);
     }
+    tr.section("reference reductions refmin / refmax: test/reduction.cc:404-424");
+    {
+        rc::Big<double, 2> A({2, 3}, rc::_1 - rc::_0), B({2, 3}, rc::_1 - rc::_0);
+        auto mn = rc::refmin(A);
+        tr.test(-1==double(mn));
+        mn = -99.;
+        B(1, 0) = -99.;
+        tr.test_eq(B.to_host(), A);
+        auto mx = rc::refmax(A);
+        tr.test(2==double(mx));
+        mx = 0.;
+        B(0, 2) = 0.;
+        tr.test_eq(B.to_host(), A);
+        auto my = rc::refmax(A);                                                      // the first of the two 1s: A(0, 1)
+        tr.test(1==double(my));
+        my = 77.;
+        B(0, 1) = 77.;
+        tr.test_eq(B.to_host(), A);
+    }
     tr.section("prepare: plan + specialise without launching (racu_prepare)");
     {
         rc::Big<float, 2> a({8, 16}, 1.f), c({8, 16}, 2.f);

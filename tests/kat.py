@@ -994,3 +994,26 @@ def laplace3d_fem_gather_scatter(ex):
     err, its = _laplace3d_fem(ex, n)
     assert err <= 0.00033 * (50. / n) ** 2, err
     assert its <= (2 if ex.name == "cuda" else 1), its             # (atomic scatter order: one extra iteration is tolerated on the device)
+
+
+@case
+def reference_reductions_refmin_refmax(ex):
+    """test/reduction.cc:404-424: refmin / refmax return a reference to the FIRST extreme element; assigning through it changes the array."""
+    A = zeros(ex, (2, 3), np.float64)
+    A.assign(ra.tindex(1) - ra.tindex(0))                 # {{0, 1, 2}, {-1, 0, 1}}
+    B = A.numpy().copy()
+    mn = ra.refmin(A)
+    eq(mn, -1.)
+    mn.assign(-99.)
+    B[1, 0] = -99
+    eq(A, B)
+    mx = ra.refmax(A)                                     # (the reference spells this refmin(A, std::greater<double>()))
+    eq(mx, 2.)
+    mx.assign(0.)
+    B[0, 2] = 0
+    eq(A, B)
+    my = ra.refmax(A)                                     # two elements equal 1: the first one in row-major order, A(0, 1)
+    eq(my, 1.)
+    my.assign(77.)
+    B[0, 1] = 77
+    eq(A, B)
