@@ -24,7 +24,13 @@
  *     ra/ra.hh:403-456
  *   Array(shape, none|value) storage, default_init         racu_alloc / racu_free / racu_memcpy_* / racu_fill
  *     ra/arrays.hh:224-327
- *   (none: the reference is single process)                racu_comm_* (NCCL over NVLink)
+ *   a(i ...) / at(a, i) with index arrays, both as         racu_map with a RACU_PTR operand + RACU_OP_LOAD (gather)
+ *     rvalue and lvalue: ra/ply.hh:461-499,531-549;          or a RACU_PTR destination (scatter)
+ *     ra/ra.hh:228-250
+ *   the compile-time instantiation of ply_ravel for an     racu_prepare (plan + specialise the kernel of a descriptor
+ *     expression type (ra/ply.hh:157-166)                    ahead of its first use; needs no GPU)
+ *   (none: the reference is single process)                racu_comm_* (NCCL over NVLink), racu_allreduce,
+ *                                                          racu_halo_exchange, racu_ipc_*, racu_stencil_push
  */
 #ifndef RACU_H
 #define RACU_H
