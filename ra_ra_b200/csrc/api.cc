@@ -30,6 +30,16 @@ run_plan(racu_desc const * d, int redop, void * reduce_out, cudaStream_t stream)
     if (int e = make_plan(d, redop, reduce_out, plan, err)) {
         if (e!=RACU_ERR_PEEL) return fail(e, err);
         // more uncollapsible axes than one launch handles: peel the outermost expression axis here
+        if (reduce_out) { // as `out OP= expr` onto a rank-0 destination, which composes slice by slice
+            racu_desc d2;
+            int t; uint64_t bits;
+            if (!peel_reduction(*d, redop, reduce_out, d2, t, bits)) return fail(RACU_ERR_UNSUPPORTED, err);
+            racu_base v;
+            if (t==RACU_F32) v.f = bits_f32(uint32_t(bits)); else if (t==RACU_F64) v.f = bits_f64(bits);
+            else if (t==RACU_I32) v.i = int32_t(uint32_t(bits)); else v.i = int64_t(bits);
+            if (cudaError_t e3 = launch_fill(reduce_out, t, v, 1, stream)) return cuda_fail(e3, "fill");
+            return run_plan(&d2, 0, nullptr, stream);
+        }
         if (!can_peel(d, reduce_out!=nullptr)) return fail(RACU_ERR_UNSUPPORTED, err);
         Shape sh;
         if (int e2 = agree(d, sh, err)) return fail(e2, err);

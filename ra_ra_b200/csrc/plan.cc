@@ -275,8 +275,37 @@ can_peel(racu_desc const * d, bool reducing)
 {
     if (reducing || d->dst<0) return false;
     racu_operand const & y = d->opnd[d->dst];
+    if (y.kind==RACU_PTR) return d->assign!=RACU_ASSIGN_SET; // scatter: accumulating updates compose in sequence (`=` with repeats: any order anyway, but keep one launch)
     if (y.rank>=1 && y.stride[0]!=0) return true;        // independent slices of the destination
     return d->assign!=RACU_ASSIGN_SET;                    // accumulating folds compose in sequence
+}
+
+// A whole-expression reduction with more uncollapsible axes than one launch handles: the same reduction written as the fold by
+// assignment `out OP= expr` onto a rank-0 destination at reduce_out (which the caller first fills with the identity); that form
+// composes slice by slice (can_peel). Returns false if the descriptor has no room for the extra operand.
+bool
+peel_reduction(racu_desc const & d, int redop, void * reduce_out, racu_desc & out, int & acc_type, uint64_t & identity)
+{
+    std::string err;
+    int const rt = check_program(&d, err);
+    if (rt<0 || d.nopnd>=RACU_MAX_OPND || d.dst!=-1) return false;
+    int assign;
+    switch (redop) {
+    case RACU_RED_SUM: assign = RACU_ASSIGN_ADD; break;
+    case RACU_RED_PROD: assign = RACU_ASSIGN_MUL; break;
+    case RACU_RED_AMIN: assign = RACU_ASSIGN_AMIN; break;
+    case RACU_RED_AMAX: assign = RACU_ASSIGN_AMAX; break;
+    default: return false;
+    }
+    out = d;
+    racu_operand & y = out.opnd[out.nopnd];
+    std::memset(&y, 0, sizeof(y));
+    y.kind = RACU_MEM; y.dtype = rt; y.rank = 0; y.base.ptr = reduce_out;
+    out.dst = out.nopnd++;
+    out.assign = assign;
+    acc_type = rt;
+    identity = identity_bits(assign, rt);
+    return true;
 }
 
 // Slice every operand at index i of expression axis 0 (prefix matching aligns operand axes from axis 0).

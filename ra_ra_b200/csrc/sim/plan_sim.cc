@@ -111,6 +111,13 @@ racu_sim_run(racu_desc const * d, int redop, void * reduce_out)
     plan = Plan {};
     if (int e = make_plan(d, redop, reduce_out, plan, g_sim_err)) {
         if (e!=RACU_ERR_PEEL) return e;
+        if (reduce_out) { // as api.cc run_plan: `out OP= expr` onto a rank-0 destination filled with the identity
+            racu_desc d2;
+            int t; uint64_t bits;
+            if (!peel_reduction(*d, redop, reduce_out, d2, t, bits)) return RACU_ERR_UNSUPPORTED;
+            std::memcpy(reduce_out, &bits, dtype_size(t));
+            return racu_sim_run(&d2, 0, nullptr);
+        }
         if (!can_peel(d, reduce_out!=nullptr)) return RACU_ERR_UNSUPPORTED;
         Shape sh;
         if (int e2 = agree(d, sh, g_sim_err)) return e2;

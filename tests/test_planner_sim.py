@@ -128,3 +128,17 @@ def test_planner_decisions():
     pi = plan_info()
     assert pi["mode"] == 2 and pi["nk"] == 1024 and pi["nB"] == 300
     assert np.array_equal(c2.numpy(), np.full(1024, 300, dtype=np.float32))
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2, 2, 3), (2, 3, 2, 2, 3, 2), (2,) * 8])
+@pytest.mark.parametrize("red", ["sum", "amax", "amin"])
+def test_whole_reduction_over_more_axes_than_one_launch(shape, red):
+    """Five to eight uncollapsible axes (random strides): a whole-expression reduction is run as `out OP= expr` onto a rank-0
+    destination, peeled along the outermost axis (api.cc run_plan / plan.cc peel_reduction); integer valued, so exact."""
+    vals = []
+    for ex in (OracleExecutor(), SimExecutor()):
+        rng = np.random.default_rng(77)
+        a, _ = random_view(rng, ex, shape, np.int64, True)
+        b, _ = random_view(rng, ex, shape[:3], np.int32, True)
+        vals.append(int(getattr(ra, red)(a * b - 3)))
+    assert vals[0] == vals[1]
