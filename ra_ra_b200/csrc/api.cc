@@ -44,7 +44,7 @@ run_plan(racu_desc const * d, int redop, void * reduce_out, cudaStream_t stream)
         Shape sh;
         if (int e2 = agree(d, sh, err)) return fail(e2, err);
         racu_desc sub;
-        for (int64_t i=0; i<sh.len[0]; ++i) {
+        for (int64_t i = peel_last_only(d) ? sh.len[0]-1 : 0; i<sh.len[0]; ++i) {
             peel_axis0(*d, i, sub);
             if (int e2 = run_plan(&sub, redop, reduce_out, stream)) return e2;
         }

@@ -277,7 +277,25 @@ can_peel(racu_desc const * d, bool reducing)
     racu_operand const & y = d->opnd[d->dst];
     if (y.kind==RACU_PTR) return d->assign!=RACU_ASSIGN_SET; // scatter: accumulating updates compose in sequence (`=` with repeats: any order anyway, but keep one launch)
     if (y.rank>=1 && y.stride[0]!=0) return true;        // independent slices of the destination
-    return d->assign!=RACU_ASSIGN_SET;                    // accumulating folds compose in sequence
+    return true;                                          // accumulating folds compose in sequence; `=` keeps the last slice (peel_last_only)
+}
+
+// `dst = expr` where dst does not move along expression axis 0: sequentially every slice overwrites the previous one ("last one
+// wins" in row-major order, docs/ra-ra.texi:1986-2007), so only the last slice of the peeled axis is evaluated.
+bool
+peel_last_only(racu_desc const * d)
+{
+    if (d->dst<0 || d->assign!=RACU_ASSIGN_SET) return false;
+    racu_operand const & y = d->opnd[d->dst];
+    if (y.kind!=RACU_MEM || (y.rank>=1 && y.stride[0]!=0)) return false;
+    // `dst = dst OP rest` (a running sum / max, test/reduction.cc:160-164) reads what the previous slice wrote: every slice counts
+    for (int pc=0; pc<d->nins; ++pc) {
+        if (d->ins[pc].op==RACU_OP_PUSH && d->ins[pc].arg<d->nopnd) {
+            racu_operand const & x = d->opnd[d->ins[pc].arg];
+            if (int(d->ins[pc].arg)==d->dst || (x.kind==RACU_MEM && x.base.ptr==y.base.ptr)) return false;
+        }
+    }
+    return true;
 }
 
 // A whole-expression reduction with more uncollapsible axes than one launch handles: the same reduction written as the fold by

@@ -40,6 +40,7 @@ int make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, st
 void peel_axis0(racu_desc const & d, int64_t i, racu_desc & out);
 // True when the traversal may be split along expression axis 0 into independent launches run in sequence.
 bool can_peel(racu_desc const * d, bool reducing);
+bool peel_last_only(racu_desc const * d);
 bool peel_reduction(racu_desc const & d, int redop, void * reduce_out, racu_desc & out, int & acc_type, uint64_t & identity);
 
 size_t dtype_size(int t);

@@ -122,7 +122,7 @@ racu_sim_run(racu_desc const * d, int redop, void * reduce_out)
         Shape sh;
         if (int e2 = agree(d, sh, g_sim_err)) return e2;
         racu_desc sub;
-        for (int64_t i=0; i<sh.len[0]; ++i) {
+        for (int64_t i = peel_last_only(d) ? sh.len[0]-1 : 0; i<sh.len[0]; ++i) {
             peel_axis0(*d, i, sub);
             if (int e2 = racu_sim_run(&sub, redop, reduce_out)) return e2;
         }

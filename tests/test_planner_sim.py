@@ -142,3 +142,28 @@ def test_whole_reduction_over_more_axes_than_one_launch(shape, red):
         b, _ = random_view(rng, ex, shape[:3], np.int32, True)
         vals.append(int(getattr(ra, red)(a * b - 3)))
     assert vals[0] == vals[1]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_broadcast_destination_with_many_axes(seed):
+    """Six to eight uncollapsible axes with a destination that is dead on some of them: `=` keeps the last slice of the peeled axis
+    ("last one wins", docs/ra-ra.texi:1986-2007), `+=` and the running forms `dst = dst OP expr` accumulate over every slice."""
+    shape = [(2, 3, 2, 2, 3, 2), (2,) * 8, (3, 2, 2, 2, 2, 2)][seed % 3]
+    outs = []
+    for ex in (OracleExecutor(), SimExecutor()):
+        rng = np.random.default_rng(4400 + seed)
+        k = int(rng.integers(0, len(shape)))
+        dst, _ = random_view(rng, ex, shape[:k] + shape[k + 1:], DT[rng.integers(0, 4)], True)
+        dst = dst(ra.dots(k), ra.insert(1))
+        a, _ = random_view(rng, ex, shape, DT[rng.integers(0, 4)], True)
+        form = seed % 4
+        if form == 0:
+            dst.assign(a * 2 + 1)
+        elif form == 1:
+            dst += a
+        elif form == 2:
+            dst.assign(dst + a)
+        else:
+            dst.assign(ra.max(dst, ra.cast(dst.dtype, a)))
+        outs.append(np.array(dst.owner, copy=True))
+    assert np.array_equal(outs[0], outs[1])
