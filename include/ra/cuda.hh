@@ -416,6 +416,41 @@ struct Pick: node_tag
         std::apply([&](auto const & ... q) { ((q.flatten(bb), bb.template cast<typename std::decay_t<decltype(q)>::value_type, value_type>()), ...); }, p);
         bb.emit(RACU_OP_PICK, dtype_of<value_type>, int(sizeof...(P)), dtype_of<typename S::value_type>);
     }
+    // pick / where as an lvalue (test/where.cc:148-157): `pick(sel, a0, a1, ...) OP= x` updates, per element, the branch the selector
+    // names; every branch must be an array. On the device: one masked assignment per branch, a_k = pick(sel, a_k, ..., a_k OP x, ..., a_k).
+    template <std::size_t K, class X> void assign_branch(int op, X const & x) const
+    {
+        auto const & y = std::get<K>(p);
+        using Y = std::decay_t<decltype(y)>;
+        using TY = typename Y::value_type;
+        using TX = typename X::value_type;
+        static_assert(requires { y.cp; y.dimv; } && !std::is_const_v<std::remove_pointer_t<decltype(y.cp)>>, "pick / where as an lvalue needs array branches");
+        Builder b;
+        b.d.dst = b.template mem<TY>(y.cp, y.dimv.data(), y.rank());
+        b.d.assign = RACU_ASSIGN_SET;
+        sel.flatten(b);
+        for (std::size_t j=0; j<sizeof...(P); ++j) {
+            if (j!=K) { y.flatten(b); continue; }
+            if (RACU_ASSIGN_SET==op) { x.flatten(b); b.template cast<TX, TY>(); continue; }
+            using C = decltype(std::declval<TY>()+std::declval<TX>());
+            y.flatten(b); b.template cast<TY, C>();
+            x.flatten(b); b.template cast<TX, C>();
+            b.emit(RACU_ASSIGN_ADD==op ? RACU_OP_ADD : RACU_ASSIGN_SUB==op ? RACU_OP_SUB : RACU_ASSIGN_MUL==op ? RACU_OP_MUL : RACU_OP_DIV, dtype_of<C>);
+            b.template cast<C, TY>();
+        }
+        b.emit(RACU_OP_PICK, dtype_of<TY>, int(sizeof...(P)), dtype_of<typename S::value_type>);
+        ck_status(racu_map(&b.d, stream()));
+    }
+    template <class X> void assign(int op, X const & x) const
+    {
+        [&]<std::size_t ... K>(std::index_sequence<K ...>) { (assign_branch<K>(op, x), ...); }(std::index_sequence_for<P ...> {});
+    }
+#define RACU_ASSIGNOP(OP, CODE) \
+    template <class X> requires (std::is_base_of_v<node_tag, std::decay_t<X>> || is_elem<std::decay_t<X>>) \
+    Pick const & operator OP(X const & x) const { if constexpr (is_elem<std::decay_t<X>>) assign(CODE, Scalar<std::decay_t<X>> { {}, x }); else assign(CODE, x); return *this; }
+    RACU_ASSIGNOP(=, RACU_ASSIGN_SET) RACU_ASSIGNOP(+=, RACU_ASSIGN_ADD) RACU_ASSIGNOP(-=, RACU_ASSIGN_SUB)
+    RACU_ASSIGNOP(*=, RACU_ASSIGN_MUL) RACU_ASSIGNOP(/=, RACU_ASSIGN_DIV)
+#undef RACU_ASSIGNOP
 };
 
 template <class ... A> concept tomap = ((is_operand<A> && ...) && (is_ra<A> || ...) && !(is_iota<std::decay_t<A>> && ...));
@@ -752,7 +787,7 @@ struct View: node_tag
         View<T, BR> b;
         std::vector<Dim> bv;
         dim_t pl = 0;
-        int ak = 0;
+        int ak = 0, seen = 0; // seen: source axes consumed by the fixed-size subscripts so far (sizes dots<>: ra/ply.hh:416-422)
         int const nstatic = (0 + ... + (int(UNB)==fsrc<std::decay_t<I>> ? 0 : fsrc<std::decay_t<I>>));
         auto one = [&](auto const & i0) {
             using I0 = std::decay_t<decltype(i0)>;
@@ -773,7 +808,7 @@ struct View: node_tag
                 ++ak;
             } else if constexpr (requires { []<int N>(dots_t<N>){}(i0); }) { // :416-422
                 int n = I0::N;
-                if (int(UNB)==n) n = rank()-ak-(nstatic-ak_static_before);
+                if (int(UNB)==n) n = rank()-ak-(nstatic-seen);
                 RACU_CK(n>=0 && ak+n<=rank(), "Too many subscripts.");
                 for (int q=0; q<n; ++q) bv.push_back(dimv[ak++]);
             } else if constexpr (requires { []<int N>(insert_t<N>){}(i0); }) { // :423-427
@@ -781,7 +816,7 @@ struct View: node_tag
             } else {
                 static_assert(std::integral<I0>, "unbeaten (gather) subscripts are not on the device path");
             }
-            if constexpr (int(UNB)!=fsrc<I0>) ak_static_before += fsrc<I0>;
+            if constexpr (int(UNB)!=fsrc<I0>) seen += fsrc<I0>;
         };
         (one(i), ...);
         for (; ak<rank(); ++ak) bv.push_back(dimv[ak]); // trailing axes implied, :374-381
@@ -812,9 +847,6 @@ struct View: node_tag
     // ---- host access (copies through the device boundary; for tests and small results)
     std::vector<value_type> to_host() const; // row-major ravel of the view
     operator value_type () const requires (0==R) { value_type v; ck_status(racu_memcpy_d2h(&v, cp, sizeof(v), stream())); return v; }
-
-private:
-    mutable int ak_static_before = 0;
 };
 
 

@@ -159,6 +159,64 @@ int main()
         tr.test_eq(vec<int> {90, 91, 92, 93, 94, 95, 96, 97, 98, 99}, a(rc::len-1, rc::all)); // test/fromb.cc:131-162
         tr.test(int(a(2, 3))==23, "rank 0 subscript converts to a value");
     }
+    tr.section("beatable multi-axis selectors, every form twice on one object: test/fromb.cc:166-193");
+    {
+        auto test = [&tr](auto const & a) {
+            for (int rep=0; rep<2; ++rep) { // (the second pass on the same object is the regression: dots<> sizing kept state between calls)
+                tr.test_eq(tr.host(a(0)), a(rc::dots<0>, 0), "a(dots<0>, 0)");
+                tr.test_eq(tr.host(a(1)), a(rc::dots<0>, 1), "a(dots<0>, 1)");
+                tr.test_eq(tr.host(a(rc::all, 0)), a(rc::dots<1>, 0), "a(dots<1>, 0)");
+                tr.test_eq(tr.host(a(rc::all, 1)), a(rc::dots<1>, 1), "a(dots<1>, 1)");
+                tr.test_eq(tr.host(a(rc::all, rc::all, 0)), a(rc::dots<2>, 0), "a(dots<2>, 0)");
+                tr.test_eq(tr.host(a(rc::all, rc::all, 1)), a(rc::dots<2>, 1), "a(dots<2>, 1)");
+                tr.test_eq(tr.host(a(rc::all, rc::all, 3)), a(rc::dots<2>, rc::len-1), "a(dots<2>, len-1)");
+                tr.test_eq(tr.host(a(rc::all, rc::all, 1)), a(rc::dots<>, 1), "a(dots<>, 1)");
+                tr.test_eq(tr.host(a(0, rc::all, rc::all)), a(0), "a(0)");
+                tr.test_eq(tr.host(a(1, rc::all, rc::all)), a(1), "a(1)");
+                tr.test_eq(tr.host(a(0, rc::all, rc::all)), a(0, rc::dots<2>), "a(0, dots<2>)");
+                tr.test_eq(tr.host(a(1, rc::all, rc::all)), a(1, rc::dots<2>), "a(1, dots<2>)");
+                tr.test_eq(tr.host(a(1, rc::all, rc::all)), a(rc::len-1, rc::dots<2>), "a(len-1, dots<2>)");
+                tr.test_eq(tr.host(a(1, rc::all, rc::all)), a(1, rc::dots<>), "a(1, dots<>)");
+                tr.test_eq(tr.host(a(0, rc::all, 1)), a(0, rc::dots<>, 1), "a(0, dots<>, 1)");
+                tr.test_eq(tr.host(a(1, rc::all, 0)), a(1, rc::dots<>, 0), "a(1, dots<>, 0)");
+            }
+            tr.test_eq(vec<int> {100, 101, 102, 103, 110, 111, 112, 113, 120, 121, 122, 123}, a(1, rc::dots<>), "values of a(1, dots<>)");
+            tr.test_eq(vec<int> {1, 11, 21}, a(0, rc::dots<>, 1), "values of a(0, dots<>, 1)");
+        };
+        test(rc::Big<int, 3>({2, 3, 4}, rc::_0*100 + rc::_1*10 + rc::_2)); // fixed rank
+        test(rc::Big<int>({2, 3, 4}, rc::_0*100 + rc::_1*10 + rc::_2));    // var rank
+    }
+    tr.section("insert, and insert mixed with dots: test/fromb.cc:195-255");
+    {
+        auto test = [&tr](auto const & a) {
+            tr.test_eq(tr.host(a(0)), a(rc::insert<0>, 0), "a(insert<0>, 0)");
+            rc::Big<int, 4> a1({1, 2, 3, 4}, rc::_1*100 + rc::_2*10 + rc::_3);
+            rc::Big<int, 4> a2({2, 1, 3, 4}, rc::_0*100 + rc::_2*10 + rc::_3);
+            rc::Big<int, 5> a3({2, 1, 1, 3, 4}, rc::_0*100 + rc::_3*10 + rc::_4);
+            // an inserted axis is unbounded: give it its length by matching against an array of that shape
+            rc::Big<int, 4> z1({1, 2, 3, 4}, 0), z2({2, 1, 3, 4}, 0);
+            rc::Big<int, 5> z3({2, 1, 1, 3, 4}, 0);
+            tr.test_eq(a1.to_host(), z1 + a(rc::insert<1>), "a(insert<1>)");
+            tr.test_eq(a2.to_host(), z2 + a(rc::all, rc::insert<1>), "a(all, insert<1>)");
+            tr.test_eq(a3.to_host(), z3 + a(rc::all, rc::insert<2>), "a(all, insert<2>)");
+            rc::Big<int, 3> z10({1, 3, 4}, 0);
+            tr.test_eq(a1(rc::all, 0).to_host(), z10 + a(0, rc::insert<1>), "a(0, insert<1>)");
+            tr.test_eq(a1(rc::all, 0).to_host(), z10 + a(rc::insert<1>, 0), "a(insert<1>, 0)");
+            rc::Big<int, 4> aa1({2, 2, 3, 4}, a(rc::insert<1>));
+            tr.test_eq(a.to_host(), aa1(0), "insert with undefined len 0");
+            tr.test_eq(a.to_host(), aa1(1), "insert with undefined len 1");
+            // mix insert + dots, twice on the same object
+            for (int rep=0; rep<2; ++rep) {
+                tr.test_eq(tr.host(a(rc::insert<0>, rc::dots<3>)), a(rc::insert<0>, rc::dots<>), "a(insert<0>, dots<>)");
+                tr.test_eq(tr.host(a(rc::insert<0>, rc::all, rc::all, rc::all)), a(rc::insert<0>, rc::dots<>), "a(insert<0>, all, all, all)");
+                tr.test_eq(tr.host(a(rc::insert<1>, rc::dots<3>) + rc::iota(2)), a(rc::insert<1>, rc::dots<>) + rc::iota(2), "a(insert<1>, dots<>)");
+                tr.test_eq(tr.host(a(rc::insert<1>) + rc::iota(2)), a(rc::insert<1>, rc::dots<>) + rc::iota(2), "a(insert<1>) vs a(insert<1>, dots<>)");
+                tr.test_eq(tr.host(a(rc::dots<3>, rc::insert<1>) + rc::Big<int, 4>({2, 3, 4, 2}, 0)), a(rc::dots<>, rc::insert<1>) + rc::Big<int, 4>({2, 3, 4, 2}, 0), "a(dots<>, insert<1>)");
+            }
+        };
+        test(rc::Big<int, 3>({2, 3, 4}, rc::_0*100 + rc::_1*10 + rc::_2));
+        test(rc::Big<int>({2, 3, 4}, rc::_0*100 + rc::_1*10 + rc::_2));
+    }
     tr.section("bounds and agreement are checked before launch: ra/ply.hh:395,407; test/checks.cc:159-233");
     {
         rc::Big<int, 2> a({10, 10}, 0);
@@ -196,6 +254,21 @@ int main()
         tr.test_eq(vec<int> {17, 2, 3, 17}, rc::where(rc::_0>0 && rc::_0<3, v, 17));
         rc::Big<int, 1> s {-1, 0, 1};
         tr.test_eq(vec<int> {44, 77, 99}, rc::where(s>=0, rc::where(s<1, 77, 99), 44));
+    }
+    tr.section("where as lvalue: test/where.cc:148-157");
+    {
+        rc::Big<int, 1> a { 0, 0, 0, 0 }, b { 0, 0, 0, 0 };
+        rc::where(rc::_0>0 && rc::_0<3, a, b) = 7;
+        tr.test_eq(vec<int> {0, 7, 7, 0}, a);
+        tr.test_eq(vec<int> {7, 0, 0, 7}, b);
+        rc::where(rc::_0<=0 || rc::_0>=3, a, b) += 2;
+        tr.test_eq(vec<int> {2, 7, 7, 2}, a);
+        tr.test_eq(vec<int> {7, 2, 2, 7}, b);
+        rc::Big<real, 1> x { 1, 2, 3 }, y { 10, 20, 30 };                    // pick with an array selector and an array right hand side
+        rc::Big<int, 1> p { 0, 1, 0 };
+        rc::pick(p, x, y) *= rc::Big<real, 1> { 2, 3, 4 };
+        tr.test_eq(vec<real> {2, 2, 12}, x);
+        tr.test_eq(vec<real> {10, 60, 30}, y);
     }
     tr.section("reductions: test/reduction.cc:85-138,199-201");
     {
