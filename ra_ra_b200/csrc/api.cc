@@ -28,6 +28,20 @@ run_plan(racu_desc const * d, int redop, void * reduce_out, cudaStream_t stream)
     Plan plan;
     std::string err;
     if (int e = make_plan(d, redop, reduce_out, plan, err)) {
+        if (e==RACU_ERR_SEQ) { // sequential semantics are observable: the folded axes one index at a time, in row-major order
+            Shape sh;
+            if (int e2 = agree(d, sh, err)) return fail(e2, err);
+            int const k = first_folded_axis(d, sh);
+            int64_t steps = 1;
+            for (int j=0; j<sh.rank; ++j) { if (sh.len[j]>1 && (j>=d->opnd[d->dst].rank || 0==d->opnd[d->dst].stride[j])) steps *= sh.len[j]; }
+            if (k<0 || steps>(int64_t(1)<<16)) return fail(RACU_ERR_UNSUPPORTED, err + ": more than 65536 sequential steps");
+            racu_desc sub;
+            for (int64_t i=0; i<sh.len[k]; ++i) {
+                peel_axis(*d, k, i, sub);
+                if (int e2 = run_plan(&sub, 0, nullptr, stream)) return e2;
+            }
+            return RACU_OK;
+        }
         if (e!=RACU_ERR_PEEL) return fail(e, err);
         // more uncollapsible axes than one launch handles: peel the outermost expression axis here
         if (reduce_out) { // as `out OP= expr` onto a rank-0 destination, which composes slice by slice
@@ -131,7 +145,7 @@ int racu_agree(const racu_desc * d, int32_t * rank_out, int64_t * len_out)
 
 int racu_map(const racu_desc * d, void * stream)
 {
-    if (!d) return fail(RACU_ERR_BAD_DESC, "null descriptor");
+    { std::string err; if (int e = validate_desc(d, false, err)) return fail(e, err); } // before anything indexes into the descriptor
     int handled = 0;
     if (int e = try_special_map(d, cudaStream_t(stream), &handled)) return e;
     if (handled) return RACU_OK;
@@ -143,12 +157,23 @@ int racu_prepare(const racu_desc * d, int redop, const char ** kernel_out)
     if (!d) return fail(RACU_ERR_BAD_DESC, "null descriptor");
     Plan plan;
     std::string err;
+    if (int e = validate_desc(d, redop!=0, err)) return fail(e, err);
     racu_desc sub;
     racu_desc const * cur = d;
     void * const out = redop ? reinterpret_cast<void *>(uintptr_t(256)) : nullptr; // planning only looks at its alignment
     for (int depth=0; depth<RACU_MAX_RANK; ++depth) {
         int e = make_plan(cur, redop, out, plan, err);
         if (RACU_OK==e) break;
+        if (e==RACU_ERR_SEQ) { // every step of the sequential schedule runs the same map
+            Shape sh;
+            if (int e2 = agree(cur, sh, err)) return fail(e2, err);
+            int const k = first_folded_axis(cur, sh);
+            if (k<0) return fail(RACU_ERR_UNSUPPORTED, err);
+            racu_desc next;
+            peel_axis(*cur, k, 0, next);
+            sub = next; cur = &sub;
+            continue;
+        }
         if (e!=RACU_ERR_PEEL) return fail(e, err);
         if (!can_peel(cur, out!=nullptr)) return fail(RACU_ERR_UNSUPPORTED, err);
         racu_desc next;
@@ -162,6 +187,7 @@ int racu_prepare(const racu_desc * d, int redop, const char ** kernel_out)
 int racu_reduce_dev(const racu_desc * d, int redop, void * out_dev, void * stream)
 {
     if (!d || !out_dev) return fail(RACU_ERR_BAD_DESC, "null argument");
+    { std::string err; if (int e = validate_desc(d, true, err)) return fail(e, err); }
     return run_plan(d, redop, out_dev, cudaStream_t(stream));
 }
 
@@ -169,6 +195,7 @@ int racu_reduce(const racu_desc * d, int redop, void * out_host, void * stream)
 {
     if (!d || !out_host) return fail(RACU_ERR_BAD_DESC, "null argument");
     std::string err;
+    if (int e = validate_desc(d, true, err)) return fail(e, err);
     int rt = check_program(d, err);
     if (rt<0) return fail(RACU_ERR_BAD_DESC, err);
     void * tmp = nullptr;

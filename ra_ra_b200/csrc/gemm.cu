@@ -205,6 +205,10 @@ try_special_gemm(racu_gemm_desc const * gd, cudaStream_t stream, int * handled)
     bool const f64 = gd->dtype==RACU_F64;
     int const bk = f64 ? DK : SK;
     size_t const es = f64 ? 8 : 4;
+    {   // c overlapping a or b: not for these kernels (they read tiles of a and b after other CTAs have written c); the planner rejects it
+        int64_t const lc[2] = {gd->M, gd->N}, sc[2] = {gd->ldc, 1}, la[2] = {gd->M, gd->K}, sa[2] = {gd->lda, 1}, lb[2] = {gd->K, gd->N}, sb[2] = {gd->ldb, 1};
+        if (gd->M>0 && gd->N>0 && gd->K>0 && (views_overlap(gd->c, 2, lc, sc, gd->a, 2, la, sa, es) || views_overlap(gd->c, 2, lc, sc, gd->b, 2, lb, sb, es))) return RACU_OK;
+    }
     if (gd->M<=0 || gd->N<=0 || gd->K<=0) { *handled = 1; return RACU_OK; } // nothing to add (test/reduction.cc:300-310: 0x0 corner)
     if (!f64) { // f32: tcgen05 / TMEM kernel first (gemm_tc5.cu, any shape); the mma.sync 3xTF32 kernel below is the second choice
         if (int e = try_tcgen05_sgemm(gd, stream, handled)) return e;

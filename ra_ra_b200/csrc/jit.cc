@@ -167,35 +167,47 @@ cache_dir()
     return "jit_cache";
 }
 
+// Cache file = header + cubin. The header ties the file to the exact kernel text it was compiled from and to its own content, so
+// a truncated, stale or foreign file is never handed to cuModuleLoadData.
+struct CacheHeader { char magic[8]; uint64_t key; uint64_t size; uint64_t content_hash; };
+static constexpr char CACHE_MAGIC[8] = {'R', 'A', 'C', 'U', 'J', 'I', 'T', '2'};
+
 static bool
-read_file(std::string const & path, std::vector<char> & out)
+read_cache(std::string const & path, uint64_t key, std::vector<char> & out)
 {
     FILE * f = std::fopen(path.c_str(), "rb");
     if (!f) return false;
-    std::fseek(f, 0, SEEK_END);
-    long n = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    out.resize(n>0 ? size_t(n) : 0);
-    bool ok = n>0 && std::fread(out.data(), 1, size_t(n), f)==size_t(n);
+    CacheHeader h;
+    bool ok = std::fread(&h, 1, sizeof(h), f)==sizeof(h) && 0==std::memcmp(h.magic, CACHE_MAGIC, 8) && h.key==key && h.size>0 && h.size<(uint64_t(1)<<28);
+    if (ok) {
+        out.resize(size_t(h.size));
+        ok = std::fread(out.data(), 1, out.size(), f)==out.size() && EOF==std::fgetc(f) && fnv1a(out.data(), out.size())==h.content_hash;
+    }
     std::fclose(f);
+    if (!ok) { out.clear(); std::remove(path.c_str()); } // recompiled (and rewritten) by the caller
     return ok;
 }
 
 static void
-write_file(std::string const & dir, std::string const & path, std::vector<char> const & data)
+write_cache(std::string const & dir, std::string const & path, uint64_t key, std::vector<char> const & data)
 {
     mkdir(dir.c_str(), 0755);
     std::string tmp = path + ".tmp" + std::to_string(long(getpid()));
     FILE * f = std::fopen(tmp.c_str(), "wb");
     if (!f) return;
-    bool ok = std::fwrite(data.data(), 1, data.size(), f)==data.size();
-    std::fclose(f);
+    CacheHeader h;
+    std::memcpy(h.magic, CACHE_MAGIC, 8);
+    h.key = key; h.size = data.size(); h.content_hash = fnv1a(data.data(), data.size());
+    bool ok = std::fwrite(&h, 1, sizeof(h), f)==sizeof(h) && std::fwrite(data.data(), 1, data.size(), f)==data.size();
+    ok = (0==std::fclose(f)) && ok;
     if (ok) std::rename(tmp.c_str(), path.c_str()); else std::remove(tmp.c_str());
 }
 
-// Compile (or fetch from the disk cache) the cubin of one specialisation. Needs no GPU.
+static int64_t jit_compiles = 0; // NVRTC compilations in this process (disk cache hits do not count)
+
+// Compile (or fetch from the disk cache) the cubin of one specialisation. Needs no GPU. force: ignore (and replace) the cached file.
 static bool
-jit_cubin(SProg const & P, int mode, int variant, int fold_op, std::vector<char> & cubin, std::string & err)
+jit_cubin(SProg const & P, int mode, int variant, int fold_op, std::vector<char> & cubin, std::string & err, bool force=false)
 {
     std::string const src = jit_kernel_text(P, mode, variant, fold_op);
     uint64_t const key = fnv1a(src.data(), src.size(), sources_hash());
@@ -203,7 +215,8 @@ jit_cubin(SProg const & P, int mode, int variant, int fold_op, std::vector<char>
     std::snprintf(name, sizeof(name), "%016llx.cubin", static_cast<unsigned long long>(key));
     std::string const dir = cache_dir(), path = dir + "/" + name;
     bool const use_disk = !std::getenv("RACU_JIT_NO_DISK");
-    if (use_disk && read_file(path, cubin)) return true;
+    if (force) std::remove(path.c_str());
+    else if (use_disk && read_cache(path, key, cubin)) return true;
     if (!nvrtc_load()) { err = "NVRTC (libnvrtc.so.12) is not available"; return false; }
     constexpr int nh = int(sizeof(jit_sources)/sizeof(jit_sources[0]));
     char const * names[nh]; char const * texts[nh];
@@ -227,15 +240,15 @@ jit_cubin(SProg const & P, int mode, int variant, int fold_op, std::vector<char>
     int const r2 = nvrtc.GetCUBIN(prog, cubin.data());
     nvrtc.DestroyProgram(&prog);
     if (r2) { err = "nvrtcGetCUBIN failed"; return false; }
-    if (use_disk) write_file(dir, path, cubin);
+    ++jit_compiles;
+    if (use_disk) write_cache(dir, path, key, cubin);
     return true;
 }
 
 // ---- per-device kernel cache
 
 static std::mutex jit_mutex;
-static std::map<std::string, CUfunction> jit_loaded;   // key: device + kernel text
-static int64_t jit_compiles = 0;
+static std::map<std::string, CUfunction> jit_loaded;   // key: device, mode, variant, fold class + the program's bytes
 
 static int
 variant_of(Plan const & plan)
@@ -255,14 +268,19 @@ jit_prepare(Plan & plan, std::string & err)
     int dev = -1;
     bool have_dev = cudaSuccess==cudaGetDevice(&dev) && dev>=0; // (cheap: no context work on the per-call path)
     if (!have_dev) cudaGetLastError();
-    std::string const src = jit_kernel_text(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op);
-    std::string const key = std::to_string(dev) + "|" + src;
+    // in-memory key: no kernel text is generated on the per-call path
+    SProg const & P = plan.jit_prog;
+    int32_t const head[5] = {dev, plan.sp.mode, variant, plan.sp.mode==K_MAP ? 0 : fold_class(plan.sp.fold_op), P.n};
+    std::string key(reinterpret_cast<char const *>(head), sizeof(head));
+    key.append(reinterpret_cast<char const *>(P.ins), sizeof(SIns)*size_t(P.n));
+    int32_t const tail[3] = {P.nin, P.yrole, int32_t(P.fold) | (int32_t(P.otype)<<8)};
+    key.append(reinterpret_cast<char const *>(tail), sizeof(tail));
+    key.append(reinterpret_cast<char const *>(P.rtype), size_t(P.nin));
     std::lock_guard<std::mutex> lock(jit_mutex);
     auto it = jit_loaded.find(key);
     if (it!=jit_loaded.end()) { plan.jit_fn = it->second; return true; }
     std::vector<char> cubin;
     if (!jit_cubin(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op, cubin, err)) return false;
-    ++jit_compiles;
     if (have_dev && cudaSuccess!=cudaFree(nullptr)) { cudaGetLastError(); have_dev = false; } // make the primary context current before loading
     if (std::getenv("RACU_JIT_VERBOSE")) std::fprintf(stderr, "racu jit: specialised %s (mode %d variant %d fold %d) for device %d, %zu bytes\n",
                                                       jit_prog_text(plan.jit_prog).c_str(), plan.sp.mode, variant, plan.sp.fold_op, dev, cubin.size());
@@ -270,7 +288,11 @@ jit_prepare(Plan & plan, std::string & err)
     if (!drv_load()) { err = "driver entry points for module loading are not available"; return false; }
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
-    if (CUresult r = drv.ModuleLoadData(&mod, cubin.data())) { err = "cuModuleLoadData failed: " + std::to_string(int(r)); return false; }
+    if (CUresult r = drv.ModuleLoadData(&mod, cubin.data())) {
+        // a cached cubin the driver will not take (another toolkit, a damaged file that still hashes): compile it again, once
+        if (!jit_cubin(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op, cubin, err, true)) return false;
+        if (CUresult r2 = drv.ModuleLoadData(&mod, cubin.data())) { err = "cuModuleLoadData failed: " + std::to_string(int(r)) + ", after recompiling: " + std::to_string(int(r2)); return false; }
+    }
     if (CUresult r = drv.ModuleGetFunction(&fn, mod, "racu_jit_kernel")) { err = "cuModuleGetFunction failed: " + std::to_string(int(r)); return false; }
     jit_loaded.emplace(key, fn);
     plan.jit_fn = fn;
@@ -283,8 +305,7 @@ launch_jit(Plan const & plan, cudaStream_t stream)
     if (!plan.jit_fn || !drv_load()) return cudaErrorInvalidDeviceFunction;
     void * args[2] = {const_cast<SParams *>(&plan.sp), const_cast<FinishParams *>(&plan.fp)};
     CUresult r = drv.LaunchKernel(static_cast<CUfunction>(plan.jit_fn), plan.grid_x, plan.grid_y, 1, KBLOCK, 1, 1, 0, stream, args, nullptr);
-    if (CUDA_SUCCESS!=r) return cudaErrorLaunchFailure;
-    return cudaSuccess;
+    return cudaError_t(r); // driver and runtime share the error numbering (CUDA_SUCCESS == cudaSuccess == 0)
 }
 
 int64_t jit_compile_count() { return jit_compiles; }

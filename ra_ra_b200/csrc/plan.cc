@@ -241,6 +241,42 @@ same_view(Work const & w, WOp const & a, WOp const & b)
     return true;
 }
 
+// Two views with the SAME steps whose bounding ranges overlap may still be disjoint (even / odd, red / black updates:
+// A(iota(n/2, 0, 2)) = A(iota(n/2, 1, 2)) is legal and order independent in the reference). They share an element iff the offset
+// between their origins is sum d_k*st_k with |d_k| < len_k: a bounded search over the axes, largest step first, pruned by what the
+// remaining axes can still reach (non self-overlapping views leave at most two candidates per axis). Inconclusive => not disjoint.
+bool
+provably_disjoint(Work const & w, WOp const & a, WOp const & b)
+{
+    if (a.dtype!=b.dtype) return false;
+    for (int k=0; k<w.rank; ++k) { if (a.st[k]!=b.st[k]) return false; }
+    int64_t const es = int64_t(dtype_size(a.dtype));
+    int64_t const dbytes = int64_t(a.base-b.base);
+    if (0!=dbytes%es) return false;
+    int ax[KMAXR], n = 0;
+    for (int k=0; k<w.rank; ++k) { if (0!=a.st[k] && w.len[k]>1) ax[n++] = k; }
+    for (int i=1; i<n; ++i) { for (int j=i; j>0 && std::llabs(a.st[ax[j]])>std::llabs(a.st[ax[j-1]]); --j) std::swap(ax[j], ax[j-1]); } // largest step first
+    int64_t reach[KMAXR+1]; // reach[i]: largest |offset| axes i.. can produce
+    reach[n] = 0;
+    for (int i=n-1; i>=0; --i) reach[i] = reach[i+1] + (w.len[ax[i]]-1)*std::llabs(a.st[ax[i]]);
+    int budget = 4096;
+    bool inconclusive = false;
+    auto rec = [&](auto && self, int i, int64_t r) -> bool { // can r be written with axes i.. ?
+        if (--budget<0) { inconclusive = true; return true; }
+        if (i==n) return 0==r;
+        if (std::llabs(r)>reach[i]) return false;
+        int64_t const st = std::llabs(a.st[ax[i]]), L = w.len[ax[i]]-1;
+        // d*st must land within reach[i+1] of r
+        auto fdiv = [](int64_t x, int64_t y) { int64_t q = x/y; return (x%y!=0 && ((x<0)!=(y<0))) ? q-1 : q; };
+        int64_t lo = -fdiv(-(r-reach[i+1]), st) /* ceil */, hi = fdiv(r+reach[i+1], st);
+        lo = std::max(lo, -L); hi = std::min(hi, L);
+        for (int64_t d=lo; d<=hi; ++d) { if (self(self, i+1, r-d*st)) return true; }
+        return false;
+    };
+    bool const hit = rec(rec, 0, dbytes/es);
+    return !hit && !inconclusive;
+}
+
 void
 emit(std::vector<racu_ins> & v, int op, int type, int arg=0, int aux=0)
 {
@@ -341,6 +377,46 @@ peel_axis0(racu_desc const & d, int64_t i, racu_desc & out)
         for (int k=0; k+1<p.rank; ++k) { p.len[k] = p.len[k+1]; p.stride[k] = p.stride[k+1]; }
         --p.rank;
     }
+}
+
+void
+peel_axis(racu_desc const & d, int k, int64_t i, racu_desc & out)
+{
+    out = d;
+    for (int o=0; o<out.nopnd; ++o) {
+        racu_operand & p = out.opnd[o];
+        if (p.rank<=k || p.kind==RACU_SCALAR || p.kind==RACU_PTR) continue;
+        int64_t off = i*p.stride[k];
+        if (p.kind==RACU_MEM) p.base.ptr = static_cast<char *>(p.base.ptr) + off*int64_t(dtype_size(p.dtype));
+        else if (is_float(p.dtype)) p.base.f += double(off);
+        else p.base.i += off;
+        for (int j=k; j+1<p.rank; ++j) { p.len[j] = p.len[j+1]; p.stride[j] = p.stride[j+1]; }
+        --p.rank;
+    }
+}
+
+int
+first_folded_axis(racu_desc const * d, Shape const & sh)
+{
+    if (d->dst<0 || d->dst>=d->nopnd) return -1;
+    racu_operand const & y = d->opnd[d->dst];
+    for (int k=0; k<sh.rank; ++k) { if (sh.len[k]>1 && (k>=y.rank || 0==y.stride[k])) return k; }
+    return -1;
+}
+
+int
+validate_desc(racu_desc const * d, bool reducing, std::string & err)
+{
+    if (!d) { err = "null descriptor"; return RACU_ERR_BAD_DESC; }
+    if (d->nopnd<=0 || d->nopnd>RACU_MAX_OPND) { err = "bad operand count"; return RACU_ERR_BAD_DESC; }
+    if (d->nins<=0 || d->nins>RACU_MAX_INS) { err = "bad program length"; return RACU_ERR_BAD_DESC; }
+    if (reducing ? d->dst!=-1 : (d->dst<0 || d->dst>=d->nopnd)) { err = reducing ? "reduce needs dst = -1" : "bad destination"; return RACU_ERR_BAD_DESC; }
+    for (int o=0; o<d->nopnd; ++o) {
+        racu_operand const & p = d->opnd[o];
+        if (p.rank<0 || p.rank>RACU_MAX_RANK || (p.kind==RACU_SCALAR && p.rank!=0)) { err = "bad operand rank"; return RACU_ERR_BAD_DESC; }
+    }
+    if (check_program(d, err)<0) return RACU_ERR_BAD_DESC;
+    return RACU_OK;
 }
 
 // Does the canonical program have a compile-time specialised kernel (static_progs.h)? Fills plan.sp if so.
@@ -607,7 +683,11 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
             }
             if (o==dst || w.op[o].kind!=RACU_MEM) continue;
             uint64_t lo, hi; extent(w, w.op[o], lo, hi);
-            if (lo<dhi && dlo<hi) { if (same_view(w, w.op[o], w.op[dst])) alias_same = true; else alias_other = true; }
+            if (lo<dhi && dlo<hi) {
+                if (same_view(w, w.op[o], w.op[dst])) alias_same = true;
+                else if (!scatter && provably_disjoint(w, w.op[o], w.op[dst])) {} // interleaved, never the same element
+                else alias_other = true;
+            }
         }
     }
     for (int pc=0; pc<d->nins; ++pc) { if (d->ins[pc].op==RACU_OP_PUSH && int(d->ins[pc].arg)==dst) alias_same = true; } // the program reads the destination operand itself
@@ -703,6 +783,12 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
     } else {
         A = (assign==RACU_ASSIGN_AMIN || assign==RACU_ASSIGN_AMAX) ? rt : common_type(D, rt);
         if ((assign==RACU_ASSIGN_AMIN || assign==RACU_ASSIGN_AMAX) && rt!=D) { err = "amin/amax need matching types"; return RACU_ERR_BAD_DESC; }
+        // for_each(y OP= x) narrows to the destination at EVERY step (ra/expr.hh:50-53). A tree that accumulates in the common type and
+        // narrows once is the same computation when the narrowing commutes with the op: same type, integer -> narrower integer (modular),
+        // or floating point -> narrower floating point (a rounding difference, within the fold tolerance: the order is unspecified anyway).
+        // It is NOT for an integer destination with a floating point right hand side (int c += 0.5 four times is 0, not 2): those run
+        // the folded axes one index at a time.
+        if (!reducing && is_float(A) && !is_float(D)) { err = "fold that truncates to an integer destination at every step"; return RACU_ERR_SEQ; }
         prog = w.ins;
         emit_cast(prog, rt, A);
     }

@@ -7,6 +7,8 @@
 namespace racu {
 
 constexpr int RACU_ERR_PEEL = 100; // internal: peel the outermost expression axis on the host and retry
+constexpr int RACU_ERR_SEQ = 101;  // internal: a fold that must narrow to the destination at every step (integer destination, floating
+                                   // point right hand side): run the folded axes one index at a time, in row-major order
 
 
 struct Plan
@@ -38,6 +40,11 @@ int agree(racu_desc const * d, Shape & s, std::string & err);             // rac
 int make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::string & err);
 
 void peel_axis0(racu_desc const & d, int64_t i, racu_desc & out);
+void peel_axis(racu_desc const & d, int k, int64_t i, racu_desc & out);  // same for any expression axis k
+int first_folded_axis(racu_desc const * d, Shape const & sh);           // first axis the destination does not move along, or -1
+// Structural checks that must hold before anything dereferences the descriptor by index: operand / instruction counts,
+// destination index, operand kinds / dtypes / ranks, and the program (check_program). racu_status.
+int validate_desc(racu_desc const * d, bool reducing, std::string & err);
 // True when the traversal may be split along expression axis 0 into independent launches run in sequence.
 bool can_peel(racu_desc const * d, bool reducing);
 bool peel_last_only(racu_desc const * d);

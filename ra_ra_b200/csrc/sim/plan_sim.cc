@@ -110,6 +110,18 @@ racu_sim_run(racu_desc const * d, int redop, void * reduce_out)
     Plan & plan = g_sim_plan;
     plan = Plan {};
     if (int e = make_plan(d, redop, reduce_out, plan, g_sim_err)) {
+        if (e==RACU_ERR_SEQ) { // as api.cc run_plan: the folded axes one index at a time
+            Shape sh;
+            if (int e2 = agree(d, sh, g_sim_err)) return e2;
+            int const k = first_folded_axis(d, sh);
+            if (k<0) return RACU_ERR_UNSUPPORTED;
+            racu_desc sub;
+            for (int64_t i=0; i<sh.len[k]; ++i) {
+                peel_axis(*d, k, i, sub);
+                if (int e2 = racu_sim_run(&sub, 0, nullptr)) return e2;
+            }
+            return RACU_OK;
+        }
         if (e!=RACU_ERR_PEEL) return e;
         if (reduce_out) { // as api.cc run_plan: `out OP= expr` onto a rank-0 destination filled with the identity
             racu_desc d2;

@@ -384,6 +384,9 @@ try_special_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * hand
     *handled = 0;
     if (std::getenv("RACU_NO_TMA_STENCIL")) return RACU_OK;
     if (s->dtype!=RACU_F32 && s->dtype!=RACU_F64) return RACU_OK;
+    if (s->rank<1 || s->rank>3) return RACU_OK;
+    // An in-place sweep (dst overlapping src) would be a race here; the planner rejects it ("traversal order would be observable").
+    if (views_overlap(s->src, s->rank, s->len, s->src_stride, s->dst, s->rank, s->len, s->dst_stride, s->dtype==RACU_F32 ? 4 : 8)) return RACU_OK;
 #define RACU_ST(KIND) (s->dtype==RACU_F32 ? launch_stencil<float, KIND>(s, stream, handled) : launch_stencil<double, KIND>(s, stream, handled))
     switch (s->kind) {
     case RACU_STENCIL_3D7: return 3==s->rank ? RACU_ST(RACU_STENCIL_3D7) : RACU_OK;
@@ -403,6 +406,8 @@ stencil_push(racu_stencil_desc const * s, racu_halo_push const * h, cudaStream_t
     if (0!=s->lo0 || 0!=s->hi0) return fail(RACU_ERR_BAD_DESC, "racu_stencil_push sweeps the whole local interior");
     if (!h->flags || (h->push_lo && !h->signal_lo) || (h->push_hi && !h->signal_hi)) return fail(RACU_ERR_BAD_DESC, "racu_stencil_push: missing flag words");
     if (s->len[0]<3) return fail(RACU_ERR_BAD_DESC, "racu_stencil_push: a slab needs at least one owned plane between its ghosts");
+    if (views_overlap(s->src, 3, s->len, s->src_stride, s->dst, 3, s->len, s->dst_stride, s->dtype==RACU_F32 ? 4 : 8))
+        return fail(RACU_ERR_UNSUPPORTED, "racu_stencil_push: destination overlaps the source: traversal order would be observable");
     int handled = 0;
     int e = s->dtype==RACU_F32 ? launch_stencil<float, RACU_STENCIL_3D7>(s, stream, &handled, h) : launch_stencil<double, RACU_STENCIL_3D7>(s, stream, &handled, h);
     if (e) return e;
@@ -431,8 +436,7 @@ try_special_map(racu_desc const * d, cudaStream_t stream, int * handled)
             std::memset(&g, 0, sizeof(g));
             g.dtype = T; g.M = c.len[0]; g.N = c.len[2]; g.K = a.len[1];
             g.a = a.base.ptr; g.lda = a.stride[0]; g.b = b.base.ptr; g.ldb = b.stride[1]; g.c = c.base.ptr; g.ldc = c.stride[0];
-            // c must not overlap a or b (the planner would reject it as well)
-            return try_special_gemm(&g, stream, handled);
+            return try_special_gemm(&g, stream, handled); // (c overlapping a or b is not handled there: the planner then rejects it)
         }
     }
     if (d->assign!=RACU_ASSIGN_SET || d->nins<8) return RACU_OK;

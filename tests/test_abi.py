@@ -54,3 +54,41 @@ def test_agree_needs_no_device():
     d.opnd[1].len[1] = 3
     assert lib.racu_agree(C.byref(d), C.byref(rank), lens) == abi.ERR_SHAPE
     assert b"Bad shapes" in lib.racu_last_error_string()
+
+
+def test_malformed_descriptors_are_rejected_before_use():
+    """Every entry point validates counts and indices before anything dereferences opnd[dst] / opnd[ins.arg] (no GPU needed:
+    validation comes first)."""
+    lib = abi.bind(_lib())
+    buf = np.zeros(16, np.float32)
+
+    def good():
+        d = abi.Desc()
+        d.nopnd, d.nins, d.dst, d.assign = 2, 1, 0, abi.ASSIGN_SET
+        for o in range(2):
+            p = d.opnd[o]
+            p.kind, p.dtype, p.rank = abi.MEM, abi.F32, 1
+            p.base.ptr = buf.ctypes.data
+            p.len[0], p.stride[0] = 4, 1
+        d.ins[0].op, d.ins[0].type, d.ins[0].arg = abi.OP_PUSH, abi.F32, 1
+        return d
+    cases = []
+    d = good(); d.dst = 7; cases.append(d)
+    d = good(); d.dst = abi.MAX_OPND + 5; cases.append(d)
+    d = good(); d.nopnd = abi.MAX_OPND + 1; cases.append(d)
+    d = good(); d.nopnd = 0; cases.append(d)
+    d = good(); d.nins = abi.MAX_INS + 1; cases.append(d)
+    d = good(); d.nins = 0; cases.append(d)
+    d = good(); d.ins[0].arg = 255; cases.append(d)
+    d = good(); d.ins[0].type = 9; cases.append(d)
+    d = good(); d.opnd[1].rank = abi.MAX_RANK + 1; cases.append(d)
+    d = good(); d.opnd[1].kind = 17; cases.append(d)
+    # stencil-looking garbage: >= 8 instructions with a destination index out of range
+    d = good(); d.nins = 12; d.dst = 200; cases.append(d)
+    for d in cases:
+        assert lib.racu_map(C.byref(d), None) == abi.ERR_BAD_DESC
+        assert lib.racu_prepare(C.byref(d), 0, None) == abi.ERR_BAD_DESC
+    out = np.zeros(2)
+    d = good()  # reductions need dst = -1
+    assert lib.racu_reduce(C.byref(d), abi.RED_SUM, out.ctypes.data, None) == abi.ERR_BAD_DESC
+    assert lib.racu_reduce_dev(C.byref(d), abi.RED_SUM, out.ctypes.data, None) == abi.ERR_BAD_DESC

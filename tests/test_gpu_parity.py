@@ -390,3 +390,62 @@ def test_gemv_gevm_static_rows(exc):
     ra.gevm(x, a, c2)
     assert exc.last_kernel() == "sflat_fold_outer", exc.last_kernel()
     assert np.array_equal(c2.numpy(), x.numpy() @ a.numpy())
+
+
+def test_inplace_stencil_is_rejected_not_raced(exc):
+    """A(I,J,K) = -6*A(I,J,K) + A(I+1,J,K) ... written onto A itself: the sequential reference has a defined (order dependent) result;
+    a parallel sweep would race. Every entry (racu_map by pattern, racu_stencil, racu_stencil_push) must reject it like the planner."""
+    import ctypes as C
+    import torch
+    from ra_ra_b200 import cuda
+    n = (36, 40, 132)
+    a_t = torch.rand(n, device="cuda")
+    before = a_t.clone()
+    A = exc.wrap(a_t)
+    I, J, K = (ra.iota(n[k] - 2, 1) for k in range(3))
+    with pytest.raises(ra.RaError) as e:
+        A(I, J, K).assign(-6 * A(I, J, K) + A(I + 1, J, K) + A(I, J + 1, K) + A(I, J, K + 1) + A(I - 1, J, K) + A(I, J - 1, K) + A(I, J, K - 1))
+    assert e.value.status == abi.ERR_UNSUPPORTED and "overlaps" in str(e.value)
+    st = list(a_t.stride())
+    s = _stencil_desc(abi.STENCIL_3D7, np.float32, a_t.data_ptr(), a_t.data_ptr(), n, st)
+    assert cuda.lib.racu_stencil(C.byref(s), cuda.stream_ptr()) == abi.ERR_UNSUPPORTED
+    h = abi.HaloPush()
+    flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+    h.flags = flags.data_ptr()
+    assert cuda.lib.racu_stencil_push(C.byref(s), C.byref(h), cuda.stream_ptr()) == abi.ERR_UNSUPPORTED
+    # shifted by one plane: still overlapping
+    s2 = _stencil_desc(abi.STENCIL_3D7, np.float32, a_t.data_ptr(), a_t.data_ptr() + 4 * st[0], (n[0] - 1, n[1], n[2]), st)
+    assert cuda.lib.racu_stencil(C.byref(s2), cuda.stream_ptr()) == abi.ERR_UNSUPPORTED
+    torch.cuda.synchronize()
+    assert torch.equal(a_t, before)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_gemm_with_aliased_destination_is_rejected(dt, exc):
+    import ctypes as C
+    import torch
+    from ra_ra_b200 import cuda
+    n = 256
+    a = torch.ones(n, n, device="cuda", dtype=torch.float32 if dt == np.float32 else torch.float64)
+    b = torch.ones_like(a)
+    for cc in (a, b):
+        g = abi.GemmDesc()
+        g.dtype, g.M, g.N, g.K = (abi.F32 if dt == np.float32 else abi.F64), n, n, n
+        g.a, g.lda, g.b, g.ldb, g.c, g.ldc = a.data_ptr(), n, b.data_ptr(), n, cc.data_ptr(), n
+        assert cuda.lib.racu_gemm(C.byref(g), cuda.stream_ptr()) == abi.ERR_UNSUPPORTED
+    torch.cuda.synchronize()
+    assert bool((a == 1).all()) and bool((b == 1).all())
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_narrowing_fold_cuda_vs_oracle(seed, exc):
+    """Integer destination folded over a floating point right hand side: truncation at every step (ra/expr.hh:50-53)."""
+    outs = []
+    for ex in (OracleExecutor(), exc):
+        rng = np.random.default_rng(31000 + seed)
+        m, n, k = (int(x) for x in rng.integers(2, 6, 3))
+        a = ex.from_numpy(rng.uniform(-3, 3, (m, n, k)).astype([np.float32, np.float64][seed % 2]))
+        c = ex.from_numpy(rng.integers(-5, 5, (m,) if seed % 3 == 0 else (m, n)).astype([np.int32, np.int64][(seed // 2) % 2]))
+        getattr(c, ["__iadd__", "__isub__", "__imul__"][seed % 3])(a)
+        outs.append(snapshot(ex, c))
+    assert outs[0].dtype == outs[1].dtype and np.array_equal(outs[0], outs[1]), seed
