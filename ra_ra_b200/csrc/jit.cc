@@ -116,7 +116,6 @@ sources_hash()
     return h;
 }
 
-// variant: maps 0/1 = GENERAL; fold-inner 0/1 = REUSE; fold-outer 0
 static int
 fold_class(int fold_op)
 {
@@ -143,14 +142,20 @@ jit_prog_text(SProg const & P)
     return s;
 }
 
+// What, beyond the program, a specialisation is compiled for. Maps: GENERAL. Folds: the operand kind of every role and the re-read
+// mask (compile-time in the fold bodies, static_device.h), and for fold-inner whether a warp or a CTA owns a kept row.
+struct JitVariant { int general = 0, rows = 0, rmask = 0; uint32_t kinds = 0; };
+
 std::string
-jit_kernel_text(SProg const & P, int mode, int variant, int fold_op)
+jit_kernel_text(SProg const & P, int mode, JitVariant const & v, int fold_op)
 {
     std::string s = "#define RACU_JIT_PROG " + jit_prog_text(P) + "\n#include \"static_device.h\"\n";
     s += "extern \"C\" __global__ void __launch_bounds__(racu::KBLOCK)\nracu_jit_kernel(const __grid_constant__ racu::SParams p";
-    if (mode==K_MAP) s += std::string(")\n{ racu::smap_body<racu::SP_JIT, ") + (variant ? "true" : "false") + ">(p); }\n";
-    else if (mode==K_FOLD_INNER) s += ", const __grid_constant__ racu::FinishParams f)\n{ racu::sfold_inner_body<racu::SP_JIT, " + std::to_string(fold_class(fold_op)) + ", " + (variant ? "true" : "false") + ">(p, f); }\n";
-    else s += ", const __grid_constant__ racu::FinishParams f)\n{ racu::sfold_outer_body<racu::SP_JIT, " + std::to_string(fold_class(fold_op)) + ">(p, f); }\n";
+    std::string const fold = std::to_string(fold_class(fold_op)), kinds = std::to_string(v.kinds) + "u";
+    if (mode==K_MAP) s += std::string(")\n{ racu::smap_body<racu::SP_JIT, ") + (v.general ? "true" : "false") + ">(p); }\n";
+    else if (mode==K_FOLD_INNER) s += std::string(", const __grid_constant__ racu::FinishParams f)\n{ racu::") + (v.rows ? "sfold_inner_rows_body" : "sfold_inner_body")
+                                      + "<racu::SP_JIT, " + fold + ", " + std::to_string(v.rmask) + ", " + kinds + ">(p, f); }\n";
+    else s += ", const __grid_constant__ racu::FinishParams f)\n{ racu::sfold_outer_body<racu::SP_JIT, " + fold + ", " + kinds + ">(p, f); }\n";
     return s;
 }
 
@@ -207,7 +212,7 @@ static int64_t jit_compiles = 0; // NVRTC compilations in this process (disk cac
 
 // Compile (or fetch from the disk cache) the cubin of one specialisation. Needs no GPU. force: ignore (and replace) the cached file.
 static bool
-jit_cubin(SProg const & P, int mode, int variant, int fold_op, std::vector<char> & cubin, std::string & err, bool force=false)
+jit_cubin(SProg const & P, int mode, JitVariant const & variant, int fold_op, std::vector<char> & cubin, std::string & err, bool force=false)
 {
     std::string const src = jit_kernel_text(P, mode, variant, fold_op);
     uint64_t const key = fnv1a(src.data(), src.size(), sources_hash());
@@ -250,13 +255,15 @@ jit_cubin(SProg const & P, int mode, int variant, int fold_op, std::vector<char>
 static std::mutex jit_mutex;
 static std::map<std::string, CUfunction> jit_loaded;   // key: device, mode, variant, fold class + the program's bytes
 
-static int
+static JitVariant
 variant_of(Plan const & plan)
 {
     SParams const & sp = plan.sp;
-    if (sp.mode==K_MAP) return sp.general ? 1 : 0;
-    if (sp.mode==K_FOLD_INNER) { bool any = false; for (int k=0; k<SP_MAXIN; ++k) any = any || sp.reused[k]; return any ? 1 : 0; }
-    return 0;
+    JitVariant v;
+    if (sp.mode==K_MAP) { v.general = sp.general ? 1 : 0; return v; }
+    for (int k=0; k<plan.jit_prog.nin; ++k) { v.kinds |= uint32_t(sp.kind[k])<<(4*k); if (sp.mode==K_FOLD_INNER && sp.reused[k]) v.rmask |= 1<<k; }
+    v.rows = sp.mode==K_FOLD_INNER && sp.inner_rows;
+    return v;
 }
 
 // Planner hook (plan.cc: g_jit_prepare): make sure the specialisation of plan.jit_prog exists. With a device, the kernel is
@@ -264,13 +271,13 @@ variant_of(Plan const & plan)
 static bool
 jit_prepare(Plan & plan, std::string & err)
 {
-    int const variant = variant_of(plan);
+    JitVariant const variant = variant_of(plan);
     int dev = -1;
     bool have_dev = cudaSuccess==cudaGetDevice(&dev) && dev>=0; // (cheap: no context work on the per-call path)
     if (!have_dev) cudaGetLastError();
     // in-memory key: no kernel text is generated on the per-call path
     SProg const & P = plan.jit_prog;
-    int32_t const head[5] = {dev, plan.sp.mode, variant, plan.sp.mode==K_MAP ? 0 : fold_class(plan.sp.fold_op), P.n};
+    int32_t const head[8] = {dev, plan.sp.mode, variant.general, variant.rows, variant.rmask, int32_t(variant.kinds), plan.sp.mode==K_MAP ? 0 : fold_class(plan.sp.fold_op), P.n};
     std::string key(reinterpret_cast<char const *>(head), sizeof(head));
     key.append(reinterpret_cast<char const *>(P.ins), sizeof(SIns)*size_t(P.n));
     int32_t const tail[3] = {P.nin, P.yrole, int32_t(P.fold) | (int32_t(P.otype)<<8)};
@@ -282,8 +289,8 @@ jit_prepare(Plan & plan, std::string & err)
     std::vector<char> cubin;
     if (!jit_cubin(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op, cubin, err)) return false;
     if (have_dev && cudaSuccess!=cudaFree(nullptr)) { cudaGetLastError(); have_dev = false; } // make the primary context current before loading
-    if (std::getenv("RACU_JIT_VERBOSE")) std::fprintf(stderr, "racu jit: specialised %s (mode %d variant %d fold %d) for device %d, %zu bytes\n",
-                                                      jit_prog_text(plan.jit_prog).c_str(), plan.sp.mode, variant, plan.sp.fold_op, dev, cubin.size());
+    if (std::getenv("RACU_JIT_VERBOSE")) std::fprintf(stderr, "racu jit: specialised %s (mode %d general %d rows %d rmask %d kinds %x fold %d) for device %d, %zu bytes\n",
+                                                      jit_prog_text(plan.jit_prog).c_str(), plan.sp.mode, variant.general, variant.rows, variant.rmask, variant.kinds, plan.sp.fold_op, dev, cubin.size());
     if (!have_dev) { plan.jit_fn = nullptr; return true; }
     if (!drv_load()) { err = "driver entry points for module loading are not available"; return false; }
     CUmodule mod = nullptr;

@@ -501,10 +501,18 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
     std::memset(&sp, 0, sizeof(sp));
     int64_t const nvec0 = kp.len0/SV;
     int const target = 148*8;
+    bool const pwide = prog_wide(SP_JIT==id ? plan.jit_prog : static_prog(id));
+    auto knob = [](char const * name, int64_t dflt) { char const * e = std::getenv(name); return e ? int64_t(std::atoll(e)) : dflt; }; // tuning knobs
     if (fold) {
         if (kp.fold_op==RACU_ASSIGN_SET) return;
         if ((kp.nk>1 || kp.mode==K_FOLD_OUTER) && 0!=kp.len0%SV) return;
-        if (kp.mode==K_FOLD_INNER) { // chunk the row in units of SV-element vectors
+        if (kp.mode==K_FOLD_INNER && kp.nk>=knob("RACU_ROWS_MINROWS", 148*16) && nvec0<=knob("RACU_ROWS_MAXVEC", 8192)) {
+            // many kept rows of moderate length (gemv, sum-cols): one warp per row, no chunks, no finish pass
+            if ((kp.nk+KBLOCK/32-1)/(KBLOCK/32)>=(int64_t(1)<<31)) return;
+            sp.inner_rows = 1;
+            kp.nchunks = 1; kp.chunk_len = nvec0;
+            plan.grid_x = unsigned((kp.nk+KBLOCK/32-1)/(KBLOCK/32)); plan.grid_y = 1;
+        } else if (kp.mode==K_FOLD_INNER) { // chunk the row in units of SV-element vectors
             int64_t per = int64_t(KBLOCK)*4; // upper bound of the kernel's vectors per iteration
             int64_t maxchunks = std::max<int64_t>(1, nvec0/(per*2));
             int64_t want = std::max<int64_t>(1, (int64_t(target)*2)/std::max<int64_t>(1, kp.nk));
@@ -516,9 +524,10 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
             kp.nchunks = int(nch); kp.chunk_len = cl;
             plan.grid_x = unsigned(kp.nk*nch); plan.grid_y = 1;
         } else {
-            int64_t nbx = (nvec0+KBLOCK-1)/KBLOCK;
+            int64_t const per = int64_t(KBLOCK)*(pwide ? 1 : 2); // kept vectors per CTA (SPO<ID>::KV per thread)
+            int64_t nbx = (nvec0+per-1)/per;
             if (nbx<1 || nbx>=(int64_t(1)<<31)) return;
-            int64_t want = std::max<int64_t>(1, (int64_t(target)*2)/nbx);
+            int64_t want = std::max<int64_t>(1, knob("RACU_OUTER_CTAS", int64_t(target)*2)/nbx);
             int64_t maxchunks = std::max<int64_t>(1, kp.nB/32);
             int64_t nch = std::min<int64_t>(std::min(maxchunks, want), 65535);
             int64_t cl = (kp.nB+nch-1)/nch;

@@ -278,22 +278,58 @@ emit_partial(SParams const & p, FinishParams const & f, int64_t chunk, int64_t n
     }
 }
 
-// fold kernels: role k of vector g of the row at byte offset rowoff -> raw words
-template <int ID, int FORM> __device__ __forceinline__ void
-fetch_fold_role(SParams const & p, int k, uint32_t * x, unsigned char const * rowbase, int64_t g)
+// ---- folds. KINDS: the operand kind of every role, 4 bits each (role k at bits 4k..4k+3), or SK_RUNTIME = read p.kind[] at run time.
+// RMASK: bit k set = role k does not move along the kept rows (the vector of gemv, ra/ra.hh:418: every row re-reads it) and is loaded
+// through L1; everything else streams past L1. Both are compile-time so that, after unrolling over the roles, every load is ONE
+// instruction of a fixed form: measured (round 1) on the gevm kernel with run-time kinds, the per-row switch made a 4096-instruction
+// body with jump tables that ran at 0.36 of the HBM peak.
+template <uint32_t KINDS> __device__ __forceinline__ int
+role_kind(SParams const & p, int k) { if constexpr (KINDS==SK_RUNTIME) return int(p.kind[k]); else return int((KINDS>>(4*k))&15u); }
+
+__device__ __forceinline__ void
+load_words_form(int form, uint32_t * x, unsigned char const * p, int t)
+{
+    if (LD_STREAM==form) load_words<LD_STREAM>(x, p, t); else if (LD_REUSED==form) load_words<LD_REUSED>(x, p, t); else load_words<LD_RW>(x, p, t);
+}
+
+// role k of vector g of the row at rowbase -> raw words (SEQ roles carry the row's element offset in rowbase: no memory)
+template <int ID, uint32_t KINDS> __device__ __forceinline__ void
+fetch_fold_role(SParams const & p, int k, int form, uint32_t * x, unsigned char const * rowbase, int64_t g)
 {
     constexpr SProg P = SPT<ID>::P;
-    int const t = P.rtype[k], es = es_of(t);
-    if (SK_SCALAR==p.kind[k]) splat_bits(x, p.in[k], t);
-    else if (SK_PTR==p.kind[k]) {}
-    else if (SK_SEQ==p.kind[k]) seq_words(x, p.in[k], int64_t(reinterpret_cast<intptr_t>(rowbase)) + g*SV*p.sA[k][0], p.sA[k][0], t); // rowbase: the row's offset
-    else if (SK_ROW==p.kind[k]) splat_words(x, rowbase, t);
-    else load_words<FORM>(x, rowbase + g*SV*es, t);
+    int const t = P.rtype[k], es = es_of(t), kd = role_kind<KINDS>(p, k);
+    if (SK_SCALAR==kd) splat_bits(x, p.in[k], t);
+    else if (SK_PTR==kd) {}
+    else if (SK_SEQ==kd) seq_words(x, p.in[k], int64_t(reinterpret_cast<intptr_t>(rowbase)) + g*SV*p.sA[k][0], p.sA[k][0], t);
+    else if (SK_ROW==kd) splat_words(x, rowbase, t);
+    else load_words_form(form, x, rowbase + g*SV*es, t);
+}
+
+// kept row kb -> per role: where the row starts (bytes; SEQ: the element offset itself)
+template <int ID, uint32_t KINDS> __device__ __forceinline__ void
+fold_row_bases(SParams const & p, uint32_t kb, unsigned char const ** rowbase)
+{
+    constexpr SProg P = SPT<ID>::P;
+    uint32_t n = kb, q, ib[KGR] = {0, 0, 0, 0};
+    if (p.rankB<=1) ib[0] = n;
+    else {
+        q = fastdiv(n, p.dB[0]); ib[0] = n-q*p.dB[0].len; n = q;
+        if (2==p.rankB) ib[1] = n;
+        else { q = fastdiv(n, p.dB[1]); ib[1] = n-q*p.dB[1].len; n = q;
+            if (3==p.rankB) ib[2] = n; else { q = fastdiv(n, p.dB[2]); ib[2] = n-q*p.dB[2].len; ib[3] = q; } }
+    }
+#pragma unroll
+    for (int k=0; k<P.nin; ++k) {
+        int64_t off = 0;
+#pragma unroll
+        for (int j=0; j<KGR; ++j) { if (j<p.rankB) off += int64_t(ib[j])*p.sB[k][j]; }
+        if (SK_SEQ==role_kind<KINDS>(p, k)) rowbase[k] = reinterpret_cast<unsigned char const *>(intptr_t(off)); // no memory: carry the offset itself
+        else rowbase[k] = reinterpret_cast<unsigned char const *>(p.in[k]) + off*int64_t(es_of(P.rtype[k]));
+    }
 }
 
 // ---- fold-inner, flat rows: CTA = (row kb, chunk c); row length n (multiple of SV unless there is a single row).
-// REUSE: some input does not move along the kept rows (the vector of gemv, ra/ra.hh:418): loads allocate in L1.
-template <int ID, int FOLD, bool REUSE> __device__ __forceinline__ void
+template <int ID, int FOLD, int RMASK, uint32_t KINDS> __device__ __forceinline__ void
 sfold_inner_body(SParams const & p, FinishParams const & f)
 {
     using W = typename SPT<ID>::W;
@@ -302,25 +338,7 @@ sfold_inner_body(SParams const & p, FinishParams const & f)
     __shared__ W red[KBLOCK/32];
     uint32_t const kb = blockIdx.x/uint32_t(p.nchunks), c = blockIdx.x-kb*uint32_t(p.nchunks);
     unsigned char const * rowbase[P.nin];
-    {
-        // row kb -> group-B position -> per input byte offset
-        uint32_t n = kb, q, ib[KGR] = {0, 0, 0, 0};
-        if (p.rankB<=1) ib[0] = n;
-        else {
-            q = fastdiv(n, p.dB[0]); ib[0] = n-q*p.dB[0].len; n = q;
-            if (2==p.rankB) ib[1] = n;
-            else { q = fastdiv(n, p.dB[1]); ib[1] = n-q*p.dB[1].len; n = q;
-                if (3==p.rankB) ib[2] = n; else { q = fastdiv(n, p.dB[2]); ib[2] = n-q*p.dB[2].len; ib[3] = q; } }
-        }
-#pragma unroll
-        for (int k=0; k<P.nin; ++k) {
-            int64_t off = 0;
-#pragma unroll
-            for (int j=0; j<KGR; ++j) { if (j<p.rankB) off += int64_t(ib[j])*p.sB[k][j]; }
-            if (SK_SEQ==p.kind[k]) rowbase[k] = reinterpret_cast<unsigned char const *>(intptr_t(off)); // no memory: carry the offset itself
-            else rowbase[k] = reinterpret_cast<unsigned char const *>(p.in[k]) + off*int64_t(es_of(P.rtype[k]));
-        }
-    }
+    fold_row_bases<ID, KINDS>(p, kb, rowbase);
     int64_t const nfull = p.n/SV;
     int64_t const start = int64_t(c)*p.chunk_len;
     int64_t const end = start+p.chunk_len<nfull ? start+p.chunk_len : nfull;
@@ -335,7 +353,7 @@ sfold_inner_body(SParams const & p, FinishParams const & f)
             int64_t g = g0 + int64_t(u)*KBLOCK;
             if (g<end) {
 #pragma unroll
-                for (int k=0; k<P.nin; ++k) fetch_fold_role<ID, REUSE ? LD_REUSED : LD_STREAM>(p, k, x[u][k], rowbase[k], g);
+                for (int k=0; k<P.nin; ++k) fetch_fold_role<ID, KINDS>(p, k, (RMASK>>k)&1 ? LD_REUSED : LD_STREAM, x[u][k], rowbase[k], g);
             }
         }
 #pragma unroll
@@ -358,10 +376,11 @@ sfold_inner_body(SParams const & p, FinishParams const & f)
             W out[SV];
 #pragma unroll
             for (int k=0; k<P.nin; ++k) {
-                if (SK_SCALAR==p.kind[k]) splat_bits(x[k], p.in[k], P.rtype[k]);
-                else if (SK_PTR==p.kind[k]) {}
-                else if (SK_SEQ==p.kind[k]) seq_words(x[k], p.in[k], int64_t(reinterpret_cast<intptr_t>(rowbase[k])) + e*p.sA[k][0], 0, P.rtype[k]);
-                else splat_words(x[k], rowbase[k] + (SK_ROW==p.kind[k] ? 0 : e)*es_of(P.rtype[k]), P.rtype[k]);
+                int const kd = role_kind<KINDS>(p, k);
+                if (SK_SCALAR==kd) splat_bits(x[k], p.in[k], P.rtype[k]);
+                else if (SK_PTR==kd) {}
+                else if (SK_SEQ==kd) seq_words(x[k], p.in[k], int64_t(reinterpret_cast<intptr_t>(rowbase[k])) + e*p.sA[k][0], 0, P.rtype[k]);
+                else splat_words(x[k], rowbase[k] + (SK_ROW==kd ? 0 : e)*es_of(P.rtype[k]), P.rtype[k]);
             }
             eval_static<ID>(p, x, out);
             r = combine<W>(FOLD, AT, r, out[0]);
@@ -371,37 +390,39 @@ sfold_inner_body(SParams const & p, FinishParams const & f)
     if (0==threadIdx.x) emit_partial<W>(p, f, c, kb, r);
 }
 
-// ---- fold-outer, flat: thread = kept vector g (lanes are kept elements), blockIdx.y = chunk of the folded rows
-template <int ID, int FOLD> __device__ __forceinline__ void
-sfold_outer_body(SParams const & p, FinishParams const & f)
+// ---- fold-inner, one WARP per kept row (gemv ra/ra.hh:414-425, bench-sum-cols.cc:62-65 when the rows are many and of moderate
+// length): no CTA barrier and no shared memory, a row is 32 lanes x UNR vectors in flight until it ends, then five shuffles. With a
+// CTA per 64 KiB row (round 1) a CTA lived for four iterations and most of its time went into starting and draining: 0.56 of the HBM peak.
+// Rows are whole vectors (n % SV == 0), one chunk (the result goes straight to the destination).
+template <int ID, int FOLD, int RMASK, uint32_t KINDS> __device__ __forceinline__ void
+sfold_inner_rows_body(SParams const & p, FinishParams const & f)
 {
     using W = typename SPT<ID>::W;
     constexpr SProg P = SPT<ID>::P;
     constexpr int AT = P.otype, UNR = SPX<ID>::UNR, XW = SPX<ID>::XW;
-    int64_t const g = int64_t(blockIdx.x)*KBLOCK + threadIdx.x;
-    if (g>=p.n/SV) return;
-    uint32_t const c = blockIdx.y;
-    int64_t const r0 = int64_t(c)*p.chunk_len;
-    int64_t const r1 = r0+p.chunk_len<p.nB ? r0+p.chunk_len : p.nB;
+    int const lane = threadIdx.x&31;
+    int64_t const row = int64_t(blockIdx.x)*(KBLOCK/32) + (threadIdx.x>>5);
+    if (row>=p.nk) return; // whole warp
+    unsigned char const * rowbase[P.nin];
+    fold_row_bases<ID, KINDS>(p, uint32_t(row), rowbase);
+    int64_t const nfull = p.n/SV;
     W acc[SV];
 #pragma unroll
     for (int j=0; j<SV; ++j) acc[j] = W(p.identity);
-    for (int64_t r = r0; r<r1; r += UNR) {
+    for (int64_t g0 = lane; g0<nfull; g0 += 32*UNR) {
         uint32_t x[UNR][P.nin][XW];
 #pragma unroll
         for (int u=0; u<UNR; ++u) {
-            if (r+u<r1) {
+            int64_t g = g0 + u*32;
+            if (g<nfull) {
 #pragma unroll
-                for (int k=0; k<P.nin; ++k) { // gevm: c(j) += a(i)*b(i,j): a is one value per folded row (SK_ROW)
-                    unsigned char const * rowbase = SK_SEQ==p.kind[k] ? reinterpret_cast<unsigned char const *>(intptr_t((r+u)*p.sB[k][0]))
-                        : reinterpret_cast<unsigned char const *>(p.in[k]) + (r+u)*p.sB[k][0]*es_of(P.rtype[k]);
-                    fetch_fold_role<ID, LD_STREAM>(p, k, x[u][k], rowbase, g);
-                }
+                for (int k=0; k<P.nin; ++k) fetch_fold_role<ID, KINDS>(p, k, (RMASK>>k)&1 ? LD_REUSED : LD_STREAM, x[u][k], rowbase[k], g);
             }
         }
 #pragma unroll
         for (int u=0; u<UNR; ++u) {
-            if (r+u<r1) {
+            int64_t g = g0 + u*32;
+            if (g<nfull) {
                 W out[SV];
                 eval_static<ID>(p, x[u], out);
 #pragma unroll
@@ -409,8 +430,95 @@ sfold_outer_body(SParams const & p, FinishParams const & f)
             }
         }
     }
+    W r = acc[0];
 #pragma unroll
-    for (int j=0; j<SV; ++j) emit_partial<W>(p, f, c, g*SV+j, acc[j]);
+    for (int j=1; j<SV; ++j) r = combine<W>(FOLD, AT, r, acc[j]);
+    for (int o=16; o>0; o>>=1) { W other = shfl_xor_w<W>(r, o); r = combine<W>(FOLD, AT, r, other); }
+    if (0==lane) emit_partial<W>(p, f, 0, row, r);
+}
+
+// ---- fold-outer, flat: a thread owns KV kept vectors (lanes are kept elements: 32 bytes of the destination row per thread) and walks
+// the folded rows of chunk blockIdx.y with UNR rows in flight. Row addresses advance by pointer bumps (gevm ra/ra.hh:427-438: c(j) += a(i)*b(i,j),
+// a is one value per folded row, SK_ROW; bench-sum-rows.cc:58-81).
+template <int ID> struct SPO
+{
+    static constexpr int KV = SPT<ID>::wide ? 1 : 2;
+    static constexpr int UNR = SPX<ID>::UNR; // folded rows in flight (x KV vectors each)
+};
+
+template <int ID, int FOLD, uint32_t KINDS> __device__ __forceinline__ void
+sfold_outer_body(SParams const & p, FinishParams const & f)
+{
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    constexpr int AT = P.otype, XW = SPX<ID>::XW, KV = SPO<ID>::KV, UNR = SPO<ID>::UNR;
+    int64_t const nvec = p.n/SV;
+    int64_t const g0 = int64_t(blockIdx.x)*(KBLOCK*KV) + threadIdx.x;
+    if (g0>=nvec) return;
+    bool ok[KV];
+#pragma unroll
+    for (int v=0; v<KV; ++v) ok[v] = g0 + v*KBLOCK<nvec;
+    uint32_t const c = blockIdx.y;
+    int64_t const r0 = int64_t(c)*p.chunk_len;
+    int64_t const r1 = r0+p.chunk_len<p.nB ? r0+p.chunk_len : p.nB;
+    // per role: the address (SEQ: element offset) of folded row r0, and what one row adds to it
+    unsigned char const * rowp[P.nin];
+    int64_t rowstep[P.nin];
+#pragma unroll
+    for (int k=0; k<P.nin; ++k) {
+        int const kd = role_kind<KINDS>(p, k);
+        int64_t const scale = SK_SEQ==kd ? 1 : es_of(P.rtype[k]);
+        rowstep[k] = p.sB[k][0]*scale;
+        rowp[k] = (SK_SEQ==kd ? static_cast<unsigned char const *>(nullptr) : reinterpret_cast<unsigned char const *>(p.in[k])) + r0*rowstep[k];
+    }
+    W acc[KV][SV];
+#pragma unroll
+    for (int v=0; v<KV; ++v)
+#pragma unroll
+        for (int j=0; j<SV; ++j) acc[v][j] = W(p.identity);
+    for (int64_t r = r0; r<r1; r += UNR) {
+        uint32_t x[UNR][KV][P.nin][XW];
+#pragma unroll
+        for (int u=0; u<UNR; ++u) {
+            if (r+u<r1) {
+#pragma unroll
+                for (int k=0; k<P.nin; ++k) {
+                    int const kd = role_kind<KINDS>(p, k);
+                    bool const per_row = SK_SCALAR==kd || SK_ROW==kd || SK_PTR==kd; // the same for every kept vector: fetch once
+#pragma unroll
+                    for (int v=0; v<KV; ++v) {
+                        if (per_row && v>0) {
+#pragma unroll
+                            for (int q=0; q<XW; ++q) x[u][v][k][q] = x[u][0][k][q];
+                        } else if (ok[v]) fetch_fold_role<ID, KINDS>(p, k, LD_STREAM, x[u][v][k], rowp[k] + u*rowstep[k], g0 + v*KBLOCK);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u=0; u<UNR; ++u) {
+            if (r+u<r1) {
+#pragma unroll
+                for (int v=0; v<KV; ++v) {
+                    if (ok[v]) {
+                        W out[SV];
+                        eval_static<ID>(p, x[u][v], out);
+#pragma unroll
+                        for (int j=0; j<SV; ++j) acc[v][j] = combine<W>(FOLD, AT, acc[v][j], out[j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k=0; k<P.nin; ++k) rowp[k] += UNR*rowstep[k];
+    }
+#pragma unroll
+    for (int v=0; v<KV; ++v) {
+        if (ok[v]) {
+#pragma unroll
+            for (int j=0; j<SV; ++j) emit_partial<W>(p, f, c, (g0 + v*KBLOCK)*SV+j, acc[v][j]);
+        }
+    }
 }
 
 } // namespace racu

@@ -22,12 +22,20 @@ namespace racu {
 // kernels: thin __global__ wrappers of the bodies in static_device.h
 template <int ID, bool GENERAL> __global__ void __launch_bounds__(KBLOCK)
 smap_kernel(const __grid_constant__ SParams p) { smap_body<ID, GENERAL>(p); }
-template <int ID, int FOLD, bool REUSE> __global__ void __launch_bounds__(KBLOCK)
-sfold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f) { sfold_inner_body<ID, FOLD, REUSE>(p, f); }
-template <int ID, int FOLD> __global__ void __launch_bounds__(KBLOCK)
-sfold_outer_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f) { sfold_outer_body<ID, FOLD>(p, f); }
+template <int ID, int FOLD, int RMASK, uint32_t KINDS> __global__ void __launch_bounds__(KBLOCK)
+sfold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f) { sfold_inner_body<ID, FOLD, RMASK, KINDS>(p, f); }
+template <int ID, int FOLD, int RMASK, uint32_t KINDS> __global__ void __launch_bounds__(KBLOCK)
+sfold_inner_rows_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f) { sfold_inner_rows_body<ID, FOLD, RMASK, KINDS>(p, f); }
+template <int ID, int FOLD, uint32_t KINDS> __global__ void __launch_bounds__(KBLOCK)
+sfold_outer_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f) { sfold_outer_body<ID, FOLD, KINDS>(p, f); }
 
 // ---------------- dispatch ----------------
+// Pre-compiled fold variants per program. Sums (the configs' folds: sum, dot, reduce_sqrm, row / column sums, gemv, gevm) get the
+// operand kinds and the reuse mask as compile-time constants for the layouts that occur there: every role a unit-step vector, and
+// for two-role programs one value per folded row against a vector (gevm) or one role re-read by every kept row (gemv). Any other
+// layout, and the other combiners (prod, amin, amax), run the same bodies with the kinds read at run time.
+
+template <int ID> constexpr uint32_t all_vec_kinds() { uint32_t k = 0; for (int r=0; r<SPT<ID>::P.nin; ++r) k |= uint32_t(SK_VEC)<<(4*r); return k; }
 
 template <int ID> static cudaError_t
 launch_one(Plan const & plan, dim3 grid, cudaStream_t stream)
@@ -39,19 +47,52 @@ launch_one(Plan const & plan, dim3 grid, cudaStream_t stream)
             if (p.general) smap_kernel<ID, true><<<grid, KBLOCK, 0, stream>>>(p); else smap_kernel<ID, false><<<grid, KBLOCK, 0, stream>>>(p);
         }
     } else if constexpr (P.fold) {
-        bool any = false;
-        for (int k=0; k<SP_MAXIN; ++k) any = any || p.reused[k];
-#define RACU_SF(KERNEL, ...) \
-        switch (p.fold_op) { \
-        case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: KERNEL<ID, RACU_ASSIGN_ADD __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        case RACU_ASSIGN_AMIN: KERNEL<ID, RACU_ASSIGN_AMIN __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        case RACU_ASSIGN_AMAX: KERNEL<ID, RACU_ASSIGN_AMAX __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        default: KERNEL<ID, RACU_ASSIGN_MUL __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); break; \
-        }
+        uint32_t kinds = 0; int rmask = 0;
+        for (int k=0; k<P.nin; ++k) { kinds |= uint32_t(p.kind[k])<<(4*k); rmask |= (p.reused[k] ? 1 : 0)<<k; }
+        constexpr uint32_t VV = all_vec_kinds<ID>();
+#define RACU_GO(KERNEL, ...) do { KERNEL<ID, __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); return cudaGetLastError(); } while (0)
+        bool const sum = p.fold_op==RACU_ASSIGN_ADD || p.fold_op==RACU_ASSIGN_SUB;
         if (p.mode==K_FOLD_INNER) {
-            if (any) { RACU_SF(sfold_inner_kernel, , true) } else { RACU_SF(sfold_inner_kernel, , false) }
-        } else { RACU_SF(sfold_outer_kernel) }
-#undef RACU_SF
+            if (sum && kinds==VV) { // dot, sum, sqrm, sum-cols, gemv
+                if (p.inner_rows) {
+                    if (0==rmask) RACU_GO(sfold_inner_rows_kernel, RACU_ASSIGN_ADD, 0, VV);
+                    if constexpr (2==P.nin) { if (1==rmask) RACU_GO(sfold_inner_rows_kernel, RACU_ASSIGN_ADD, 1, VV); if (2==rmask) RACU_GO(sfold_inner_rows_kernel, RACU_ASSIGN_ADD, 2, VV); }
+                } else {
+                    if (0==rmask) RACU_GO(sfold_inner_kernel, RACU_ASSIGN_ADD, 0, VV);
+                    if constexpr (2==P.nin) { if (1==rmask) RACU_GO(sfold_inner_kernel, RACU_ASSIGN_ADD, 1, VV); if (2==rmask) RACU_GO(sfold_inner_kernel, RACU_ASSIGN_ADD, 2, VV); }
+                }
+            }
+            constexpr int ALL = (1<<P.nin)-1; // run-time kinds: loads of a kernel with any re-read role all go through L1
+            if (p.inner_rows) {
+                switch (p.fold_op) {
+                case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: if (rmask) RACU_GO(sfold_inner_rows_kernel, RACU_ASSIGN_ADD, ALL, SK_RUNTIME); else RACU_GO(sfold_inner_rows_kernel, RACU_ASSIGN_ADD, 0, SK_RUNTIME);
+                case RACU_ASSIGN_AMIN: RACU_GO(sfold_inner_rows_kernel, RACU_ASSIGN_AMIN, 0, SK_RUNTIME);
+                case RACU_ASSIGN_AMAX: RACU_GO(sfold_inner_rows_kernel, RACU_ASSIGN_AMAX, 0, SK_RUNTIME);
+                default: RACU_GO(sfold_inner_rows_kernel, RACU_ASSIGN_MUL, 0, SK_RUNTIME);
+                }
+            }
+            switch (p.fold_op) {
+            case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: if (rmask) RACU_GO(sfold_inner_kernel, RACU_ASSIGN_ADD, ALL, SK_RUNTIME); else RACU_GO(sfold_inner_kernel, RACU_ASSIGN_ADD, 0, SK_RUNTIME);
+            case RACU_ASSIGN_AMIN: RACU_GO(sfold_inner_kernel, RACU_ASSIGN_AMIN, 0, SK_RUNTIME);
+            case RACU_ASSIGN_AMAX: RACU_GO(sfold_inner_kernel, RACU_ASSIGN_AMAX, 0, SK_RUNTIME);
+            default: RACU_GO(sfold_inner_kernel, RACU_ASSIGN_MUL, 0, SK_RUNTIME);
+            }
+        } else {
+            if (sum) {
+                if (kinds==VV) RACU_GO(sfold_outer_kernel, RACU_ASSIGN_ADD, VV); // sum-rows
+                if constexpr (2==P.nin) {
+                    if (kinds==sk_pack(SK_ROW, SK_VEC)) RACU_GO(sfold_outer_kernel, RACU_ASSIGN_ADD, sk_pack(SK_ROW, SK_VEC)); // gevm
+                    if (kinds==sk_pack(SK_VEC, SK_ROW)) RACU_GO(sfold_outer_kernel, RACU_ASSIGN_ADD, sk_pack(SK_VEC, SK_ROW));
+                }
+            }
+            switch (p.fold_op) {
+            case RACU_ASSIGN_ADD: case RACU_ASSIGN_SUB: RACU_GO(sfold_outer_kernel, RACU_ASSIGN_ADD, SK_RUNTIME);
+            case RACU_ASSIGN_AMIN: RACU_GO(sfold_outer_kernel, RACU_ASSIGN_AMIN, SK_RUNTIME);
+            case RACU_ASSIGN_AMAX: RACU_GO(sfold_outer_kernel, RACU_ASSIGN_AMAX, SK_RUNTIME);
+            default: RACU_GO(sfold_outer_kernel, RACU_ASSIGN_MUL, SK_RUNTIME);
+            }
+        }
+#undef RACU_GO
     }
     return cudaGetLastError();
 }

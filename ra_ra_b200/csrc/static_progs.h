@@ -118,6 +118,9 @@ enum { SK_SCALAR = 0, SK_VEC = 1, SK_VECREV = 2 /* unit step backwards: aligned 
        SK_SEQ = 4 /* iota / tindex (ra/expr.hh:79-100): value = origin + element offset, no memory */,
        SK_PTR = 5 /* gathered array (RACU_OP_LOAD): in[] = base address, sA[][0..1] = valid element offsets; never fetched */ };
 
+constexpr uint32_t SK_RUNTIME = 0xffffffffu; // KINDS template argument of the fold kernels: operand kinds read from SParams::kind at run time
+constexpr uint32_t sk_pack(int k0, int k1=0, int k2=0, int k3=0) { return uint32_t(k0) | (uint32_t(k1)<<4) | (uint32_t(k2)<<8) | (uint32_t(k3)<<12); }
+
 struct SParams
 {
     int32_t id, mode, fold_op, nchunks, rankB, rankA;
@@ -132,6 +135,8 @@ struct SParams
     uint64_t in[SP_MAXIN];        // role -> base address (vector inputs) or value bits in the role's type (scalars)
     uint8_t kind[SP_MAXIN];       // SK_*
     uint8_t reused[SP_MAXIN];     // folds: the operand does not move along the kept rows (every row re-reads it): cache in L1
+    int32_t inner_rows;           // fold-inner: one warp per kept row (sfold_inner_rows_body) instead of one CTA per (row, chunk)
+    int32_t pad1;
     int64_t sB[SP_MAXIN][KGR];    // role -> element strides over group B
     KDim dB[KGR];
     // maps over up to KGR uncollapsible axes (axis 0 vectorised)
