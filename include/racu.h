@@ -218,6 +218,9 @@ typedef enum {
 int racu_reduce(const racu_desc * d, int redop, void * out_host, void * stream);
 /* Same, result left in device memory (asynchronous). */
 int racu_reduce_dev(const racu_desc * d, int redop, void * out_dev, void * stream);
+/* Same, asynchronous, result written by the device into page-locked HOST memory from racu_host_alloc (valid after a
+ * racu_stream_sync of `stream`): a chain of reductions costs one synchronise, not one per scalar. */
+int racu_reduce_async(const racu_desc * d, int redop, void * out_pinned, void * stream);
 /* Plan d exactly as racu_map would (redop == 0) or racu_reduce (redop != 0) and make sure its kernel exists, WITHOUT
  * launching anything. A program that is not in the pre-compiled table is specialised now (NVRTC) and cached in memory and
  * on disk ($RACU_JIT_CACHE, default: jit_cache/ next to the library), so the first real call does not pay for it. Needs
@@ -231,6 +234,8 @@ int64_t racu_launch_count(void);
 void racu_launch_count_reset(void);
 /* Name of the kernel family the last racu_map / racu_reduce on this thread dispatched to. */
 const char * racu_last_kernel(void);
+/* Plans are cached per thread (key: descriptor + destination + device); counters of this thread's lookups. */
+void racu_plan_cache_stats(int64_t * hits, int64_t * misses);
 
 /* ---- stencils ---- */
 typedef enum {

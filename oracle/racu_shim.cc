@@ -44,6 +44,8 @@ int racu_agree(const racu_desc * d, int32_t * r, int64_t * l) { return oracle_ag
 int racu_map(const racu_desc * d, void *) { return oracle_map(d); }
 int racu_reduce(const racu_desc * d, int redop, void * out, void *) { return oracle_reduce(d, redop, out); }
 int racu_reduce_dev(const racu_desc * d, int redop, void * out, void *) { return oracle_reduce(d, redop, out); }
+int racu_reduce_async(const racu_desc * d, int redop, void * out, void *) { return oracle_reduce(d, redop, out); }
+void racu_plan_cache_stats(int64_t * h, int64_t * m) { if (h) *h = 0; if (m) *m = 0; }
 int racu_prepare(const racu_desc *, int, const char ** k) { if (k) *k = "oracle"; return RACU_OK; }
 int64_t racu_launch_count(void) { return 0; }
 void racu_launch_count_reset(void) {}

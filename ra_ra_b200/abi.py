@@ -132,6 +132,8 @@ SYMBOLS = [
     ("racu_map", C.c_int, [C.POINTER(Desc), _P]),
     ("racu_reduce", C.c_int, [C.POINTER(Desc), C.c_int, _P, _P]),
     ("racu_reduce_dev", C.c_int, [C.POINTER(Desc), C.c_int, _P, _P]),
+    ("racu_reduce_async", C.c_int, [C.POINTER(Desc), C.c_int, _P, _P]),
+    ("racu_plan_cache_stats", None, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("racu_prepare", C.c_int, [C.POINTER(Desc), C.c_int, C.POINTER(C.c_char_p)]),
     ("racu_launch_count", C.c_int64, []),
     ("racu_launch_count_reset", None, []),

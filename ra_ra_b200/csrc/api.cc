@@ -3,8 +3,11 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "launch.h"
 #include "special.h"
@@ -22,12 +25,89 @@ int cuda_fail(cudaError_t e, char const * where)
 }
 void set_kernel(const char * k) { g_kernel = k; }
 
+// ---- per-call overhead: plans are cached, fold scratch is kept.
+//
+// Plan cache (per thread): key = the bytes of the descriptor that are in use + redop + the reduce destination + the device. Base
+// pointers are part of the key on purpose: alignment and aliasing decide the plan. A loop that issues the same expression again
+// (benchmarks, the CG iteration, a pointer-swapping sweep = two entries) skips make_plan and the specialiser's lookup.
+// RACU_NO_PLAN_CACHE=1 plans every call (the tuning knobs are read at plan time).
+struct PlanKey
+{
+    std::string bytes;
+    bool operator==(PlanKey const & o) const { return bytes==o.bytes; }
+};
+static void
+make_key(racu_desc const * d, int redop, void * reduce_out, PlanKey & k)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev)) { cudaGetLastError(); dev = -1; }
+    // the planner's environment knobs are read at plan time: their values are part of the key, so changing one takes effect at once
+    uint64_t env = 1469598103934665603ull;
+    for (char const * name: {"RACU_NO_STATIC", "RACU_NO_JIT", "RACU_U", "RACU_NO_TRANSPOSE", "RACU_ROWS_MINROWS", "RACU_ROWS_MAXVEC", "RACU_OUTER_CTAS"}) {
+        char const * v = std::getenv(name);
+        env = (env ^ (v ? 0x9e : 0x3b))*1099511628211ull;
+        for (; v && *v; ++v) env = (env ^ uint8_t(*v))*1099511628211ull;
+    }
+    int64_t const head[5] = {(int64_t(d->nopnd)<<32) | uint32_t(d->nins), (int64_t(d->dst)<<32) | uint32_t(d->assign), (int64_t(redop)<<32) | uint32_t(dev), int64_t(uintptr_t(reduce_out)), int64_t(env)};
+    k.bytes.assign(reinterpret_cast<char const *>(head), sizeof(head));
+    k.bytes.append(reinterpret_cast<char const *>(d->opnd), sizeof(racu_operand)*size_t(d->nopnd));
+    k.bytes.append(reinterpret_cast<char const *>(d->ins), sizeof(racu_ins)*size_t(d->nins));
+}
+struct PlanCache
+{
+    static constexpr int N = 64;
+    struct Entry { PlanKey key; Plan plan; uint64_t used = 0; bool valid = false; };
+    Entry e[N];
+    uint64_t tick = 0;
+    Plan * find(PlanKey const & k)
+    {
+        for (auto & x: e) { if (x.valid && x.key==k) { x.used = ++tick; return &x.plan; } }
+        return nullptr;
+    }
+    Plan * insert(PlanKey && k, Plan const & p)
+    {
+        Entry * v = &e[0];
+        for (auto & x: e) { if (!x.valid) { v = &x; break; } if (x.used<v->used) v = &x; }
+        v->key = std::move(k); v->plan = p; v->used = ++tick; v->valid = true;
+        return &v->plan;
+    }
+};
+static PlanCache & plan_cache() { static thread_local PlanCache * c = new PlanCache; return *c; } // (leaked at thread exit: no CUDA calls in a destructor)
+static thread_local int64_t g_plan_hits = 0, g_plan_misses = 0;
+
+// Fold scratch (per thread, device and stream): the partials of a chunked fold. Work on one stream is ordered, so consecutive folds
+// share the allocation; it only grows. Replaces a cudaMallocAsync / cudaFreeAsync pair per fold.
+struct Scratch { int dev; cudaStream_t stream; void * ptr; size_t bytes; };
+static void *
+fold_scratch(size_t bytes, cudaStream_t stream, cudaError_t & err)
+{
+    static thread_local std::vector<Scratch> * all = new std::vector<Scratch>;
+    int dev = 0;
+    if ((err = cudaGetDevice(&dev))) return nullptr;
+    Scratch * s = nullptr;
+    for (auto & x: *all) { if (x.dev==dev && x.stream==stream) { s = &x; break; } }
+    if (!s) { all->push_back(Scratch {dev, stream, nullptr, 0}); s = &all->back(); }
+    if (s->bytes<bytes) {
+        if (s->ptr) { if ((err = cudaStreamSynchronize(stream))) return nullptr; cudaFree(s->ptr); s->ptr = nullptr; s->bytes = 0; }
+        size_t const want = std::max<size_t>(bytes+bytes/2, size_t(1)<<20);
+        if ((err = cudaMalloc(&s->ptr, want))) { s->ptr = nullptr; return nullptr; }
+        s->bytes = want;
+    }
+    return s->ptr;
+}
+
 static int
 run_plan(racu_desc const * d, int redop, void * reduce_out, cudaStream_t stream)
 {
-    Plan plan;
+    static bool const no_cache = nullptr!=std::getenv("RACU_NO_PLAN_CACHE");
+    PlanKey key;
+    Plan * cached = nullptr;
+    if (!no_cache) { make_key(d, redop, reduce_out, key); cached = plan_cache().find(key); }
+    Plan local;
     std::string err;
-    if (int e = make_plan(d, redop, reduce_out, plan, err)) {
+    if (cached) ++g_plan_hits;
+    else ++g_plan_misses;
+    if (int e = cached ? RACU_OK : make_plan(d, redop, reduce_out, local, err)) {
         if (e==RACU_ERR_SEQ) { // sequential semantics are observable: the folded axes one index at a time, in row-major order
             Shape sh;
             if (int e2 = agree(d, sh, err)) return fail(e2, err);
@@ -64,6 +144,8 @@ run_plan(racu_desc const * d, int redop, void * reduce_out, cudaStream_t stream)
         }
         return RACU_OK;
     }
+    if (!cached && !no_cache) cached = plan_cache().insert(std::move(key), local);
+    Plan & plan = cached ? *cached : local;
     if (plan.empty) {
         g_kernel = "none (empty)";
         if (plan.fill_identity) { // empty reduction: the start value (test/reduction.cc:199-201, :236-238)
@@ -75,16 +157,15 @@ run_plan(racu_desc const * d, int redop, void * reduce_out, cudaStream_t stream)
         }
         return RACU_OK;
     }
-    void * partial = nullptr;
+    cudaError_t e = cudaSuccess;
     if (plan.partial_bytes) {
-        if (cudaError_t e = cudaMallocAsync(&partial, plan.partial_bytes, stream)) return cuda_fail(e, "cudaMallocAsync");
+        void * partial = fold_scratch(plan.partial_bytes, stream, e);
+        if (!partial) return cuda_fail(e, "fold scratch");
         plan.kp.partial = partial; plan.fp.partial = partial; plan.sp.partial = partial;
     }
     plan.fp.identity = plan.kp.identity;
     g_kernel = plan.kernel;
-    cudaError_t e = cudaSuccess;
     if (!try_transpose(plan, stream, e)) e = launch_plan(plan, stream);
-    if (partial) { cudaError_t e2 = cudaFreeAsync(partial, stream); if (!e) e = e2; }
     if (e) return cuda_fail(e, plan.kernel);
     return RACU_OK;
 }
@@ -130,7 +211,7 @@ int racu_fill(void * d, int dtype, racu_base v, size_t count, void * st)
     return RACU_OK;
 }
 int racu_stream_sync(void * st) { if (cudaError_t e = cudaStreamSynchronize(cudaStream_t(st))) return cuda_fail(e, "stream sync"); return RACU_OK; }
-int racu_host_alloc(void ** ptr, size_t bytes) { if (cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 16)) { cudaGetLastError(); g_error = cudaGetErrorString(e); return RACU_ERR_ALLOC; } return RACU_OK; }
+int racu_host_alloc(void ** ptr, size_t bytes) { if (cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocPortable | cudaHostAllocMapped)) { cudaGetLastError(); g_error = cudaGetErrorString(e); return RACU_ERR_ALLOC; } return RACU_OK; }
 int racu_host_free(void * ptr) { if (cudaError_t e = cudaFreeHost(ptr)) return cuda_fail(e, "cudaFreeHost"); return RACU_OK; }
 
 int racu_agree(const racu_desc * d, int32_t * rank_out, int64_t * len_out)
@@ -191,6 +272,16 @@ int racu_reduce_dev(const racu_desc * d, int redop, void * out_dev, void * strea
     return run_plan(d, redop, out_dev, cudaStream_t(stream));
 }
 
+// The scalar goes straight into page-locked host memory that the device writes over PCIe (one slot per thread): no allocation, no
+// copy call, one stream synchronise. (Round 1: cudaMallocAsync + kernel + finish + cudaMemcpyAsync + sync + cudaFreeAsync per call.)
+static void *
+result_slot()
+{
+    static thread_local void * slot = nullptr;
+    if (!slot) { if (cudaError_t e = cudaHostAlloc(&slot, 64, cudaHostAllocPortable | cudaHostAllocMapped)) { (void)e; cudaGetLastError(); slot = nullptr; } }
+    return slot;
+}
+
 int racu_reduce(const racu_desc * d, int redop, void * out_host, void * stream)
 {
     if (!d || !out_host) return fail(RACU_ERR_BAD_DESC, "null argument");
@@ -198,18 +289,29 @@ int racu_reduce(const racu_desc * d, int redop, void * out_host, void * stream)
     if (int e = validate_desc(d, true, err)) return fail(e, err);
     int rt = check_program(d, err);
     if (rt<0) return fail(RACU_ERR_BAD_DESC, err);
-    void * tmp = nullptr;
+    void * slot = result_slot();
+    if (!slot) return fail(RACU_ERR_ALLOC, "cudaHostAlloc failed");
     cudaStream_t st = cudaStream_t(stream);
-    if (cudaError_t e = cudaMallocAsync(&tmp, 16, st)) return cuda_fail(e, "cudaMallocAsync");
-    int r = run_plan(d, redop, tmp, st);
+    int r = run_plan(d, redop, slot, st);
     if (RACU_OK==r) {
-        cudaError_t e = cudaMemcpyAsync(out_host, tmp, dtype_size(rt), cudaMemcpyDeviceToHost, st);
-        if (!e) e = cudaStreamSynchronize(st);
-        if (e) r = cuda_fail(e, "reduce readback");
+        if (cudaError_t e = cudaStreamSynchronize(st)) return cuda_fail(e, "reduce sync");
+        std::memcpy(out_host, slot, dtype_size(rt));
     }
-    cudaFreeAsync(tmp, st);
     return r;
 }
+
+int racu_reduce_async(const racu_desc * d, int redop, void * out_pinned, void * stream)
+{
+    if (!d || !out_pinned) return fail(RACU_ERR_BAD_DESC, "null argument");
+    { std::string err; if (int e = validate_desc(d, true, err)) return fail(e, err); }
+    cudaPointerAttributes at;
+    if (cudaError_t e = cudaPointerGetAttributes(&at, out_pinned)) { cudaGetLastError(); return cuda_fail(e, "racu_reduce_async"); }
+    if (at.type!=cudaMemoryTypeHost && at.type!=cudaMemoryTypeManaged && at.type!=cudaMemoryTypeDevice)
+        return fail(RACU_ERR_BAD_DESC, "racu_reduce_async: the result must go to page-locked host memory (racu_host_alloc) or device memory");
+    return run_plan(d, redop, at.type==cudaMemoryTypeHost ? at.devicePointer : out_pinned, cudaStream_t(stream));
+}
+
+void racu_plan_cache_stats(int64_t * hits, int64_t * misses) { if (hits) *hits = g_plan_hits; if (misses) *misses = g_plan_misses; }
 
 int64_t racu_launch_count(void) { return launch_count(); }
 void racu_launch_count_reset(void) { launch_count_reset(); }

@@ -72,6 +72,7 @@ static struct Drv
     CUresult (*ModuleLoadData)(CUmodule *, void const *) = nullptr;
     CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, char const *) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **) = nullptr;
+    CUresult (*Occupancy)(int *, CUfunction, int, size_t) = nullptr;
     bool ok = false;
 } drv;
 
@@ -90,6 +91,7 @@ drv_load()
         drv.ModuleLoadData = reinterpret_cast<decltype(drv.ModuleLoadData)>(get("cuModuleLoadData"));
         drv.ModuleGetFunction = reinterpret_cast<decltype(drv.ModuleGetFunction)>(get("cuModuleGetFunction"));
         drv.LaunchKernel = reinterpret_cast<decltype(drv.LaunchKernel)>(get("cuLaunchKernel"));
+        drv.Occupancy = reinterpret_cast<decltype(drv.Occupancy)>(get("cuOccupancyMaxActiveBlocksPerMultiprocessor"));
         drv.ok = drv.ModuleLoadData && drv.ModuleGetFunction && drv.LaunchKernel;
     });
     return drv.ok;
@@ -313,6 +315,20 @@ launch_jit(Plan const & plan, cudaStream_t stream)
     void * args[2] = {const_cast<SParams *>(&plan.sp), const_cast<FinishParams *>(&plan.fp)};
     CUresult r = drv.LaunchKernel(static_cast<CUfunction>(plan.jit_fn), plan.grid_x, plan.grid_y, 1, KBLOCK, 1, 1, 0, stream, args, nullptr);
     return cudaError_t(r); // driver and runtime share the error numbering (CUDA_SUCCESS == cudaSuccess == 0)
+}
+
+int
+jit_occupancy(Plan const & plan)
+{
+    if (!plan.jit_fn || !drv_load() || !drv.Occupancy) return 0;
+    static std::map<void *, int> cache;
+    std::lock_guard<std::mutex> lock(jit_mutex);
+    auto it = cache.find(plan.jit_fn);
+    if (it!=cache.end()) return it->second;
+    int n = 0;
+    if (CUDA_SUCCESS!=drv.Occupancy(&n, static_cast<CUfunction>(plan.jit_fn), KBLOCK, 0)) return 0;
+    cache.emplace(plan.jit_fn, n);
+    return n;
 }
 
 int64_t jit_compile_count() { return jit_compiles; }

@@ -8,6 +8,7 @@ namespace racu {
 cudaError_t launch_plan(Plan const & plan, cudaStream_t stream);
 cudaError_t launch_static(Plan const & plan, cudaStream_t stream);
 cudaError_t launch_jit(Plan const & plan, cudaStream_t stream);
+int jit_occupancy(Plan const & plan);      // resident CTAs per SM of the plan's run-time specialised kernel (0: unknown)
 bool try_transpose(Plan const & plan, cudaStream_t stream, cudaError_t & err);
 cudaError_t launch_fill(void * dst, int dtype, racu_base v, size_t n, cudaStream_t stream);
 int64_t launch_count();

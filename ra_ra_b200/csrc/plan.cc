@@ -506,7 +506,7 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
     if (fold) {
         if (kp.fold_op==RACU_ASSIGN_SET) return;
         if ((kp.nk>1 || kp.mode==K_FOLD_OUTER) && 0!=kp.len0%SV) return;
-        if (kp.mode==K_FOLD_INNER && kp.nk>=knob("RACU_ROWS_MINROWS", 148*16) && nvec0<=knob("RACU_ROWS_MAXVEC", 8192)) {
+        if (kp.mode==K_FOLD_INNER && kp.nk>=knob("RACU_ROWS_MINROWS", 148*16) && nvec0<=knob("RACU_ROWS_MAXVEC", 4096)) {
             // many kept rows of moderate length (gemv, sum-cols): one warp per row, no chunks, no finish pass
             if ((kp.nk+KBLOCK/32-1)/(KBLOCK/32)>=(int64_t(1)<<31)) return;
             sp.inner_rows = 1;
@@ -524,17 +524,12 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
             kp.nchunks = int(nch); kp.chunk_len = cl;
             plan.grid_x = unsigned(kp.nk*nch); plan.grid_y = 1;
         } else {
-            int64_t const per = int64_t(KBLOCK)*(pwide ? 1 : 2); // kept vectors per CTA (SPO<ID>::KV per thread)
+            // geometry below (outer_geometry), once the kernel is known
+            int64_t const per = 32*(pwide ? 1 : 2);
             int64_t nbx = (nvec0+per-1)/per;
             if (nbx<1 || nbx>=(int64_t(1)<<31)) return;
-            int64_t want = std::max<int64_t>(1, knob("RACU_OUTER_CTAS", int64_t(target)*2)/nbx);
-            int64_t maxchunks = std::max<int64_t>(1, kp.nB/32);
-            int64_t nch = std::min<int64_t>(std::min(maxchunks, want), 65535);
-            int64_t cl = (kp.nB+nch-1)/nch;
-            cl = ((cl+3)/4)*4;
-            nch = (kp.nB+cl-1)/cl;
-            kp.nchunks = int(nch); kp.chunk_len = cl;
-            plan.grid_x = unsigned(nbx); plan.grid_y = unsigned(nch);
+            kp.nchunks = 1; kp.chunk_len = kp.nB;
+            plan.grid_x = unsigned(nbx); plan.grid_y = 1;
         }
         plan.fp.nchunks = kp.nchunks;
         plan.need_finish = kp.nchunks>1;
@@ -586,12 +581,44 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
         std::string err;
         if (!g_jit_prepare(plan, err)) { if (std::getenv("RACU_JIT_VERBOSE")) std::fprintf(stderr, "racu jit: %s\n", err.c_str()); return; }
     }
+    if (fold && kp.mode==K_FOLD_OUTER) {
+        // A CTA owns 32*KV kept vectors (SPO<ID>::TILE) and one chunk of the folded rows, which its 8 warps share (UNR rows each per turn).
+        // Chunks cost a partials pass, and these CTAs all take the same time, so the grid is sized in WHOLE WAVES of the kernel's own
+        // occupancy: measured on 16384^2, gevm f32 (3 CTAs / SM) ran at 0.97 of the HBM peak with 888 CTAs and 0.90 with 1184, gevm f64
+        // (4 / SM) at 1.02 with 1184 and 0.89 with 888.
+        int64_t const nbx = plan.grid_x;
+        int occ = g_static_occupancy ? g_static_occupancy(plan) : 0;
+        if (occ<=0) occ = 3;
+        int64_t const slots = int64_t(148)*occ;
+        int64_t const maxchunks = std::min<int64_t>(std::max<int64_t>(1, kp.nB/64), 65535);
+        int64_t nch = 1;
+        if (int64_t forced = knob("RACU_OUTER_CTAS", 0)) nch = std::max<int64_t>(1, forced/nbx);
+        else {
+            double best = -1;
+            for (int64_t c = 1; c<=maxchunks && nbx*c<=slots*3; ++c) { // up to three waves; prefer fuller last waves, then more CTAs per slot
+                int64_t const ctas = nbx*c, waves = (ctas+slots-1)/slots;
+                double const eff = double(ctas)/double(waves*slots) - 0.02/double(waves); // a single wave has no one to hide its start / drain behind
+                if (eff>best) { best = eff; nch = c; }
+            }
+        }
+        nch = std::min(nch, maxchunks);
+        int64_t cl = (kp.nB+nch-1)/nch;
+        cl = ((cl+31)/32)*32;
+        nch = (kp.nB+cl-1)/cl;
+        kp.nchunks = int(nch); kp.chunk_len = cl;
+        plan.grid_y = unsigned(nch);
+        plan.fp.nchunks = kp.nchunks;
+        plan.need_finish = kp.nchunks>1;
+        plan.partial_bytes = plan.need_finish ? size_t(kp.nchunks)*size_t(kp.nk)*(plan.fp.wide ? 8 : 4) : 0;
+        sp.nchunks = kp.nchunks; sp.chunk_len = kp.chunk_len;
+    }
     plan.is_static = true;
     static const char * names[6] = {"sflat_map", "sflat_fold_inner", "sflat_fold_outer", "jit_map", "jit_fold_inner", "jit_fold_outer"};
     plan.kernel = names[kp.mode + (SP_JIT==id ? 3 : 0)];
 }
 
 bool (*g_jit_prepare)(Plan &, std::string &) = nullptr;
+int (*g_static_occupancy)(Plan const &) = nullptr;
 
 // The static / run-time specialised kernels use their own launch geometry: if no specialisation applies in the end (or the
 // specialiser fails), the interpreter's plan must come back untouched.

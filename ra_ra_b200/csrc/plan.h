@@ -30,6 +30,8 @@ struct Plan
 
 // Set by jit.cc when the library carries the run-time specialiser (never in the CPU plan simulator).
 extern bool (*g_jit_prepare)(Plan &, std::string &);
+// Set by static_kernels.cu: CTAs of the plan's specialised kernel that fit on one SM (0 when there is no device to ask).
+extern int (*g_static_occupancy)(Plan const &);
 
 // What the expression computes, before any layout decision.
 struct Shape { int rank; int64_t len[KMAXR]; };

@@ -437,13 +437,17 @@ sfold_inner_rows_body(SParams const & p, FinishParams const & f)
     if (0==lane) emit_partial<W>(p, f, 0, row, r);
 }
 
-// ---- fold-outer, flat: a thread owns KV kept vectors (lanes are kept elements: 32 bytes of the destination row per thread) and walks
-// the folded rows of chunk blockIdx.y with UNR rows in flight. Row addresses advance by pointer bumps (gevm ra/ra.hh:427-438: c(j) += a(i)*b(i,j),
-// a is one value per folded row, SK_ROW; bench-sum-rows.cc:58-81).
+// ---- fold-outer, flat (gevm ra/ra.hh:427-438: c(j) += a(i)*b(i,j), a is one value per folded row, SK_ROW; bench-sum-rows.cc:58-81).
+// A CTA owns a tile of 32*KV kept vectors (a lane owns KV of them: lanes are kept elements, 32 bytes of the destination row per thread)
+// and chunk blockIdx.y of the folded rows; its 8 warps take the rows of the chunk in turns, UNR rows in flight each, addresses advancing
+// by pointer bumps, and combine their accumulators through shared memory in warp order (deterministic). Splitting the rows inside
+// the CTA keeps the number of chunks - partials written, read again and combined by ply_finish - 8x lower for the same number of
+// threads: with a thread per kept vector and 150-300 chunks (round 1) the partials pass cost as much as the sweep on 8192^2.
 template <int ID> struct SPO
 {
     static constexpr int KV = SPT<ID>::wide ? 1 : 2;
-    static constexpr int UNR = SPX<ID>::UNR; // folded rows in flight (x KV vectors each)
+    static constexpr int UNR = SPX<ID>::UNR; // folded rows in flight per warp (x KV vectors each)
+    static constexpr int TILE = 32*KV;       // kept vectors per CTA
 };
 
 template <int ID, int FOLD, uint32_t KINDS> __device__ __forceinline__ void
@@ -451,17 +455,18 @@ sfold_outer_body(SParams const & p, FinishParams const & f)
 {
     using W = typename SPT<ID>::W;
     constexpr SProg P = SPT<ID>::P;
-    constexpr int AT = P.otype, XW = SPX<ID>::XW, KV = SPO<ID>::KV, UNR = SPO<ID>::UNR;
+    constexpr int AT = P.otype, XW = SPX<ID>::XW, KV = SPO<ID>::KV, UNR = SPO<ID>::UNR, NW = KBLOCK/32;
+    __shared__ W sacc[NW][KV*SV][32];
+    int const lane = threadIdx.x&31, warp = threadIdx.x>>5;
     int64_t const nvec = p.n/SV;
-    int64_t const g0 = int64_t(blockIdx.x)*(KBLOCK*KV) + threadIdx.x;
-    if (g0>=nvec) return;
+    int64_t const g0 = int64_t(blockIdx.x)*SPO<ID>::TILE + lane;
     bool ok[KV];
 #pragma unroll
-    for (int v=0; v<KV; ++v) ok[v] = g0 + v*KBLOCK<nvec;
+    for (int v=0; v<KV; ++v) ok[v] = g0 + v*32<nvec;
     uint32_t const c = blockIdx.y;
     int64_t const r0 = int64_t(c)*p.chunk_len;
     int64_t const r1 = r0+p.chunk_len<p.nB ? r0+p.chunk_len : p.nB;
-    // per role: the address (SEQ: element offset) of folded row r0, and what one row adds to it
+    // per role: the address (SEQ: element offset) of this warp's first row, and what one row adds to it
     unsigned char const * rowp[P.nin];
     int64_t rowstep[P.nin];
 #pragma unroll
@@ -469,14 +474,14 @@ sfold_outer_body(SParams const & p, FinishParams const & f)
         int const kd = role_kind<KINDS>(p, k);
         int64_t const scale = SK_SEQ==kd ? 1 : es_of(P.rtype[k]);
         rowstep[k] = p.sB[k][0]*scale;
-        rowp[k] = (SK_SEQ==kd ? static_cast<unsigned char const *>(nullptr) : reinterpret_cast<unsigned char const *>(p.in[k])) + r0*rowstep[k];
+        rowp[k] = (SK_SEQ==kd ? static_cast<unsigned char const *>(nullptr) : reinterpret_cast<unsigned char const *>(p.in[k])) + (r0 + warp*UNR)*rowstep[k];
     }
     W acc[KV][SV];
 #pragma unroll
     for (int v=0; v<KV; ++v)
 #pragma unroll
         for (int j=0; j<SV; ++j) acc[v][j] = W(p.identity);
-    for (int64_t r = r0; r<r1; r += UNR) {
+    for (int64_t r = r0 + warp*UNR; r<r1; r += NW*UNR) {
         uint32_t x[UNR][KV][P.nin][XW];
 #pragma unroll
         for (int u=0; u<UNR; ++u) {
@@ -490,7 +495,7 @@ sfold_outer_body(SParams const & p, FinishParams const & f)
                         if (per_row && v>0) {
 #pragma unroll
                             for (int q=0; q<XW; ++q) x[u][v][k][q] = x[u][0][k][q];
-                        } else if (ok[v]) fetch_fold_role<ID, KINDS>(p, k, LD_STREAM, x[u][v][k], rowp[k] + u*rowstep[k], g0 + v*KBLOCK);
+                        } else if (ok[v] || per_row) fetch_fold_role<ID, KINDS>(p, k, LD_STREAM, x[u][v][k], rowp[k] + u*rowstep[k], g0 + v*32);
                     }
                 }
             }
@@ -510,13 +515,22 @@ sfold_outer_body(SParams const & p, FinishParams const & f)
             }
         }
 #pragma unroll
-        for (int k=0; k<P.nin; ++k) rowp[k] += UNR*rowstep[k];
+        for (int k=0; k<P.nin; ++k) rowp[k] += NW*UNR*rowstep[k];
     }
 #pragma unroll
-    for (int v=0; v<KV; ++v) {
-        if (ok[v]) {
+    for (int v=0; v<KV; ++v)
 #pragma unroll
-            for (int j=0; j<SV; ++j) emit_partial<W>(p, f, c, (g0 + v*KBLOCK)*SV+j, acc[v][j]);
+        for (int j=0; j<SV; ++j) sacc[warp][v*SV+j][lane] = acc[v][j];
+    __syncthreads();
+    // thread t combines kept element (e = t / 32, lane t % 32) over the warps, in warp order
+    if (int(threadIdx.x)<KV*SV*32) {
+        int const e = threadIdx.x>>5, v = e/SV, j = e-v*SV;
+        int64_t const g = g0 + v*32;
+        if (g<nvec) {
+            W r = sacc[0][e][lane];
+#pragma unroll
+            for (int w=1; w<NW; ++w) r = combine<W>(FOLD, AT, r, sacc[w][e][lane]);
+            emit_partial<W>(p, f, c, g*SV+j, r);
         }
     }
 }

@@ -14,6 +14,8 @@
 // into temporaries and select right after each load, which serialises the loads on their latency (dot 7.0 -> 3.0 TB/s).
 // Operand kinds that change the load form are therefore compile-time template switches (GENERAL, REUSE).
 #include <cuda_runtime.h>
+#include <map>
+#include <mutex>
 #include "launch.h"
 #include "static_device.h"
 
@@ -37,20 +39,18 @@ sfold_outer_kernel(const __grid_constant__ SParams p, const __grid_constant__ Fi
 
 template <int ID> constexpr uint32_t all_vec_kinds() { uint32_t k = 0; for (int r=0; r<SPT<ID>::P.nin; ++r) k |= uint32_t(SK_VEC)<<(4*r); return k; }
 
-template <int ID> static cudaError_t
-launch_one(Plan const & plan, dim3 grid, cudaStream_t stream)
+// The kernel a plan runs on (a __global__ function pointer), or null.
+template <int ID> static void const *
+select_kernel(SParams const & p)
 {
-    SParams const & p = plan.sp;
     constexpr SProg P = SPT<ID>::P;
+#define RACU_GO(KERNEL, ...) return reinterpret_cast<void const *>(&KERNEL<ID, __VA_ARGS__>)
     if (p.mode==K_MAP) {
-        if constexpr (!P.fold) {
-            if (p.general) smap_kernel<ID, true><<<grid, KBLOCK, 0, stream>>>(p); else smap_kernel<ID, false><<<grid, KBLOCK, 0, stream>>>(p);
-        }
+        if constexpr (!P.fold) { if (p.general) RACU_GO(smap_kernel, true); else RACU_GO(smap_kernel, false); }
     } else if constexpr (P.fold) {
         uint32_t kinds = 0; int rmask = 0;
         for (int k=0; k<P.nin; ++k) { kinds |= uint32_t(p.kind[k])<<(4*k); rmask |= (p.reused[k] ? 1 : 0)<<k; }
         constexpr uint32_t VV = all_vec_kinds<ID>();
-#define RACU_GO(KERNEL, ...) do { KERNEL<ID, __VA_ARGS__><<<grid, KBLOCK, 0, stream>>>(p, plan.fp); return cudaGetLastError(); } while (0)
         bool const sum = p.fold_op==RACU_ASSIGN_ADD || p.fold_op==RACU_ASSIGN_SUB;
         if (p.mode==K_FOLD_INNER) {
             if (sum && kinds==VV) { // dot, sum, sqrm, sum-cols, gemv
@@ -92,9 +92,9 @@ launch_one(Plan const & plan, dim3 grid, cudaStream_t stream)
             default: RACU_GO(sfold_outer_kernel, RACU_ASSIGN_MUL, SK_RUNTIME);
             }
         }
-#undef RACU_GO
     }
-    return cudaGetLastError();
+#undef RACU_GO
+    return nullptr;
 }
 
 // The table is compiled in SP_NPART translation units (ids congruent to SP_PART), in parallel: build.py.
@@ -103,48 +103,73 @@ launch_one(Plan const & plan, dim3 grid, cudaStream_t stream)
 #define SP_PART 0
 #endif
 
-template <int ID=SP_PART> static cudaError_t
-launch_id(Plan const & plan, dim3 grid, cudaStream_t stream)
+template <int ID=SP_PART> static void const *
+kernel_of(SParams const & p)
 {
     if constexpr (ID<SP_COUNT) {
-        if (plan.sp.id==ID) return launch_one<ID>(plan, grid, stream);
-        return launch_id<ID+SP_NPART>(plan, grid, stream);
+        if (p.id==ID) return select_kernel<ID>(p);
+        return kernel_of<ID+SP_NPART>(p);
     } else {
-        return cudaErrorInvalidValue;
+        return nullptr;
     }
 }
 
 #define RACU_CAT_(a, b) a##b
 #define RACU_CAT(a, b) RACU_CAT_(a, b)
-cudaError_t
-RACU_CAT(launch_static_part, SP_PART)(Plan const & plan, cudaStream_t stream)
-{
-    dim3 grid(plan.grid_x, plan.grid_y);
-    return launch_id<>(plan, grid, stream);
-}
+void const * RACU_CAT(static_kernel_part, SP_PART)(SParams const & p) { return kernel_of<>(p); }
 
 #if SP_PART==0
-cudaError_t launch_static_part1(Plan const & plan, cudaStream_t stream);
-cudaError_t launch_static_part2(Plan const & plan, cudaStream_t stream);
-cudaError_t launch_static_part3(Plan const & plan, cudaStream_t stream);
+void const * static_kernel_part1(SParams const & p);
+void const * static_kernel_part2(SParams const & p);
+void const * static_kernel_part3(SParams const & p);
+
+static void const *
+static_kernel(SParams const & p)
+{
+    switch (p.id % SP_NPART) {
+    case 0: return static_kernel_part0(p);
+#if SP_NPART>1
+    case 1: return static_kernel_part1(p);
+#endif
+#if SP_NPART>2
+    case 2: return static_kernel_part2(p);
+#endif
+#if SP_NPART>3
+    case 3: return static_kernel_part3(p);
+#endif
+    default: return nullptr;
+    }
+}
+
 cudaError_t
 launch_static(Plan const & plan, cudaStream_t stream)
 {
     if (SP_JIT==plan.sp.id) return launch_jit(plan, stream);
-    switch (plan.sp.id % SP_NPART) {
-    case 0: return launch_static_part0(plan, stream);
-#if SP_NPART>1
-    case 1: return launch_static_part1(plan, stream);
-#endif
-#if SP_NPART>2
-    case 2: return launch_static_part2(plan, stream);
-#endif
-#if SP_NPART>3
-    case 3: return launch_static_part3(plan, stream);
-#endif
-    default: return cudaErrorInvalidValue;
-    }
+    void const * fn = static_kernel(plan.sp);
+    if (!fn) return cudaErrorInvalidValue;
+    void * args[2] = {const_cast<SParams *>(&plan.sp), const_cast<FinishParams *>(&plan.fp)};
+    return cudaLaunchKernel(fn, dim3(plan.grid_x, plan.grid_y), dim3(KBLOCK), args, 0, stream);
 }
+
+// CTAs of the plan's kernel that fit on one SM (0: unknown - no device). The planner sizes fold grids in whole waves with it.
+int
+static_occupancy(Plan const & plan)
+{
+    if (SP_JIT==plan.sp.id) return jit_occupancy(plan);
+    void const * fn = static_kernel(plan.sp);
+    if (!fn) return 0;
+    static std::mutex mu;
+    static std::map<void const *, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(fn);
+    if (it!=cache.end()) return it->second;
+    int n = 0;
+    if (cudaSuccess!=cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, KBLOCK, 0)) { cudaGetLastError(); return 0; } // (not cached: no device yet)
+    cache.emplace(fn, n);
+    return n;
+}
+
+static struct OccInstall { OccInstall() { g_static_occupancy = &static_occupancy; } } occ_install;
 #endif
 
 } // namespace racu

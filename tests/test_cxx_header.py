@@ -26,6 +26,20 @@ def build_kat(which):
     return out
 
 
+def build_bench(which="cuda"):
+    """tests/cxx/bench_header.cc: the header timed end to end (run by bench.py on the GPU box)."""
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, f"bench_header_{which}")
+    libdir, lib = {"oracle": (os.path.join(ROOT, "oracle"), "racu_oracle"), "cuda": (os.path.join(ROOT, "ra_ra_b200"), "racu")}[which]
+    deps = [os.path.join(CXX, "bench_header.cc"), os.path.join(ROOT, "include", "ra", "cuda.hh"), os.path.join(ROOT, "include", "racu.h"),
+            os.path.join(libdir, f"lib{lib}.so")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-std=c++23", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-o", out,
+                        os.path.join(CXX, "bench_header.cc"), "-L", libdir, f"-l{lib}", f"-Wl,-rpath,$ORIGIN/../../../{os.path.relpath(libdir, ROOT)}"],
+                       check=True)
+    return out
+
+
 def test_header_kat_on_oracle():
     exe = build_kat("oracle")
     r = subprocess.run([exe], capture_output=True, text=True)
