@@ -363,15 +363,15 @@ struct MapF2: node_tag
     }
 };
 
-enum class un_kind { same, floating, logical }; // result type rule
+enum class un_kind { same, floating, logical, classify }; // result type rule (classify: floating operand, bool result)
 template <int OPCODE, un_kind K, class A>
 struct Map1: node_tag
 {
     using TA = typename A::value_type;
     using promoted = decltype(+std::declval<TA>());
-    using operand_t = std::conditional_t<K==un_kind::floating, std::conditional_t<std::is_floating_point_v<TA>, TA, double>,
+    using operand_t = std::conditional_t<K==un_kind::floating || K==un_kind::classify, std::conditional_t<std::is_floating_point_v<TA>, TA, double>,
                                          std::conditional_t<K==un_kind::logical, TA, promoted>>;
-    using value_type = std::conditional_t<K==un_kind::logical, bool, operand_t>;
+    using value_type = std::conditional_t<K==un_kind::logical || K==un_kind::classify, bool, operand_t>;
     A a;
     void flatten(Builder & bb) const
     {
@@ -388,17 +388,19 @@ struct CastNode: node_tag // ra::cast<T>, ra/expr.hh:680-681
     void flatten(Builder & bb) const { a.flatten(bb); bb.template cast<typename A::value_type, T>(); }
 };
 
-template <class A, class B, class C>
+template <class A, class B, class C, int OPCODE=RACU_OP_FMA>
 struct Fma: node_tag
 {
-    using value_type = decltype(std::fma(std::declval<typename A::value_type>(), std::declval<typename B::value_type>(), std::declval<typename C::value_type>()));
+    // fma / lerp: the floating point type the three promote to; clamp: their common type
+    using common3 = decltype(std::declval<typename A::value_type>()+std::declval<typename B::value_type>()+std::declval<typename C::value_type>());
+    using value_type = std::conditional_t<OPCODE==RACU_OP_CLAMP, common3, std::conditional_t<std::is_floating_point_v<common3>, common3, double>>;
     A a; B b; C c;
     void flatten(Builder & bb) const
     {
         a.flatten(bb); bb.template cast<typename A::value_type, value_type>();
         b.flatten(bb); bb.template cast<typename B::value_type, value_type>();
         c.flatten(bb); bb.template cast<typename C::value_type, value_type>();
-        bb.emit(RACU_OP_FMA, dtype_of<value_type>);
+        bb.emit(OPCODE, dtype_of<value_type>);
     }
 };
 
@@ -479,6 +481,14 @@ RACU_UNFN(abs, RACU_OP_ABS, un_kind::same)   RACU_UNFN(sqr, RACU_OP_SQR, un_kind
 RACU_UNFN(sqrt, RACU_OP_SQRT, un_kind::floating) RACU_UNFN(exp, RACU_OP_EXP, un_kind::floating)
 RACU_UNFN(log, RACU_OP_LOG, un_kind::floating)   RACU_UNFN(sin, RACU_OP_SIN, un_kind::floating)
 RACU_UNFN(cos, RACU_OP_COS, un_kind::floating)
+// the rest of the using-declared <cmath> functions of ra/ra.hh:221-222
+RACU_UNFN(tan, RACU_OP_TAN, un_kind::floating)     RACU_UNFN(sinh, RACU_OP_SINH, un_kind::floating)
+RACU_UNFN(cosh, RACU_OP_COSH, un_kind::floating)   RACU_UNFN(tanh, RACU_OP_TANH, un_kind::floating)
+RACU_UNFN(asin, RACU_OP_ASIN, un_kind::floating)   RACU_UNFN(acos, RACU_OP_ACOS, un_kind::floating)
+RACU_UNFN(atan, RACU_OP_ATAN, un_kind::floating)   RACU_UNFN(expm1, RACU_OP_EXPM1, un_kind::floating)
+RACU_UNFN(log1p, RACU_OP_LOG1P, un_kind::floating) RACU_UNFN(log10, RACU_OP_LOG10, un_kind::floating)
+RACU_UNFN(isfinite, RACU_OP_ISFINITE, un_kind::classify) RACU_UNFN(isnan, RACU_OP_ISNAN, un_kind::classify)
+RACU_UNFN(isinf, RACU_OP_ISINF, un_kind::classify)
 #undef RACU_UNFN
 
 template <class A, class B> requires (tomap<A, B>)
@@ -491,6 +501,12 @@ template <class A, class B> requires (tomap<A, B>)
 constexpr auto atan2(A && a, B && b) { return MapF2<RACU_OP_ATAN2, node_t<A>, node_t<B>> { {}, iter(std::forward<A>(a)), iter(std::forward<B>(b)) }; }
 template <class A, class B, class C> requires (tomap<A, B, C>)
 constexpr auto fma(A && a, B && b, C && c) { return Fma<node_t<A>, node_t<B>, node_t<C>> { {}, iter(std::forward<A>(a)), iter(std::forward<B>(b)), iter(std::forward<C>(c)) }; }
+
+// std::clamp / std::lerp (ra/ra.hh:222)
+template <class A, class B, class C> requires (tomap<A, B, C>)
+constexpr auto clamp(A && a, B && b, C && c) { return Fma<node_t<A>, node_t<B>, node_t<C>, RACU_OP_CLAMP> { {}, iter(std::forward<A>(a)), iter(std::forward<B>(b)), iter(std::forward<C>(c)) }; }
+template <class A, class B, class C> requires (tomap<A, B, C>)
+constexpr auto lerp(A && a, B && b, C && c) { return Fma<node_t<A>, node_t<B>, node_t<C>, RACU_OP_LERP> { {}, iter(std::forward<A>(a)), iter(std::forward<B>(b)), iter(std::forward<C>(c)) }; }
 
 // sqrm(x) = x*x, sqrm(x, y) = sqr(x-y): ra/ra.hh:71-72.
 template <class A> requires (tomap<A>) constexpr auto sqrm(A && a) { return sqr(std::forward<A>(a)); }
@@ -513,6 +529,29 @@ constexpr auto operator&&(A && a, B && b) { return where(std::forward<A>(a), cas
 template <class A, class B> requires (tomap<A, B>)
 constexpr auto operator||(A && a, B && b) { return where(std::forward<A>(a), true, cast<bool>(std::forward<B>(b))); }
 
+
+// odd(x) (ra/ra.hh:61: N & 1), rel_error(a, b) (ra/ra.hh:94: D = |a|+|b|, D==0 ? 0. : 2.*|a-b|/D, with the double literals) and
+// operator<=> (ra/ra.hh:190) are written with the opcodes above. `<=>` yields an int: -1, 0, +1, and 2 where the operands are
+// unordered (the reference yields std::partial_ordering objects, which are not array elements on the device).
+template <class A> requires (tomap<A> && std::is_integral_v<value_t<A>>)
+constexpr auto odd(A && a) { return (std::forward<A>(a) & 1) != 0; }
+template <class A, class B> requires (tomap<A, B>)
+constexpr auto rel_error(A && a, B && b)
+{
+    using C0 = decltype(std::declval<value_t<A>>()+std::declval<value_t<B>>());
+    using R = std::conditional_t<std::is_floating_point_v<C0>, C0, double>;
+    auto x = cast<R>(std::forward<A>(a));
+    auto y = cast<R>(std::forward<B>(b));
+    auto D = abs(x) + abs(y);
+    return cast<R>(where(D==R(0), 0., 2.*abs(x-y)/D));
+}
+template <class A, class B> requires (tomap<A, B>)
+constexpr auto operator<=>(A && a, B && b)
+{
+    auto x = iter(std::forward<A>(a));
+    auto y = iter(std::forward<B>(b));
+    return where(x<y, -1, where(x>y, 1, where(x==y, 0, 2)));
+}
 
 // a(i ...) with unbeaten subscripts (index arrays / index expressions): ra/ply.hh:461-499,531-549. The reference maps
 // a-as-a-function over the subscripts, each on its own axes (fromu_loop / wrank); here the element offset

@@ -143,9 +143,18 @@ typedef enum {
     RACU_OP_PICK = 41, /* sel x0 .. x(n-1) -> x[sel]; arg = n, aux = selector type, type = T of branches.
                           ra::pick ra/expr.hh:686-728; where(w,t,f) = pick(bool(w), f, t) ra/ra.hh:255-256.
                           Only the chosen branch is observable: the opcode set is side-effect free. */
-    RACU_OP_LOAD = 42  /* off -> opnd[arg][off]: gather. arg = index of a RACU_PTR operand, type = its element dtype,
+    RACU_OP_LOAD = 42, /* off -> opnd[arg][off]: gather. arg = index of a RACU_PTR operand, type = its element dtype,
                           aux = integer type of the offset (I32 or I64). The host writes A(I, J) as
                           LOAD(A, I*step0 + J*step1) with I and J placed on their own expression axes (ra/ply.hh:461-499). */
+    RACU_OP_CLAMP = 43, /* v lo hi -> std::clamp(v, lo, hi) = v<lo ? lo : hi<v ? hi : v   (ra/ra.hh:222), any arithmetic T */
+    RACU_OP_LERP = 44,  /* a b t -> std::lerp(a, b, t) (ra/ra.hh:222), float T: exact at t = 0 and t = 1, monotonic */
+    /* the rest of the named functions of ra/ra.hh:221-222. unary float T -> T */
+    RACU_OP_TAN = 48, RACU_OP_SINH = 49, RACU_OP_COSH = 50, RACU_OP_TANH = 51, RACU_OP_ASIN = 52, RACU_OP_ACOS = 53, RACU_OP_ATAN = 54,
+    RACU_OP_EXPM1 = 55, RACU_OP_LOG1P = 56, RACU_OP_LOG10 = 57,
+    /* unary float T -> BOOL */
+    RACU_OP_ISFINITE = 58, RACU_OP_ISNAN = 59, RACU_OP_ISINF = 60
+    /* odd(x), rel_error(a, b) (ra/ra.hh:61,94-95,210) and `<=>` (ra/ra.hh:190) need no opcode: the host headers write them with
+       the ones above ((x & 1) != 0; D = |a|+|b|, D==0 ? 0. : 2.*|a-b|/D; a<b ? -1 : a>b ? 1 : a==b ? 0 : 2 (unordered)). */
 } racu_opcode;
 
 typedef struct {

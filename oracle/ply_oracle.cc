@@ -13,6 +13,7 @@
 
 #include "../include/racu.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -97,8 +98,16 @@ check_program(racu_desc const * d)
             if (sp<1 || st[sp-1]!=in.type || isb) return -1;
             break;
         case RACU_OP_SQRT: case RACU_OP_EXP: case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS:
+        case RACU_OP_TAN: case RACU_OP_SINH: case RACU_OP_COSH: case RACU_OP_TANH: case RACU_OP_ASIN: case RACU_OP_ACOS: case RACU_OP_ATAN:
+        case RACU_OP_EXPM1: case RACU_OP_LOG1P: case RACU_OP_LOG10:
             if (sp<1 || st[sp-1]!=in.type || !isf) return -1;
             break;
+        case RACU_OP_ISFINITE: case RACU_OP_ISNAN: case RACU_OP_ISINF:
+            if (sp<1 || st[sp-1]!=in.type || !isf) return -1;
+            st[sp-1] = RACU_BOOL; break;
+        case RACU_OP_CLAMP: case RACU_OP_LERP:
+            if (sp<3 || st[sp-1]!=in.type || st[sp-2]!=in.type || st[sp-3]!=in.type || isb || (in.op==RACU_OP_LERP && !isf)) return -1;
+            sp -= 2; break;
         case RACU_OP_NOT:
             if (sp<1 || st[sp-1]!=in.type) return -1;
             st[sp-1] = RACU_BOOL; break;
@@ -218,6 +227,20 @@ unary(int op, T a)
             case RACU_OP_LOG: return mk<T>(std::log(a));
             case RACU_OP_SIN: return mk<T>(std::sin(a));
             case RACU_OP_COS: return mk<T>(std::cos(a));
+            // the using-declared <cmath> functions of ra/ra.hh:221-222
+            case RACU_OP_TAN: return mk<T>(std::tan(a));
+            case RACU_OP_SINH: return mk<T>(std::sinh(a));
+            case RACU_OP_COSH: return mk<T>(std::cosh(a));
+            case RACU_OP_TANH: return mk<T>(std::tanh(a));
+            case RACU_OP_ASIN: return mk<T>(std::asin(a));
+            case RACU_OP_ACOS: return mk<T>(std::acos(a));
+            case RACU_OP_ATAN: return mk<T>(std::atan(a));
+            case RACU_OP_EXPM1: return mk<T>(std::expm1(a));
+            case RACU_OP_LOG1P: return mk<T>(std::log1p(a));
+            case RACU_OP_LOG10: return mk<T>(std::log10(a));
+            case RACU_OP_ISFINITE: return mk<bool>(std::isfinite(a));
+            case RACU_OP_ISNAN: return mk<bool>(std::isnan(a));
+            case RACU_OP_ISINF: return mk<bool>(std::isinf(a));
             }
         }
     }
@@ -283,8 +306,24 @@ eval(racu_desc const * d, Leaf const * leaf, Val * second=nullptr)
             break;
         case RACU_OP_NEG: case RACU_OP_ABS: case RACU_OP_SQRT: case RACU_OP_SQR: case RACU_OP_EXP:
         case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS: case RACU_OP_NOT:
+        case RACU_OP_TAN: case RACU_OP_SINH: case RACU_OP_COSH: case RACU_OP_TANH: case RACU_OP_ASIN: case RACU_OP_ACOS: case RACU_OP_ATAN:
+        case RACU_OP_EXPM1: case RACU_OP_LOG1P: case RACU_OP_LOG10: case RACU_OP_ISFINITE: case RACU_OP_ISNAN: case RACU_OP_ISINF:
             st[sp-1] = with_type(in.type, [&](auto t) { return unary<decltype(t)>(in.op, get<decltype(t)>(st[sp-1])); });
             break;
+        case RACU_OP_CLAMP: // std::clamp, ra/ra.hh:222
+            st[sp-3] = with_type(in.type, [&](auto t) {
+                using T = decltype(t);
+                if constexpr (!std::is_same_v<T, bool>) return mk<T>(std::clamp(get<T>(st[sp-3]), get<T>(st[sp-2]), get<T>(st[sp-1])));
+                else return st[sp-3];
+            });
+            sp -= 2; break;
+        case RACU_OP_LERP: // std::lerp, ra/ra.hh:222
+            st[sp-3] = with_type(in.type, [&](auto t) {
+                using T = decltype(t);
+                if constexpr (std::is_floating_point_v<T>) return mk<T>(std::lerp(get<T>(st[sp-3]), get<T>(st[sp-2]), get<T>(st[sp-1])));
+                else return st[sp-3];
+            });
+            sp -= 2; break;
         case RACU_OP_FMA:
             st[sp-3] = with_type(in.type, [&](auto t) {
                 using T = decltype(t);

@@ -24,7 +24,9 @@ OP_PUSH, OP_CAST = 0, 1
 OP_NEG, OP_ABS, OP_SQRT, OP_SQR, OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_NOT = range(2, 11)
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_MOD, OP_MIN, OP_MAX, OP_POW, OP_ATAN2, OP_BAND, OP_BOR, OP_BXOR = range(16, 28)
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE = range(32, 38)
-OP_FMA, OP_PICK, OP_LOAD = 40, 41, 42
+OP_FMA, OP_PICK, OP_LOAD, OP_CLAMP, OP_LERP = 40, 41, 42, 43, 44
+(OP_TAN, OP_SINH, OP_COSH, OP_TANH, OP_ASIN, OP_ACOS, OP_ATAN, OP_EXPM1, OP_LOG1P, OP_LOG10,
+ OP_ISFINITE, OP_ISNAN, OP_ISINF) = range(48, 61)
 
 ASSIGN_SET, ASSIGN_ADD, ASSIGN_SUB, ASSIGN_MUL, ASSIGN_DIV, ASSIGN_AMIN, ASSIGN_AMAX = range(7)
 RED_SUM, RED_PROD, RED_AMIN, RED_AMAX = 1, 3, 5, 6

@@ -146,15 +146,16 @@ jit_prog_text(SProg const & P)
 
 // What, beyond the program, a specialisation is compiled for. Maps: GENERAL. Folds: the operand kind of every role and the re-read
 // mask (compile-time in the fold bodies, static_device.h), and for fold-inner whether a warp or a CTA owns a kept row.
-struct JitVariant { int general = 0, rows = 0, rmask = 0; uint32_t kinds = 0; };
+struct JitVariant { int general = 0, rows = 0, rmask = 0, lanes = 0; uint64_t kinds = 0; };
 
 std::string
 jit_kernel_text(SProg const & P, int mode, JitVariant const & v, int fold_op)
 {
     std::string s = "#define RACU_JIT_PROG " + jit_prog_text(P) + "\n#include \"static_device.h\"\n";
     s += "extern \"C\" __global__ void __launch_bounds__(racu::KBLOCK)\nracu_jit_kernel(const __grid_constant__ racu::SParams p";
-    std::string const fold = std::to_string(fold_class(fold_op)), kinds = std::to_string(v.kinds) + "u";
-    if (mode==K_MAP) s += std::string(")\n{ racu::smap_body<racu::SP_JIT, ") + (v.general ? "true" : "false") + ">(p); }\n";
+    std::string const fold = std::to_string(fold_class(fold_op)), kinds = std::to_string(v.kinds) + "ull";
+    if (mode==K_MAP && v.lanes) s += ")\n{ racu::smap_lanes_body<racu::SP_JIT, " + kinds + ">(p); }\n";
+    else if (mode==K_MAP) s += std::string(")\n{ racu::smap_body<racu::SP_JIT, ") + (v.general ? "true" : "false") + ", " + kinds + ">(p); }\n";
     else if (mode==K_FOLD_INNER) s += std::string(", const __grid_constant__ racu::FinishParams f)\n{ racu::") + (v.rows ? "sfold_inner_rows_body" : "sfold_inner_body")
                                       + "<racu::SP_JIT, " + fold + ", " + std::to_string(v.rmask) + ", " + kinds + ">(p, f); }\n";
     else s += ", const __grid_constant__ racu::FinishParams f)\n{ racu::sfold_outer_body<racu::SP_JIT, " + fold + ", " + kinds + ">(p, f); }\n";
@@ -262,8 +263,8 @@ variant_of(Plan const & plan)
 {
     SParams const & sp = plan.sp;
     JitVariant v;
-    if (sp.mode==K_MAP) { v.general = sp.general ? 1 : 0; return v; }
-    for (int k=0; k<plan.jit_prog.nin; ++k) { v.kinds |= uint32_t(sp.kind[k])<<(4*k); if (sp.mode==K_FOLD_INNER && sp.reused[k]) v.rmask |= 1<<k; }
+    for (int k=0; k<plan.jit_prog.nin; ++k) { v.kinds |= uint64_t(sp.kind[k])<<(4*k); if (sp.mode==K_FOLD_INNER && sp.reused[k]) v.rmask |= 1<<k; }
+    if (sp.mode==K_MAP) { v.general = sp.general ? 1 : 0; v.lanes = sp.lanes ? 1 : 0; return v; }
     v.rows = sp.mode==K_FOLD_INNER && sp.inner_rows;
     return v;
 }
@@ -279,7 +280,8 @@ jit_prepare(Plan & plan, std::string & err)
     if (!have_dev) cudaGetLastError();
     // in-memory key: no kernel text is generated on the per-call path
     SProg const & P = plan.jit_prog;
-    int32_t const head[8] = {dev, plan.sp.mode, variant.general, variant.rows, variant.rmask, int32_t(variant.kinds), plan.sp.mode==K_MAP ? 0 : fold_class(plan.sp.fold_op), P.n};
+    int32_t const head[10] = {dev, plan.sp.mode, variant.general, variant.rows, variant.rmask, variant.lanes, int32_t(uint32_t(variant.kinds)), int32_t(uint32_t(variant.kinds>>32)),
+                              plan.sp.mode==K_MAP ? 0 : fold_class(plan.sp.fold_op), P.n};
     std::string key(reinterpret_cast<char const *>(head), sizeof(head));
     key.append(reinterpret_cast<char const *>(P.ins), sizeof(SIns)*size_t(P.n));
     int32_t const tail[3] = {P.nin, P.yrole, int32_t(P.fold) | (int32_t(P.otype)<<8)};
@@ -291,8 +293,8 @@ jit_prepare(Plan & plan, std::string & err)
     std::vector<char> cubin;
     if (!jit_cubin(plan.jit_prog, plan.sp.mode, variant, plan.sp.fold_op, cubin, err)) return false;
     if (have_dev && cudaSuccess!=cudaFree(nullptr)) { cudaGetLastError(); have_dev = false; } // make the primary context current before loading
-    if (std::getenv("RACU_JIT_VERBOSE")) std::fprintf(stderr, "racu jit: specialised %s (mode %d general %d rows %d rmask %d kinds %x fold %d) for device %d, %zu bytes\n",
-                                                      jit_prog_text(plan.jit_prog).c_str(), plan.sp.mode, variant.general, variant.rows, variant.rmask, variant.kinds, plan.sp.fold_op, dev, cubin.size());
+    if (std::getenv("RACU_JIT_VERBOSE")) std::fprintf(stderr, "racu jit: specialised %s (mode %d general %d lanes %d rows %d rmask %d kinds %llx fold %d) for device %d, %zu bytes\n",
+                                                      jit_prog_text(plan.jit_prog).c_str(), plan.sp.mode, variant.general, variant.lanes, variant.rows, variant.rmask, (unsigned long long)variant.kinds, plan.sp.fold_op, dev, cubin.size());
     if (!have_dev) { plan.jit_fn = nullptr; return true; }
     if (!drv_load()) { err = "driver entry points for module loading are not available"; return false; }
     CUmodule mod = nullptr;

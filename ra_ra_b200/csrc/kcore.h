@@ -216,11 +216,40 @@ template <> struct Ty<double> { template <class W> static RACU_HD double get(W a
 // Transcendentals and other long sequences are kept out of line: they would otherwise be unrolled V times per case.
 RACU_HD_NOINLINE float slow_un_f32(int op, float a)
 {
-    switch (op) { case RACU_OP_EXP: return expf(a); case RACU_OP_LOG: return logf(a); case RACU_OP_SIN: return sinf(a); default: return cosf(a); }
+    switch (op) {
+    case RACU_OP_EXP: return expf(a); case RACU_OP_LOG: return logf(a); case RACU_OP_SIN: return sinf(a); case RACU_OP_COS: return cosf(a);
+    case RACU_OP_TAN: return tanf(a); case RACU_OP_SINH: return sinhf(a); case RACU_OP_COSH: return coshf(a); case RACU_OP_TANH: return tanhf(a);
+    case RACU_OP_ASIN: return asinf(a); case RACU_OP_ACOS: return acosf(a); case RACU_OP_ATAN: return atanf(a);
+    case RACU_OP_EXPM1: return expm1f(a); case RACU_OP_LOG1P: return log1pf(a); default: return log10f(a);
+    }
 }
 RACU_HD_NOINLINE double slow_un_f64(int op, double a)
 {
-    switch (op) { case RACU_OP_EXP: return exp(a); case RACU_OP_LOG: return log(a); case RACU_OP_SIN: return sin(a); default: return cos(a); }
+    switch (op) {
+    case RACU_OP_EXP: return exp(a); case RACU_OP_LOG: return log(a); case RACU_OP_SIN: return sin(a); case RACU_OP_COS: return cos(a);
+    case RACU_OP_TAN: return tan(a); case RACU_OP_SINH: return sinh(a); case RACU_OP_COSH: return cosh(a); case RACU_OP_TANH: return tanh(a);
+    case RACU_OP_ASIN: return asin(a); case RACU_OP_ACOS: return acos(a); case RACU_OP_ATAN: return atan(a);
+    case RACU_OP_EXPM1: return expm1(a); case RACU_OP_LOG1P: return log1p(a); default: return log10(a);
+    }
+}
+// isfinite / isnan / isinf on the bit patterns (the same answer on the host simulator and on the device, whatever the math flags)
+RACU_HD bool classify_f32(int op, float a)
+{
+    uint32_t const m = f32_bits(a) & 0x7fffffffu;
+    return op==RACU_OP_ISFINITE ? m<0x7f800000u : op==RACU_OP_ISNAN ? m>0x7f800000u : m==0x7f800000u;
+}
+RACU_HD bool classify_f64(int op, double a)
+{
+    uint64_t const m = f64_bits(a) & 0x7fffffffffffffffull;
+    return op==RACU_OP_ISFINITE ? m<0x7ff0000000000000ull : op==RACU_OP_ISNAN ? m>0x7ff0000000000000ull : m==0x7ff0000000000000ull;
+}
+// std::lerp as libstdc++ computes it (<cmath> __lerp): exact at t = 0 and t = 1, monotonic, no contraction (the library is built -fmad=false)
+template <class T> RACU_HD T t_lerp(T a, T b, T t)
+{
+    if ((a<=T(0) && b>=T(0)) || (a>=T(0) && b<=T(0))) return t*b + (T(1)-t)*a;
+    if (t==T(1)) return b;
+    T const x = a + t*(b-a);
+    return (t>T(1))==(b>a) ? (b<x ? x : b) : (b>x ? x : b);
 }
 RACU_HD_NOINLINE float slow_bin_f32(int op, float a, float b)
 {
@@ -241,6 +270,8 @@ template <class W, class T> RACU_HD W un1(int op, W a)
 {
     T x = Ty<T>::template get<W>(a);
     if (op==RACU_OP_NOT) return Ty<bool>::template put<W>(!x);
+    if constexpr (std::is_same_v<T, float>) { if (op>=RACU_OP_ISFINITE && op<=RACU_OP_ISINF) return Ty<bool>::template put<W>(classify_f32(op, x)); }
+    if constexpr (std::is_same_v<T, double>) { if (op>=RACU_OP_ISFINITE && op<=RACU_OP_ISINF) return Ty<bool>::template put<W>(classify_f64(op, x)); }
     if constexpr (!std::is_same_v<T, bool>) {
         switch (op) {
         case RACU_OP_NEG: return Ty<T>::template put<W>(T(-x));
@@ -369,6 +400,25 @@ template <class W> RACU_HD W fma_any(int type, W a, W b, W c)
     if (type==RACU_F32) return Ty<float>::template put<W>(fmaf(Ty<float>::template get<W>(a), Ty<float>::template get<W>(b), Ty<float>::template get<W>(c)));
     if constexpr (sizeof(W)==8) { if (type==RACU_F64) return Ty<double>::template put<W>(fma(Ty<double>::template get<W>(a), Ty<double>::template get<W>(b), Ty<double>::template get<W>(c))); }
     return c;
+}
+// ternary ops: fma(a, b, c), clamp(v, lo, hi), lerp(a, b, t)
+template <class W, class T> RACU_HD W tern1(int op, W a, W b, W c)
+{
+    T const x = Ty<T>::template get<W>(a), y = Ty<T>::template get<W>(b), z = Ty<T>::template get<W>(c);
+    if (op==RACU_OP_CLAMP) return Ty<T>::template put<W>(x<y ? y : z<x ? z : x); // std::clamp
+    if constexpr (std::is_same_v<T, float> || std::is_same_v<T, double>) { if (op==RACU_OP_LERP) return Ty<T>::template put<W>(t_lerp<T>(x, y, z)); }
+    return a;
+}
+template <class W> RACU_HD W tern_any(int op, int type, W a, W b, W c)
+{
+    if (op==RACU_OP_FMA) return fma_any<W>(type, a, b, c);
+    switch (type) {
+    case RACU_I32: return tern1<W, int32_t>(op, a, b, c);
+    case RACU_F32: return tern1<W, float>(op, a, b, c);
+    default:
+        if constexpr (sizeof(W)==8) { return type==RACU_I64 ? tern1<W, int64_t>(op, a, b, c) : tern1<W, double>(op, a, b, c); }
+        return a;
+    }
 }
 
 // Fold combiners over accumulator type `type`. SUB and DIV accumulate the sum / product; the finish applies dst - s, dst / s.
@@ -583,13 +633,15 @@ interp(KParams const & p, unsigned char const * stage, unsigned char * stack, in
             break;
         case RACU_OP_NEG: case RACU_OP_ABS: case RACU_OP_SQRT: case RACU_OP_SQR: case RACU_OP_EXP:
         case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS: case RACU_OP_NOT:
+        case RACU_OP_TAN: case RACU_OP_SINH: case RACU_OP_COSH: case RACU_OP_TANH: case RACU_OP_ASIN: case RACU_OP_ACOS: case RACU_OP_ATAN:
+        case RACU_OP_EXPM1: case RACU_OP_LOG1P: case RACU_OP_LOG10: case RACU_OP_ISFINITE: case RACU_OP_ISNAN: case RACU_OP_ISINF:
             RACU_TYPE_SWITCH(in.type, (group_unary<W, U, T>(in.op, t)))
             break;
-        case RACU_OP_FMA: {
+        case RACU_OP_FMA: case RACU_OP_CLAMP: case RACU_OP_LERP: {
             RACU_LANES {
                 W const * la = reinterpret_cast<W const *>(lv + u*sstride);
                 W const * lb = reinterpret_cast<W const *>(lv + (U+u)*sstride);
-                t[u][j] = fma_any<W>(in.type, la[j], lb[j], t[u][j]);
+                t[u][j] = tern_any<W>(in.op, in.type, la[j], lb[j], t[u][j]);
             }
             break;
         }

@@ -57,8 +57,19 @@ check_ins(racu_ins const * ins, int nins, racu_operand const * opnd, int nopnd, 
             if (!need(1) || isb) return bad(pc, "unary");
             break;
         case RACU_OP_SQRT: case RACU_OP_EXP: case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS:
+        case RACU_OP_TAN: case RACU_OP_SINH: case RACU_OP_COSH: case RACU_OP_TANH: case RACU_OP_ASIN: case RACU_OP_ACOS: case RACU_OP_ATAN:
+        case RACU_OP_EXPM1: case RACU_OP_LOG1P: case RACU_OP_LOG10:
             if (!need(1) || !isf) return bad(pc, "float unary");
             break;
+        case RACU_OP_ISFINITE: case RACU_OP_ISNAN: case RACU_OP_ISINF:
+            if (!need(1) || !isf) return bad(pc, "float classification");
+            st[sp-1] = RACU_BOOL; break;
+        case RACU_OP_CLAMP:
+            if (!need(3) || isb) return bad(pc, "clamp");
+            sp -= 2; break;
+        case RACU_OP_LERP:
+            if (!need(3) || !isf) return bad(pc, "lerp");
+            sp -= 2; break;
         case RACU_OP_NOT:
             if (!need(1)) return bad(pc, "not");
             st[sp-1] = RACU_BOOL; break;
@@ -444,9 +455,9 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
         if (k.kind==RACU_SEQ) return k.dtype==RACU_BOOL ? -1 : SK_SEQ;
         if (k.kind!=RACU_MEM) return -1;
         int64_t const es = k.esize;
-        if (1==k.sA[0]) return (0==k.base%16 && aligned_outer(k)) ? SK_VEC : -1;
+        if (1==k.sA[0]) return (0==k.base%16 && aligned_outer(k)) ? SK_VEC : (map && 0==k.base%es) ? SK_VECU : -1; // unaligned rows: the lane-wise map kernel
         if (0==k.sA[0]) return SK_ROW;
-        if (-1==k.sA[0] && map) return (0==(k.base-uint64_t((SV-1)*es))%16 && aligned_outer(k)) ? SK_VECREV : -1;
+        if (-1==k.sA[0] && map) return (0==(k.base-uint64_t((SV-1)*es))%16 && aligned_outer(k)) ? SK_VECREV : 0==k.base%es ? SK_VECREVU : -1;
         return -1;
     };
     // roles by first appearance
@@ -462,7 +473,7 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
                 KOpnd const & k = kp.opnd[i.arg];
                 int kd = kind_of(k);
                 if (kd<0 || (!map && kd==SK_VECREV)) return;
-                if (!fold && int(i.arg)==dst) { if (kd!=SK_VEC) return; yrole = nrole; }
+                if (!fold && int(i.arg)==dst) { if (kd!=SK_VEC && kd!=SK_VECU) return; yrole = nrole; }
                 rtype[nrole] = k.dtype;
                 role_of[i.arg] = nrole++;
             }
@@ -537,13 +548,17 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
         sp.wide_partials = plan.fp.wide;
     } else {
         KOpnd const & y = kp.opnd[dst];
-        if (1!=y.sA[0] || 0!=y.base%16 || !aligned_outer(y)) return;
-        if (kp.rankA>1 && 0!=kp.len0%SV) return; // rows must be whole vectors
+        if (1!=y.sA[0] || 0!=y.base%y.esize) return;
+        // rows that are not 16-byte aligned (destination or any input) or not whole vectors: the lane-wise kernel (smap_lanes_body)
+        bool lanes = 0!=y.base%16 || !aligned_outer(y) || (kp.rankA>1 && 0!=kp.len0%SV);
+        for (int o=0; o<kp.nopnd; ++o) { if (role_of[o]>=0) { int const kd = kind_of(kp.opnd[o]); lanes = lanes || SK_VECU==kd || SK_VECREVU==kd; } }
+        sp.lanes = lanes;
+        int64_t const nvrow = lanes ? ((kp.len0+32*SV-1)/(32*SV))*32 : nvec0; // lane-wise: rows padded to whole warp tiles of 32*SV elements
         sp.dst = reinterpret_cast<void *>(uintptr_t(y.base));
-        sp.vpr = nvec0;
-        sp.nvec = nvec0;
+        sp.vpr = nvrow;
+        sp.nvec = nvrow;
         for (int j=1; j<kp.rankA; ++j) sp.nvec *= kp.dA[j].len;
-        if (kp.rankA>1) { if (nvec0<1 || sp.nvec>=(int64_t(1)<<31)) return; sp.vprdiv = make_div(nvec0); }
+        if (kp.rankA>1) { if (nvrow<1 || sp.nvec>=(int64_t(1)<<31)) return; sp.vprdiv = make_div(nvrow); }
         for (int j=0; j<KGR; ++j) { sp.dA[j] = kp.dA[j]; sp.dsA[j] = j<kp.rankA ? y.sA[j] : 0; }
         int64_t nb = (sp.nvec+int64_t(KBLOCK)*4-1)/(int64_t(KBLOCK)*4);
         plan.grid_x = unsigned(std::max<int64_t>(1, std::min<int64_t>(nb, int64_t(target)*4))); plan.grid_y = 1;
@@ -556,7 +571,7 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
         if (r<0) continue;
         KOpnd const & k = kp.opnd[o];
         sp.kind[r] = uint8_t(kind_of(k));
-        if (sp.kind[r]==SK_VECREV || sp.kind[r]==SK_SEQ || sp.kind[r]==SK_PTR || (map && sp.kind[r]==SK_ROW)) sp.general = 1;
+        if (sp.kind[r]==SK_VECREV || sp.kind[r]==SK_VECU || sp.kind[r]==SK_VECREVU || sp.kind[r]==SK_SEQ || sp.kind[r]==SK_PTR || (map && sp.kind[r]==SK_ROW)) sp.general = 1;
         if (k.kind==RACU_SCALAR) { // value bits in the role's type
             switch (k.dtype) {
             case RACU_F32: sp.in[r] = f32_bits(float(bits_f64(k.base))); break;
@@ -969,8 +984,10 @@ make_plan(racu_desc const * d, int redop, void * reduce_out, Plan & plan, std::s
         switch (i.op) {
         case RACU_OP_PUSH: if (sd>=1) { k.lvl = uint8_t(sd-1); depth = std::max(depth, sd); } ++sd; break;
         case RACU_OP_CAST: case RACU_OP_NEG: case RACU_OP_ABS: case RACU_OP_SQRT: case RACU_OP_SQR: case RACU_OP_EXP:
-        case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS: case RACU_OP_NOT: case RACU_OP_LOAD: break;
-        case RACU_OP_FMA: k.lvl = uint8_t(sd-3); sd -= 2; break;
+        case RACU_OP_LOG: case RACU_OP_SIN: case RACU_OP_COS: case RACU_OP_NOT: case RACU_OP_LOAD:
+        case RACU_OP_TAN: case RACU_OP_SINH: case RACU_OP_COSH: case RACU_OP_TANH: case RACU_OP_ASIN: case RACU_OP_ACOS: case RACU_OP_ATAN:
+        case RACU_OP_EXPM1: case RACU_OP_LOG1P: case RACU_OP_LOG10: case RACU_OP_ISFINITE: case RACU_OP_ISNAN: case RACU_OP_ISINF: break;
+        case RACU_OP_FMA: case RACU_OP_CLAMP: case RACU_OP_LERP: k.lvl = uint8_t(sd-3); sd -= 2; break;
         case RACU_OP_PICK: k.lvl = uint8_t(sd-1-i.arg); sd -= i.arg; break;
         default: k.lvl = uint8_t(sd-2); --sd; break;
         }

@@ -22,13 +22,15 @@
 namespace racu {
 
 // kernels: thin __global__ wrappers of the bodies in static_device.h
-template <int ID, bool GENERAL> __global__ void __launch_bounds__(KBLOCK)
-smap_kernel(const __grid_constant__ SParams p) { smap_body<ID, GENERAL>(p); }
-template <int ID, int FOLD, int RMASK, uint32_t KINDS> __global__ void __launch_bounds__(KBLOCK)
+template <int ID, bool GENERAL, uint64_t KINDS=SK_RUNTIME> __global__ void __launch_bounds__(KBLOCK)
+smap_kernel(const __grid_constant__ SParams p) { smap_body<ID, GENERAL, KINDS>(p); }
+template <int ID, uint64_t KINDS> __global__ void __launch_bounds__(KBLOCK)
+smap_lanes_kernel(const __grid_constant__ SParams p) { smap_lanes_body<ID, KINDS>(p); }
+template <int ID, int FOLD, int RMASK, uint64_t KINDS> __global__ void __launch_bounds__(KBLOCK)
 sfold_inner_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f) { sfold_inner_body<ID, FOLD, RMASK, KINDS>(p, f); }
-template <int ID, int FOLD, int RMASK, uint32_t KINDS> __global__ void __launch_bounds__(KBLOCK)
+template <int ID, int FOLD, int RMASK, uint64_t KINDS> __global__ void __launch_bounds__(KBLOCK)
 sfold_inner_rows_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f) { sfold_inner_rows_body<ID, FOLD, RMASK, KINDS>(p, f); }
-template <int ID, int FOLD, uint32_t KINDS> __global__ void __launch_bounds__(KBLOCK)
+template <int ID, int FOLD, uint64_t KINDS> __global__ void __launch_bounds__(KBLOCK)
 sfold_outer_kernel(const __grid_constant__ SParams p, const __grid_constant__ FinishParams f) { sfold_outer_body<ID, FOLD, KINDS>(p, f); }
 
 // ---------------- dispatch ----------------
@@ -37,7 +39,7 @@ sfold_outer_kernel(const __grid_constant__ SParams p, const __grid_constant__ Fi
 // for two-role programs one value per folded row against a vector (gevm) or one role re-read by every kept row (gemv). Any other
 // layout, and the other combiners (prod, amin, amax), run the same bodies with the kinds read at run time.
 
-template <int ID> constexpr uint32_t all_vec_kinds() { uint32_t k = 0; for (int r=0; r<SPT<ID>::P.nin; ++r) k |= uint32_t(SK_VEC)<<(4*r); return k; }
+template <int ID> constexpr uint64_t all_vec_kinds() { uint64_t k = 0; for (int r=0; r<SPT<ID>::P.nin; ++r) k |= uint64_t(SK_VEC)<<(4*r); return k; }
 
 // The kernel a plan runs on (a __global__ function pointer), or null.
 template <int ID> static void const *
@@ -46,11 +48,19 @@ select_kernel(SParams const & p)
     constexpr SProg P = SPT<ID>::P;
 #define RACU_GO(KERNEL, ...) return reinterpret_cast<void const *>(&KERNEL<ID, __VA_ARGS__>)
     if (p.mode==K_MAP) {
-        if constexpr (!P.fold) { if (p.general) RACU_GO(smap_kernel, true); else RACU_GO(smap_kernel, false); }
+        if constexpr (!P.fold) {
+            if constexpr (4==P.nin && 0==P.yrole) { // B += A*C + v with v matched on the rows (examples/read-me.cc:32): kinds known at build time
+                uint64_t kinds = 0;
+                for (int k=0; k<P.nin; ++k) kinds |= uint64_t(p.kind[k])<<(4*k);
+                if (!p.lanes && kinds==sk_pack(SK_VEC, SK_VEC, SK_VEC, SK_ROW)) RACU_GO(smap_kernel, true, sk_pack(SK_VEC, SK_VEC, SK_VEC, SK_ROW));
+            }
+            if (p.lanes) RACU_GO(smap_lanes_kernel, SK_RUNTIME);
+            if (p.general) RACU_GO(smap_kernel, true); else RACU_GO(smap_kernel, false);
+        }
     } else if constexpr (P.fold) {
-        uint32_t kinds = 0; int rmask = 0;
-        for (int k=0; k<P.nin; ++k) { kinds |= uint32_t(p.kind[k])<<(4*k); rmask |= (p.reused[k] ? 1 : 0)<<k; }
-        constexpr uint32_t VV = all_vec_kinds<ID>();
+        uint64_t kinds = 0; int rmask = 0;
+        for (int k=0; k<P.nin; ++k) { kinds |= uint64_t(p.kind[k])<<(4*k); rmask |= (p.reused[k] ? 1 : 0)<<k; }
+        constexpr uint64_t VV = all_vec_kinds<ID>();
         bool const sum = p.fold_op==RACU_ASSIGN_ADD || p.fold_op==RACU_ASSIGN_SUB;
         if (p.mode==K_FOLD_INNER) {
             if (sum && kinds==VV) { // dot, sum, sqrm, sum-cols, gemv

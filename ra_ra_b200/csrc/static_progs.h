@@ -10,7 +10,7 @@
 
 namespace racu {
 
-constexpr int SP_MAXINS = 32, SP_MAXIN = 8;
+constexpr int SP_MAXINS = 32, SP_MAXIN = 12; // (12 = RACU_MAX_OPND: the 2-D mass stencil of examples/laplace2d.cc:48 has 7 slices + 3 scalars)
 struct SIns { uint8_t op, arg, type, aux; };
 struct SProg
 {
@@ -116,10 +116,13 @@ constexpr int SV = 4; // elements per static vector (16 bytes of 4-byte elements
 
 enum { SK_SCALAR = 0, SK_VEC = 1, SK_VECREV = 2 /* unit step backwards: aligned loads, lanes reversed */, SK_ROW = 3 /* step 0 on axis 0: one value per row */,
        SK_SEQ = 4 /* iota / tindex (ra/expr.hh:79-100): value = origin + element offset, no memory */,
-       SK_PTR = 5 /* gathered array (RACU_OP_LOAD): in[] = base address, sA[][0..1] = valid element offsets; never fetched */ };
+       SK_PTR = 5 /* gathered array (RACU_OP_LOAD): in[] = base address, sA[][0..1] = valid element offsets; never fetched */,
+       SK_VECU = 6 /* unit step forwards, rows NOT 16-byte aligned (slices shifted by one element: A(I, J+1) of a user-written stencil,
+                      examples/laplace2d.cc:48, bench/bench-stencil1.cc:45): lane-wise kernel only (smap_lanes_body) */,
+       SK_VECREVU = 7 /* unit step backwards, not aligned: lane-wise kernel only */ };
 
-constexpr uint32_t SK_RUNTIME = 0xffffffffu; // KINDS template argument of the fold kernels: operand kinds read from SParams::kind at run time
-constexpr uint32_t sk_pack(int k0, int k1=0, int k2=0, int k3=0) { return uint32_t(k0) | (uint32_t(k1)<<4) | (uint32_t(k2)<<8) | (uint32_t(k3)<<12); }
+constexpr uint64_t SK_RUNTIME = ~uint64_t(0); // KINDS template argument: operand kinds read from SParams::kind at run time
+constexpr uint64_t sk_pack(int k0, int k1=0, int k2=0, int k3=0) { return uint64_t(k0) | (uint64_t(k1)<<4) | (uint64_t(k2)<<8) | (uint64_t(k3)<<12); }
 
 struct SParams
 {
@@ -136,6 +139,8 @@ struct SParams
     uint8_t kind[SP_MAXIN];       // SK_*
     uint8_t reused[SP_MAXIN];     // folds: the operand does not move along the kept rows (every row re-reads it): cache in L1
     int32_t inner_rows;           // fold-inner: one warp per kept row (sfold_inner_rows_body) instead of one CTA per (row, chunk)
+    int32_t zero;                 // always 0, and the compiler cannot know: see loads_issued() in static_device.h
+    int32_t lanes;                // maps: lane-wise kernel (smap_lanes_body): rows that are not 16-byte aligned or not whole vectors
     int32_t pad1;
     int64_t sB[SP_MAXIN][KGR];    // role -> element strides over group B
     KDim dB[KGR];

@@ -399,6 +399,67 @@ def exp(a): return _unary_float(abi.OP_EXP, a)
 def log(a): return _unary_float(abi.OP_LOG, a)
 def sin(a): return _unary_float(abi.OP_SIN, a)
 def cos(a): return _unary_float(abi.OP_COS, a)
+# the rest of the using-declared <cmath> functions of ra/ra.hh:221-222
+def tan(a): return _unary_float(abi.OP_TAN, a)
+def sinh(a): return _unary_float(abi.OP_SINH, a)
+def cosh(a): return _unary_float(abi.OP_COSH, a)
+def tanh(a): return _unary_float(abi.OP_TANH, a)
+def asin(a): return _unary_float(abi.OP_ASIN, a)
+def acos(a): return _unary_float(abi.OP_ACOS, a)
+def atan(a): return _unary_float(abi.OP_ATAN, a)
+def expm1(a): return _unary_float(abi.OP_EXPM1, a)
+def log1p(a): return _unary_float(abi.OP_LOG1P, a)
+def log10(a): return _unary_float(abi.OP_LOG10, a)
+
+
+def _classify(op, a):
+    a = as_expr(a)
+    t = a.dtype if is_float(a.dtype) else F64
+    return Op(op, [cast(t, a)], t, BOOL)
+
+
+def isfinite(a): return _classify(abi.OP_ISFINITE, a)
+def isnan(a): return _classify(abi.OP_ISNAN, a)
+def isinf(a): return _classify(abi.OP_ISINF, a)
+
+
+def clamp(v, lo, hi):
+    """std::clamp (ra/ra.hh:222): v < lo ? lo : hi < v ? hi : v, in the common type of the three."""
+    v, lo, hi = as_expr(v), as_expr(lo), as_expr(hi)
+    t = common_type(common_type(v.dtype, lo.dtype), hi.dtype)
+    return Op(abi.OP_CLAMP, [cast(t, v), cast(t, lo), cast(t, hi)], t, t)
+
+
+def lerp(a, b, t_):
+    """std::lerp (ra/ra.hh:222)."""
+    a, b, t_ = as_expr(a), as_expr(b), as_expr(t_)
+    t = common_type(common_type(a.dtype, b.dtype), t_.dtype)
+    t = t if is_float(t) else F64
+    return Op(abi.OP_LERP, [cast(t, a), cast(t, b), cast(t, t_)], t, t)
+
+
+def odd(a):
+    """ra/ra.hh:61: N & 1 on the value converted to unsigned int."""
+    a = as_expr(a)
+    _ck(not is_float(a.dtype), "odd() of a floating point value", abi.ERR_BAD_DESC)
+    return (cast(promote(a.dtype), a) & 1).ne(0)
+
+
+def rel_error(a, b):
+    """ra/ra.hh:94: D = |a| + |b|; D == 0 ? 0. : 2.*|a - b| / D, computed with the double literals and returned in the real type."""
+    a, b = as_expr(a), as_expr(b)
+    R = common_type(a.dtype, b.dtype)
+    R = R if is_float(R) else F64
+    a, b = cast(R, a), cast(R, b)
+    D = abs(a) + abs(b)
+    return cast(R, where(D.eq(0), 0., 2. * abs(a - b) / D))
+
+
+def cmp3(a, b):
+    """operator<=> (ra/ra.hh:190) as an int: -1, 0, +1, and 2 where the operands are unordered (a NaN). The reference yields
+    std::partial_ordering objects, which are not array elements on the device; comparing the result with 0 reads the same."""
+    a, b = as_expr(a), as_expr(b)
+    return where(a < b, -1, where(a > b, 1, where(a.eq(b), 0, 2)))
 
 
 def abs(a):  # noqa: A001

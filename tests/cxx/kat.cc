@@ -270,6 +270,42 @@ int main()
         tr.test_eq(vec<real> {2, 2, 12}, x);
         tr.test_eq(vec<real> {10, 60, 30}, y);
     }
+    tr.section("named functions and <=>: ra/ra.hh:190,210,221-222; test/operators.cc:58,65-68; test/test.cc:86-88; test/reexported.cc:25-26");
+    {
+        tr.test_eq(vec<bool> {true, false, true, true}, rc::odd(rc::Big<int, 1> {1, 2, 3, -1}));
+        rc::Big<int, 1> i3 {3, 4, 5};
+        rc::Big<real, 1> d3 {2., 4., 6.};
+        auto c3 = TestRecorder::host(i3 <=> d3);
+        std::string sign;
+        for (int z: c3) sign += z>0 ? '+' : z<0 ? '-' : '0';
+        tr.test(sign=="+0-", "<=> maps to +0-");
+        tr.test_eq(vec<bool> {true, false, false}, (i3 <=> d3) > 0);
+        real const inf = std::numeric_limits<real>::infinity(), nan = std::numeric_limits<real>::quiet_NaN();
+        rc::Big<real, 1> x {3., inf, nan, -inf};
+        tr.test_eq(vec<bool> {true, false, false, false}, rc::isfinite(x));
+        tr.test_eq(vec<bool> {false, false, true, false}, rc::isnan(x));
+        tr.test_eq(vec<bool> {false, true, false, true}, rc::isinf(x));
+        tr.test_eq(vec<real> {2.5, 4., 1.}, rc::lerp(rc::Big<real, 1> {4., 4., 4.}, 1., rc::Big<real, 1> {0.5, 0., 1.}));
+        tr.test_eq(vec<int> {-1, 0, 3, 4}, rc::clamp(rc::Big<int, 1> {-5, 0, 3, 9}, -1, 4));
+        tr.test_eq(vec<real> {0., 0., 2./3.}, rc::rel_error(rc::Big<real, 1> {1., 0., 2.}, rc::Big<real, 1> {1., 0., 1.}));
+        auto close = [&](auto const & e, vec<real> const & want, char const * what) {
+            auto got = TestRecorder::host(e);
+            bool ok = got.size()==want.size();
+            for (size_t k=0; ok && k<got.size(); ++k) ok = std::abs(got[k]-want[k])<=1e-14*std::max(1., std::abs(want[k]));
+            tr.test(ok, what);
+        };
+        rc::Big<real, 1> v {-0.75, 0., 0.3};
+        close(rc::tan(v), {std::tan(-0.75), 0., std::tan(0.3)}, "tan");
+        close(rc::sinh(v), {std::sinh(-0.75), 0., std::sinh(0.3)}, "sinh");
+        close(rc::cosh(v), {std::cosh(-0.75), 1., std::cosh(0.3)}, "cosh");
+        close(rc::tanh(v), {std::tanh(-0.75), 0., std::tanh(0.3)}, "tanh");
+        close(rc::asin(v), {std::asin(-0.75), 0., std::asin(0.3)}, "asin");
+        close(rc::acos(v), {std::acos(-0.75), std::acos(0.), std::acos(0.3)}, "acos");
+        close(rc::atan(v), {std::atan(-0.75), 0., std::atan(0.3)}, "atan");
+        close(rc::expm1(v), {std::expm1(-0.75), 0., std::expm1(0.3)}, "expm1");
+        close(rc::log1p(v), {std::log1p(-0.75), 0., std::log1p(0.3)}, "log1p");
+        close(rc::log10(v+2.), {std::log10(1.25), std::log10(2.), std::log10(2.3)}, "log10");
+    }
     tr.section("reductions: test/reduction.cc:85-138,199-201");
     {
         rc::Big<real, 1> a {1, 2}, b {3, 4};

@@ -1017,3 +1017,38 @@ def reference_reductions_refmin_refmax(ex):
     my.assign(77.)
     B[0, 1] = 77
     eq(A, B)
+
+
+@case
+def named_functions_opcode_table(ex):
+    """The rest of the named functions of ra/ra.hh:210,221-222 and `<=>` (ra/ra.hh:190). Known answers: test/operators.cc:58 (odd of
+    {1, 2, 3, -1} -> {true, false, true, true}), :65-68 (`<=>` of {3, 4, 5} with {2., 4., 6.} -> "+0-"), test/test.cc:86-88 (isfinite of
+    3., +inf, nan), test/reexported.cc:25-26 (lerp(4., 1., 0.5) = 2.5); clamp / lerp / classification exact, libm functions to 4 ulp."""
+    eq(concrete(ex, ra.odd(arr(ex, [1, 2, 3, -1], np.int32)), (4,), np.bool_), [True, False, True, True])
+    c3 = concrete(ex, ra.cmp3(arr(ex, [3, 4, 5], np.int32), arr(ex, [2., 4., 6.], np.float64)), (3,), np.int32)
+    eq(c3, [1, 0, -1])
+    assert "".join("+0-"[1 - int(z)] for z in c3.numpy()) == "+0-"
+    eq(concrete(ex, ra.cmp3(arr(ex, [1., np.nan], np.float64), arr(ex, [np.nan, 2.], np.float64)), (2,), np.int32), [2, 2])  # unordered
+    x = arr(ex, [3., np.inf, np.nan, -np.inf, -0.], np.float64)
+    eq(concrete(ex, ra.isfinite(x), (5,), np.bool_), [True, False, False, False, True])
+    eq(concrete(ex, ra.isnan(x), (5,), np.bool_), [False, False, True, False, False])
+    eq(concrete(ex, ra.isinf(x), (5,), np.bool_), [False, True, False, True, False])
+    xf = arr(ex, [3., np.inf, np.nan], np.float32)
+    eq(concrete(ex, ra.isfinite(xf), (3,), np.bool_), [True, False, False])
+    eq(concrete(ex, ra.lerp(arr(ex, [4., 4., 4., -1.], np.float64), 1., arr(ex, [0.5, 0., 1., 2.], np.float64)), (4,), np.float64), [2.5, 4., 1., 3.])
+    eq(concrete(ex, ra.lerp(arr(ex, [1., 2.], np.float32), arr(ex, [3., 2.], np.float32), arr(ex, [0.25, 7.], np.float32)), (2,), np.float32),
+       np.array([1.5, 2.], np.float32))
+    eq(concrete(ex, ra.clamp(arr(ex, [-5, 0, 3, 9], np.int32), -1, 4), (4,), np.int32), [-1, 0, 3, 4])
+    eq(concrete(ex, ra.clamp(arr(ex, [-5., 0.5, 9.], np.float64), arr(ex, [0., 0., 0.], np.float64), 1.), (3,), np.float64), [0., 0.5, 1.])
+    eq(concrete(ex, ra.rel_error(arr(ex, [1., 0., 2.], np.float64), arr(ex, [1., 0., 1.], np.float64)), (3,), np.float64), [0., 0., 2. * 1. / 3.])
+    eq(concrete(ex, ra.rel_error(arr(ex, [1., 3.], np.float32), arr(ex, [3., 1.], np.float32)), (2,), np.float32), np.array([1., 1.], np.float32))
+    v = np.array([-0.75, -0.1, 0.0, 0.3, 0.9])
+    for dt, ulp in ((np.float64, 4 * np.finfo(np.float64).eps), (np.float32, 4 * np.finfo(np.float32).eps)):
+        a = arr(ex, v, dt)
+        for fn, ref in ((ra.tan, np.tan), (ra.sinh, np.sinh), (ra.cosh, np.cosh), (ra.tanh, np.tanh), (ra.asin, np.arcsin), (ra.acos, np.arccos),
+                        (ra.atan, np.arctan), (ra.expm1, np.expm1), (ra.log1p, np.log1p)):
+            got = concrete(ex, fn(a), (5,), dt).numpy()
+            want = ref(v.astype(dt).astype(np.float64))
+            assert np.all(np.abs(got - want) <= ulp * np.maximum(1.0, np.abs(want))), (fn.__name__, got, want)
+        got = concrete(ex, ra.log10(a + 2), (5,), dt).numpy()
+        assert np.all(np.abs(got - np.log10(v.astype(dt).astype(np.float64) + 2)) <= ulp)

@@ -449,3 +449,34 @@ def test_narrowing_fold_cuda_vs_oracle(seed, exc):
         getattr(c, ["__iadd__", "__isub__", "__imul__"][seed % 3])(a)
         outs.append(snapshot(ex, c))
     assert outs[0].dtype == outs[1].dtype and np.array_equal(outs[0], outs[1]), seed
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [130, 257])
+def test_shifted_slice_expressions_run_specialised(dt, n, exc):
+    """User-written stencils over slices shifted by one element - rows that are not 16-byte aligned and whose length is not a whole
+    number of vectors - run on the specialised map kernels (element-wise loads for the unaligned roles, partial vectors at the row ends),
+    not on the interpreter, and equal the oracle bit for bit: the 2-D 7-point mass stencil of examples/laplace2d.cc:48 (with its /2. and
+    /12. association), the 1-D 3-point stencil of bench/bench-stencil1.cc:45, and an unaligned flat copy."""
+    rng = np.random.default_rng(77)
+    v0 = rng.uniform(-1, 1, (n, n)).astype(dt)
+    a0 = rng.uniform(-1, 1, n * n).astype(dt)
+    h = 1.0 / n
+    outs = []
+    for ex in (OracleExecutor(), exc):
+        v, w = ex.from_numpy(v0), ex.from_numpy(np.zeros_like(v0))
+        i, j = ra.iota(n - 2, 1), ra.iota(n - 2, 1)
+        w(i, j).assign(ra.sqrm(h) * (v(i, j) / 2. + (v(i - 1, j) + v(i, j - 1) + v(i + 1, j) + v(i, j + 1) + v(i + 1, j + 1) + v(i - 1, j - 1)) / 12.))
+        k1 = ex.last_kernel() if ex.name == "cuda" else None
+        A, An = ex.from_numpy(a0), ex.from_numpy(np.zeros_like(a0))
+        I = ra.iota(n * n - 2, 1)
+        An(I).assign(-2 * A(I) + A(I + 1) + A(I - 1))
+        k2 = ex.last_kernel() if ex.name == "cuda" else None
+        B = ex.from_numpy(np.zeros_like(a0))
+        B(ra.iota(n * n - 3, 2)).assign(A(ra.iota(n * n - 3, 1)) * 2)
+        k3 = ex.last_kernel() if ex.name == "cuda" else None
+        outs.append((snapshot(ex, w), snapshot(ex, An), snapshot(ex, B)))
+        if ex.name == "cuda":
+            assert all(k in ("jit_map", "sflat_map") for k in (k1, k2, k3)), (k1, k2, k3)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
