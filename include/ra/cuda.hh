@@ -1147,6 +1147,158 @@ template <class T, rank_t R> auto diag(View<T, R> const & a) { return transpose<
 
 
 // ---------------------
+// cell iterators and rank conjunction: iter<k>(a) (ra/expr.hh:317-328), scalar(a) (ra/expr.hh:128), wrank<cr ...>(op) (ra/expr.hh:469-499).
+//
+// In the reference these build iterators over the k-cells of an array / apply an op to cells of given ranks with the FRAMES (the axes
+// in front of the cells) matched by prefix, and any callable may sit inside. On the device the callable has to be one of the
+// enumerated assignment functors below, and each spelling LOWERS to the one fused descriptor the planner already knows: every argument
+// gets dead (inserted) axes where its frame is shorter than the longest one, and the op is then the ordinary prefix-matched
+// assignment. So the seven spellings of "sum the rows" of test/reduction.cc:182-222 and bench/bench-sum-rows.cc:62-81
+//     sum(iter<1>(a));  iter<1>(c) += iter<1>(a);  scalar(c) += iter<1>(a);  for_each(wrank<1, 1>(add_assign), c, a);
+//     for_each(wrank<1, 1>(wrank<0, 0>(add_assign)), c, a);  c += transpose(a);  c(insert<1>) += a
+// all are the fold `c(insert<1>) += a` (sflat_fold_outer), and gemm1 of bench/bench-gemm.cc:25-30,
+//     for_each(wrank<1, 2, 1>(wrank<0, 1, 1>(maybe_fma)), a, b, c)
+// is c(all, insert<1>) += a * b(insert<1>): the contraction kernel.
+// ---------------------
+
+template <class T> using ViewAny = View<T, ANY>;
+
+// `frame` axes of v are kept, then `extra` dead axes, then its cells.
+template <class T, rank_t R>
+ViewAny<T> insert_after_frame(View<T, R> const & v, int frame, int extra)
+{
+    ViewAny<T> out;
+    out.cp = v.cp;
+    RACU_CK(0<=frame && frame<=v.rank() && extra>=0, "Bad cell rank.");
+    out.dimv.assign(v.dimv.begin(), v.dimv.begin()+frame);
+    for (int q=0; q<extra; ++q) out.dimv.push_back(Dim {UNB, 0});
+    out.dimv.insert(out.dimv.end(), v.dimv.begin()+frame, v.dimv.end());
+    RACU_CK(out.rank()<=RACU_MAX_RANK, "Rank too large.");
+    return out;
+}
+
+template <class T, rank_t R, int k>
+struct CellIter // iter<k>(a): the k-cells of a; k < 0 counts frame axes (ra/expr.hh:323: cell rank = rank + k)
+{
+    View<T, R> v;
+    int cell_rank() const { int c = k>=0 ? k : v.rank()+k; RACU_CK(0<=c && c<=v.rank(), "Bad cell rank."); return c; }
+    int frame_rank() const { return v.rank()-cell_rank(); }
+    template <class T2, rank_t R2, int k2> void assign(int op, CellIter<T2, R2, k2> const & x) const
+    {
+        int const F = std::max(frame_rank(), x.frame_rank());
+        insert_after_frame(v, frame_rank(), F-frame_rank()).assign(op, insert_after_frame(x.v, x.frame_rank(), F-x.frame_rank()));
+    }
+#define RACU_ASSIGNOP(OP, CODE) \
+    template <class T2, rank_t R2, int k2> CellIter const & operator OP(CellIter<T2, R2, k2> const & x) const { assign(CODE, x); return *this; }
+    RACU_ASSIGNOP(=, RACU_ASSIGN_SET) RACU_ASSIGNOP(+=, RACU_ASSIGN_ADD) RACU_ASSIGNOP(-=, RACU_ASSIGN_SUB)
+    RACU_ASSIGNOP(*=, RACU_ASSIGN_MUL) RACU_ASSIGNOP(/=, RACU_ASSIGN_DIV)
+#undef RACU_ASSIGNOP
+};
+
+template <int k, class T, rank_t R> auto iter(View<T, R> const & a) { return CellIter<T, R, k> {a}; }
+template <int k, class A> requires (requires (A const & a) { a.view(); }) auto iter(A const & a) { return iter<k>(a.view()); }
+// ra::scalar(c): c as ONE cell (every cell of the other side is combined into the whole of it): scalar(c) += iter<1>(a)
+template <class T, rank_t R> auto scalar(View<T, R> const & a) { return CellIter<T, R, (ANY==R ? 0 : R)> {a}; }
+template <class A> requires (requires (A const & a) { a.view(); }) auto scalar(A const & a) { return scalar(a.view()); }
+template <class T> struct CellIter<T, ANY, 0> // (dynamic rank: scalar() means the whole array, iter<0> its elements; told apart by a flag)
+{
+    View<T, ANY> v;
+    bool whole = true;
+    int cell_rank() const { return whole ? v.rank() : 0; }
+    int frame_rank() const { return v.rank()-cell_rank(); }
+    template <class X> void assign(int op, X const & x) const
+    {
+        int const F = std::max(frame_rank(), x.frame_rank());
+        insert_after_frame(v, frame_rank(), F-frame_rank()).assign(op, insert_after_frame(x.v, x.frame_rank(), F-x.frame_rank()));
+    }
+#define RACU_ASSIGNOP(OP, CODE) template <class X> CellIter const & operator OP(X const & x) const { assign(CODE, x); return *this; }
+    RACU_ASSIGNOP(+=, RACU_ASSIGN_ADD) RACU_ASSIGNOP(-=, RACU_ASSIGN_SUB) RACU_ASSIGNOP(*=, RACU_ASSIGN_MUL) RACU_ASSIGNOP(/=, RACU_ASSIGN_DIV)
+#undef RACU_ASSIGNOP
+};
+
+// sum / prod over the cells (test/reduction.cc:189,197-201): an array of the cell's shape; no cells: 0 / 1.
+template <class T, rank_t R, int k>
+auto reduce_cells(CellIter<T, R, k> const & it, int op, std::remove_cv_t<T> start)
+{
+    using V0 = std::remove_cv_t<T>;
+    std::vector<dim_t> sh;
+    for (int q=it.frame_rank(); q<it.v.rank(); ++q) sh.push_back(it.v.len(q));
+    Big<V0, ANY> c(sh, start);
+    CellIter<V0, ANY, 0> whole {c.view(), true};
+    whole.assign(op, it);
+    return c;
+}
+template <class T, rank_t R, int k> auto sum(CellIter<T, R, k> const & it) { return reduce_cells(it, RACU_ASSIGN_ADD, std::remove_cv_t<T>(0)); }
+template <class T, rank_t R, int k> auto prod(CellIter<T, R, k> const & it) { return reduce_cells(it, RACU_ASSIGN_MUL, std::remove_cv_t<T>(1)); }
+
+// The callables a device for_each takes: y OP= x on cells (destination FIRST, as in for_each([](auto & c, auto a) { c += a; }, c, a)),
+// and maybe_fma(a, b, c): c += a*b (ra/ra.hh:364-374; destination LAST, as bench/bench-gemm.cc:25-30 writes it).
+template <int CODE> struct assign_fn { static constexpr int code = CODE; };
+constexpr assign_fn<RACU_ASSIGN_SET> set_assign {};
+constexpr assign_fn<RACU_ASSIGN_ADD> add_assign {};
+constexpr assign_fn<RACU_ASSIGN_SUB> sub_assign {};
+constexpr assign_fn<RACU_ASSIGN_MUL> mul_assign {};
+constexpr assign_fn<RACU_ASSIGN_DIV> div_assign {};
+struct maybe_fma_fn {};
+constexpr maybe_fma_fn maybe_fma {};
+
+template <class Op, int ... cr> struct Wrank { Op op; };
+template <int ... cr, class Op> constexpr auto wrank(Op const & op) { return Wrank<Op, cr ...> {op}; }
+
+namespace detail {
+// one rank-conjunction level: argument i keeps pos[i] axes as frame already; its cells at this level have rank cr[i]
+template <std::size_t N> void
+conjoin(std::array<std::vector<Dim>, N> & dv, std::array<int, N> & pos, std::array<int, N> const & cr)
+{
+    int f[N], F = 0;
+    for (std::size_t i=0; i<N; ++i) {
+        int const left = int(dv[i].size())-pos[i];
+        int const c = cr[i]>=0 ? cr[i] : left+cr[i];
+        RACU_CK(0<=c && c<=left, "Bad cell rank.");
+        f[i] = left-c; F = std::max(F, f[i]);
+    }
+    for (std::size_t i=0; i<N; ++i) {
+        dv[i].insert(dv[i].begin()+pos[i]+f[i], std::size_t(F-f[i]), Dim {UNB, 0});
+        pos[i] += F;
+        RACU_CK(int(dv[i].size())<=RACU_MAX_RANK, "Rank too large.");
+    }
+}
+template <class Op> struct final_op { using type = Op; };
+template <class Op, int ... cr> struct final_op<Wrank<Op, cr ...>> { using type = typename final_op<Op>::type; };
+template <std::size_t N, class Op> void conjoin_all(Op const &, std::array<std::vector<Dim>, N> &, std::array<int, N> &) {}
+template <std::size_t N, class Op, int ... cr> void
+conjoin_all(Wrank<Op, cr ...> const & w, std::array<std::vector<Dim>, N> & dv, std::array<int, N> & pos)
+{
+    static_assert(sizeof...(cr)==N, "wrank<> needs one cell rank per argument");
+    conjoin<N>(dv, pos, std::array<int, N> {cr ...});
+    conjoin_all<N>(w.op, dv, pos);
+}
+} // namespace detail
+
+// for_each(wrank<cr ...>(op), args ...) for the enumerated ops (ra/ply.hh:168 + ra/expr.hh:469-499).
+template <class Op, int ... cr, class ... A>
+void for_each(Wrank<Op, cr ...> const & w, A const & ... a)
+{
+    constexpr std::size_t N = sizeof...(A);
+    using F = typename detail::final_op<Op>::type;
+    auto views = std::make_tuple(ViewAny<typename node_t<A>::value_type>(iter(a)) ...);
+    std::array<std::vector<Dim>, N> dv;
+    std::array<int, N> pos {};
+    [&]<std::size_t ... I>(std::index_sequence<I ...>) { ((dv[I] = std::get<I>(views).dimv), ...); }(std::make_index_sequence<N> {});
+    detail::conjoin_all<N>(w, dv, pos);
+    [&]<std::size_t ... I>(std::index_sequence<I ...>) { ((std::get<I>(views).dimv = dv[I]), ...); }(std::make_index_sequence<N> {});
+    if constexpr (std::is_same_v<F, maybe_fma_fn>) {
+        static_assert(3==N, "maybe_fma(a, b, c)");
+        std::get<2>(views) += std::get<0>(views) * std::get<1>(views);
+    } else {
+        static_assert(2==N, "y OP= x");
+        std::get<0>(views).assign(F::code, std::get<1>(views));
+    }
+}
+// without a rank conjunction the op applies element by element
+template <int CODE, class Y, class X> void for_each(assign_fn<CODE>, Y const & y, X const & x) { iter(y).assign(CODE, x); }
+
+// ---------------------
 // BLAS-like: ra/ra.hh:403-456. Same expressions as the reference; the library recognises them and runs the contraction kernels.
 // ---------------------
 

@@ -15,6 +15,9 @@
 // shared-memory pitches padded so that fragment reads are bank-conflict free.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "launch.h"
 #include "special.h"
 
@@ -45,12 +48,19 @@ __device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.
 struct GParams { void const * a; void const * b; void * c; int64_t lda, ldb, ldc; int32_t M, N, K; };
 
 // ---------------- f64 ----------------
-constexpr int DK = 16, DPA = DK+4 /* A pitch (doubles) */, DPB = GN+4 /* B pitch */;
-constexpr int DSTAGE = GM*DPA + DK*DPB; // doubles per stage
+// (sm_100a has ONE FP64 tensor instruction, DMMA.8x8x4: mma.sync.m16n8k16.f64 compiles to eight of them, so the larger PTX shapes buy
+// nothing. At one DMMA per 16 cycles and SM sub-partition the pipe peaks at 37.2 TFLOP/s at 1965 MHz; cuBLAS reaches 36.1.)
+template <int BK> struct DTile
+{
+    static constexpr int PA = BK+4 /* A pitch (doubles) */, PB = GN+4 /* B pitch */;
+    static constexpr int STAGE = GM*PA + BK*PB; // doubles per stage
+};
+constexpr int DK = 16;
 
-__global__ void __launch_bounds__(GTHREADS)
+template <int BK, int STAGES> __global__ void __launch_bounds__(GTHREADS)
 dgemm_kernel(const __grid_constant__ GParams p)
 {
+    constexpr int DPA = DTile<BK>::PA, DPB = DTile<BK>::PB, DSTAGE = DTile<BK>::STAGE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double * const sm = reinterpret_cast<double *>(smem_raw);
     int const tid = threadIdx.x, lane = tid&31, warp = tid>>5;
@@ -61,14 +71,14 @@ dgemm_kernel(const __grid_constant__ GParams p)
     double const * B = static_cast<double const *>(p.b) + n0;
     auto load_stage = [&](int s, int kt) {
         double * As = sm + s*DSTAGE, * Bs = As + GM*DPA;
-        int64_t const k0 = int64_t(kt)*DK;
+        int64_t const k0 = int64_t(kt)*BK;
 #pragma unroll
-        for (int i=0; i<4; ++i) { // A tile 128 x 16: 8 x 16-byte copies per row
-            int c = tid + i*GTHREADS, r = c>>3, q = c&7;
+        for (int i=0; i<GM*BK/2/GTHREADS; ++i) { // A tile 128 x BK: BK/2 16-byte copies per row
+            int c = tid + i*GTHREADS, r = c/(BK/2), q = c%(BK/2);
             cp16(As + r*DPA + q*2, A + r*p.lda + k0 + q*2);
         }
 #pragma unroll
-        for (int i=0; i<4; ++i) { // B tile 16 x 128: 64 copies per row
+        for (int i=0; i<BK*GN/2/GTHREADS; ++i) { // B tile BK x 128: 64 copies per row
             int c = tid + i*GTHREADS, r = c>>6, q = c&63;
             cp16(Bs + r*DPB + q*2, B + (k0+r)*p.ldb + q*2);
         }
@@ -78,17 +88,17 @@ dgemm_kernel(const __grid_constant__ GParams p)
     for (int i=0; i<8; ++i)
 #pragma unroll
         for (int j=0; j<4; ++j) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
-    int const nk = p.K/DK;
+    int const nk = p.K/BK;
 #pragma unroll
-    for (int s=0; s<GSTAGES-1; ++s) { if (s<nk) load_stage(s, s); cp_commit(); }
+    for (int s=0; s<STAGES-1; ++s) { if (s<nk) load_stage(s, s); cp_commit(); }
     for (int kt=0; kt<nk; ++kt) {
-        cp_wait<GSTAGES-2>();
+        cp_wait<STAGES-2>();
         __syncthreads();
-        if (kt+GSTAGES-1<nk) load_stage((kt+GSTAGES-1)%GSTAGES, kt+GSTAGES-1);
+        if (kt+STAGES-1<nk) load_stage((kt+STAGES-1)%STAGES, kt+STAGES-1);
         cp_commit();
-        double const * As = sm + (kt%GSTAGES)*DSTAGE + (wm*64)*DPA, * Bs = sm + (kt%GSTAGES)*DSTAGE + GM*DPA + wn*32;
+        double const * As = sm + (kt%STAGES)*DSTAGE + (wm*64)*DPA, * Bs = sm + (kt%STAGES)*DSTAGE + GM*DPA + wn*32;
 #pragma unroll
-        for (int kk=0; kk<DK; kk+=4) {
+        for (int kk=0; kk<BK; kk+=4) {
             double af[8], bf[4];
 #pragma unroll
             for (int i=0; i<8; ++i) af[i] = As[(i*8+g)*DPA + kk + t];
@@ -222,11 +232,17 @@ try_special_gemm(racu_gemm_desc const * gd, cudaStream_t stream, int * handled)
     GParams p {gd->a, gd->b, gd->c, gd->lda, gd->ldb, gd->ldc, int32_t(gd->M), int32_t(gd->N), int32_t(gd->K)};
     dim3 grid {unsigned(gd->N/GN), unsigned(gd->M/GM), 1};
     if (grid.y>65535) return RACU_OK;
-    size_t smem = size_t(GSTAGES)*(f64 ? DSTAGE*8 : SSTAGE*4);
+    size_t smem = size_t(GSTAGES)*SSTAGE*4;
     cudaError_t e;
     if (f64) {
-        if ((e = cudaFuncSetAttribute(dgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return cuda_fail(e, "dgemm smem");
-        dgemm_kernel<<<grid, GTHREADS, smem, stream>>>(p);
+        // tuning knob RACU_DGEMM: "16x3" (BK x stages, round 1), "16x4", "32x3"
+        char const * which = std::getenv("RACU_DGEMM");
+        int const v = !which ? 1 : 0==std::strcmp(which, "16x3") ? 0 : 0==std::strcmp(which, "32x3") ? 2 : 1;
+        auto kernel = 0==v ? dgemm_kernel<16, 3> : 1==v ? dgemm_kernel<16, 4> : dgemm_kernel<32, 3>;
+        smem = 0==v ? size_t(3)*DTile<16>::STAGE*8 : 1==v ? size_t(4)*DTile<16>::STAGE*8 : size_t(3)*DTile<32>::STAGE*8;
+        if (2==v && 0!=gd->K%32) { kernel = dgemm_kernel<16, 4>; smem = size_t(4)*DTile<16>::STAGE*8; }
+        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return cuda_fail(e, "dgemm smem");
+        kernel<<<grid, GTHREADS, smem, stream>>>(p);
         set_kernel("dgemm_dmma884");
     } else {
         if ((e = cudaFuncSetAttribute(sgemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return cuda_fail(e, "sgemm smem");

@@ -132,13 +132,23 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     int const k0 = blockIdx.x*TK, j0 = 1 + (band*p.gyb + int(blockIdx.y))*ST_TJ; // first output k of the tile (vector aligned), first output j
     if (j0>=p.n1-1) return;                                    // last band may be short (whole CTA leaves before any barrier)
     int const k = k0 + tk*VT, j = j0 + tj;
-    // FUSED: the two edge chunks (0 and gz-1: they read a ghost plane and feed the neighbours) are scheduled in the middle
-    // of the grid, so that the neighbours' flags have long arrived when they start and the pushed planes have long landed
-    // when the kernel ends; every other chunk keeps its order.
+    // FUSED: the two edge chunks (0 and gz-1: they read a ghost plane and feed the neighbours) are SPREAD over the grid: tile q of a band
+    // runs its two edge chunks at grid positions z = 2q, 2q+1 (mod the first three quarters of the band) and its interior chunks, in
+    // order, at the others. Every slab of the grid then carries a few percent of edge CTAs - their flag waits, remote stores and
+    // fences hide behind the interior CTAs resident with them - instead of one wave made of nothing else (round 1: the two edge chunks
+    // of all tiles ran together in mid-grid and cost 87 % -> the rest of the strong-scaling loss at 8 GPUs). Nothing is scheduled in
+    // the last quarter, so the pushed planes have landed and the neighbour's flag is up long before the next step needs them.
     int chunk = is3d ? int(blockIdx.z) - band*p.gz : 0;
     if constexpr (FUSED) {
-        int const gz = p.gz, e = (gz-2)/2;
-        if (gz>2) chunk = chunk<e ? chunk+1 : (chunk==e ? 0 : (chunk==e+1 ? gz-1 : chunk-1));
+        int const gz = p.gz;
+        if (gz>=4) {
+            int const zmax = max(2, (3*gz/4)&~1), q = int(blockIdx.y)*int(gridDim.x) + int(blockIdx.x);
+            int const zlo = (2*q)%zmax, zhi = zlo+1, z = chunk;
+            chunk = z==zlo ? 0 : z==zhi ? gz-1 : 1 + z - (z>zlo) - (z>zhi);
+        } else if (gz>2) {
+            int const e = (gz-2)/2;
+            chunk = chunk<e ? chunk+1 : (chunk==e ? 0 : (chunk==e+1 ? gz-1 : chunk-1));
+        }
     }
     int const ilo = is3d ? p.i_lo + chunk*p.ci : 0;
     int const ihi = is3d ? min(p.i_hi, ilo + p.ci) : 1;

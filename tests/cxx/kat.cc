@@ -337,6 +337,33 @@ int main()
         D(rc::insert<1>) += A;
         tr.test_eq(Br, D);
     }
+    tr.section("sum rows, seven spellings: test/reduction.cc:182-222, bench/bench-sum-rows.cc:62-81");
+    {
+        rc::Big<real, 2> A({100, 111}, rc::_0 - rc::_1);
+        vec<real> B(111);
+        for (int j=0; j<111; ++j) { real s = 0; for (int i=0; i<100; ++i) s += i-j; B[j] = s; }
+        std::string kernels;
+        auto check = [&](auto const & C, char const * what) { tr.test_eq(B, C, what); kernels += std::string(racu_last_kernel()) + " "; };
+        tr.test_eq(B, rc::sum(rc::iter<1>(A)), "sum(iter<1>(A))");
+        { rc::Big<real, 1> C({111}, 0.); rc::iter<1>(C) += rc::iter<1>(A); check(C, "iter<1>(C) += iter<1>(A)"); }
+        { rc::Big<real, 1> C({111}, 0.); rc::scalar(C) += rc::iter<1>(A); check(C, "scalar(C) += iter<1>(A)"); }
+        { rc::Big<real, 1> C({111}, 0.); rc::for_each(rc::wrank<1, 1>(rc::add_assign), C, A); check(C, "rank conjunction"); }
+        { rc::Big<real, 1> C({111}, 0.); rc::for_each(rc::wrank<1, 1>(rc::wrank<0, 0>(rc::add_assign)), C, A); check(C, "double rank conjunction"); }
+        { rc::Big<real, 1> C({111}, 0.); C += rc::transpose(A.view()); check(C, "C += transpose(A)"); }
+        { rc::Big<real, 1> C({111}, 0.); C(rc::insert<1>) += A; check(C, "C(insert<1>) += A"); }
+        rc::Big<real, 2> E({0, 111}, 0.);
+        tr.test_eq(vec<real>(111, 0.), rc::sum(rc::iter<1>(E)), "no cells: sum = 0");
+        tr.test_eq(vec<real>(111, 1.), rc::prod(rc::iter<1>(E)), "no cells: prod = 1");
+        std::printf("    kernels: %s\n", kernels.c_str());
+        // every spelling is the same descriptor: the same kernel family ran each time
+        bool same = true;
+        { size_t p0 = kernels.find(' '); std::string first = kernels.substr(0, p0); for (size_t q=0; q<kernels.size();) { size_t e = kernels.find(' ', q); same = same && kernels.substr(q, e-q)==first; q = e+1; } }
+        tr.test(same, "all spellings dispatch to one kernel");
+        // gemm1 of bench/bench-gemm.cc:25-30 through a double rank conjunction: the contraction descriptor
+        rc::Big<real, 2> a({3, 2}, 2.), b({2, 4}, 3.), c({3, 4}, 0.);
+        rc::for_each(rc::wrank<1, 2, 1>(rc::wrank<0, 1, 1>(rc::maybe_fma)), a, b, c);
+        tr.test_eq(vec<real>(12, 12.), c, "gemm1: wrank<1, 2, 1>(wrank<0, 1, 1>(maybe_fma))");
+    }
     tr.section("gemv / gevm / gemm: test/reduction.cc:241-333, bench/bench-gemm.cc:229-237");
     {
         rc::Big<real, 2> a({3, 4}, rc::_0 - rc::_1);
