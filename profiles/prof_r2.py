@@ -54,6 +54,14 @@ for w in which:
                 B2 += A2 * C2
             else:
                 B2 += A2 * C2 + v
+    elif w in ("stiff32", "stiff64"):  # user-written 5-point stencil over shifted slices, odd size: the lane-wise map kernel
+        n = 8193
+        dt = torch.float32 if w.endswith("32") else torch.float64
+        v = ex.wrap(torch.rand(n, n, device=dev, dtype=dt))
+        ww = ex.wrap(torch.zeros(n, n, device=dev, dtype=dt))
+        i, j = ra.iota(n - 2, 1), ra.iota(n - 2, 1)
+        for _ in range(reps):
+            ww(i, j).assign(4 * v(i, j) - v(i - 1, j) - v(i, j - 1) - v(i + 1, j) - v(i, j + 1))
     elif w == "stencil":
         n3 = 1024
         bufs = [torch.rand(n3, n3, n3, device=dev), torch.zeros(n3, n3, n3, device=dev)]

@@ -561,6 +561,12 @@ match_static_(Plan & plan, std::vector<racu_ins> const & prog, int dst, bool fol
         if (kp.rankA>1) { if (nvrow<1 || sp.nvec>=(int64_t(1)<<31)) return; sp.vprdiv = make_div(nvrow); }
         for (int j=0; j<KGR; ++j) { sp.dA[j] = kp.dA[j]; sp.dsA[j] = j<kp.rankA ? y.sA[j] : 0; }
         int64_t nb = (sp.nvec+int64_t(KBLOCK)*4-1)/(int64_t(KBLOCK)*4);
+        if (lanes) { // work units of the lane-wise kernel: patches of 8 rows x SLANES_CT warp tiles (rows), or 8*SLANES_CT consecutive tiles (flat)
+            int64_t const wpr = nvrow/32, ppb = (wpr+SLANES_CT-1)/SLANES_CT, nrows = kp.rankA>1 ? sp.nvec/nvrow : 1;
+            nb = kp.rankA>1 ? ((nrows+7)/8)*ppb : (wpr+8*SLANES_CT-1)/(8*SLANES_CT);
+            if (nb>=(int64_t(1)<<31)) return;
+            if (kp.rankA>1) sp.vprdiv = make_div(ppb); // the kernel divides unit ids by the patches per band, not vectors by the row length
+        }
         plan.grid_x = unsigned(std::max<int64_t>(1, std::min<int64_t>(nb, int64_t(target)*4))); plan.grid_y = 1;
     }
     sp.id = id; sp.mode = kp.mode; sp.fold_op = kp.fold_op; sp.nchunks = kp.nchunks; sp.rankB = kp.rankB; sp.rankA = kp.rankA;

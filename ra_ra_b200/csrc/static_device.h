@@ -305,55 +305,64 @@ smap_lanes_body(SParams const & p)
 {
     using W = typename SPT<ID>::W;
     constexpr SProg P = SPT<ID>::P;
-    constexpr int des = es_of(P.otype), UNR = SPX<ID>::UNR>2 ? 2 : SPX<ID>::UNR, XW = SPX<ID>::XW, NW = KBLOCK/32;
+    constexpr int des = es_of(P.otype), UNR = SPX<ID>::UNR>2 ? 2 : SPX<ID>::UNR, XW = SPX<ID>::XW, NW = KBLOCK/32, CT = SLANES_CT;
     int const lane = threadIdx.x&31, warp = threadIdx.x>>5;
-    // Work units of KBLOCK*UNR vectors. Flat traversals take them in order. Traversals over rows take PATCHES of NW rows x UNR warp
-    // tiles (warp w owns row w of the patch): the rows i-1, i, i+1 that a stencil expression reads are then loaded by the same CTA
-    // and the re-reads hit L1. In row-major order each CTA held half a row and every one of the five slices of the 5-point stencil came
-    // from L2: measured 12 TB/s of L2 reads for 5 TB/s of HBM traffic, the L2 was the limit (0.57-0.76 of the HBM peak at 4097^2 / 8193^2).
+    // Work units. Traversals over rows take PATCHES of NW rows x CT warp tiles (warp w owns row w of the patch and walks its CT tiles):
+    // the rows i-1, i, i+1 that a stencil expression reads are then loaded by the same CTA and the re-reads hit L1 (measured: 72 %
+    // L1 hits on the 5-point stencil), and everything that depends on the row only - the index decomposition, one pointer per role -
+    // is computed once per CT*128 elements: the first version of this kernel spent 78 instructions per element, most of them on
+    // that, and was issue bound (83 % issue slots busy at 0.5 of the HBM peak). Flat traversals: a unit is NW*CT consecutive tiles.
     bool const rows = p.rankA>1;
-    int64_t const wpr = p.vpr/32, nrows = rows ? p.nvec/p.vpr : 1;   // warp tiles per row
-    int64_t const ppb = (wpr+UNR-1)/UNR;                              // patches per band of NW rows
-    int64_t const nunits = rows ? ((nrows+NW-1)/NW)*ppb : (p.nvec+int64_t(KBLOCK)*UNR-1)/(int64_t(KBLOCK)*UNR);
+    int64_t const wpr = p.vpr/32, nrows = rows ? p.nvec/p.vpr : 1;   // warp tiles per (padded) row
+    uint32_t const ppb = uint32_t((wpr+CT-1)/CT);                     // patches per band of NW rows
+    int64_t const nunits = rows ? ((nrows+NW-1)/NW)*int64_t(ppb) : (wpr+int64_t(NW)*CT-1)/(int64_t(NW)*CT);
     for (int64_t unit = blockIdx.x; unit<nunits; unit += gridDim.x) {
-        uint32_t x[UNR][P.nin][XW];
-        int64_t doff[UNR], e0[UNR];
-        int64_t const band = rows ? unit/ppb : 0, patch = unit-band*ppb;
+        int64_t row = 0, wt0, wt1;
+        if (rows) {
+            uint32_t const band = fastdiv(uint32_t(unit), p.vprdiv), patch = uint32_t(unit)-band*ppb; // (vprdiv divides by ppb here)
+            row = int64_t(band)*NW + warp;
+            if (row>=nrows) continue; // (the kernel has no barrier)
+            wt0 = int64_t(patch)*CT;
+        } else wt0 = (unit*NW + warp)*CT;
+        wt1 = wt0+CT<wpr ? wt0+CT : wpr;
+        if (wt0>=wt1) continue;
+        // once per row: where the row starts in the destination and in every role
+        uint32_t i1 = 0, i2 = 0, i3 = 0;
+        if (rows) {
+            uint32_t n = uint32_t(row), q;
+            if (2==p.rankA) i1 = n;
+            else { q = fastdiv(n, p.dA[1]); i1 = n-q*p.dA[1].len; n = q;
+                if (3==p.rankA) i2 = n; else { q = fastdiv(n, p.dA[2]); i2 = n-q*p.dA[2].len; i3 = q; } }
+        }
+        unsigned char * const drow = static_cast<unsigned char *>(p.dst) + (int64_t(i1)*p.dsA[1] + int64_t(i2)*p.dsA[2] + int64_t(i3)*p.dsA[3])*des;
+        unsigned char const * rowp[P.nin]; // MEM roles: address of the row's element 0. SEQ: the row's element offset
 #pragma unroll
-        for (int u=0; u<UNR; ++u) {
-            // (row, vector within the padded row) of this thread's u-th vector
-            int64_t row = 0, r;
-            bool valid;
-            if (rows) { row = band*NW + warp; int64_t const wt = patch*UNR + u; r = wt*32 + lane; valid = row<nrows && wt<wpr; }
-            else { r = (unit*UNR + u)*KBLOCK + threadIdx.x; valid = r<p.nvec; }
-            e0[u] = p.n; // (nothing to do)
-            if (valid) {
-                uint32_t i1 = 0, i2 = 0, i3 = 0;
-                if (rows) {
-                    uint32_t n = uint32_t(row), q;
-                    if (2==p.rankA) i1 = n;
-                    else { q = fastdiv(n, p.dA[1]); i1 = n-q*p.dA[1].len; n = q;
-                        if (3==p.rankA) i2 = n; else { q = fastdiv(n, p.dA[2]); i2 = n-q*p.dA[2].len; i3 = q; } }
-                }
-                e0[u] = (r & ~int64_t(31))*SV + (r & 31);       // this lane's first element of the warp tile; the others are 32 apart
-                doff[u] = int64_t(i1)*p.dsA[1] + int64_t(i2)*p.dsA[2] + int64_t(i3)*p.dsA[3];
-                bool live[SV];                                  // which of this lane's elements are inside the row: once for every role
+        for (int k=0; k<P.nin; ++k) {
+            int const kd = KINDS!=SK_RUNTIME ? int((KINDS>>(4*k))&15u) : int(p.kind[k]);
+            int64_t const off = int64_t(i1)*p.sA[k][1] + int64_t(i2)*p.sA[k][2] + int64_t(i3)*p.sA[k][3];
+            rowp[k] = SK_SEQ==kd ? reinterpret_cast<unsigned char const *>(intptr_t(off)) : reinterpret_cast<unsigned char const *>(p.in[k]) + off*es_of(P.rtype[k]);
+        }
+        for (int64_t wt = wt0; wt<wt1; wt += UNR) {
+            uint32_t x[UNR][P.nin][XW];
+            int64_t e0[UNR];
+#pragma unroll
+            for (int u=0; u<UNR; ++u) {
+                e0[u] = wt+u<wt1 ? (wt+u)*(32*SV) + lane : p.n;   // this lane's first element of the warp tile; the others are 32 apart
+                bool live[SV];                                    // which of this lane's elements are inside the row: once for every role
 #pragma unroll
                 for (int j=0; j<SV; ++j) live[j] = e0[u] + 32*j<p.n;
 #pragma unroll
                 for (int k=0; k<P.nin; ++k) {
                     int const t = P.rtype[k], es = es_of(t);
                     int const kd = KINDS!=SK_RUNTIME ? int((KINDS>>(4*k))&15u) : int(p.kind[k]);
-                    int64_t const off = int64_t(i1)*p.sA[k][1] + int64_t(i2)*p.sA[k][2] + int64_t(i3)*p.sA[k][3];
-                    unsigned char const * base = reinterpret_cast<unsigned char const *>(p.in[k]);
                     uint32_t * xv = x[u][k];
                     if (SK_SCALAR==kd) splat_bits(xv, p.in[k], t);
                     else if (SK_PTR==kd) {}
-                    else if (SK_SEQ==kd) seq_words(xv, p.in[k], off + e0[u]*p.sA[k][0], 32*p.sA[k][0], t);
-                    else if (SK_ROW==kd) splat_words(xv, base + off*es, t);
-                    else { // one pointer per role and vector, the four loads at fixed distances from it
+                    else if (SK_SEQ==kd) seq_words(xv, p.in[k], int64_t(reinterpret_cast<intptr_t>(rowp[k])) + e0[u]*p.sA[k][0], 32*p.sA[k][0], t);
+                    else if (SK_ROW==kd) splat_words(xv, rowp[k], t);
+                    else { // the four loads at fixed distances from one pointer
                         bool const rev = SK_VECREV==kd || SK_VECREVU==kd;
-                        unsigned char const * const q0 = base + (rev ? off-e0[u] : off+e0[u])*es;
+                        unsigned char const * const q0 = rowp[k] + (rev ? -e0[u] : e0[u])*es;
                         int const step = rev ? -32*es : 32*es;
                         if (1==es) xv[0] = 0;
 #pragma unroll
@@ -366,15 +375,14 @@ smap_lanes_body(SParams const & p)
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int u=0; u<UNR; ++u) {
-            if (e0[u]<p.n) {
-                W out[SV];
-                eval_static<ID>(p, x[u], out);
-                unsigned char * const d = static_cast<unsigned char *>(p.dst) + doff[u]*des;
+            for (int u=0; u<UNR; ++u) {
+                if (e0[u]<p.n) {
+                    W out[SV];
+                    eval_static<ID>(p, x[u], out);
 #pragma unroll
-                for (int j=0; j<SV; ++j) { int64_t const e = e0[u] + 32*j; if (e<p.n) store_elem<W>(d + e*des, P.otype, out[j]); }
+                    for (int j=0; j<SV; ++j) { int64_t const e = e0[u] + 32*j; if (e<p.n) store_elem<W>(drow + e*des, P.otype, out[j]); }
+                }
             }
         }
     }

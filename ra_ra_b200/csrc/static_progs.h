@@ -113,6 +113,7 @@ prog_wide(SProg const & P)
 }
 
 constexpr int SV = 4; // elements per static vector (16 bytes of 4-byte elements, 32 bytes of 8-byte ones)
+constexpr int SLANES_CT = 8; // lane-wise map kernel: warp tiles (of 32*SV elements) a warp walks per work unit
 
 enum { SK_SCALAR = 0, SK_VEC = 1, SK_VECREV = 2 /* unit step backwards: aligned loads, lanes reversed */, SK_ROW = 3 /* step 0 on axis 0: one value per row */,
        SK_SEQ = 4 /* iota / tindex (ra/expr.hh:79-100): value = origin + element offset, no memory */,
