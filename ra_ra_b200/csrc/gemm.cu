@@ -237,7 +237,7 @@ try_special_gemm(racu_gemm_desc const * gd, cudaStream_t stream, int * handled)
     if (f64) {
         // tuning knob RACU_DGEMM: "16x3" (BK x stages, round 1), "16x4", "32x3"
         char const * which = std::getenv("RACU_DGEMM");
-        int const v = !which ? 1 : 0==std::strcmp(which, "16x3") ? 0 : 0==std::strcmp(which, "32x3") ? 2 : 1;
+        int const v = !which ? 2 : 0==std::strcmp(which, "16x3") ? 0 : 0==std::strcmp(which, "16x4") ? 1 : 2; // default: BK = 32, 3 stages (+2 % over 16 x 3 at 8192^3)
         auto kernel = 0==v ? dgemm_kernel<16, 3> : 1==v ? dgemm_kernel<16, 4> : dgemm_kernel<32, 3>;
         smem = 0==v ? size_t(3)*DTile<16>::STAGE*8 : 1==v ? size_t(4)*DTile<16>::STAGE*8 : size_t(3)*DTile<32>::STAGE*8;
         if (2==v && 0!=gd->K%32) { kernel = dgemm_kernel<16, 4>; smem = size_t(4)*DTile<16>::STAGE*8; }
