@@ -11,8 +11,10 @@
 //        mma.sync.m16n8k8.tf32 with fp32 accumulation. Dropped term lo*lo ~ 2^-22 |a||b|: error comparable to an fp32 FMA
 //        chain (bound stated in DESIGN.md; tests compare against an fp64 reference).
 //
-// Tiling: CTA 128x128, 8 warps as 2 (M) x 4 (N), warp tile 64x32, BK = 16 (f64) / 32 (f32), 3-stage cp.async pipeline,
-// shared-memory pitches padded so that fragment reads are bank-conflict free.
+// Tiling: CTA 128x128, 8 MMA warps as 2 (M) x 4 (N), warp tile 64x32, BK = 32, 3-stage cp.async pipeline, shared-memory pitches
+// padded so that fragment reads are bank-conflict free. f64 (default form "w"): two more warps are the producers and the stages are
+// handed over with mbarriers, so the MMA warps carry no copies, no address arithmetic and no CTA barrier (8192^3 on B200: 35.2 TFLOP/s
+// against 32.2 for the form where every warp copies and multiplies, and 35.5 for cuBLAS; profiles/r02_dgemm_forms_8192.log).
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -31,6 +33,7 @@ __device__ __forceinline__ void cp16(void * s, void const * g)
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ void
 dmma884(double & d0, double & d1, double a, double b)
@@ -57,10 +60,11 @@ template <int BK> struct DTile
 };
 constexpr int DK = 16;
 
-template <int BK, int STAGES> __global__ void __launch_bounds__(GTHREADS)
+template <int BK, int STAGES, bool SPREAD> __global__ void __launch_bounds__(GTHREADS)
 dgemm_kernel(const __grid_constant__ GParams p)
 {
     constexpr int DPA = DTile<BK>::PA, DPB = DTile<BK>::PB, DSTAGE = DTile<BK>::STAGE;
+    constexpr int NA = GM*BK/2/GTHREADS, NB = BK*GN/2/GTHREADS; // 16-byte copies per thread and stage (A, B)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double * const sm = reinterpret_cast<double *>(smem_raw);
     int const tid = threadIdx.x, lane = tid&31, warp = tid>>5;
@@ -69,19 +73,19 @@ dgemm_kernel(const __grid_constant__ GParams p)
     int64_t const m0 = int64_t(blockIdx.y)*GM, n0 = int64_t(blockIdx.x)*GN;
     double const * A = static_cast<double const *>(p.a) + m0*p.lda;
     double const * B = static_cast<double const *>(p.b) + n0;
+    auto load_a = [&](int s, int kt, int i) { // A tile 128 x BK: BK/2 16-byte copies per row
+        int c = tid + i*GTHREADS, r = c/(BK/2), q = c%(BK/2);
+        cp16(sm + s*DSTAGE + r*DPA + q*2, A + r*p.lda + int64_t(kt)*BK + q*2);
+    };
+    auto load_b = [&](int s, int kt, int i) { // B tile BK x 128: 64 copies per row
+        int c = tid + i*GTHREADS, r = c>>6, q = c&63;
+        cp16(sm + s*DSTAGE + GM*DPA + r*DPB + q*2, B + (int64_t(kt)*BK+r)*p.ldb + q*2);
+    };
     auto load_stage = [&](int s, int kt) {
-        double * As = sm + s*DSTAGE, * Bs = As + GM*DPA;
-        int64_t const k0 = int64_t(kt)*BK;
 #pragma unroll
-        for (int i=0; i<GM*BK/2/GTHREADS; ++i) { // A tile 128 x BK: BK/2 16-byte copies per row
-            int c = tid + i*GTHREADS, r = c/(BK/2), q = c%(BK/2);
-            cp16(As + r*DPA + q*2, A + r*p.lda + k0 + q*2);
-        }
+        for (int i=0; i<NA; ++i) load_a(s, kt, i);
 #pragma unroll
-        for (int i=0; i<BK*GN/2/GTHREADS; ++i) { // B tile BK x 128: 64 copies per row
-            int c = tid + i*GTHREADS, r = c>>6, q = c&63;
-            cp16(Bs + r*DPB + q*2, B + (k0+r)*p.ldb + q*2);
-        }
+        for (int i=0; i<NB; ++i) load_b(s, kt, i);
     };
     double acc[8][4][2];
 #pragma unroll
@@ -94,9 +98,128 @@ dgemm_kernel(const __grid_constant__ GParams p)
     for (int kt=0; kt<nk; ++kt) {
         cp_wait<STAGES-2>();
         __syncthreads();
-        if (kt+STAGES-1<nk) load_stage((kt+STAGES-1)%STAGES, kt+STAGES-1);
-        cp_commit();
+        // SPREAD: the copies of the stage after next are issued a few at a time between the MMAs of this k-tile. Issued in one block
+        // right after the barrier (round 1), the 8 warps of the CTA queue 64 KiB of LDGSTS on the load/store unit at the same moment,
+        // and since a warp issues in order none of them reaches its first DMMA until its own copies have been accepted.
+        bool const more = kt+STAGES-1<nk;
+        int const ls = (kt+STAGES-1)%STAGES, lk = kt+STAGES-1;
+        if constexpr (!SPREAD) { if (more) load_stage(ls, lk); cp_commit(); }
         double const * As = sm + (kt%STAGES)*DSTAGE + (wm*64)*DPA, * Bs = sm + (kt%STAGES)*DSTAGE + GM*DPA + wn*32;
+#pragma unroll
+        for (int kk=0; kk<BK; kk+=4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i=0; i<8; ++i) af[i] = As[(i*8+g)*DPA + kk + t];
+#pragma unroll
+            for (int j=0; j<4; ++j) bf[j] = Bs[(kk+t)*DPB + j*8 + g];
+#pragma unroll
+            for (int i=0; i<8; ++i) {
+                if constexpr (SPREAD) { // NA + NB copies over BK/4 * 8 slots (a slot = 4 MMAs), evenly
+                    constexpr int SLOTS = BK/4*8, EVERY = SLOTS/(NA+NB);
+                    static_assert(EVERY>=1 && EVERY*(NA+NB)==SLOTS);
+                    int const slot = (kk/4)*8 + i;
+                    if (more && 0==slot%EVERY) { int const c = slot/EVERY; if (c<NA) load_a(ls, lk, c); else load_b(ls, lk, c-NA); }
+                }
+#pragma unroll
+                for (int j=0; j<4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        }
+        if constexpr (SPREAD) cp_commit();
+    }
+    cp_wait<0>();
+    double * Cp = static_cast<double *>(p.c) + (m0+wm*64)*p.ldc + n0 + wn*32;
+#pragma unroll
+    for (int i=0; i<8; ++i)
+#pragma unroll
+        for (int j=0; j<4; ++j) {
+            double2 * dst = reinterpret_cast<double2 *>(Cp + (i*8+g)*p.ldc + j*8 + t*2);
+            double2 c = *dst;
+            c.x += acc[i][j][0]; c.y += acc[i][j][1];
+            *dst = c;
+        }
+}
+
+// Warp-specialised form: warps 0-7 only multiply (no barrier, no address arithmetic, no global loads in their instruction stream), warps 8
+// and 9 are the producers (A and B tiles, cp.async into the same padded layout) and the stages are handed over with mbarriers:
+// full[s] completes when the 64 producer lanes' copies of stage s have landed (cp.async.mbarrier.arrive.noinc), empty[s] when the 8
+// consumer warps have read it.
+constexpr int GWS_THREADS = GTHREADS+64;
+
+__device__ __forceinline__ uint32_t g_smem_u32(void const * p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void g_mbar_init(uint64_t * bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(g_smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void g_mbar_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(g_smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void g_mbar_arrive_cp(uint64_t * bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(g_smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void g_mbar_wait(uint64_t * bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GW_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GW_DONE;\n"
+        "bra GW_LOOP;\n"
+        "GW_DONE:\n"
+        "}\n" :: "r"(g_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int BK, int STAGES> __global__ void __launch_bounds__(GWS_THREADS)
+dgemm_ws_kernel(const __grid_constant__ GParams p)
+{
+    constexpr int DPA = DTile<BK>::PA, DPB = DTile<BK>::PB, DSTAGE = DTile<BK>::STAGE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double * const sm = reinterpret_cast<double *>(smem_raw);
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+    int const tid = threadIdx.x, lane = tid&31, warp = tid>>5;
+    int64_t const m0 = int64_t(blockIdx.y)*GM, n0 = int64_t(blockIdx.x)*GN;
+    int const nk = p.K/BK;
+    if (0==tid) {
+#pragma unroll
+        for (int s=0; s<STAGES; ++s) { g_mbar_init(&full[s], 64); g_mbar_init(&empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp>=8) {
+        bool const isb = 9==warp;
+        double const * A = static_cast<double const *>(p.a) + m0*p.lda;
+        double const * B = static_cast<double const *>(p.b) + n0;
+        for (int kt=0; kt<nk; ++kt) {
+            int const s = kt%STAGES;
+            if (kt>=STAGES) g_mbar_wait(&empty[s], uint32_t((kt/STAGES-1)&1));
+            double * As = sm + s*DSTAGE, * Bs = As + GM*DPA;
+            int64_t const k0 = int64_t(kt)*BK;
+            if (!isb) {
+                // A tile 128 x BK: BK/2 copies per row; a warp instruction covers 32/(BK/2) rows
+                constexpr int CPR = BK/2, RPI = 32/CPR;
+                int const r0 = lane/CPR, q = lane%CPR;
+                double const * src = A + int64_t(r0)*p.lda + k0 + q*2;
+                double * dst = As + r0*DPA + q*2;
+#pragma unroll 8
+                for (int i=0; i<GM/RPI; ++i) { cp16(dst, src); src += int64_t(RPI)*p.lda; dst += RPI*DPA; }
+            } else {
+                // B tile BK x 128: 64 copies per row, two warp instructions per row
+                double const * src = B + k0*p.ldb + lane*2;
+                double * dst = Bs + lane*2;
+#pragma unroll 8
+                for (int r=0; r<BK; ++r) { cp16(dst, src); cp16(dst+64, src+64); src += p.ldb; dst += DPB; }
+            }
+            g_mbar_arrive_cp(&full[s]);
+        }
+        cp_wait_all();
+        return;
+    }
+    int const wm = warp>>2, wn = warp&3;   // 2 x 4 consumer warps
+    int const g = lane>>2, t = lane&3;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i=0; i<8; ++i)
+#pragma unroll
+        for (int j=0; j<4; ++j) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+    // (Double buffering the fragments by hand across the stage wait needs 24 more registers than the 168 a 10-warp CTA can have - three
+    // warps share a sub-partition's 16 K registers - and spills; the k-tile boundary costs 0.2 % as it is: BK = 16 and 32 time the same.)
+    for (int kt=0; kt<nk; ++kt) {
+        int const s = kt%STAGES;
+        g_mbar_wait(&full[s], uint32_t((kt/STAGES)&1));
+        double const * As = sm + s*DSTAGE + (wm*64)*DPA, * Bs = sm + s*DSTAGE + GM*DPA + wn*32;
 #pragma unroll
         for (int kk=0; kk<BK; kk+=4) {
             double af[8], bf[4];
@@ -109,8 +232,9 @@ dgemm_kernel(const __grid_constant__ GParams p)
 #pragma unroll
                 for (int j=0; j<4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
+        __syncwarp();
+        if (0==lane) g_mbar_arrive(&empty[s]); // every lane's fragment reads of this stage fed MMAs that have been issued
     }
-    cp_wait<0>();
     double * Cp = static_cast<double *>(p.c) + (m0+wm*64)*p.ldc + n0 + wn*32;
 #pragma unroll
     for (int i=0; i<8; ++i)
@@ -235,14 +359,21 @@ try_special_gemm(racu_gemm_desc const * gd, cudaStream_t stream, int * handled)
     size_t smem = size_t(GSTAGES)*SSTAGE*4;
     cudaError_t e;
     if (f64) {
-        // tuning knob RACU_DGEMM: "16x3" (BK x stages, round 1), "16x4", "32x3"
+        // RACU_DGEMM = <form><BK>x<stages>: form "b" = every warp copies and multiplies, copies in one block after the barrier (round 1),
+        // "s" = the same with the copies spread between the MMAs, "w" = warp specialised (two producer warps, mbarriers). BK 16 or 32, 3 or 4 stages.
         char const * which = std::getenv("RACU_DGEMM");
-        int const v = !which ? 2 : 0==std::strcmp(which, "16x3") ? 0 : 0==std::strcmp(which, "16x4") ? 1 : 2; // default: BK = 32, 3 stages (+2 % over 16 x 3 at 8192^3)
-        auto kernel = 0==v ? dgemm_kernel<16, 3> : 1==v ? dgemm_kernel<16, 4> : dgemm_kernel<32, 3>;
-        smem = 0==v ? size_t(3)*DTile<16>::STAGE*8 : 1==v ? size_t(4)*DTile<16>::STAGE*8 : size_t(3)*DTile<32>::STAGE*8;
-        if (2==v && 0!=gd->K%32) { kernel = dgemm_kernel<16, 4>; smem = size_t(4)*DTile<16>::STAGE*8; }
+        char form = 'w'; int bkv = 32, st = 3;
+        if (which && (which[0]=='b' || which[0]=='s' || which[0]=='w')) { form = which[0]; ++which; }
+        if (which && 0==std::strcmp(which, "16x3")) { bkv = 16; st = 3; } else if (which && 0==std::strcmp(which, "16x4")) { bkv = 16; st = 4; }
+        if (32==bkv && 0!=gd->K%32) { bkv = 16; st = 4; }
+        using Kern = void (*)(GParams);
+        Kern kernel; unsigned threads = GTHREADS;
+        if ('w'==form) { kernel = 32==bkv ? dgemm_ws_kernel<32, 3> : 3==st ? dgemm_ws_kernel<16, 3> : dgemm_ws_kernel<16, 4>; threads = GWS_THREADS; }
+        else if ('s'==form) kernel = 32==bkv ? dgemm_kernel<32, 3, true> : 3==st ? dgemm_kernel<16, 3, true> : dgemm_kernel<16, 4, true>;
+        else kernel = 32==bkv ? dgemm_kernel<32, 3, false> : 3==st ? dgemm_kernel<16, 3, false> : dgemm_kernel<16, 4, false>;
+        smem = 32==bkv ? size_t(3)*DTile<32>::STAGE*8 : size_t(st)*DTile<16>::STAGE*8;
         if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return cuda_fail(e, "dgemm smem");
-        kernel<<<grid, GTHREADS, smem, stream>>>(p);
+        kernel<<<grid, threads, smem, stream>>>(p);
         set_kernel("dgemm_dmma884");
     } else {
         if ((e = cudaFuncSetAttribute(sgemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))) return cuda_fail(e, "sgemm smem");

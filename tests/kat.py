@@ -993,7 +993,7 @@ def laplace3d_fem_gather_scatter(ex):
     n = 12 if ex.name == "sim" else 50
     err, its = _laplace3d_fem(ex, n)
     assert err <= 0.00033 * (50. / n) ** 2, err
-    assert its <= (2 if ex.name == "cuda" else 1), its             # (atomic scatter order: one extra iteration is tolerated on the device)
+    assert its <= 1, its    # the reference's own pin, on every executor (device: 5 runs at n = 50, its = 1 each time, profiles/r02_fem_its.log)
 
 
 @case
