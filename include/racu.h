@@ -18,7 +18,8 @@
  *   sum prod amin amax dot reduce_sqrm                     racu_reduce / racu_reduce_dev
  *     ra/ra.hh:306-322,348-401
  *   Anext(I,J,K) = -6*A(I,J,K) + A(I+1,J,K)... ; swap      racu_stencil (also reached from racu_map
- *     bench/bench-stencil3.cc:55-64, bench-stencil2.cc:49-58,    by pattern recognition)
+ *     bench/bench-stencil3.cc:55-64, bench-stencil2.cc:49-58,    by pattern recognition); racu_stencil_steps
+ *                                                                = the benchmark's loop of T such steps
  *     examples/laplace2d.cc:36
  *   gemm / gemv / gevm                                     racu_gemm / racu_gemv
  *     ra/ra.hh:403-456
@@ -270,6 +271,14 @@ typedef struct {
     int64_t lo0, hi0;      /* 0,0 = whole interior */
 } racu_stencil_desc;
 int racu_stencil(const racu_stencil_desc * s, void * stream);
+
+/* `steps` ping-pong sweeps, as the reference's benchmark loop writes them (bench/bench-stencil3.cc:55-64 + std::swap, :117-121):
+ * src -> dst, dst -> src, ... On return state `steps` is in (steps odd ? dst : src) and state steps-1 in the other buffer, boundary cells
+ * of both untouched: exactly what `steps` calls of racu_stencil with the roles swapped leave, bit for bit. For the 3-D 7-point sweep over
+ * arrays a TMA tensor map can describe (innermost stride 1, 16-byte aligned rows) the steps are taken TWO PER PASS (the intermediate state
+ * lives in shared memory only: half the HBM traffic per step) through a scratch buffer of the extent of the array; `scratch` = NULL lets the
+ * library allocate it on the stream for the duration of the call. Anything else runs as single steps. lo0/hi0 must be 0. */
+int racu_stencil_steps(const racu_stencil_desc * s, int32_t steps, void * scratch, void * stream);
 
 /* ---- dense contraction ---- */
 /* c(M,N) += a(M,K) * b(K,N), row-major with leading dimensions in elements. ra/ra.hh:403-412.

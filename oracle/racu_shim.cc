@@ -51,6 +51,17 @@ int64_t racu_launch_count(void) { return 0; }
 void racu_launch_count_reset(void) {}
 const char * racu_last_kernel(void) { return "oracle"; }
 int racu_stencil(const racu_stencil_desc * s, void *) { return oracle_stencil_raw(s); }
+// the meaning of racu_stencil_steps: `steps` single sweeps with the roles of the two buffers swapped after each (bench/bench-stencil3.cc:117-121)
+int racu_stencil_steps(const racu_stencil_desc * s, int32_t steps, void *, void *)
+{
+    if (steps<0 || 0!=s->lo0 || 0!=s->hi0) return RACU_ERR_BAD_DESC;
+    for (int t=0; t<steps; ++t) {
+        racu_stencil_desc d = *s;
+        if (t&1) { d.src = s->dst; d.dst = const_cast<void *>(s->src); for (int k=0; k<3; ++k) { d.src_stride[k] = s->dst_stride[k]; d.dst_stride[k] = s->src_stride[k]; } }
+        if (int e = oracle_stencil_raw(&d)) return e;
+    }
+    return RACU_OK;
+}
 int racu_gemm(const racu_gemm_desc * g, void *) { return oracle_gemm_raw(g); }
 int racu_gemv(int dtype, int trans, int64_t M, int64_t N, const void * a, int64_t lda, const void * x, int64_t incx,
               void * y, int64_t incy, void *)

@@ -141,6 +141,7 @@ SYMBOLS = [
     ("racu_launch_count_reset", None, []),
     ("racu_last_kernel", C.c_char_p, []),
     ("racu_stencil", C.c_int, [C.POINTER(StencilDesc), _P]),
+    ("racu_stencil_steps", C.c_int, [C.POINTER(StencilDesc), C.c_int32, _P, _P]),
     ("racu_gemm", C.c_int, [C.POINTER(GemmDesc), _P]),
     ("racu_gemv", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P]),
     ("racu_comm_unique_id", C.c_int, [_P]),

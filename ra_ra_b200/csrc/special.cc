@@ -75,6 +75,8 @@ build_stencil_desc(racu_stencil_desc const * s, racu_desc & d)
     return RACU_OK;
 }
 
+int racu_stencil_c(const racu_stencil_desc * s, void * stream) { return racu_stencil(s, stream); }
+
 } // namespace racu
 
 using namespace racu;
@@ -92,6 +94,12 @@ int racu_stencil(const racu_stencil_desc * s, void * stream)
     racu_desc d;
     if (int e = build_stencil_desc(s, d)) return e;
     return racu_map(&d, stream);
+}
+
+int racu_stencil_steps(const racu_stencil_desc * s, int32_t steps, void * scratch, void * stream)
+{
+    if (!s || !s->src || !s->dst || s->rank<1 || s->rank>3) return fail(RACU_ERR_BAD_DESC, "bad stencil descriptor");
+    return stencil_steps(s, steps, scratch, cudaStream_t(stream));
 }
 
 int racu_stencil_push(const racu_stencil_desc * s, const racu_halo_push * h, void * stream)

@@ -14,6 +14,8 @@ void set_kernel(const char * k);
 int try_special_map(racu_desc const * d, cudaStream_t stream, int * handled);
 int try_special_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled);
 int stencil_push(racu_stencil_desc const * s, racu_halo_push const * h, cudaStream_t stream);
+int stencil_steps(racu_stencil_desc const * s, int steps, void * scratch, cudaStream_t stream);
+int racu_stencil_c(const racu_stencil_desc * s, void * stream); // racu_stencil (special.cc), callable from the other translation units
 int try_tcgen05_sgemm(racu_gemm_desc const * g, cudaStream_t stream, int * handled);
 int try_special_gemm(racu_gemm_desc const * g, cudaStream_t stream, int * handled);
 int build_stencil_desc(racu_stencil_desc const * s, racu_desc & d);

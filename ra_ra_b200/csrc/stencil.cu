@@ -99,6 +99,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
         "WAIT_DONE:\n"
         "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITA_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAITA_DONE;\n"
+        "bra WAITA_LOOP;\n"
+        "WAITA_DONE:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void * smem, CUtensorMap const * tmap, int c0, int c1, int c2, uint64_t * bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -291,6 +303,226 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
 }
 
+// ---------------- two sweeps per pass (temporal blocking of the 7-point sweep) ----------------
+// T ping-pong steps read and write the whole grid T times. This kernel makes TWO steps per pass: state t is streamed in with the same TMA
+// ring, state t+1 exists only as three planes of shared memory, state t+2 is written out - 8 B per cell for two steps instead of 16.
+// Every cell of t+1 and t+2 is produced by the same expression in the same association order as a single step, so the results are
+// bit-identical to two single steps (asserted by the tests on both buffers).
+//
+// Geometry: stage 1 (t -> t+1) of a CTA covers ST_TJ x TK cells of a plane, exactly what the single-step kernel computes from the same
+// (ST_TJ+2) x TKB box; stage 2 (t+1 -> t+2) covers the cells whose neighbours stage 1 produced: rows 1 .. ST_TJ-2 and the vectors
+// 1 .. TK/VT-2 of the tile. Tiles therefore overlap by two rows and two vectors (14 x 120 outputs per 18 x 136 box for f32) and a chunk of
+// P output planes reads P+4 input planes; the overlaps are L2 hits like the halos of the single-step kernel. A thread owns two ADJACENT
+// rows (each row's j+1 / j-1 neighbour of the other comes from registers: 6 instead of 10 16-byte shared-memory loads per thread and
+// plane) and marches along axis 0 with the centre values of t (i-1, i, i+1) and of t+1 (i-2, i-1, i) in registers; t+1 goes through a ring
+// of THREE shared planes so that one CTA barrier per plane is enough.
+//
+// Boundary cells keep the values of the buffer a state lives in (bench/bench-stencil3.cc:125-126), and in the reference's ping-pong the
+// odd states live in the OTHER buffer: the boundary cells of t+1 are read from `bsrc` (that buffer), those of t+2 are never written.
+template <class T> struct St2Tile
+{
+    static constexpr int VT = StTile<T>::VT, TK = StTile<T>::TK, HO = StTile<T>::HO, TKB = StTile<T>::TKB, PLANE = StTile<T>::PLANE;
+    static constexpr int OUT_J = ST_TJ-2, OUT_K = TK-2*VT;   // outputs per tile and plane
+    static constexpr int IPLANE = ST_TJ*TK;                   // one plane of t+1
+    static_assert(HO>=2 && TK/VT==32 && ST_RPT==2);
+};
+
+struct St2Params
+{
+    void * dst; int64_t ds0, ds1, ds2;
+    void const * bsrc; int64_t bs0, bs1, bs2;   // the buffer whose boundary cells state t+1 carries
+    int32_t n0, n1, n2;
+    int32_t i_lo, i_hi;                          // output planes [i_lo, i_hi)
+    int32_t ci, gz, gyb;
+    int32_t vec_store;
+};
+
+constexpr int S2_STAGES_DEFAULT = 5;   // TMA ring of the two-step kernel: plane m+5 is requested when plane m is released, four planes ahead of its use (the loads are DRAM
+                               // latency under load; with a ring of three the CTAs waited for data most of the time: 37 % issue-slot utilisation in the lean loop)
+
+template <class T, int S2_STAGES> __global__ void __launch_bounds__(ST_THREADS)
+stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St2Params p)
+{
+    using TL = St2Tile<T>;
+    constexpr int VT = TL::VT, TK = TL::TK, HO = TL::HO, TKB = TL::TKB, PLANE = TL::PLANE, IPLANE = TL::IPLANE, KIND = RACU_STENCIL_3D7;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T * const stages = reinterpret_cast<T *>(smem_raw);
+    T * const inter = stages + size_t(S2_STAGES)*PLANE;       // 3 planes of t+1 (+ one row of slack behind them)
+    __shared__ __align__(8) uint64_t full[S2_STAGES];
+
+    int const tid = threadIdx.x, tk = tid&31, tj = tid>>5;
+    int const band = int(blockIdx.z)/p.gz, chunk = int(blockIdx.z) - band*p.gz;
+    int const kb = int(blockIdx.x)*TL::OUT_K - VT;                                   // first stage-1 column of the tile (may be -VT)
+    int const jb = (band*p.gyb + int(blockIdx.y))*TL::OUT_J - 1;                     // first stage-1 row (may be -1)
+    if (jb+1>=p.n1-1) return;                                                        // no output row (whole CTA, before any barrier)
+    int const ilo = p.i_lo + chunk*p.ci, ihi = min(p.i_hi, ilo+p.ci);
+    int const nin = (ihi-ilo+2+2)/3*3 + 2;                                           // input planes ilo-2 .. ihi+1, rounded up so that the planes of t+1 are a multiple of three
+    constexpr uint32_t plane_bytes = (ST_TJ+2)*TKB*sizeof(T);
+
+    if (0==tid) {
+#pragma unroll
+        for (int s=0; s<S2_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int q, int s) { // input plane q of this chunk -> stage s = q % S2_STAGES
+        mbar_expect_tx(&full[s], plane_bytes);
+        tma_load_3d(stages + size_t(s)*PLANE, &tmap, kb-HO, jb-1, ilo-2+q, &full[s]); // planes -1 and >= n0 are zero filled (never used)
+    };
+    if (0==tid) { for (int q=0; q<S2_STAGES && q<nin; ++q) issue(q, q); }
+
+    int const k = kb + tk*VT;
+    // per row of this thread (tile rows 2*tj, 2*tj+1): which lanes of t+1 come from bsrc, which lanes of t+2 are stored
+    uint32_t fix[2], dom[2]; bool lane_ok[2][VT], all_ok[2], any_ok[2];
+#pragma unroll
+    for (int r=0; r<2; ++r) {
+        int const R = 2*tj+r, j = jb+R;
+        bool const row_in = j>=0 && j<p.n1, row_bd = 0==j || j==p.n1-1, row_out = R>=1 && R<=ST_TJ-2 && j>=1 && j<p.n1-1 && tk>=1 && tk<=30;
+        fix[r] = 0; dom[r] = 0; all_ok[r] = true; any_ok[r] = false;
+#pragma unroll
+        for (int l=0; l<VT; ++l) {
+            bool const in = row_in && k+l>=0 && k+l<p.n2, bd = row_bd || 0==k+l || k+l==p.n2-1;
+            if (in) dom[r] |= 1u<<l;
+            if (in && bd) fix[r] |= 1u<<l;
+            lane_ok[r][l] = row_out && k+l>=1 && k+l<p.n2-1;
+            all_ok[r] = all_ok[r] && lane_ok[r][l]; any_ok[r] = any_ok[r] || lane_ok[r][l];
+        }
+    }
+    auto load_vec = [&](T const * st, int off, T * v) { uint4 q = *reinterpret_cast<uint4 const *>(st + off); memcpy(v, &q, 16); };
+    auto store_vec_s = [&](T * st, int off, T const * v) { uint4 q; memcpy(&q, v, 16); *reinterpret_cast<uint4 *>(st + off) = q; };
+
+    // Everything that does not change from plane to plane is computed here, every shared-memory access of the loop is one base pointer
+    // plus an immediate, and CTAs whose tile and chunk touch no boundary run a loop without the boundary code. The first version spent
+    // 27 instructions per cell update (7 of them arithmetic) and was issue bound: 72 % issue-slot utilisation, DRAM at 31 %
+    // (profiles/r02_stencil2_*).
+    T const * const sp = stages + (2*tj+1)*TKB + HO + tk*VT;   // this thread's first centre vector in stage 0; its second row: + TKB
+    T * const ip = inter + (2*tj)*TK + tk*VT;                  // the same in plane 0 of t+1; second row: + TK
+    T const * const ipj0 = tj>0 ? ip-TK : ip, * const ipj1 = tj<ST_TR-1 ? ip+2*TK : ip+TK; // rows above / below for stage 2 (tile rows 0 and 15 store nothing)
+    T * dptr[2];                                        // where this thread's vector of t+2 at plane ilo goes; + ds0 per plane
+    int smode[2];                                       // 0: stores nothing, 1: one 16-byte store, 2: lane by lane
+#pragma unroll
+    for (int r=0; r<2; ++r) {
+        dptr[r] = static_cast<T *>(p.dst) + int64_t(ilo)*p.ds0 + int64_t(jb+2*tj+r)*p.ds1 + int64_t(k)*p.ds2;
+        smode[r] = !any_ok[r] ? 0 : (all_ok[r] && p.vec_store) ? 1 : 2;
+    }
+    int64_t const ds0 = p.ds0;
+    int const n0m1 = p.n0-1;
+    bool const t0 = 0==tid;
+    // no boundary cell of t+1 in this CTA's tile and planes, whole vectors, no plane past the end of the chunk
+    bool const interior = jb>=1 && jb+ST_TJ<=p.n1-1 && kb>=1 && kb+TK<=p.n2-1 && ilo>=2 && ilo-2+(nin-2)<=p.n0-2 && nin==ihi-ilo+4 && p.vec_store;
+
+    struct Regs { T v[2][VT]; };
+    Regs p1, c1, n1v;                     // state t at planes m-1, m, m+1
+    Regs p2, c2, n2v;                     // state t+1 at planes m-2, m-1, m
+#pragma unroll
+    for (int r=0; r<2; ++r)
+#pragma unroll
+        for (int l=0; l<VT; ++l) { p2.v[r][l] = T(0); c2.v[r][l] = T(0); n2v.v[r][l] = T(0); }
+    mbar_wait(&full[0], 0);
+#pragma unroll
+    for (int r=0; r<2; ++r) load_vec(sp, r*TKB, p1.v[r]);
+    mbar_wait(&full[1], 0);
+#pragma unroll
+    for (int r=0; r<2; ++r) load_vec(sp, PLANE + r*TKB, c1.v[r]);
+    __syncthreads();                                    // everyone is done with plane 0
+    if (t0 && S2_STAGES<nin) issue(S2_STAGES, 0);
+    // the ring: plane m of t sits in stage si (pointer pst), plane m+1 in stage sni (psn, waited for with parity npar)
+    T const * pst = sp + PLANE, * psn = sp + 2*PLANE;
+    int si = 1, sni = 2;
+    uint32_t npar = 0;
+    uint32_t const bar0 = smem_u32(&full[0]);
+
+    // One plane m = 3g+1+PH. PH is a compile-time value (the loop below is unrolled by three): t+1 at plane m goes to plane (1+PH)%3 of
+    // `inter` and its neighbours at plane m-1 are read from plane PH; the six register sets rotate by renaming, without copies.
+    auto plane = [&]<int PH, bool INTERIOR>(std::integral_constant<int, PH>, std::integral_constant<bool, INTERIOR>, int m,
+                                            Regs & rP1, Regs & rC1, Regs & rN1, Regs & rP2, Regs & rC2, Regs & rN2) {
+        auto & P1 = rP1.v; auto & C1 = rC1.v; auto & N1 = rN1.v; auto & P2 = rP2.v; auto & C2 = rC2.v; auto & N2 = rN2.v;
+        constexpr int IW = (1+PH)%3, IB = PH;
+        int const gi = ilo-2+m;
+        mbar_wait_a(bar0 + 8u*uint32_t(sni), npar);
+#pragma unroll
+        for (int r=0; r<2; ++r) load_vec(psn, r*TKB, N1[r]);
+        // ---- stage 1: t+1 at plane m
+        {
+            T jm0[VT], jp1[VT];
+            load_vec(pst, -TKB, jm0); load_vec(pst, 2*TKB, jp1);
+#pragma unroll
+            for (int r=0; r<2; ++r) {
+                T const left = pst[r*TKB - 1], right = pst[r*TKB + VT];
+#pragma unroll
+                for (int l=0; l<VT; ++l) {
+                    T const km = l==0 ? left : C1[r][l-1], kp = l==VT-1 ? right : C1[r][l+1];
+                    T const jp = 0==r ? C1[1][l] : jp1[l], jm = 0==r ? jm0[l] : C1[0][l];
+                    N2[r][l] = stencil_value<T, KIND>(C1[r][l], N1[r][l], jp, kp, P1[r][l], jm, km);
+                }
+                if constexpr (!INTERIOR) {
+                    uint32_t const need = (0==gi || gi==n0m1) ? dom[r] : fix[r];   // boundary cells of t+1: the values of the buffer t+1 lives in
+                    if (need && gi<=n0m1) {
+                        T const * b = static_cast<T const *>(p.bsrc) + int64_t(gi)*p.bs0 + int64_t(jb+2*tj+r)*p.bs1 + int64_t(k)*p.bs2;
+#pragma unroll
+                        for (int l=0; l<VT; ++l) { if ((need>>l)&1u) N2[r][l] = b[int64_t(l)*p.bs2]; }
+                    }
+                }
+                store_vec_s(ip, IW*IPLANE + r*TK, N2[r]);
+            }
+        }
+        __syncthreads();                                // t+1 at plane m is visible; plane m of t is no longer read by anyone
+        if (t0 && m+S2_STAGES<nin) issue(m+S2_STAGES, si);
+        si = sni; pst = psn;
+        if (++sni==S2_STAGES) { sni = 0; psn = sp; npar ^= 1u; } else psn += PLANE;
+        // ---- stage 2: t+2 at plane m-1 from t+1 at planes m-2, m-1 (neighbours in shared memory), m
+        if (m>=3) {
+            T jm0[VT], jp1[VT];
+            load_vec(ipj0, IB*IPLANE, jm0); load_vec(ipj1, IB*IPLANE, jp1);
+            bool const live = INTERIOR || gi-1<ihi;     // (the last chunk may run planes past its end: the loop count is a multiple of three)
+#pragma unroll
+            for (int r=0; r<2; ++r) {
+                T const left = ip[IB*IPLANE + r*TK - 1], right = ip[IB*IPLANE + r*TK + VT];
+                T o[VT];
+#pragma unroll
+                for (int l=0; l<VT; ++l) {
+                    T const km = l==0 ? left : C2[r][l-1], kp = l==VT-1 ? right : C2[r][l+1];
+                    T const jp = 0==r ? C2[1][l] : jp1[l], jm = 0==r ? jm0[l] : C2[0][l];
+                    o[l] = stencil_value<T, KIND>(C2[r][l], N2[r][l], jp, kp, P2[r][l], jm, km);
+                }
+                if (1==smode[r] && live) { uint4 q; memcpy(&q, o, 16); *reinterpret_cast<uint4 *>(dptr[r]) = q; }
+                if constexpr (!INTERIOR) {
+                    if (2==smode[r] && live) {
+#pragma unroll
+                        for (int l=0; l<VT; ++l) { if (lane_ok[r][l]) dptr[r][int64_t(l)*p.ds2] = o[l]; }
+                    }
+                }
+                dptr[r] += ds0;
+            }
+        }
+    };
+    // nin-2 planes of t+1, a multiple of three (planes past n0 are zero filled by TMA and never stored)
+    auto run = [&](auto interior_tag) {
+        for (int m=1; m+1<nin; m+=3) {
+            plane(std::integral_constant<int, 0> {}, interior_tag, m, p1, c1, n1v, p2, c2, n2v);
+            plane(std::integral_constant<int, 1> {}, interior_tag, m+1, c1, n1v, p1, c2, n2v, p2);
+            plane(std::integral_constant<int, 2> {}, interior_tag, m+2, n1v, p1, c1, n2v, p2, c2);
+        }
+    };
+    if (interior) run(std::true_type {}); else run(std::false_type {});
+}
+
+// copies the boundary cells (the six faces) of one buffer into another of the same shape
+template <class T> __global__ void
+copy_faces_kernel(T const * src, int64_t ss0, int64_t ss1, int64_t ss2, T * dst, int64_t ds0, int64_t ds1, int64_t ds2, int n0, int n1, int n2)
+{
+    int const face = blockIdx.y; // 0,1: i = 0 / n0-1; 2,3: j; 4,5: k
+    int64_t const na = face<2 ? n1 : n0, nb = face<4 ? n2 : n1, total = na*nb;
+    for (int64_t e = int64_t(blockIdx.x)*blockDim.x + threadIdx.x; e<total; e += int64_t(gridDim.x)*blockDim.x) {
+        int64_t const a = e/nb, b = e - a*nb;
+        int64_t i, j, k;
+        if (face<2) { i = (face&1) ? n0-1 : 0; j = a; k = b; }
+        else if (face<4) { i = a; j = (face&1) ? n1-1 : 0; k = b; }
+        else { i = a; j = b; k = (face&1) ? n2-1 : 0; }
+        dst[i*ds0 + j*ds1 + k*ds2] = src[i*ss0 + j*ss1 + k*ss2];
+    }
+}
+
 // ---------------- host ----------------
 
 using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -405,6 +637,145 @@ try_special_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * hand
     default: return RACU_OK;
     }
 #undef RACU_ST
+}
+
+// ---- racu_stencil_steps: T ping-pong steps src -> dst -> src ..., two per pass where the arrays allow it
+struct Buf3 { void * p; int64_t st[3]; };
+
+template <class T> static bool
+tma_ok(Buf3 const & b, int64_t const * n)
+{
+    size_t const es = sizeof(T);
+    return 1==b.st[2] && 0==(uintptr_t(b.p)%16) && 0==((b.st[1]*es)%16) && 0==((b.st[0]*es)%16) && b.st[1]>0 && b.st[0]>0
+        && n[0]<(int64_t(1)<<31) && n[1]<(int64_t(1)<<31) && n[2]<(int64_t(1)<<31) && n[0]>=3 && n[1]>=3 && n[2]>=3;
+}
+
+// one pass: dst interior = two steps from src; the boundary cells of the intermediate state are those of bsrc
+template <class T> static int
+launch_stencil2(Buf3 const & src, Buf3 const & dst, Buf3 const & bsrc, int64_t const * n, cudaStream_t stream)
+{
+    using TL = St2Tile<T>;
+    size_t const es = sizeof(T);
+    EncodeTiled enc = encode_fn();
+    if (!enc) return fail(RACU_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+    CUtensorMap tmap;
+    cuuint64_t gdim[3] = {cuuint64_t(n[2]), cuuint64_t(n[1]), cuuint64_t(n[0])};
+    cuuint64_t gstr[2] = {cuuint64_t(src.st[1]*es), cuuint64_t(src.st[0]*es)};
+    cuuint32_t box[3] = {cuuint32_t(TL::TKB), cuuint32_t(ST_TJ+2), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = enc(&tmap, sizeof(T)==4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, src.p,
+                      gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (CUDA_SUCCESS!=cr) return fail(RACU_ERR_UNSUPPORTED, "racu_stencil_steps: the array is not expressible as a TMA tensor map");
+    St2Params p {};
+    p.dst = dst.p; p.ds0 = dst.st[0]; p.ds1 = dst.st[1]; p.ds2 = dst.st[2];
+    p.bsrc = bsrc.p; p.bs0 = bsrc.st[0]; p.bs1 = bsrc.st[1]; p.bs2 = bsrc.st[2];
+    p.n0 = int32_t(n[0]); p.n1 = int32_t(n[1]); p.n2 = int32_t(n[2]);
+    p.i_lo = 1; p.i_hi = int32_t(n[0]-1);
+    p.vec_store = 1==dst.st[2] && 0==(uintptr_t(dst.p)%16) && 0==((dst.st[1]*es)%16) && 0==((dst.st[0]*es)%16);
+    int64_t const planes = n[0]-2;
+    // P output planes per CTA read P+4 input planes and compute P+2 planes of t+1: long chunks (measured on 1024^3 f32: 975 Gcells/s per step
+    // at P = 16, 1018 at 61, 1006 at 94), of equal length, with P+2 a multiple of three (the kernel's loop is unrolled by three)
+    int64_t const nchunks = (planes+60)/61;
+    p.ci = int32_t((planes+nchunks-1)/nchunks);
+    while (0!=(p.ci+2)%3) ++p.ci;
+    if (char const * e = std::getenv("RACU_ST2_CI")) p.ci = std::max(1, std::atoi(e)); // tuning knob
+    unsigned gx = unsigned((n[2]-1+TL::OUT_K-1)/TL::OUT_K), gy = unsigned((n[1]-1+TL::OUT_J-1)/TL::OUT_J), gz = unsigned((planes+p.ci-1)/p.ci);
+    if (gz>65535) { p.ci = int32_t((planes+65534)/65535); gz = unsigned((planes+p.ci-1)/p.ci); }
+    p.gz = int32_t(gz); p.gyb = int32_t(gy);
+    {   // bands of tiles, as in the single-step kernel
+        int64_t band_tiles = 512;
+        if (char const * e = std::getenv("RACU_ST_BAND")) band_tiles = std::max(1, std::atoi(e));
+        unsigned gyb = unsigned(std::max<int64_t>(1, band_tiles/gx));
+        unsigned nb = (gy+gyb-1)/gyb;
+        if (nb>1 && uint64_t(nb)*gz<=65535) { p.gyb = int32_t(gyb); gy = gyb; gz *= nb; }
+    }
+    int stages = S2_STAGES_DEFAULT;
+    if (char const * e = std::getenv("RACU_ST2_STAGES")) stages = std::atoi(e); // tuning knob: 3 .. 6
+    if (stages<3 || stages>6) stages = S2_STAGES_DEFAULT;
+    size_t const smem = (size_t(stages)*TL::PLANE + 3*size_t(TL::IPLANE) + TL::TK)*es;
+    auto kernel = 3==stages ? stencil2_tma_kernel<T, 3> : 4==stages ? stencil2_tma_kernel<T, 4> : 6==stages ? stencil2_tma_kernel<T, 6> : stencil2_tma_kernel<T, 5>;
+    if (cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return cuda_fail(e, "stencil2 smem");
+    kernel<<<dim3(gx, gy, gz), ST_THREADS, smem, stream>>>(tmap, p);
+    launch_count_add(1);
+    if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "stencil2_tma");
+    set_kernel("stencil_tma<3D7, two steps>");
+    return RACU_OK;
+}
+
+template <class T> static int
+copy_faces(Buf3 const & src, Buf3 const & dst, int64_t const * n, cudaStream_t stream)
+{
+    int64_t const big = std::max(n[0]*n[1], std::max(n[0]*n[2], n[1]*n[2]));
+    copy_faces_kernel<T><<<dim3(unsigned(std::min<int64_t>((big+255)/256, 1184)), 6), 256, 0, stream>>>(
+        static_cast<T const *>(src.p), src.st[0], src.st[1], src.st[2], static_cast<T *>(dst.p), dst.st[0], dst.st[1], dst.st[2], int(n[0]), int(n[1]), int(n[2]));
+    launch_count_add(1);
+    if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "copy_faces");
+    return RACU_OK;
+}
+
+int racu_stencil_c(const racu_stencil_desc * s, void * stream); // (special.cc: racu_stencil)
+
+template <class T> static int
+stencil_steps_t(racu_stencil_desc const * s, int steps, void * scratch, cudaStream_t stream)
+{
+    int64_t const * n = s->len;
+    Buf3 A {const_cast<void *>(s->src), {s->src_stride[0], s->src_stride[1], s->src_stride[2]}};
+    Buf3 B {s->dst, {s->dst_stride[0], s->dst_stride[1], s->dst_stride[2]}};
+    auto single = [&](Buf3 const & x, Buf3 const & y) {
+        racu_stencil_desc d = *s;
+        d.src = x.p; d.dst = y.p; d.lo0 = 0; d.hi0 = 0;
+        for (int k=0; k<3; ++k) { d.src_stride[k] = x.st[k]; d.dst_stride[k] = y.st[k]; }
+        return racu_stencil_c(&d, stream);
+    };
+    bool const fused = steps>=4 && tma_ok<T>(A, n) && tma_ok<T>(B, n) && !std::getenv("RACU_NO_TMA_STENCIL") && !std::getenv("RACU_NO_STENCIL2") && encode_fn();
+    if (!fused) {
+        for (int t=0; t<steps; ++t) { if (int e = (t&1) ? single(B, A) : single(A, B)) return e; }
+        return RACU_OK;
+    }
+    // States t, t+2, ... live with the boundary of E, the odd ones with the boundary of O. The pairs ping-pong between E and a scratch buffer
+    // C that carries E's boundary; the last two steps are single ones, so that on return BOTH buffers hold what T single steps leave:
+    // state T in (T odd ? dst : src) and state T-1 in the other.
+    Buf3 E = A, O = B;
+    int left = steps;
+    if (steps&1) { if (int e = single(A, B)) return e; E = B; O = A; --left; }
+    int64_t const bytes = ((n[0]-1)*E.st[0] + (n[1]-1)*E.st[1] + n[2])*int64_t(sizeof(T));
+    void * own = nullptr;
+    if (!scratch) {
+        if (cudaError_t e = cudaMallocAsync(&own, size_t(bytes), stream)) return cuda_fail(e, "racu_stencil_steps scratch");
+        scratch = own;
+    }
+    Buf3 C {scratch, {E.st[0], E.st[1], E.st[2]}};
+    int rc = copy_faces<T>(E, C, n, stream);
+    Buf3 X = E;
+    for (int pair = 0; !rc && pair<left/2-1; ++pair) {
+        Buf3 const & Y = X.p==E.p ? C : E;
+        rc = launch_stencil2<T>(X, Y, O, n, stream);
+        X = Y;
+    }
+    if (!rc) rc = single(X, O);
+    if (!rc) rc = single(O, E);
+    if (own) cudaFreeAsync(own, stream);
+    return rc;
+}
+
+int
+stencil_steps(racu_stencil_desc const * s, int steps, void * scratch, cudaStream_t stream)
+{
+    if (steps<0) return fail(RACU_ERR_BAD_DESC, "racu_stencil_steps: negative step count");
+    if (s->kind!=RACU_STENCIL_3D7 || 3!=s->rank || (s->dtype!=RACU_F32 && s->dtype!=RACU_F64) || 0!=s->lo0 || 0!=s->hi0) {
+        // any other sweep: single steps (racu_stencil validates)
+        for (int t=0; t<steps; ++t) {
+            racu_stencil_desc d = *s;
+            if (t&1) { d.src = s->dst; d.dst = const_cast<void *>(s->src); for (int k=0; k<3; ++k) { d.src_stride[k] = s->dst_stride[k]; d.dst_stride[k] = s->src_stride[k]; } }
+            if (int e = racu_stencil_c(&d, stream)) return e;
+        }
+        return RACU_OK;
+    }
+    size_t const es = s->dtype==RACU_F32 ? 4 : 8;
+    if (views_overlap(s->src, 3, s->len, s->src_stride, s->dst, 3, s->len, s->dst_stride, es))
+        return fail(RACU_ERR_UNSUPPORTED, "racu_stencil_steps: destination overlaps the source: traversal order would be observable");
+    return s->dtype==RACU_F32 ? stencil_steps_t<float>(s, steps, scratch, stream) : stencil_steps_t<double>(s, steps, scratch, stream);
 }
 
 // One step of a slab-sharded 7-point sweep as ONE launch: sweep + halo push + neighbour lock step (see include/racu.h).

@@ -113,6 +113,20 @@ def stencil_sweep(kind=abi.STENCIL_3D7, dtype=abi.F32):
     return sweep
 
 
+def stencil_steps(a, anext, steps, kind=abi.STENCIL_3D7, scratch=None):
+    """`steps` ping-pong sweeps a -> anext -> a ... (bench/bench-stencil3.cc:55-64 with its std::swap, :117-121) on two torch tensors of the
+    same shape through racu_stencil_steps: two steps per pass where the TMA kernel applies. Returns the tensor that holds the last state
+    (anext when steps is odd); the other one holds the state before, like the reference's loop leaves them."""
+    assert a.shape == anext.shape and a.dtype == anext.dtype and a.stride() == anext.stride()
+    s = abi.StencilDesc()
+    s.kind, s.dtype, s.rank = kind, (abi.F32 if a.element_size() == 4 else abi.F64), a.dim()
+    s.src, s.dst = a.data_ptr(), anext.data_ptr()
+    for k in range(a.dim()):
+        s.len[k], s.src_stride[k], s.dst_stride[k] = a.shape[k], a.stride(k), anext.stride(k)
+    check(lib.racu_stencil_steps(C.byref(s), int(steps), scratch.data_ptr() if scratch is not None else None, stream_ptr()))
+    return anext if steps & 1 else a
+
+
 def stencil_sweep_push(kind=abi.STENCIL_3D7, dtype=abi.F32):
     """sweep_push(...) through racu_stencil_push, for parallel.SlabStencil3D.step_push."""
     def sweep_push(src_ptr, dst_ptr, shape, strides, push_lo, push_hi, flags, signal_lo, signal_hi, step):
