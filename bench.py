@@ -702,7 +702,56 @@ def run_stencil(ctx, n, n0, steps, warmup, check=False):
         slab.close()
     del cur, step
     torch.cuda.empty_cache()
+    if world == 1 and n0 == n and line is not None:
+        line["two_steps_per_pass"] = run_stencil_two_per_pass(ctx, n, nsteps, ms)
     return line
+
+
+def run_stencil_two_per_pass(ctx, n, nsteps, ms_single):
+    """The same T steps through racu_stencil_steps: the benchmark's loop (bench/bench-stencil3.cc:55-64 + swap, :117-121) handed to the library
+    as ONE call, which takes the steps two per pass (state t+1 only in shared memory: 8 B/cell of HBM traffic for two steps). One GPU.
+    check: 10 steps leave BOTH buffers bit-identical to 10 single steps (int64 sums of the bit patterns)."""
+    torch, ex, lib, cuda = (ctx[k] for k in ("torch", "ex", "lib", "cuda"))
+    dev = ex.device
+    sweep = cuda.stencil_sweep(ctx["abi"].STENCIL_3D7, ctx["abi"].F32)
+    sums = []
+    scratch = torch.empty((n, n, n), device=dev, dtype=torch.float32)
+    for fused in (False, True):
+        A = global_field(torch, 0, n, (n, n), dev)
+        An = torch.zeros_like(A)
+        if fused:
+            cuda.stencil_steps(A, An, 10, scratch=scratch)
+        else:
+            b2 = [A, An]
+            for _ in range(10):
+                sweep(b2[0].data_ptr(), b2[1].data_ptr(), (n, n, n), (n * n, n, 1), 0, 0)
+                b2.reverse()
+        torch.cuda.synchronize()
+        sums.append((bits_checksum(torch, A), bits_checksum(torch, An)))
+    cuda.stencil_steps(A, An, 6, scratch=scratch)   # warm-up
+    torch.cuda.synchronize()
+    lib.racu_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    cuda.stencil_steps(A, An, nsteps, scratch=scratch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / nsteps
+    launches = int(lib.racu_launch_count())
+    peak, _ = read_peak()
+    cells = float(n) ** 3
+    tr = ctx.get("traffic", {}).get(f"stencil3d7_two_steps_f32_{n}^3")
+    out = {"metric": "laplace3d Gcells/s", "value": cells / (ms * 1e-3) / 1e9, "unit": "Gcells/s per step", "steps": nsteps, "ms_per_step": ms,
+           "speedup_over_single_steps": ms_single / ms, "gpu_launches": launches,
+           "kernel": "stencil_tma<3D7, two steps> (%d passes) + copy_faces + 2 single steps" % (nsteps // 2 - 1),
+           "roofline": {"bound": "hbm", "achieved": 8 * cells / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": 8 * cells / (ms * 1e-3) / 1e9 / peak,
+                        "traffic": tr,
+                        "note": "achieved = the 8 B/cell/step a single-step sweep needs / time per step: above 1.0 because a pass reads and writes the grid once for TWO steps "
+                                "(the pass itself moves 8 B/cell: its own HBM fraction is half of this)"},
+           "check": {"steps": 10, "single_steps": list(sums[0]), "two_per_pass": list(sums[1]), "equal_both_buffers": sums[0] == sums[1]}}
+    del A, An, scratch
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_map_sharded(ctx):

@@ -1019,6 +1019,30 @@ View<T, ANY> stencil(View<T, R> const & a, dim_t lo, dim_t hi)
 template <class A> requires (requires (A const & a) { a.view(); })
 auto stencil(A const & a, dim_t lo, dim_t hi) { return stencil(a.view(), lo, hi); }
 
+// The time loop of bench/bench-stencil3.cc (`Anext(I, J, K) = -6*A(I, J, K) + A(I+1, J, K) + ...; std::swap(A.cp, Anext.cp);`, :55-64 and
+// :117-121, T times) handed to the library as ONE call (racu_stencil_steps): on return a and anext hold exactly what the loop leaves in the two
+// buffers - state T in anext if T is odd, else in a; the state before it in the other; boundary cells untouched - but the steps were taken
+// two per pass over the grid where the arrays allow it. Returns true when the last state is in anext (the caller swaps like the loop would).
+template <class T, rank_t R>
+bool stencil_steps(View<T, R> const & a, View<T, R> const & anext, int steps)
+{
+    static_assert(std::is_same_v<T, float> || std::is_same_v<T, double>, "stencil sweeps are for float and double");
+    rank_t const r = a.rank();
+    RACU_CK(r==anext.rank() && r>=1 && r<=3, "Bad shapes for stencil_steps.");
+    racu_stencil_desc s {};
+    s.kind = 3==r ? RACU_STENCIL_3D7 : 2==r ? RACU_STENCIL_2D5 : RACU_STENCIL_1D3;
+    s.dtype = dtype_of<T>; s.rank = int32_t(r);
+    s.src = a.cp; s.dst = anext.cp;
+    for (rank_t k=0; k<r; ++k) {
+        RACU_CK(a.len(k)==anext.len(k), "Bad shapes for stencil_steps.");
+        s.len[k] = a.len(k); s.src_stride[k] = a.dimv[k].step; s.dst_stride[k] = anext.dimv[k].step;
+    }
+    ck_status(racu_stencil_steps(&s, int32_t(steps), nullptr, stream()));
+    return 0!=(steps&1);
+}
+template <class A, class B> requires (requires (A & a, B & b) { a.view(); b.view(); })
+bool stencil_steps(A & a, B & anext, int steps) { return stencil_steps(a.view(), anext.view(), steps); }
+
 // refmin / refmax (ra/ra.hh:326-346): a REFERENCE to the first smallest / largest element in row-major order - here a rank-0 view of
 // it, assignable like the reference's `double &`. Two folds: the extreme value, then the smallest row-major position holding it.
 template <class T, rank_t R>

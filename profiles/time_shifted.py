@@ -30,7 +30,7 @@ def timed(fn, steps=20, warmup=3):
 
 
 out = {}
-for n in (4097, 8193):
+for n in [int(x) for x in os.environ.get("NSH", "4097,8193,8196").split(",")]:
     for dt, name, es in ((torch.float64, "f64", 8), (torch.float32, "f32", 4)):
         v = ex.wrap(torch.rand(n, n, device=ex.device, dtype=dt))
         w = ex.wrap(torch.zeros(n, n, device=ex.device, dtype=dt))
@@ -54,4 +54,9 @@ I = ra.iota(N - 2, 1)
 ms = timed(lambda: An(I).assign(-2 * A(I) + A(I + 1) + A(I - 1)))
 out["1D3 (bench-stencil1.cc:45) f32 2^26"] = {"ms": round(ms, 4), "GB/s": round(8 * N / ms / 1e6, 1), "frac": round(8 * N / ms / 1e6 / PEAK, 3), "kernel": lib.racu_last_kernel().decode()}
 print("1D3", out["1D3 (bench-stencil1.cc:45) f32 2^26"])
+Ad = ex.wrap(torch.rand(N, device=ex.device, dtype=torch.float64))
+And = ex.wrap(torch.zeros(N, device=ex.device, dtype=torch.float64))
+ms = timed(lambda: And(I).assign(-2 * Ad(I) + Ad(I + 1) + Ad(I - 1)))
+out["1D3 (bench-stencil1.cc:45) f64 2^26"] = {"ms": round(ms, 4), "GB/s": round(16 * N / ms / 1e6, 1), "frac": round(16 * N / ms / 1e6 / PEAK, 3), "kernel": lib.racu_last_kernel().decode()}
+print("1D3 f64", out["1D3 (bench-stencil1.cc:45) f64 2^26"])
 print(json.dumps(out))

@@ -4,6 +4,10 @@
 //   3D7   Anext(I,J,K) = -6*A(I,J,K) + A(I+1,J,K) + A(I,J+1,K) + A(I,J,K+1) + A(I-1,J,K) + A(I,J-1,K) + A(I,J,K-1)   bench/bench-stencil3.cc:59-61
 //   2D5   Anext(I,J)   = -4*A(I,J) + A(I+1,J) + A(I,J+1) + A(I-1,J) + A(I,J-1)                                         bench/bench-stencil2.cc:53-55
 //   STIFF w(i,j)       =  4*v(i,j) - v(i-1,j) - v(i,j-1) - v(i+1,j) - v(i,j+1)                                         examples/laplace2d.cc:36
+//   MASS  w(i,j)       =  sqrm(h) * (v(i,j)/2. + (v(i-1,j) + v(i,j-1) + v(i+1,j) + v(i,j+1) + v(i+1,j+1) + v(i-1,j-1))/12.)    examples/laplace2d.cc:48
+//         (reached from racu_map only: the three scalars are operands of the expression; for float arrays the six are summed in float and
+//          the rest is double arithmetic, as C++ promotes it)
+//   1D3   Anext(I)     = -2*A(I) + A(I+1) + A(I-1)                                                                          bench/bench-stencil1.cc:45
 // Boundary cells of the destination are never written (bench/bench-stencil3.cc:125-126).
 //
 // 2.5-D streaming: a CTA owns a (TJ x TK) tile of the two inner axes and marches along axis 0. Every plane tile
@@ -30,6 +34,7 @@
 
 namespace racu {
 
+constexpr int ST_KIND_MASS = 100; // internal: the 2-D 7-point mass stencil (no public racu_stencil_kind: it carries three scalars)
 constexpr int ST_TR = 8;        // thread rows per tile
 constexpr int ST_RPT = 2;       // rows per thread (rows tj and tj+ST_TR): halves the j halo and the per-plane fixed costs
 constexpr int ST_TJ = ST_TR*ST_RPT; // tile rows
@@ -62,6 +67,7 @@ struct StParams
     uint32_t step;                       // steps completed before this launch
     int32_t edge_ctas;                   // CTAs per edge chunk (gridDim.x*gridDim.y)
     int32_t dbg;                         // measurement knobs (RACU_PUSH_DEBUG): 1 = no remote stores, 2 = no waits, 4 = no fence / signal. Wrong results.
+    double c0, c1, c2;                   // MASS only: sqrm(h), the divisor of the centre, the divisor of the six
 };
 
 // ---- system-scope flag helpers for the fused halo push
@@ -141,7 +147,8 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // one starts, so that the CTAs resident together - consecutive chunks of one band - find each other's halo planes in L2
     // whatever the plane size (2048^2 planes: a whole plane's worth of tiles per chunk is 4x what the GPU holds at once).
     int const band = is3d ? int(blockIdx.z)/p.gz : 0;
-    int const k0 = blockIdx.x*TK, j0 = 1 + (band*p.gyb + int(blockIdx.y))*ST_TJ; // first output k of the tile (vector aligned), first output j
+    // 2-D: a CTA takes p.ci consecutive tile rows of its column strip, one after the other through the same TMA ring (p.gyb = tile rows in all)
+    int const k0 = blockIdx.x*TK, j0 = 1 + (is3d ? band*p.gyb + int(blockIdx.y) : int(blockIdx.y)*p.ci)*ST_TJ; // first output k of the tile (vector aligned), first output j
     if (j0>=p.n1-1) return;                                    // last band may be short (whole CTA leaves before any barrier)
     int const k = k0 + tk*VT, j = j0 + tj;
     // FUSED: the two edge chunks (0 and gz-1: they read a ghost plane and feed the neighbours) are SPREAD over the grid: tile q of a band
@@ -165,7 +172,7 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     int const ilo = is3d ? p.i_lo + chunk*p.ci : 0;
     int const ihi = is3d ? min(p.i_hi, ilo + p.ci) : 1;
     bool const touch_lo = FUSED && p.push_lo && 1==ilo, touch_hi = FUSED && p.push_hi && ihi==p.n0-1;
-    int const nplanes = is3d ? (ihi-ilo+2) : 1;                // input planes ilo-1 .. ihi
+    int const nplanes = is3d ? (ihi-ilo+2) : min(p.ci, p.gyb - int(blockIdx.y)*p.ci); // input planes ilo-1 .. ihi; 2-D: tiles of this CTA
     constexpr uint32_t plane_bytes = (ST_TJ+2)*TKB*sizeof(T); // bytes one TMA box delivers
 
     if (0==tid) {
@@ -184,7 +191,7 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     auto issue = [&](int q) { // input plane q of this chunk -> stage q % STAGES
         int s = q % ST_STAGES;
         mbar_expect_tx(&full[s], plane_bytes);
-        tma_load_3d(stages + size_t(s)*PLANE, &tmap, k0-HO, j0-1, is3d ? ilo-1+q : 0, &full[s]);
+        tma_load_3d(stages + size_t(s)*PLANE, &tmap, k0-HO, is3d ? j0-1 : j0-1+q*ST_TJ, is3d ? ilo-1+q : 0, &full[s]);
     };
     if (0==tid) { for (int q=0; q<ST_STAGES && q<nplanes; ++q) issue(q); }
 
@@ -229,20 +236,47 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     };
 
     if constexpr (!is3d) {
-        mbar_wait(&full[0], 0);
-        T const * st = stages;
+        // One tile per CTA (round 1) left the TMA latency and the CTA start-up exposed: 0.57-0.78 of the HBM peak on 4100^2 / 8196^2. Now the
+        // tiles of a strip stream through the ring like the planes of the 3-D sweep.
+        bool kok[VT], kall = true;
 #pragma unroll
-        for (int r=0; r<ST_RPT; ++r) {
-            int const sr = so + r*ST_TR*TKB;
-            T c[VT], jp[VT], jm[VT], o[VT];
-            load_vec(st, sr, c); load_vec(st, sr+TKB, jp); load_vec(st, sr-TKB, jm);
-            T const left = st[sr-1], right = st[sr+VT];
+        for (int l=0; l<VT; ++l) { kok[l] = (k+l>=1) && (k+l<p.n2-1); kall = kall && kok[l]; }
+        for (int q=0; q<nplanes; ++q) {
+            mbar_wait(&full[q % ST_STAGES], uint32_t((q/ST_STAGES)&1));
+            T const * st = stages + size_t(q % ST_STAGES)*PLANE;
 #pragma unroll
-            for (int l=0; l<VT; ++l) {
-                T km = l==0 ? left : c[l-1], kp = l==VT-1 ? right : c[l+1];
-                o[l] = stencil_value<T, KIND>(c[l], T(0), jp[l], kp, T(0), jm[l], km);
+            for (int r=0; r<ST_RPT; ++r) {
+                int const sr = so + r*ST_TR*TKB, jr = j + q*ST_TJ + r*ST_TR;
+                T c[VT], jp[VT], jm[VT], o[VT];
+                load_vec(st, sr, c); load_vec(st, sr+TKB, jp); load_vec(st, sr-TKB, jm);
+                T const left = st[sr-1], right = st[sr+VT];
+                if constexpr (KIND==ST_KIND_MASS) {
+                    T const jpr = st[sr+TKB+VT], jml = st[sr-TKB-1];   // the two diagonal neighbours outside this thread's vectors
+#pragma unroll
+                    for (int l=0; l<VT; ++l) {
+                        T const km = l==0 ? left : c[l-1], kp = l==VT-1 ? right : c[l+1];
+                        T const dpp = l==VT-1 ? jpr : jp[l+1], dmm = l==0 ? jml : jm[l-1];
+                        T const six = ((((jm[l] + km) + jp[l]) + kp) + dpp) + dmm;          // in T, in the order written (rows are axis 0 of the expression)
+                        o[l] = T(p.c0 * (double(c[l])/p.c1 + double(six)/p.c2));
+                    }
+                } else {
+#pragma unroll
+                    for (int l=0; l<VT; ++l) {
+                        T km = l==0 ? left : c[l-1], kp = l==VT-1 ? right : c[l+1];
+                        o[l] = stencil_value<T, KIND>(c[l], T(0), jp[l], kp, T(0), jm[l], km);
+                    }
+                }
+                if (jr<p.n1-1) {
+                    T * d = static_cast<T *>(p.dst) + int64_t(jr)*p.ds1 + int64_t(k)*p.ds2;
+                    if (kall && p.vec_store) { uint4 v; memcpy(&v, o, 16); *reinterpret_cast<uint4 *>(d) = v; }
+                    else {
+#pragma unroll
+                        for (int l=0; l<VT; ++l) { if (kok[l]) d[int64_t(l)*p.ds2] = o[l]; }
+                    }
+                }
             }
-            store_out(std::false_type {}, 0, r, o);
+            __syncthreads();                                   // tile q is no longer read by anyone
+            if (0==tid && q+ST_STAGES<nplanes) issue(q+ST_STAGES);
         }
     } else {
       auto march = [&](auto push_tag) {
@@ -310,9 +344,14 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 // bit-identical to two single steps (asserted by the tests on both buffers).
 //
 // Geometry: stage 1 (t -> t+1) of a CTA covers ST_TJ x TK cells of a plane, exactly what the single-step kernel computes from the same
-// (ST_TJ+2) x TKB box; stage 2 (t+1 -> t+2) covers the cells whose neighbours stage 1 produced: rows 1 .. ST_TJ-2 and the vectors
-// 1 .. TK/VT-2 of the tile. Tiles therefore overlap by two rows and two vectors (14 x 120 outputs per 18 x 136 box for f32) and a chunk of
-// P output planes reads P+4 input planes; the overlaps are L2 hits like the halos of the single-step kernel. A thread owns two ADJACENT
+// rows; stage 2 (t+1 -> t+2) covers the cells whose neighbours stage 1 produced: rows 1 .. ST_TJ-2 and the vectors 1 .. TK/VT-2 of the
+// tile. Tiles therefore overlap by two rows and two vectors (14 x 120 outputs per 18 x 128 box for f32) and a chunk of P output planes
+// reads P+4 input planes; the overlaps are L2 hits like the halos of the single-step kernel. The k-1 / k+1 neighbours of a thread's
+// vector come from the neighbouring LANES (two shuffles per row): the first and last lane of a warp then compute garbage in the outermost
+// cell of the tile row, which nothing uses (stage 2 needs t+1 from the last cell of vector 0 and the first of vector 31 only), so the box
+// needs no halo along k - and the 4-byte shared-memory reads at a stride of 16 bytes that the single-step kernel makes for these two
+// neighbours (a 4-way bank conflict each; 39 % of the first version's shared-memory wavefronts, which ran the shared-memory pipe at
+// 70 %) are gone. A thread owns two ADJACENT
 // rows (each row's j+1 / j-1 neighbour of the other comes from registers: 6 instead of 10 16-byte shared-memory loads per thread and
 // plane) and marches along axis 0 with the centre values of t (i-1, i, i+1) and of t+1 (i-2, i-1, i) in registers; t+1 goes through a ring
 // of THREE shared planes so that one CTA barrier per plane is enough.
@@ -321,10 +360,11 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 // odd states live in the OTHER buffer: the boundary cells of t+1 are read from `bsrc` (that buffer), those of t+2 are never written.
 template <class T> struct St2Tile
 {
-    static constexpr int VT = StTile<T>::VT, TK = StTile<T>::TK, HO = StTile<T>::HO, TKB = StTile<T>::TKB, PLANE = StTile<T>::PLANE;
-    static constexpr int OUT_J = ST_TJ-2, OUT_K = TK-2*VT;   // outputs per tile and plane
+    static constexpr int VT = StTile<T>::VT, TK = StTile<T>::TK;
+    static constexpr int PLANE = (ST_TJ+2)*TK;                // the TMA box: ST_TJ+2 rows of TK cells, NO halo along k (see the kernel)
+    static constexpr int OUT_J = ST_TJ-2, OUT_K = TK-2*VT;    // outputs per tile and plane
     static constexpr int IPLANE = ST_TJ*TK;                   // one plane of t+1
-    static_assert(HO>=2 && TK/VT==32 && ST_RPT==2);
+    static_assert(TK/VT==32 && ST_RPT==2 && 0==(PLANE*sizeof(T))%128);
 };
 
 struct St2Params
@@ -344,7 +384,7 @@ template <class T, int S2_STAGES> __global__ void __launch_bounds__(ST_THREADS)
 stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St2Params p)
 {
     using TL = St2Tile<T>;
-    constexpr int VT = TL::VT, TK = TL::TK, HO = TL::HO, TKB = TL::TKB, PLANE = TL::PLANE, IPLANE = TL::IPLANE, KIND = RACU_STENCIL_3D7;
+    constexpr int VT = TL::VT, TK = TL::TK, TKB = TK, PLANE = TL::PLANE, IPLANE = TL::IPLANE, KIND = RACU_STENCIL_3D7;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T * const stages = reinterpret_cast<T *>(smem_raw);
     T * const inter = stages + size_t(S2_STAGES)*PLANE;       // 3 planes of t+1 (+ one row of slack behind them)
@@ -357,7 +397,7 @@ stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     if (jb+1>=p.n1-1) return;                                                        // no output row (whole CTA, before any barrier)
     int const ilo = p.i_lo + chunk*p.ci, ihi = min(p.i_hi, ilo+p.ci);
     int const nin = (ihi-ilo+2+2)/3*3 + 2;                                           // input planes ilo-2 .. ihi+1, rounded up so that the planes of t+1 are a multiple of three
-    constexpr uint32_t plane_bytes = (ST_TJ+2)*TKB*sizeof(T);
+    constexpr uint32_t plane_bytes = PLANE*sizeof(T);
 
     if (0==tid) {
 #pragma unroll
@@ -367,7 +407,7 @@ stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     __syncthreads();
     auto issue = [&](int q, int s) { // input plane q of this chunk -> stage s = q % S2_STAGES
         mbar_expect_tx(&full[s], plane_bytes);
-        tma_load_3d(stages + size_t(s)*PLANE, &tmap, kb-HO, jb-1, ilo-2+q, &full[s]); // planes -1 and >= n0 are zero filled (never used)
+        tma_load_3d(stages + size_t(s)*PLANE, &tmap, kb, jb-1, ilo-2+q, &full[s]); // planes -1 and >= n0 are zero filled (never used)
     };
     if (0==tid) { for (int q=0; q<S2_STAGES && q<nin; ++q) issue(q, q); }
 
@@ -395,7 +435,7 @@ stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     // plus an immediate, and CTAs whose tile and chunk touch no boundary run a loop without the boundary code. The first version spent
     // 27 instructions per cell update (7 of them arithmetic) and was issue bound: 72 % issue-slot utilisation, DRAM at 31 %
     // (profiles/r02_stencil2_*).
-    T const * const sp = stages + (2*tj+1)*TKB + HO + tk*VT;   // this thread's first centre vector in stage 0; its second row: + TKB
+    T const * const sp = stages + (2*tj+1)*TKB + tk*VT;        // this thread's first centre vector in stage 0; its second row: + TKB
     T * const ip = inter + (2*tj)*TK + tk*VT;                  // the same in plane 0 of t+1; second row: + TK
     T const * const ipj0 = tj>0 ? ip-TK : ip, * const ipj1 = tj<ST_TR-1 ? ip+2*TK : ip+TK; // rows above / below for stage 2 (tile rows 0 and 15 store nothing)
     T * dptr[2];                                        // where this thread's vector of t+2 at plane ilo goes; + ds0 per plane
@@ -448,7 +488,7 @@ stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             load_vec(pst, -TKB, jm0); load_vec(pst, 2*TKB, jp1);
 #pragma unroll
             for (int r=0; r<2; ++r) {
-                T const left = pst[r*TKB - 1], right = pst[r*TKB + VT];
+                T const left = __shfl_up_sync(0xffffffffu, C1[r][VT-1], 1), right = __shfl_down_sync(0xffffffffu, C1[r][0], 1);
 #pragma unroll
                 for (int l=0; l<VT; ++l) {
                     T const km = l==0 ? left : C1[r][l-1], kp = l==VT-1 ? right : C1[r][l+1];
@@ -477,7 +517,7 @@ stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             bool const live = INTERIOR || gi-1<ihi;     // (the last chunk may run planes past its end: the loop count is a multiple of three)
 #pragma unroll
             for (int r=0; r<2; ++r) {
-                T const left = ip[IB*IPLANE + r*TK - 1], right = ip[IB*IPLANE + r*TK + VT];
+                T const left = __shfl_up_sync(0xffffffffu, C2[r][VT-1], 1), right = __shfl_down_sync(0xffffffffu, C2[r][0], 1);
                 T o[VT];
 #pragma unroll
                 for (int l=0; l<VT; ++l) {
@@ -523,6 +563,54 @@ copy_faces_kernel(T const * src, int64_t ss0, int64_t ss1, int64_t ss2, T * dst,
     }
 }
 
+// ---------------- 1-D 3-point sweep: Anext(I) = -2*A(I) + A(I+1) + A(I-1) (bench/bench-stencil1.cc:45) ----------------
+// No staging at all: a lane loads whole 16-byte vectors of the row, its k-1 / k+1 neighbours are the neighbouring lanes' registers (two
+// shuffles per vector); only the first and the last lane of a warp read one more element each (a sector their neighbours load anyway).
+// The slice expression shifts every operand by one element, so the vector kernels of the planner cannot take it (rows not 16-byte
+// aligned) and the lane-wise kernel pays three 4-byte loads per element: 0.73 of the HBM peak; this one reads and writes every byte once.
+constexpr int S1_UNR = 4;
+
+template <class T> __global__ void __launch_bounds__(ST_THREADS, 3)
+stencil1d3_kernel(T const * __restrict__ src, T * __restrict__ dst, int64_t ds, int64_t n, int vec_store)
+{
+    constexpr int VT = 16/sizeof(T);
+    int const lane = threadIdx.x&31;
+    int64_t const nvec = (n+VT-1)/VT, warps = int64_t(gridDim.x)*(ST_THREADS/32), w = int64_t(blockIdx.x)*(ST_THREADS/32) + (threadIdx.x>>5);
+    for (int64_t v0 = w*32*S1_UNR; v0<nvec; v0 += warps*32*S1_UNR) {   // (v0 is the same for the whole warp: every lane reaches the shuffles)
+        T c[S1_UNR][VT], left[S1_UNR], right[S1_UNR];
+#pragma unroll
+        for (int u=0; u<S1_UNR; ++u) {
+            int64_t const e = (v0 + u*32 + lane)*VT;
+            if (e+VT<=n) { uint4 q = *reinterpret_cast<uint4 const *>(src + e); memcpy(c[u], &q, 16); }
+            else {
+#pragma unroll
+                for (int l=0; l<VT; ++l) c[u][l] = e+l<n ? src[e+l] : T(0);
+            }
+            left[u] = T(0); right[u] = T(0);
+            if (0==lane && e>0 && e<=n) left[u] = src[e-1];
+            if (31==lane && e+VT<n) right[u] = src[e+VT];
+        }
+#pragma unroll
+        for (int u=0; u<S1_UNR; ++u) {
+            int64_t const e = (v0 + u*32 + lane)*VT;
+            T const lf = __shfl_up_sync(0xffffffffu, c[u][VT-1], 1), rt = __shfl_down_sync(0xffffffffu, c[u][0], 1);
+            if (0!=lane) left[u] = lf;
+            if (31!=lane) right[u] = rt;
+            T o[VT];
+#pragma unroll
+            for (int l=0; l<VT; ++l) {
+                T const km = l==0 ? left[u] : c[u][l-1], kp = l==VT-1 ? right[u] : c[u][l+1];
+                o[l] = ((T(-2)*c[u][l]) + kp) + km;
+            }
+            if (vec_store && e>=1 && e+VT<=n-1) { uint4 q; memcpy(&q, o, 16); *reinterpret_cast<uint4 *>(dst + e) = q; }
+            else {
+#pragma unroll
+                for (int l=0; l<VT; ++l) { if (e+l>=1 && e+l<n-1) dst[(e+l)*ds] = o[l]; }
+            }
+        }
+    }
+}
+
 // ---------------- host ----------------
 
 using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -544,7 +632,7 @@ encode_fn()
 }
 
 template <class T, int KIND> static int
-launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled, racu_halo_push const * h = nullptr)
+launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled, racu_halo_push const * h = nullptr, double const * coef = nullptr)
 {
     using TL = StTile<T>;
     constexpr bool is3d = KIND==RACU_STENCIL_3D7;
@@ -580,6 +668,7 @@ launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled, 
     p.n0 = int32_t(n0); p.n1 = int32_t(n1); p.n2 = int32_t(n2);
     p.i_lo = int32_t(lo); p.i_hi = int32_t(hi);
     p.vec_store = 1==ds2 && 0==(uintptr_t(s->dst)%16) && 0==((ds1*es)%16) && (!is3d || 0==((ds0*es)%16));
+    if (coef) { p.c0 = coef[0]; p.c1 = coef[1]; p.c2 = coef[2]; }
     unsigned gx = unsigned((n2+TL::TK-1)/TL::TK), gy = unsigned((n1-2+ST_TJ-1)/ST_TJ), gz = 1;
     if (is3d) {
         // Short chunks of the marching axis: measured on B200 (1024^3 f32), 4-6 planes per CTA give 826-829 Gcells/s against
@@ -593,6 +682,12 @@ launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled, 
     }
     p.gz = int32_t(gz); p.gyb = int32_t(gy);
     unsigned const tiles_y = gy;                 // valid tile rows (edge CTA count of the fused step)
+    if (!is3d) {                                 // 2-D: 2 or 4 tile rows per CTA (8196^2 on B200, fraction of the HBM peak for 2 / 4 / 8 / 16: stiffness f64 0.99 / 0.99 / 0.96 / 0.92,
+                                                 // f32 0.87 / 0.89 / 0.91 / 0.82; one tile per CTA, round 1: 0.75 / 0.78)
+        p.ci = int64_t(gx)*gy>=20000 ? 4 : int64_t(gx)*gy>=1480 ? 2 : 1;
+        if (char const * e = std::getenv("RACU_ST_CI2")) p.ci = std::max(1, std::atoi(e)); // tuning knob
+        gy = (gy+p.ci-1)/p.ci;
+    }
     if (is3d) {
         // bands of about 512 tiles (the 1024^2 plane this was tuned on: 8 x 64 tiles per chunk)
         int64_t band_tiles = 512;
@@ -615,7 +710,7 @@ launch_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * handled, 
     kernel<<<dim3(gx, gy, gz), ST_THREADS, smem, stream>>>(tmap, p);
     launch_count_add(1);
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "stencil_tma");
-    set_kernel(is3d ? (h ? "stencil_tma<3D7, halo push>" : "stencil_tma<3D7>") : (KIND==RACU_STENCIL_2D5 ? "stencil_tma<2D5>" : "stencil_tma<2D5_STIFF>"));
+    set_kernel(is3d ? (h ? "stencil_tma<3D7, halo push>" : "stencil_tma<3D7>") : (KIND==RACU_STENCIL_2D5 ? "stencil_tma<2D5>" : KIND==ST_KIND_MASS ? "stencil_tma<2D7_MASS>" : "stencil_tma<2D5_STIFF>"));
     *handled = 1;
     return RACU_OK;
 }
@@ -630,6 +725,19 @@ try_special_stencil(racu_stencil_desc const * s, cudaStream_t stream, int * hand
     // An in-place sweep (dst overlapping src) would be a race here; the planner rejects it ("traversal order would be observable").
     if (views_overlap(s->src, s->rank, s->len, s->src_stride, s->dst, s->rank, s->len, s->dst_stride, s->dtype==RACU_F32 ? 4 : 8)) return RACU_OK;
 #define RACU_ST(KIND) (s->dtype==RACU_F32 ? launch_stencil<float, KIND>(s, stream, handled) : launch_stencil<double, KIND>(s, stream, handled))
+    if (RACU_STENCIL_1D3==s->kind) {
+        if (1!=s->rank || 1!=s->src_stride[0] || 0!=(uintptr_t(s->src)%16) || s->len[0]<3 || 0!=s->lo0 || 0!=s->hi0 || s->dst_stride[0]<=0) return RACU_OK;
+        int64_t const n = s->len[0], nvec = (n+(s->dtype==RACU_F32 ? 3 : 1))/(s->dtype==RACU_F32 ? 4 : 2);
+        unsigned const grid = unsigned(std::min<int64_t>((nvec+32*S1_UNR*(ST_THREADS/32)-1)/(32*S1_UNR*(ST_THREADS/32)), 148*8));
+        int const vs = 1==s->dst_stride[0] && 0==(uintptr_t(s->dst)%16);
+        if (s->dtype==RACU_F32) stencil1d3_kernel<float><<<grid, ST_THREADS, 0, stream>>>(static_cast<float const *>(s->src), static_cast<float *>(s->dst), s->dst_stride[0], n, vs);
+        else stencil1d3_kernel<double><<<grid, ST_THREADS, 0, stream>>>(static_cast<double const *>(s->src), static_cast<double *>(s->dst), s->dst_stride[0], n, vs);
+        launch_count_add(1);
+        if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "stencil1d3");
+        set_kernel("stencil_1d3");
+        *handled = 1;
+        return RACU_OK;
+    }
     switch (s->kind) {
     case RACU_STENCIL_3D7: return 3==s->rank ? RACU_ST(RACU_STENCIL_3D7) : RACU_OK;
     case RACU_STENCIL_2D5: return 2==s->rank ? RACU_ST(RACU_STENCIL_2D5) : RACU_OK;
@@ -661,7 +769,7 @@ launch_stencil2(Buf3 const & src, Buf3 const & dst, Buf3 const & bsrc, int64_t c
     CUtensorMap tmap;
     cuuint64_t gdim[3] = {cuuint64_t(n[2]), cuuint64_t(n[1]), cuuint64_t(n[0])};
     cuuint64_t gstr[2] = {cuuint64_t(src.st[1]*es), cuuint64_t(src.st[0]*es)};
-    cuuint32_t box[3] = {cuuint32_t(TL::TKB), cuuint32_t(ST_TJ+2), 1};
+    cuuint32_t box[3] = {cuuint32_t(TL::TK), cuuint32_t(ST_TJ+2), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult cr = enc(&tmap, sizeof(T)==4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, src.p,
                       gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -796,6 +904,73 @@ stencil_push(racu_stencil_desc const * s, racu_halo_push const * h, cudaStream_t
     return RACU_OK;
 }
 
+// examples/laplace2d.cc:48 as the host headers flatten it:
+//   PUSH h [SQR] | PUSH c [CAST f64] PUSH s1 DIV | PUSH x0 (PUSH xk ADD) x 5 [CAST f64] PUSH s2 DIV | ADD MUL
+// with the scalar arithmetic in f64, the six summed in the element type, and the six operands the views shifted by
+// (-1,0) (0,-1) (+1,0) (0,+1) (+1,+1) (-1,-1), in this order.
+static int
+try_mass_stencil(racu_desc const * d, cudaStream_t stream, int * handled)
+{
+    if (std::getenv("RACU_NO_TMA_STENCIL")) return RACU_OK;
+    racu_operand const & y = d->opnd[d->dst];
+    int const T = y.dtype;
+    if ((T!=RACU_F32 && T!=RACU_F64) || 2!=y.rank || y.kind!=RACU_MEM) return RACU_OK;
+    racu_ins const * in = d->ins;
+    int q = 0;
+    int const n = d->nins;
+    auto is = [&](int op, int type) { return q<n && in[q].op==op && in[q].type==type; };
+    auto scalar = [&](double & v) {
+        if (!is(RACU_OP_PUSH, RACU_F64)) return false;
+        racu_operand const & o = d->opnd[in[q].arg];
+        if (o.kind!=RACU_SCALAR || o.dtype!=RACU_F64) return false;
+        v = o.base.f; ++q;
+        return true;
+    };
+    auto view = [&](racu_operand const * & o) {
+        if (!is(RACU_OP_PUSH, T)) return false;
+        o = &d->opnd[in[q].arg];
+        if (o->kind!=RACU_MEM || o->dtype!=T || 2!=o->rank) return false;
+        ++q;
+        return true;
+    };
+    double coef[3];
+    racu_operand const * c = nullptr, * x[6];
+    if (!scalar(coef[0])) return RACU_OK;
+    if (is(RACU_OP_SQR, RACU_F64)) { coef[0] = coef[0]*coef[0]; ++q; }
+    if (!view(c)) return RACU_OK;
+    if (T==RACU_F32) { if (!is(RACU_OP_CAST, RACU_F64)) return RACU_OK; ++q; }
+    if (!scalar(coef[1]) || !is(RACU_OP_DIV, RACU_F64)) return RACU_OK;
+    ++q;
+    for (int k=0; k<6; ++k) {
+        if (!view(x[k])) return RACU_OK;
+        if (k>0) { if (!is(RACU_OP_ADD, T)) return RACU_OK; ++q; }
+    }
+    if (T==RACU_F32) { if (!is(RACU_OP_CAST, RACU_F64)) return RACU_OK; ++q; }
+    if (!scalar(coef[2]) || !is(RACU_OP_DIV, RACU_F64)) return RACU_OK;
+    ++q;
+    if (!is(RACU_OP_ADD, RACU_F64)) return RACU_OK;
+    ++q;
+    if (!is(RACU_OP_MUL, RACU_F64)) return RACU_OK;
+    ++q;
+    if (q!=n) return RACU_OK;
+    static constexpr int sh[6][2] = {{-1, 0}, {0, -1}, {1, 0}, {0, 1}, {1, 1}, {-1, -1}};
+    int64_t const es = T==RACU_F32 ? 4 : 8;
+    for (int k=0; k<2; ++k) { if (y.len[k]!=c->len[k] || c->len[k]<1) return RACU_OK; }
+    for (int k=0; k<6; ++k) {
+        for (int a=0; a<2; ++a) { if (x[k]->len[a]!=c->len[a] || x[k]->stride[a]!=c->stride[a]) return RACU_OK; }
+        int64_t const delta = static_cast<char *>(x[k]->base.ptr)-static_cast<char *>(c->base.ptr);
+        if (delta!=(sh[k][0]*c->stride[0] + sh[k][1]*c->stride[1])*es) return RACU_OK;
+    }
+    racu_stencil_desc s;
+    std::memset(&s, 0, sizeof(s));
+    s.kind = ST_KIND_MASS; s.dtype = T; s.rank = 2;
+    for (int k=0; k<2; ++k) { s.len[k] = c->len[k]+2; s.src_stride[k] = c->stride[k]; s.dst_stride[k] = y.stride[k]; }
+    s.src = static_cast<char *>(c->base.ptr) - (c->stride[0]+c->stride[1])*es;
+    s.dst = static_cast<char *>(y.base.ptr) - (y.stride[0]+y.stride[1])*es;
+    if (views_overlap(s.src, 2, s.len, s.src_stride, s.dst, 2, s.len, s.dst_stride, size_t(es))) return RACU_OK;
+    return T==RACU_F32 ? launch_stencil<float, ST_KIND_MASS>(&s, stream, handled, nullptr, coef) : launch_stencil<double, ST_KIND_MASS>(&s, stream, handled, nullptr, coef);
+}
+
 // racu_map pattern recognition: is this descriptor one of the reference's stencil slice expressions? (special.cc builds the
 // canonical form; a descriptor flattened by a host header may order / share operands differently, so compare by meaning.)
 int
@@ -821,9 +996,11 @@ try_special_map(racu_desc const * d, cudaStream_t stream, int * handled)
         }
     }
     if (d->assign!=RACU_ASSIGN_SET || d->nins<8) return RACU_OK;
+    if (int e = try_mass_stencil(d, stream, handled)) return e;
+    if (*handled) return RACU_OK;
     racu_operand const & y = d->opnd[d->dst];
     int const T = y.dtype, r = y.rank;
-    if ((T!=RACU_F32 && T!=RACU_F64) || r<2 || r>3) return RACU_OK;
+    if ((T!=RACU_F32 && T!=RACU_F64) || r<1 || r>3) return RACU_OK;
     // program: PUSH s(i32) CAST PUSH c MUL (PUSH x OP)*
     racu_ins const * in = d->ins;
     if (in[0].op!=RACU_OP_PUSH || in[1].op!=RACU_OP_CAST || in[1].type!=T || in[2].op!=RACU_OP_PUSH || in[3].op!=RACU_OP_MUL || in[3].type!=T) return RACU_OK;
@@ -840,6 +1017,7 @@ try_special_map(racu_desc const * d, cudaStream_t stream, int * handled)
     if (3==r && op==RACU_OP_ADD && sc.base.i==-6) { kind = RACU_STENCIL_3D7; Sh w[6] = {{0, 1}, {1, 1}, {2, 1}, {0, -1}, {1, -1}, {2, -1}}; std::memcpy(want, w, sizeof(w)); }
     else if (2==r && op==RACU_OP_ADD && sc.base.i==-4) { kind = RACU_STENCIL_2D5; Sh w[4] = {{0, 1}, {1, 1}, {0, -1}, {1, -1}}; std::memcpy(want, w, sizeof(w)); }
     else if (2==r && op==RACU_OP_SUB && sc.base.i==4) { kind = RACU_STENCIL_2D5_STIFF; Sh w[4] = {{0, -1}, {1, -1}, {0, 1}, {1, 1}}; std::memcpy(want, w, sizeof(w)); }
+    else if (1==r && op==RACU_OP_ADD && sc.base.i==-2) { kind = RACU_STENCIL_1D3; Sh w[2] = {{0, 1}, {0, -1}}; std::memcpy(want, w, sizeof(w)); }
     else return RACU_OK;
     size_t const es = T==RACU_F32 ? 4 : 8;
     for (int k=0; k<r; ++k) { if (y.len[k]!=c.len[k] || c.len[k]<1) return RACU_OK; }

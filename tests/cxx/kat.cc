@@ -400,6 +400,22 @@ int main()
         tr.test_eq(ref, A);
         tr.test_eq(refn, Anext);
     }
+    tr.section("the benchmark's time loop as one call (stencil_steps): bench/bench-stencil3.cc:55-64 with its swap :117-121, T = 7 and 10 on 20 x 18 x 136");
+    {
+        int const nx = 20, ny = 18, nz = 136;
+        for (int T: {7, 10}) {
+            rc::Big<float, 3> A({nx, ny, nz}, (rc::cast<float>((rc::_0*7 + rc::_1*3 + rc::_2*5) % 11) - 5.f) * 0.125f), Anext({nx, ny, nz}, 0.25f);
+            rc::Big<float, 3> B({nx, ny, nz}, (rc::cast<float>((rc::_0*7 + rc::_1*3 + rc::_2*5) % 11) - 5.f) * 0.125f), Bnext({nx, ny, nz}, 0.25f);
+            auto I = rc::iota(nx-2, 1), J = rc::iota(ny-2, 1), K = rc::iota(nz-2, 1);
+            for (int t=0; t<T; ++t) {
+                Anext(I, J, K) = -6*A(I, J, K) + A(I+1, J, K) + A(I, J+1, K) + A(I, J, K+1) + A(I-1, J, K) + A(I, J-1, K) + A(I, J, K-1);
+                std::swap(A.cp, Anext.cp);
+            }
+            if (rc::stencil_steps(B, Bnext, T)) std::swap(B.cp, Bnext.cp);
+            tr.test_eq(A.to_host(), B);          // state T, bit for bit (different boundary values in the two buffers, like the benchmark's value / 0)
+            tr.test_eq(Anext.to_host(), Bnext);  // state T-1
+        }
+    }
     tr.section("any / every / index / lexical_compare: test/early.cc:17-82, ra/ra.hh:279-304");
     {
         rc::Big<int, 0> a0({}, 99);

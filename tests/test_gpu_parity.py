@@ -477,6 +477,69 @@ def test_shifted_slice_expressions_run_specialised(dt, n, exc):
         k3 = ex.last_kernel() if ex.name == "cuda" else None
         outs.append((snapshot(ex, w), snapshot(ex, An), snapshot(ex, B)))
         if ex.name == "cuda":
-            assert all(k in ("jit_map", "sflat_map") for k in (k1, k2, k3)), (k1, k2, k3)
+            assert k1 in ("jit_map", "sflat_map", "stencil_tma<2D7_MASS>") and k2 == "stencil_1d3" and k3 in ("jit_map", "sflat_map"), (k1, k2, k3)
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(66, 132), (35, 260), (200, 1028), (3, 4), (18, 136)])
+def test_mass_stencil_on_the_tma_kernel(dt, shape, exc):
+    """examples/laplace2d.cc:48 on arrays whose rows are 16-byte multiples: recognised in racu_map and run by the TMA stencil kernel
+    (7 points incl. the two diagonal neighbours, /2. and /12. as IEEE divisions, for float arrays the six summed in float and the rest in
+    double, like C++ promotes the expression). Bit-exact against the oracle; the boundary of w is not written."""
+    rng = np.random.default_rng(91)
+    v0 = rng.uniform(-1, 1, shape).astype(dt)
+    h = 0.37
+    outs = []
+    for ex in (OracleExecutor(), exc):
+        v, w = ex.from_numpy(v0), ex.from_numpy(np.full(shape, 3, dtype=dt))
+        i, j = ra.iota(shape[0] - 2, 1), ra.iota(shape[1] - 2, 1)
+        w(i, j).assign(ra.sqrm(h) * (v(i, j) / 2. + (v(i - 1, j) + v(i, j - 1) + v(i + 1, j) + v(i, j + 1) + v(i + 1, j + 1) + v(i - 1, j - 1)) / 12.))
+        if ex.name == "cuda":
+            assert ex.last_kernel() == "stencil_tma<2D7_MASS>", ex.last_kernel()
+        w2 = ex.from_numpy(np.full(shape, 3, dtype=dt))
+        w2(i, j).assign(0.25 * (v(i, j) / 3. + (v(i - 1, j) + v(i, j - 1) + v(i + 1, j) + v(i, j + 1) + v(i + 1, j + 1) + v(i - 1, j - 1)) / 7.))  # other scalars, no sqrm
+        w3 = ex.from_numpy(np.full(shape, 3, dtype=dt))
+        w3(i, j).assign(0.25 * (v(i, j) / 3. + (v(i - 1, j) + v(i, j - 1) + v(i + 1, j) + v(i, j + 1) + v(i + 1, j + 1) + v(i - 1, j + 1)) / 7.))  # NOT the mass stencil: last neighbour differs
+        if ex.name == "cuda":
+            assert ex.last_kernel() != "stencil_tma<2D7_MASS>"
+        outs.append((snapshot(ex, w), snapshot(ex, w2), snapshot(ex, w3)))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [3, 4, 5, 130, 1027, 4096, 70001, (1 << 20) + 2])
+def test_stencil_1d3(dt, n, exc):
+    """bench/bench-stencil1.cc:45 as the slice expression and through racu_stencil: the shuffle kernel, bit-exact, ends untouched."""
+    import ctypes as C
+    import torch
+    from oracle_exec import lib as olib
+    from ra_ra_b200 import cuda
+    rng = np.random.default_rng(92)
+    a0 = rng.uniform(-1, 1, n).astype(dt)
+    outs = []
+    for ex in (OracleExecutor(), exc):
+        A, An = ex.from_numpy(a0), ex.from_numpy(np.full(n, 9, dtype=dt))
+        I = ra.iota(n - 2, 1)
+        An(I).assign(-2 * A(I) + A(I + 1) + A(I - 1))
+        if ex.name == "cuda":
+            assert ex.last_kernel() == "stencil_1d3", ex.last_kernel()
+        outs.append(snapshot(ex, An))
+    assert np.array_equal(outs[0], outs[1])
+    ref = np.full(n, 9, dtype=dt)
+    assert olib().oracle_stencil_raw(C.byref(_stencil_desc(abi.STENCIL_1D3, dt, a0.ctypes.data, ref.ctypes.data, (n,), [1]))) == 0
+    assert np.array_equal(ref, outs[0])
+    At = torch.from_numpy(a0).cuda()
+    out = torch.full((n,), 9, dtype=At.dtype, device="cuda")
+    cuda.check(cuda.lib.racu_stencil(C.byref(_stencil_desc(abi.STENCIL_1D3, dt, At.data_ptr(), out.data_ptr(), (n,), [1])), cuda.stream_ptr()))
+    assert cuda.lib.racu_last_kernel() == b"stencil_1d3"
+    assert np.array_equal(out.cpu().numpy(), ref)
+    # a destination with a stride: element-wise stores
+    out2 = torch.full((2 * n,), 9, dtype=At.dtype, device="cuda")
+    s = _stencil_desc(abi.STENCIL_1D3, dt, At.data_ptr(), out2.data_ptr(), (n,), [1])
+    s.dst_stride[0] = 2
+    cuda.check(cuda.lib.racu_stencil(C.byref(s), cuda.stream_ptr()))
+    o2 = out2.cpu().numpy()
+    assert np.array_equal(o2[0::2], ref) and bool((o2[1::2] == 9).all())
