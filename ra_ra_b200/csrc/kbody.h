@@ -120,6 +120,18 @@ scatter_vector(KParams const & p, W const * off, W const * x, int nvalid)
         if (RACU_ASSIGN_SET==p.fold_op || 1==es) { store_elem<W>(ptr, dt, cast_any<W>(vt, dt, x[j])); continue; }
         auto rmw = [&](W old) { return cast_any<W>(vt, dt, finish_op<W>(p.fold_op, vt, cast_any<W>(dt, vt, old), x[j])); };
 #if defined(__CUDA_ARCH__)
+        // a(i) += x / -= x in the array's own type: ONE reduction instruction at the L2 (red.global.add) instead of a read + compare-and-swap
+        // round trip per attempt. The same single IEEE addition per contribution, in the same unspecified order.
+        if ((RACU_ASSIGN_ADD==p.fold_op || RACU_ASSIGN_SUB==p.fold_op) && dt==vt && RACU_BOOL!=dt) {
+            bool const sub = RACU_ASSIGN_SUB==p.fold_op;
+            if (RACU_F32==dt) { float const v = bits_f32(uint32_t(x[j])); atomicAdd(reinterpret_cast<float *>(ptr), sub ? -v : v); }
+            else if (RACU_I32==dt) { uint32_t const v = uint32_t(x[j]); atomicAdd(reinterpret_cast<unsigned int *>(ptr), sub ? 0u-v : v); }
+            else if constexpr (sizeof(W)==8) {
+                if (RACU_F64==dt) { double const v = bits_f64(uint64_t(x[j])); atomicAdd(reinterpret_cast<double *>(ptr), sub ? -v : v); }
+                else { uint64_t const v = uint64_t(x[j]); atomicAdd(reinterpret_cast<unsigned long long *>(ptr), (unsigned long long)(sub ? 0ull-v : v)); }
+            }
+            continue;
+        }
         if (4==es) {
             unsigned int * const w = reinterpret_cast<unsigned int *>(ptr);
             unsigned int old = *w, assumed;

@@ -536,6 +536,14 @@ def test_stencil_1d3(dt, n, exc):
     cuda.check(cuda.lib.racu_stencil(C.byref(_stencil_desc(abi.STENCIL_1D3, dt, At.data_ptr(), out.data_ptr(), (n,), [1])), cuda.stream_ptr()))
     assert cuda.lib.racu_last_kernel() == b"stencil_1d3"
     assert np.array_equal(out.cpu().numpy(), ref)
+    # a source that does not start on a 16-byte boundary: not for this kernel (the lane-wise map kernel takes it), same answer
+    if n > 8:
+        big = torch.zeros(n + 1, dtype=At.dtype, device="cuda")
+        big[1:] = At
+        outu = torch.full((n,), 9, dtype=At.dtype, device="cuda")
+        cuda.check(cuda.lib.racu_stencil(C.byref(_stencil_desc(abi.STENCIL_1D3, dt, big[1:].data_ptr(), outu.data_ptr(), (n,), [1])), cuda.stream_ptr()))
+        assert cuda.lib.racu_last_kernel() != b"stencil_1d3"
+        assert np.array_equal(outu.cpu().numpy(), ref)
     # a destination with a stride: element-wise stores
     out2 = torch.full((2 * n,), 9, dtype=At.dtype, device="cuda")
     s = _stencil_desc(abi.STENCIL_1D3, dt, At.data_ptr(), out2.data_ptr(), (n,), [1])
