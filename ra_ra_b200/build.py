@@ -45,6 +45,7 @@ template <class A, class B> inline constexpr bool is_same_v = is_same<A, B>::val
 template <bool C, class A, class B> struct conditional { using type = A; };
 template <class A, class B> struct conditional<false, A, B> { using type = B; };
 template <bool C, class A, class B> using conditional_t = typename conditional<C, A, B>::type;
+template <class T, T v> struct integral_constant { static constexpr T value = v; };
 }
 """,
 }

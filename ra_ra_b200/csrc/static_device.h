@@ -293,6 +293,60 @@ smap_body(SParams const & p)
     }
 }
 
+// One group of UNR warp tiles of a row for smap_lanes_body.
+// FULL: every element of the UNR warp tiles is inside the row (all but the last group of a row). The loads and stores are then
+// unpredicated and the four accesses of a role are ONE address plus immediates; with the per-element `live` predicates the compiler
+// recomputed a 64-bit address under every predicate: 39 instructions per element on the 5-point stencil, issue bound next to the L1 limit.
+template <int ID, uint64_t KINDS, bool FULL> __device__ __forceinline__ void
+smap_lanes_group(SParams const & p, int lane, int64_t wt, int64_t wt1, unsigned char const * const * rowp, unsigned char * drow)
+{
+    using W = typename SPT<ID>::W;
+    constexpr SProg P = SPT<ID>::P;
+    constexpr int des = es_of(P.otype), UNR = SPX<ID>::UNR>2 ? 2 : SPX<ID>::UNR, XW = SPX<ID>::XW;
+    uint32_t x[UNR][P.nin][XW];
+    int64_t e0[UNR];
+#pragma unroll
+    for (int u=0; u<UNR; ++u) {
+        e0[u] = (FULL || wt+u<wt1) ? (wt+u)*(32*SV) + lane : p.n;   // this lane's first element of the warp tile; the others are 32 apart
+        bool live[SV];                                    // which of this lane's elements are inside the row: once for every role
+#pragma unroll
+        for (int j=0; j<SV; ++j) live[j] = FULL || e0[u] + 32*j<p.n;
+#pragma unroll
+        for (int k=0; k<P.nin; ++k) {
+            int const t = P.rtype[k], es = es_of(t);
+            int const kd = KINDS!=SK_RUNTIME ? int((KINDS>>(4*k))&15u) : int(p.kind[k]);
+            uint32_t * xv = x[u][k];
+            if (SK_SCALAR==kd) splat_bits(xv, p.in[k], t);
+            else if (SK_PTR==kd) {}
+            else if (SK_SEQ==kd) seq_words(xv, p.in[k], int64_t(reinterpret_cast<intptr_t>(rowp[k])) + e0[u]*p.sA[k][0], 32*p.sA[k][0], t);
+            else if (SK_ROW==kd) splat_words(xv, rowp[k], t);
+            else { // the four loads at fixed distances from one pointer
+                bool const rev = SK_VECREV==kd || SK_VECREVU==kd;
+                unsigned char const * const q0 = rowp[k] + (rev ? -e0[u] : e0[u])*es;
+                int const step = rev ? -32*es : 32*es;
+                if (1==es) xv[0] = 0;
+#pragma unroll
+                for (int j=0; j<SV; ++j) {
+                    unsigned char const * q = q0 + j*step;
+                    if (4==es) { uint32_t v = 0; if (live[j]) v = k==P.yrole ? *reinterpret_cast<uint32_t const *>(q) : __ldg(reinterpret_cast<uint32_t const *>(q)); xv[j] = v; }
+                    else if (8==es) { uint2 v = make_uint2(0, 0); if (live[j]) v = k==P.yrole ? *reinterpret_cast<uint2 const *>(q) : __ldg(reinterpret_cast<uint2 const *>(q)); xv[2*j] = v.x; xv[2*j+1] = v.y; }
+                    else { if (live[j] && *q) xv[0] |= 1u<<(8*j); }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u=0; u<UNR; ++u) {
+        if (FULL || e0[u]<p.n) {
+            W out[SV];
+            eval_static<ID>(p, x[u], out);
+            unsigned char * const d0 = drow + e0[u]*des;
+#pragma unroll
+            for (int j=0; j<SV; ++j) { if (FULL || e0[u] + 32*j<p.n) store_elem<W>(d0 + j*32*des, P.otype, out[j]); }
+        }
+    }
+}
+
 // ---- map, lane-wise: the same traversal for rows that are NOT 16-byte aligned or not a whole number of vectors - slices shifted by
 // one element (the user-written stencils of examples/laplace2d.cc:36,48 and bench/bench-stencil1.cc:45, any A(I, J+1)), odd row lengths.
 // A warp owns 32*SV consecutive elements of a row and lane l holds elements l, l+32, l+64, l+96 of them, so every load and store is
@@ -343,47 +397,8 @@ smap_lanes_body(SParams const & p)
             rowp[k] = SK_SEQ==kd ? reinterpret_cast<unsigned char const *>(intptr_t(off)) : reinterpret_cast<unsigned char const *>(p.in[k]) + off*es_of(P.rtype[k]);
         }
         for (int64_t wt = wt0; wt<wt1; wt += UNR) {
-            uint32_t x[UNR][P.nin][XW];
-            int64_t e0[UNR];
-#pragma unroll
-            for (int u=0; u<UNR; ++u) {
-                e0[u] = wt+u<wt1 ? (wt+u)*(32*SV) + lane : p.n;   // this lane's first element of the warp tile; the others are 32 apart
-                bool live[SV];                                    // which of this lane's elements are inside the row: once for every role
-#pragma unroll
-                for (int j=0; j<SV; ++j) live[j] = e0[u] + 32*j<p.n;
-#pragma unroll
-                for (int k=0; k<P.nin; ++k) {
-                    int const t = P.rtype[k], es = es_of(t);
-                    int const kd = KINDS!=SK_RUNTIME ? int((KINDS>>(4*k))&15u) : int(p.kind[k]);
-                    uint32_t * xv = x[u][k];
-                    if (SK_SCALAR==kd) splat_bits(xv, p.in[k], t);
-                    else if (SK_PTR==kd) {}
-                    else if (SK_SEQ==kd) seq_words(xv, p.in[k], int64_t(reinterpret_cast<intptr_t>(rowp[k])) + e0[u]*p.sA[k][0], 32*p.sA[k][0], t);
-                    else if (SK_ROW==kd) splat_words(xv, rowp[k], t);
-                    else { // the four loads at fixed distances from one pointer
-                        bool const rev = SK_VECREV==kd || SK_VECREVU==kd;
-                        unsigned char const * const q0 = rowp[k] + (rev ? -e0[u] : e0[u])*es;
-                        int const step = rev ? -32*es : 32*es;
-                        if (1==es) xv[0] = 0;
-#pragma unroll
-                        for (int j=0; j<SV; ++j) {
-                            unsigned char const * q = q0 + j*step;
-                            if (4==es) { uint32_t v = 0; if (live[j]) v = k==P.yrole ? *reinterpret_cast<uint32_t const *>(q) : __ldg(reinterpret_cast<uint32_t const *>(q)); xv[j] = v; }
-                            else if (8==es) { uint2 v = make_uint2(0, 0); if (live[j]) v = k==P.yrole ? *reinterpret_cast<uint2 const *>(q) : __ldg(reinterpret_cast<uint2 const *>(q)); xv[2*j] = v.x; xv[2*j+1] = v.y; }
-                            else { if (live[j] && *q) xv[0] |= 1u<<(8*j); }
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u=0; u<UNR; ++u) {
-                if (e0[u]<p.n) {
-                    W out[SV];
-                    eval_static<ID>(p, x[u], out);
-#pragma unroll
-                    for (int j=0; j<SV; ++j) { int64_t const e = e0[u] + 32*j; if (e<p.n) store_elem<W>(drow + e*des, P.otype, out[j]); }
-                }
-            }
+            if (wt+UNR<=wt1 && (wt+UNR)*int64_t(32*SV)<=p.n) smap_lanes_group<ID, KINDS, true>(p, lane, wt, wt1, rowp, drow);
+            else smap_lanes_group<ID, KINDS, false>(p, lane, wt, wt1, rowp, drow);
         }
     }
 }

@@ -511,7 +511,7 @@ def test_user_stencils_on_odd_rows(dt, shape, exc):
             w = ex.from_numpy(np.full(shape, 3, dtype=dt))
             w(I, J, K).assign(-6 * v(I, J, K) + v(I + 1, J, K) + v(I, J + 1, K) + v(I, J, K + 1) + v(I - 1, J, K) + v(I, J - 1, K) + v(I, J, K - 1))
             res.append(snapshot(ex, w)); kern.append(ex.last_kernel() if ex.name == "cuda" else None)
-        if ex.name == "cuda":
+        if ex.name == "cuda" and min(shape) >= 4:
             assert all(k in ("jit_map", "sflat_map") or k.startswith("stencil_tma") for k in kern), kern   # never the interpreter
         outs.append(res)
     for a, b in zip(*outs):
