@@ -380,7 +380,7 @@ struct St2Params
 constexpr int S2_STAGES_DEFAULT = 5;   // TMA ring of the two-step kernel: plane m+5 is requested when plane m is released, four planes ahead of its use (the loads are DRAM
                                // latency under load; with a ring of three the CTAs waited for data most of the time: 37 % issue-slot utilisation in the lean loop)
 
-template <class T, int S2_STAGES> __global__ void __launch_bounds__(ST_THREADS)
+template <class T, int S2_STAGES> __global__ void __launch_bounds__(ST_THREADS, (3==S2_STAGES ? 4 : 6==S2_STAGES ? 2 : 3))
 stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St2Params p)
 {
     using TL = St2Tile<T>;
