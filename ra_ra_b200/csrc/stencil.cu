@@ -358,6 +358,40 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 //
 // Boundary cells keep the values of the buffer a state lives in (bench/bench-stencil3.cc:125-126), and in the reference's ping-pong the
 // odd states live in the OTHER buffer: the boundary cells of t+1 are read from `bsrc` (that buffer), those of t+2 are never written.
+// One vector of 7-point updates, -6*c + ip + jp + kp + im + jm + km per lane in exactly this order. PACKED (float): the six additions of two
+// lanes at a time as add.rn.f32x2 (Blackwell's packed FP32 pipe: one instruction, two IEEE round-to-nearest additions, bit-identical to two
+// scalar ones); the products stay scalar (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false: not bit-exact). The
+// k-1 / k+1 operands straddle the lane pairs and are re-packed (three pairs per vector).
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(uint64_t x, float & a, float & b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+template <class T, bool PACKED, int VT> __device__ __forceinline__ void
+row7(T (&o)[VT], T const (&c)[VT], T const (&ip)[VT], T const (&jp)[VT], T const (&im)[VT], T const (&jm)[VT], T left, T right)
+{
+    if constexpr (PACKED && std::is_same_v<T, float> && 4==VT) {
+        uint64_t const k12 = f2_pack(c[1], c[2]);
+        uint64_t const kp[2] = {k12, f2_pack(c[3], right)}, km[2] = {f2_pack(left, c[0]), k12};
+#pragma unroll
+        for (int h=0; h<2; ++h) {
+            uint64_t t = f2_pack(T(-6)*c[2*h], T(-6)*c[2*h+1]);
+            t = f2_add(t, f2_pack(ip[2*h], ip[2*h+1]));
+            t = f2_add(t, f2_pack(jp[2*h], jp[2*h+1]));
+            t = f2_add(t, kp[h]);
+            t = f2_add(t, f2_pack(im[2*h], im[2*h+1]));
+            t = f2_add(t, f2_pack(jm[2*h], jm[2*h+1]));
+            t = f2_add(t, km[h]);
+            f2_unpack(t, o[2*h], o[2*h+1]);
+        }
+    } else {
+#pragma unroll
+        for (int l=0; l<VT; ++l) {
+            T const km = l==0 ? left : c[l-1], kp = l==VT-1 ? right : c[l+1];
+            o[l] = stencil_value<T, RACU_STENCIL_3D7>(c[l], ip[l], jp[l], kp, im[l], jm[l], km);
+        }
+    }
+}
+
 template <class T> struct St2Tile
 {
     static constexpr int VT = StTile<T>::VT, TK = StTile<T>::TK;
@@ -380,7 +414,7 @@ struct St2Params
 constexpr int S2_STAGES_DEFAULT = 5;   // TMA ring of the two-step kernel: plane m+5 is requested when plane m is released, four planes ahead of its use (the loads are DRAM
                                // latency under load; with a ring of three the CTAs waited for data most of the time: 37 % issue-slot utilisation in the lean loop)
 
-template <class T, int S2_STAGES> __global__ void __launch_bounds__(ST_THREADS, (3==S2_STAGES ? 4 : 6==S2_STAGES ? 2 : 3))
+template <class T, int S2_STAGES, bool PACKED> __global__ void __launch_bounds__(ST_THREADS, (3==S2_STAGES ? 4 : 6==S2_STAGES ? 2 : 3))
 stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St2Params p)
 {
     using TL = St2Tile<T>;
@@ -452,10 +486,11 @@ stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     // (a third of the CTAs of a 1024^3 sweep touch a boundary and ran 347 instructions per plane against 165 for the others: predicate logic
     // and a 64-bit address from scratch for every boundary read)
     T const * bptr[2];
-    uint32_t smask[2];
+    uint32_t smask[2], bneed[2];
 #pragma unroll
     for (int r=0; r<2; ++r) {
         bptr[r] = static_cast<T const *>(p.bsrc) + int64_t(ilo-1)*p.bs0 + int64_t(jb+2*tj+r)*p.bs1 + int64_t(k)*p.bs2;
+        bneed[r] = ilo-1>p.n0-1 ? 0u : (0==ilo-1 || ilo-1==p.n0-1) ? dom[r] : fix[r];
         smask[r] = 0;
 #pragma unroll
         for (int l=0; l<VT; ++l) smask[r] |= lane_ok[r][l] ? 1u<<l : 0u;
@@ -502,14 +537,10 @@ stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 #pragma unroll
             for (int r=0; r<2; ++r) {
                 T const left = __shfl_up_sync(0xffffffffu, C1[r][VT-1], 1), right = __shfl_down_sync(0xffffffffu, C1[r][0], 1);
-#pragma unroll
-                for (int l=0; l<VT; ++l) {
-                    T const km = l==0 ? left : C1[r][l-1], kp = l==VT-1 ? right : C1[r][l+1];
-                    T const jp = 0==r ? C1[1][l] : jp1[l], jm = 0==r ? jm0[l] : C1[0][l];
-                    N2[r][l] = stencil_value<T, KIND>(C1[r][l], N1[r][l], jp, kp, P1[r][l], jm, km);
-                }
+                if (0==r) row7<T, PACKED, VT>(N2[0], C1[0], N1[0], C1[1], P1[0], jm0, left, right);
+                else row7<T, PACKED, VT>(N2[1], C1[1], N1[1], jp1, P1[1], C1[0], left, right);
                 if constexpr (!INTERIOR) {
-                    uint32_t const need = gi>n0m1 ? 0u : (0==gi || gi==n0m1) ? dom[r] : fix[r];   // boundary cells of t+1: the values of the buffer t+1 lives in
+                    uint32_t const need = bneed[r];               // boundary cells of t+1: the values of the buffer t+1 lives in (which lanes: worked out one plane ahead)
                     if (need) {
 #pragma unroll
                         for (int l=0; l<VT; ++l) { if ((need>>l)&1u) N2[r][l] = bptr[r][int64_t(l)*bs2]; }
@@ -517,7 +548,9 @@ stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     bptr[r] += bs0;
                     // the boundary cells of the NEXT plane, one plane ahead: read on demand, every plane of a boundary CTA waited a DRAM round trip
                     // here before it could store t+1 and reach the barrier (ncu: the long-scoreboard stalls of the kernel sat on these stores)
-                    uint32_t const nneed = gi+1>n0m1 ? 0u : (gi+1==n0m1) ? dom[r] : fix[r];
+                    uint32_t nneed = fix[r];
+                    if (gi+1>=n0m1) nneed = gi+1==n0m1 ? dom[r] : 0u;
+                    bneed[r] = nneed;
                     if (nneed) asm volatile("prefetch.global.L1 [%0];" :: "l"(bptr[r] + ((nneed&1u) ? 0 : (VT-1)*bs2)));
                 }
                 store_vec_s(ip, IW*IPLANE + r*TK, N2[r]);
@@ -536,12 +569,8 @@ stencil2_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             for (int r=0; r<2; ++r) {
                 T const left = __shfl_up_sync(0xffffffffu, C2[r][VT-1], 1), right = __shfl_down_sync(0xffffffffu, C2[r][0], 1);
                 T o[VT];
-#pragma unroll
-                for (int l=0; l<VT; ++l) {
-                    T const km = l==0 ? left : C2[r][l-1], kp = l==VT-1 ? right : C2[r][l+1];
-                    T const jp = 0==r ? C2[1][l] : jp1[l], jm = 0==r ? jm0[l] : C2[0][l];
-                    o[l] = stencil_value<T, KIND>(C2[r][l], N2[r][l], jp, kp, P2[r][l], jm, km);
-                }
+                if (0==r) row7<T, PACKED, VT>(o, C2[0], N2[0], C2[1], P2[0], jm0, left, right);
+                else row7<T, PACKED, VT>(o, C2[1], N2[1], jp1, P2[1], C2[0], left, right);
                 if (1==smode[r] && live) { uint4 q; memcpy(&q, o, 16); *reinterpret_cast<uint4 *>(dptr[r]) = q; }
                 if constexpr (!INTERIOR) {
                     if (2==smode[r] && live) {
@@ -819,7 +848,10 @@ launch_stencil2(Buf3 const & src, Buf3 const & dst, Buf3 const & bsrc, int64_t c
     if (char const * e = std::getenv("RACU_ST2_STAGES")) stages = std::atoi(e); // tuning knob: 3 .. 6
     if (stages<3 || stages>6) stages = S2_STAGES_DEFAULT;
     size_t const smem = (size_t(stages)*TL::PLANE + 3*size_t(TL::IPLANE) + TL::TK)*es;
-    auto kernel = 3==stages ? stencil2_tma_kernel<T, 3> : 4==stages ? stencil2_tma_kernel<T, 4> : 6==stages ? stencil2_tma_kernel<T, 6> : stencil2_tma_kernel<T, 5>;
+    bool packed = false; // add.rn.f32x2 for the additions of the float sweep (knob: RACU_ST2_PACKED)
+    if (char const * e = std::getenv("RACU_ST2_PACKED")) packed = 0!=std::atoi(e);
+    auto kernel = 3==stages ? stencil2_tma_kernel<T, 3, false> : 4==stages ? stencil2_tma_kernel<T, 4, false> : 6==stages ? stencil2_tma_kernel<T, 6, false>
+                  : (packed && sizeof(T)==4) ? stencil2_tma_kernel<T, 5, true> : stencil2_tma_kernel<T, 5, false>;
     if (cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return cuda_fail(e, "stencil2 smem");
     kernel<<<dim3(gx, gy, gz), ST_THREADS, smem, stream>>>(tmap, p);
     launch_count_add(1);
