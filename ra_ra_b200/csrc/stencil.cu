@@ -351,13 +351,15 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 // cell of the tile row, which nothing uses (stage 2 needs t+1 from the last cell of vector 0 and the first of vector 31 only), so the box
 // needs no halo along k - and the 4-byte shared-memory reads at a stride of 16 bytes that the single-step kernel makes for these two
 // neighbours (a 4-way bank conflict each; 39 % of the first version's shared-memory wavefronts, which ran the shared-memory pipe at
-// 70 %) are gone. A thread owns two ADJACENT
-// rows (each row's j+1 / j-1 neighbour of the other comes from registers: 6 instead of 10 16-byte shared-memory loads per thread and
-// plane) and marches along axis 0 with the centre values of t (i-1, i, i+1) and of t+1 (i-2, i-1, i) in registers; t+1 goes through a ring
-// of THREE shared planes so that one CTA barrier per plane is enough.
+// 70 %) are gone. A thread owns two ADJACENT rows (each row's j+1 / j-1 neighbour of the other comes from registers: 6 instead of 10
+// 16-byte shared-memory loads per thread and plane) and marches along axis 0 with the centre values of t (i-1, i, i+1) and of t+1
+// (i-2, i-1, i) in registers; t+1 goes through a ring of THREE shared planes so that one CTA barrier per plane is enough.
 //
 // Boundary cells keep the values of the buffer a state lives in (bench/bench-stencil3.cc:125-126), and in the reference's ping-pong the
-// odd states live in the OTHER buffer: the boundary cells of t+1 are read from `bsrc` (that buffer), those of t+2 are never written.
+// odd states live in the OTHER buffer: the boundary cells of t+1 are read from `bsrc` (that buffer; through pointers set up once and
+// prefetched one plane ahead, see the loop), those of t+2 are never written. CTAs that touch no boundary run a copy of the loop without
+// any of this. Tuning history and ncu evidence: profiles/r02_stencil2_full_summary.md, DESIGN.md 3.7.
+
 // One vector of 7-point updates, -6*c + ip + jp + kp + im + jm + km per lane in exactly this order. PACKED (float): the six additions of two
 // lanes at a time as add.rn.f32x2 (Blackwell's packed FP32 pipe: one instruction, two IEEE round-to-nearest additions, bit-identical to two
 // scalar ones); the products stay scalar (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false: not bit-exact). The
