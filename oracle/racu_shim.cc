@@ -5,6 +5,23 @@
 #include "../include/racu.h"
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+
+// RACU_SHIM_PREPARE=<path of libracu.so>: every descriptor this stand-in executes is also handed to the product's racu_prepare (plan +
+// run-time specialisation, no GPU, nothing launched: include/racu.h), so that a CPU run of the known-answer tests leaves the kernels the GPU
+// run will need in the specialiser's disk cache. Allocations are 256-byte aligned like cudaMalloc's so that the planner sees the same
+// alignment classes.
+static void
+shim_prepare(racu_desc const * d, int redop)
+{
+    using Prepare = int (*)(racu_desc const *, int, char const **);
+    static Prepare fn = [] {
+        char const * path = std::getenv("RACU_SHIM_PREPARE");
+        void * h = path && *path ? dlopen(path, RTLD_NOW | RTLD_LOCAL) : nullptr;
+        return h ? reinterpret_cast<Prepare>(dlsym(h, "racu_prepare")) : nullptr;
+    }();
+    if (fn) { char const * k = nullptr; fn(d, redop, &k); }
+}
 
 extern "C" {
 const char * oracle_last_error_string(void);
@@ -18,7 +35,7 @@ int racu_version(void) { return -RACU_VERSION; } // negative: "this is the oracl
 const char * racu_last_error_string(void) { return oracle_last_error_string(); }
 int racu_device_count(void) { return 0; }
 int racu_set_device(int) { return RACU_OK; }
-int racu_alloc(void ** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? RACU_OK : RACU_ERR_ALLOC; }
+int racu_alloc(void ** p, size_t n) { *p = std::aligned_alloc(256, (n+255)/256*256 + 256); return *p ? RACU_OK : RACU_ERR_ALLOC; }
 int racu_free(void * p) { std::free(p); return RACU_OK; }
 int racu_memcpy_h2d(void * d, const void * s, size_t n, void *) { std::memcpy(d, s, n); return RACU_OK; }
 int racu_memcpy_d2h(void * d, const void * s, size_t n, void *) { std::memcpy(d, s, n); return RACU_OK; }
@@ -41,10 +58,10 @@ int racu_stream_sync(void *) { return RACU_OK; }
 int racu_host_alloc(void ** p, size_t n) { return racu_alloc(p, n); }
 int racu_host_free(void * p) { return racu_free(p); }
 int racu_agree(const racu_desc * d, int32_t * r, int64_t * l) { return oracle_agree(d, r, l); }
-int racu_map(const racu_desc * d, void *) { return oracle_map(d); }
-int racu_reduce(const racu_desc * d, int redop, void * out, void *) { return oracle_reduce(d, redop, out); }
-int racu_reduce_dev(const racu_desc * d, int redop, void * out, void *) { return oracle_reduce(d, redop, out); }
-int racu_reduce_async(const racu_desc * d, int redop, void * out, void *) { return oracle_reduce(d, redop, out); }
+int racu_map(const racu_desc * d, void *) { shim_prepare(d, 0); return oracle_map(d); }
+int racu_reduce(const racu_desc * d, int redop, void * out, void *) { shim_prepare(d, redop); return oracle_reduce(d, redop, out); }
+int racu_reduce_dev(const racu_desc * d, int redop, void * out, void *) { shim_prepare(d, redop); return oracle_reduce(d, redop, out); }
+int racu_reduce_async(const racu_desc * d, int redop, void * out, void *) { shim_prepare(d, redop); return oracle_reduce(d, redop, out); }
 void racu_plan_cache_stats(int64_t * h, int64_t * m) { if (h) *h = 0; if (m) *m = 0; }
 int racu_prepare(const racu_desc *, int, const char ** k) { if (k) *k = "oracle"; return RACU_OK; }
 int64_t racu_launch_count(void) { return 0; }

@@ -1,0 +1,4 @@
+set -x
+ls ra_ra_b200/jit_cache | wc -l
+timeout 900 python -m pytest tests/test_gpu_kat.py tests/test_cxx_header.py -m gpu -x -q --durations=5 > gpurun_out/r2k2_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r2k2_pytest.log; tail -10 gpurun_out/r2k2_pytest.log
+ls ra_ra_b200/jit_cache | wc -l

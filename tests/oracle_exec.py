@@ -25,6 +25,27 @@ def lib():
     return _lib
 
 
+_prep = None
+
+
+def _prepare(d, redop=0):
+    """RACU_ORACLE_PREPARE=1 (set by tests/test_oracle_golden.py): every descriptor the oracle executes is also handed to the product's
+    racu_prepare - plan + run-time specialisation, no GPU, nothing launched (include/racu.h) - so that the CPU run of the known-answer cases
+    leaves the kernels their GPU run needs in the specialiser's disk cache (ra_ra_b200/jit_cache travels with the tree)."""
+    global _prep
+    if not os.environ.get("RACU_ORACLE_PREPARE"):
+        return
+    if _prep is None:
+        try:
+            from ra_ra_b200 import build
+            _prep = abi.bind(C.CDLL(build.build_lib()))
+        except Exception:  # noqa: BLE001
+            _prep = False
+    if _prep:
+        k = C.c_char_p()
+        _prep.racu_prepare(C.byref(d), int(redop), C.byref(k))
+
+
 class OracleDim(C.Structure):
     _fields_ = [("len", C.c_int64), ("step", C.c_int64)]
 
@@ -60,6 +81,7 @@ class OracleExecutor:
         return out
 
     def map(self, d):
+        _prepare(d)
         _check(lib().oracle_map(C.byref(d)))
 
     def agree(self, d):
@@ -70,11 +92,13 @@ class OracleExecutor:
 
     def reduce(self, d, redop, rtype):
         out = np.zeros(1, dtype=ra.RACU2NP[rtype])
+        _prepare(d, redop)
         _check(lib().oracle_reduce(C.byref(d), redop, out.ctypes.data))
         return out[0]
 
 
 def _oracle_reduce_into(self, d, redop, ptr):
+    _prepare(d, redop)
     _check(lib().oracle_reduce(C.byref(d), redop, C.c_void_p(ptr)))
 
 

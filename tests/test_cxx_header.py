@@ -41,8 +41,14 @@ def build_bench(which="cuda"):
 
 
 def test_header_kat_on_oracle():
+    """With RACU_WARM_JIT=1 also warms the run-time specialiser's disk cache (ra_ra_b200/jit_cache, which travels with the tree) for the GPU
+    run of the same binary: the stand-in hands every descriptor to the product's racu_prepare (oracle/racu_shim.cc, RACU_SHIM_PREPARE)."""
     exe = build_kat("oracle")
-    r = subprocess.run([exe], capture_output=True, text=True)
+    env = dict(os.environ)
+    lib = os.path.join(ROOT, "ra_ra_b200", "libracu.so")
+    if os.path.exists(lib) and os.environ.get("RACU_WARM_JIT"):
+        env["RACU_SHIM_PREPARE"] = lib
+    r = subprocess.run([exe], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " 0 failed" in r.stdout
 

@@ -22,14 +22,15 @@ def snapshot(ex, dst):
     return np.array(dst.owner, copy=True)
 
 
-@pytest.mark.parametrize("seed", range(60))
-def test_random_maps_cuda_vs_oracle(seed, exc):
+def case_random_maps(seed, executors):
+    """The outputs of every executor for the four assignment forms of one seed (None where the expression is too long for a descriptor)."""
     rng = np.random.default_rng(1000 + seed)
     shape = SHAPES[seed % len(SHAPES)]
+    res = []
     for assign in ("assign", "__iadd__", "__isub__", "__imul__"):
         state = rng.bit_generator.state
         outs = []
-        for ex in (OracleExecutor(), exc):
+        for ex in executors:
             rng.bit_generator.state = state
             dst, _ = random_view(rng, ex, shape, DT[rng.integers(0, 4)])
             e = random_expr(rng, ex, shape, 2)
@@ -40,19 +41,30 @@ def test_random_maps_cuda_vs_oracle(seed, exc):
                 outs = None
                 break
             outs.append(snapshot(ex, dst))
-        if outs is None:
-            continue
-        assert np.array_equal(outs[0], outs[1], equal_nan=True), (seed, assign)
+        res.append((assign, outs))
+    return res
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_maps_cuda_vs_oracle(seed, exc):
+    for assign, outs in case_random_maps(seed, (OracleExecutor(), exc)):
+        if outs is not None:
+            assert np.array_equal(outs[0], outs[1], equal_nan=True), (seed, assign)
+
+
+def case_random_scatter(seed, executors):
+    outs = []
+    for ex in executors:
+        rng = np.random.default_rng(9000 + seed)
+        outs.append(snapshot(ex, random_scatter(rng, ex)))
+    return outs
 
 
 @pytest.mark.parametrize("seed", range(40))
 def test_random_scatter_cuda_vs_oracle(seed, exc):
     """a(i) OP= expr with index arrays: atomic read-modify-write on the device, sequential in the oracle; the generator keeps the
     result independent of the order (distinct indices, or integer += / -= with repeats)."""
-    outs = []
-    for ex in (OracleExecutor(), exc):
-        rng = np.random.default_rng(9000 + seed)
-        outs.append(snapshot(ex, random_scatter(rng, ex)))
+    outs = case_random_scatter(seed, (OracleExecutor(), exc))
     assert outs[0].dtype == outs[1].dtype and np.array_equal(outs[0], outs[1]), seed
 
 
@@ -68,14 +80,14 @@ def test_scatter_histogram_large(exc):
     assert torch.equal(h_t.long(), torch.bincount(idx_t.long(), minlength=bins))
 
 
-@pytest.mark.parametrize("seed", range(40))
-def test_random_folds_cuda_vs_oracle(seed, exc):
+def case_random_folds(seed, executors):
     rng = np.random.default_rng(5000 + seed)
     shape = [s for s in SHAPES if len(s) >= 2][seed % 8]
+    res = []
     for variant in range(3):
         state = rng.bit_generator.state
         outs = []
-        for ex in (OracleExecutor(), exc):
+        for ex in executors:
             rng.bit_generator.state = state
             rank = len(shape)
             if variant == 0:
@@ -94,6 +106,13 @@ def test_random_folds_cuda_vs_oracle(seed, exc):
             op = ["__iadd__", "__isub__", "assign"][int(rng.integers(0, 3))]
             getattr(dst, op)(a * b + 1)
             outs.append(snapshot(ex, dst))
+        res.append(outs)
+    return res
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_folds_cuda_vs_oracle(seed, exc):
+    for variant, outs in enumerate(case_random_folds(seed, (OracleExecutor(), exc))):
         assert np.array_equal(outs[0], outs[1]), (seed, variant)
 
 

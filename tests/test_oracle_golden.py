@@ -1,5 +1,7 @@
 """Pins the CPU oracle (oracle/ply_oracle.cc) against the reference's own known-answer tests (tests/kat.py lists
 them with file:line), and checks the oracle's view algebra against the Python host mirror."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,7 +11,11 @@ from ra_ra_b200 import abi, ra
 
 
 @pytest.mark.parametrize("case", kat.CASES, ids=lambda f: f.__name__)
-def test_kat_on_oracle(case):
+def test_kat_on_oracle(case, monkeypatch):
+    """(With RACU_WARM_JIT=1 every descriptor is also handed to the product's racu_prepare, which leaves the specialised kernels of these
+    cases in the disk cache for their GPU run, tests/test_gpu_kat.py: oracle_exec._prepare, tests/test_warm_jit.py.)"""
+    if os.environ.get("RACU_WARM_JIT"):
+        monkeypatch.setenv("RACU_ORACLE_PREPARE", "1")
     case(OracleExecutor())
 
 
