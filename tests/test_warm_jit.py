@@ -33,3 +33,29 @@ def test_warm_random_folds(seed):
 def test_warm_random_scatter(seed):
     import test_gpu_parity as gp
     gp.case_random_scatter(seed, (OracleExecutor(),))
+
+
+def _param_sets(fn):
+    """Cartesian product of the pytest.mark.parametrize marks of a test function, as dicts."""
+    import itertools
+    marks = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
+    names = [[n.strip() for n in m.args[0].split(",")] for m in marks]
+    for combo in itertools.product(*[m.args[1] for m in marks]):
+        kw = {}
+        for ns, val in zip(names, combo):
+            if len(ns) == 1:
+                kw[ns[0]] = val
+            else:
+                kw.update(dict(zip(ns, val)))
+        yield kw
+
+
+@pytest.mark.parametrize("name", ["test_shifted_slice_expressions_run_specialised", "test_user_stencils_on_odd_rows", "test_mass_stencil_on_the_tma_kernel",
+                                  "test_contiguous_map_sizes", "test_static_nd_maps_bitexact"])
+def test_warm_expression_tests(name):
+    """The expression tests of tests/test_gpu_parity.py that run `for ex in (oracle, cuda)`: here with the oracle in both seats (their kernel-name
+    assertions only apply to the cuda executor), every parameter set."""
+    import test_gpu_parity as gp
+    fn = getattr(gp, name)
+    for kw in _param_sets(fn):
+        fn(exc=OracleExecutor(), **kw)
