@@ -895,10 +895,20 @@ stencil_steps_t(racu_stencil_desc const * s, int steps, void * scratch, cudaStre
     // States t, t+2, ... live with the boundary of E, the odd ones with the boundary of O. The pairs ping-pong between E and a scratch buffer
     // C that carries E's boundary; the last two steps are single ones, so that on return BOTH buffers hold what T single steps leave:
     // state T in (T odd ? dst : src) and state T-1 in the other.
-    Buf3 E = A, O = B;
-    int left = steps;
-    if (steps&1) { if (int e = single(A, B)) return e; E = B; O = A; --left; }
+    Buf3 E = (steps&1) ? B : A, O = (steps&1) ? A : B;
     int64_t const bytes = ((n[0]-1)*E.st[0] + (n[1]-1)*E.st[1] + n[2])*int64_t(sizeof(T));
+    if (scratch) { // a caller's scratch buffer is checked before anything is launched: it is a TMA source too, and must be a third buffer
+        Buf3 const Cc {scratch, {E.st[0], E.st[1], E.st[2]}};
+        if (!tma_ok<T>(Cc, n)) return fail(RACU_ERR_BAD_DESC, "racu_stencil_steps: the scratch buffer must be 16-byte aligned");
+        auto overlaps = [&](Buf3 const & x) {
+            int64_t const xb = ((n[0]-1)*x.st[0] + (n[1]-1)*x.st[1] + n[2])*int64_t(sizeof(T));
+            uintptr_t const a0 = uintptr_t(scratch), a1 = a0+uintptr_t(bytes), b0 = uintptr_t(x.p), b1 = b0+uintptr_t(xb);
+            return a0<b1 && b0<a1;
+        };
+        if (overlaps(A) || overlaps(B)) return fail(RACU_ERR_BAD_DESC, "racu_stencil_steps: the scratch buffer overlaps one of the arrays");
+    }
+    int left = steps;
+    if (steps&1) { if (int e = single(A, B)) return e; --left; }
     void * own = nullptr;
     if (!scratch) {
         if (cudaError_t e = cudaMallocAsync(&own, size_t(bytes), stream)) return cuda_fail(e, "racu_stencil_steps scratch");

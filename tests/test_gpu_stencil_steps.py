@@ -107,6 +107,20 @@ def test_steps_reject_overlapping_buffers():
     assert cuda.lib.racu_stencil_steps(C.byref(s), 4, None, cuda.stream_ptr()) == abi.ERR_UNSUPPORTED
 
 
+def test_steps_reject_a_bad_scratch_buffer_before_touching_the_arrays():
+    import torch
+    from ra_ra_b200 import cuda
+    a = torch.rand(12, 16, 128, device="cuda")
+    b = torch.zeros_like(a)
+    a0, b0 = a.clone(), b.clone()
+    s = _desc(np.float32, a.data_ptr(), b.data_ptr(), (12, 16, 128), list(a.stride()))
+    raw = torch.zeros(12 * 16 * 128 + 8, device="cuda")
+    assert cuda.lib.racu_stencil_steps(C.byref(s), 7, raw[1:].data_ptr(), cuda.stream_ptr()) == abi.ERR_BAD_DESC      # not 16-byte aligned
+    assert cuda.lib.racu_stencil_steps(C.byref(s), 7, b.data_ptr(), cuda.stream_ptr()) == abi.ERR_BAD_DESC            # one of the arrays
+    torch.cuda.synchronize()
+    assert torch.equal(a, a0) and torch.equal(b, b0)
+
+
 def test_steps_at_256_cubed_equal_single_steps():
     import torch
     from ra_ra_b200 import cuda
